@@ -1,0 +1,293 @@
+"""ctypes binding of libhica.so (the C ABI declared in include/hica.h).
+
+There is no CPU fallback: if the shared library is missing, or no CUDA device
+is present, construction of a :class:`Handle` raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libhica.so")
+
+T_NAMES = ("upload", "distance", "linkage", "leaforder", "rank", "breakpoints", "filter", "p2_score")
+
+# every symbol include/hica.h declares (checked by tests/test_abi.py)
+ABI_SYMBOLS = (
+    "hica_version", "hica_create", "hica_destroy", "hica_last_error", "hica_launch_count", "hica_get_timers",
+    "hica_p1_upload", "hica_p1_upload_device", "hica_p1_set_row_sums", "hica_p1_distance", "hica_p1_get_distance",
+    "hica_p1_get_pairwise_row_sums", "hica_p1_get_row_sums", "hica_p1_upload_distance", "hica_p1_linkage",
+    "hica_p1_set_order", "hica_p1_get_reordered", "hica_p1_rank", "hica_p1_get_rank", "hica_p1_set_rank",
+    "hica_p1_window_sig", "hica_p1_breakpoints", "hica_p1_filter", "hica_hypergeom_less",
+    "hica_p2_upload", "hica_p2_use_p1_matrix", "hica_p2_select", "hica_p2_set_segments", "hica_p2_total",
+    "hica_p2_score_candidates", "hica_p2_score_window", "hica_p2_score_orders",
+)
+
+_lib = None
+
+
+class HicaError(RuntimeError):
+    pass
+
+
+def load_library():
+    """dlopen libhica.so; raises HicaError when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise HicaError(
+            "libhica.so not found at %s - build it with `python -m hic_genome_assembler_b200.build` "
+            "(there is no CPU fallback)" % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    vp, i64, i32, dbl = C.c_void_p, C.c_int64, C.c_int32, C.c_double
+    L.hica_version.restype = C.c_int
+    L.hica_create.argtypes = [C.c_int, C.POINTER(vp)]
+    L.hica_destroy.argtypes = [vp]
+    L.hica_last_error.argtypes = [vp]
+    L.hica_last_error.restype = C.c_char_p
+    L.hica_launch_count.argtypes = [vp]
+    L.hica_launch_count.restype = i64
+    L.hica_get_timers.argtypes = [vp, vp]
+    L.hica_p1_upload.argtypes = [vp, vp, i64]
+    L.hica_p1_upload_device.argtypes = [vp, vp, i64]
+    L.hica_p1_set_row_sums.argtypes = [vp, vp]
+    L.hica_p1_distance.argtypes = [vp]
+    L.hica_p1_get_distance.argtypes = [vp, vp]
+    L.hica_p1_get_pairwise_row_sums.argtypes = [vp, vp]
+    L.hica_p1_get_row_sums.argtypes = [vp, vp]
+    L.hica_p1_upload_distance.argtypes = [vp, vp, i64]
+    L.hica_p1_linkage.argtypes = [vp, vp, vp]
+    L.hica_p1_set_order.argtypes = [vp, vp]
+    L.hica_p1_get_reordered.argtypes = [vp, C.c_int, vp]
+    L.hica_p1_rank.argtypes = [vp]
+    L.hica_p1_get_rank.argtypes = [vp, vp]
+    L.hica_p1_set_rank.argtypes = [vp, vp, i64]
+    L.hica_p1_window_sig.argtypes = [vp, i64, i64, i64, dbl, C.c_int, vp, vp, vp]
+    L.hica_p1_breakpoints.argtypes = [vp, i64, dbl, vp, i64, vp, vp]
+    L.hica_p1_filter.argtypes = [vp, vp, i64, dbl, vp, vp, vp]
+    L.hica_hypergeom_less.argtypes = [vp, vp, vp, vp, vp, i64, dbl, vp]
+    L.hica_p2_upload.argtypes = [vp, vp, i64]
+    L.hica_p2_use_p1_matrix.argtypes = [vp]
+    L.hica_p2_select.argtypes = [vp, vp, i32]
+    L.hica_p2_set_segments.argtypes = [vp, vp, vp, i32]
+    L.hica_p2_total.argtypes = [vp, vp, i32, vp]
+    L.hica_p2_score_candidates.argtypes = [vp, vp, i64, i32, dbl, dbl, vp, vp, vp]
+    L.hica_p2_score_window.argtypes = [vp, vp, i32, i32, i32, vp, i32, vp, i32, i64, i64, dbl, dbl, vp, vp, vp]
+    L.hica_p2_score_orders.argtypes = [vp, vp, i64, i32, dbl, dbl, vp, vp, vp]
+    _lib = L
+    return L
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _c(a, dtype) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+class Handle:
+    """One GPU context of libhica (one per device, not re-entrant)."""
+
+    def __init__(self, device: int = 0):
+        self._L = load_library()
+        h = C.c_void_p()
+        rc = self._L.hica_create(int(device), C.byref(h))
+        if rc != 0:
+            raise HicaError("hica_create failed: %s" % self._L.hica_last_error(None).decode())
+        self._h = h
+        self.device = device
+        self.n = 0
+
+    # -- plumbing ---------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.hica_destroy(self._h)
+            self._h = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise HicaError(self._L.hica_last_error(self._h).decode() or ("libhica error %d" % rc))
+
+    @property
+    def launches(self) -> int:
+        return int(self._L.hica_launch_count(self._h))
+
+    def timers(self) -> dict:
+        ms = np.zeros(len(T_NAMES))
+        self._check(self._L.hica_get_timers(self._h, _ptr(ms)))
+        return dict(zip(T_NAMES, ms.tolist()))
+
+    # -- Part 1 -----------------------------------------------------------
+    def p1_upload(self, A: np.ndarray):
+        A = _c(A, np.float64)
+        if A.ndim != 2 or A.shape[0] != A.shape[1]:
+            raise ValueError("square matrix expected")
+        self.n = A.shape[0]
+        self._check(self._L.hica_p1_upload(self._h, _ptr(A), self.n))
+
+    def p1_upload_device(self, dev_ptr: int, n: int):
+        self.n = int(n)
+        self._check(self._L.hica_p1_upload_device(self._h, C.c_void_p(dev_ptr), self.n))
+
+    def p1_upload_distance(self, D: np.ndarray):
+        D = _c(D, np.float64)
+        self.n = D.shape[0]
+        self._check(self._L.hica_p1_upload_distance(self._h, _ptr(D), self.n))
+
+    def p1_set_row_sums(self, rs: Optional[np.ndarray] = None):
+        rs = None if rs is None else _c(rs, np.float64)
+        self._check(self._L.hica_p1_set_row_sums(self._h, _ptr(rs)))
+
+    def p1_distance(self):
+        self._check(self._L.hica_p1_distance(self._h))
+
+    def p1_get_distance(self) -> np.ndarray:
+        D = np.empty((self.n, self.n))
+        self._check(self._L.hica_p1_get_distance(self._h, _ptr(D)))
+        return D
+
+    def p1_get_pairwise_row_sums(self) -> np.ndarray:
+        s = np.empty(self.n)
+        self._check(self._L.hica_p1_get_pairwise_row_sums(self._h, _ptr(s)))
+        return s
+
+    def p1_get_row_sums(self) -> np.ndarray:
+        s = np.empty(self.n)
+        self._check(self._L.hica_p1_get_row_sums(self._h, _ptr(s)))
+        return s
+
+    def p1_linkage(self, want_Z: bool = True) -> Tuple[Optional[np.ndarray], np.ndarray]:
+        Z = np.empty((self.n - 1, 4)) if want_Z else None
+        leaves = np.empty(self.n, dtype=np.int32)
+        self._check(self._L.hica_p1_linkage(self._h, _ptr(Z), _ptr(leaves)))
+        return Z, leaves
+
+    def p1_set_order(self, order: Sequence[int]):
+        o = _c(order, np.int32)
+        if o.size != self.n:
+            raise ValueError("order must have n entries")
+        self._check(self._L.hica_p1_set_order(self._h, _ptr(o)))
+
+    def p1_get_reordered(self, what: int) -> np.ndarray:
+        out = np.empty((self.n, self.n))
+        self._check(self._L.hica_p1_get_reordered(self._h, int(what), _ptr(out)))
+        return out
+
+    def p1_rank(self):
+        self._check(self._L.hica_p1_rank(self._h))
+
+    def p1_get_rank(self) -> np.ndarray:
+        R = np.empty((self.n, self.n), dtype=np.int64)
+        self._check(self._L.hica_p1_get_rank(self._h, _ptr(R)))
+        return R
+
+    def p1_set_rank(self, R: np.ndarray):
+        R = _c(R, np.int64)
+        self.n = R.shape[0]
+        self._check(self._L.hica_p1_set_rank(self._h, _ptr(R), self.n))
+
+    def p1_window_sig(self, start: int, M: int, psig: float = .05, mode: int = 0, cut: int = 0):
+        L = self.n - start
+        sig = np.empty(L, dtype=np.uint8)
+        x = np.empty(L, dtype=np.int64)
+        amb = C.c_int64(0)
+        self._check(self._L.hica_p1_window_sig(self._h, start, cut, M, psig, mode, _ptr(sig), _ptr(x), C.byref(amb)))
+        return sig, x, amb.value
+
+    def p1_breakpoints(self, min_size: int = 5, min_frac: float = .05):
+        cuts = np.empty(max(16, self.n), dtype=np.int64)
+        n = C.c_int64(0)
+        amb = C.c_int64(0)
+        self._check(self._L.hica_p1_breakpoints(self._h, int(min_size), float(min_frac), _ptr(cuts), cuts.size,
+                                                C.byref(n), C.byref(amb)))
+        return [int(v) for v in cuts[: n.value]], amb.value
+
+    def p1_filter(self, cuts: Sequence[int], psig: float = .05):
+        cin = _c(list(cuts), np.int64)
+        cout = np.empty(max(1, cin.size), dtype=np.int64)
+        n = C.c_int64(0)
+        amb = C.c_int64(0)
+        self._check(self._L.hica_p1_filter(self._h, _ptr(cin), cin.size, float(psig), _ptr(cout), C.byref(n),
+                                           C.byref(amb)))
+        return [int(v) for v in cout[: n.value]], amb.value
+
+    def hypergeom_less(self, x, M, n, N, psig: float = .05) -> np.ndarray:
+        x, M, n, N = (_c(np.broadcast_to(np.asarray(v), np.broadcast(x, M, n, N).shape).ravel(), np.int64)
+                      for v in (x, M, n, N))
+        out = np.empty(x.size, dtype=np.uint8)
+        self._check(self._L.hica_hypergeom_less(self._h, _ptr(x), _ptr(M), _ptr(n), _ptr(N), x.size, psig, _ptr(out)))
+        return out
+
+    # -- Part 2 -----------------------------------------------------------
+    def p2_upload(self, G: np.ndarray):
+        G = _c(G, np.float64)
+        self._check(self._L.hica_p2_upload(self._h, _ptr(G), G.shape[0]))
+
+    def p2_use_p1_matrix(self):
+        self._check(self._L.hica_p2_use_p1_matrix(self._h))
+
+    def p2_select(self, idx: Sequence[int]):
+        idx = _c(idx, np.int32)
+        self._check(self._L.hica_p2_select(self._h, _ptr(idx), idx.size))
+
+    def p2_set_segments(self, seg_ptr: Sequence[int], seg_bins: Sequence[int]):
+        sp = _c(seg_ptr, np.int32)
+        sb = _c(seg_bins, np.int32)
+        self._check(self._L.hica_p2_set_segments(self._h, _ptr(sp), _ptr(sb), sp.size - 1))
+
+    def p2_total(self, cand: Sequence[int]) -> float:
+        c = _c(cand, np.int32)
+        t = C.c_double(0)
+        self._check(self._L.hica_p2_total(self._h, _ptr(c), c.size, C.byref(t)))
+        return t.value
+
+    def _score_out(self, B, want_scores):
+        return (np.empty(B) if want_scores else None), C.c_double(0), C.c_int64(-1)
+
+    def p2_score_candidates(self, cands: np.ndarray, total: float, carried: float = 0.0, want_scores: bool = False):
+        cands = _c(cands, np.int32)
+        B, ns = cands.shape
+        sc, best, bi = self._score_out(B, want_scores)
+        self._check(self._L.hica_p2_score_candidates(self._h, _ptr(cands), B, ns, total, carried, C.byref(best),
+                                                     C.byref(bi), _ptr(sc)))
+        return best.value, bi.value, sc
+
+    def p2_score_window(self, base: Sequence[int], win_start: int, win_n: int, order_table: np.ndarray,
+                        orient_table: np.ndarray, total: float, carried: float = 0.0,
+                        cand_lo: int = 0, cand_hi: Optional[int] = None, want_scores: bool = False):
+        base = _c(base, np.int32)
+        ot = _c(order_table, np.uint8)
+        rt = _c(orient_table, np.uint8)
+        ncand = ot.shape[0] * rt.shape[0]
+        cand_hi = ncand if cand_hi is None else cand_hi
+        sc, best, bi = self._score_out(cand_hi - cand_lo, want_scores)
+        self._check(self._L.hica_p2_score_window(self._h, _ptr(base), base.size, win_start, win_n, _ptr(ot), ot.shape[0],
+                                                 _ptr(rt), rt.shape[0], cand_lo, cand_hi, total, carried,
+                                                 C.byref(best), C.byref(bi), _ptr(sc)))
+        return best.value, bi.value, sc
+
+    def p2_score_orders(self, orders: np.ndarray, total: float, carried: float = 0.0, want_scores: bool = False):
+        orders = _c(orders, np.int32)
+        B, n = orders.shape
+        sc, best, bi = self._score_out(B, want_scores)
+        self._check(self._L.hica_p2_score_orders(self._h, _ptr(orders), B, n, total, carried, C.byref(best),
+                                                 C.byref(bi), _ptr(sc)))
+        return best.value, bi.value, sc

@@ -1,0 +1,62 @@
+"""Build libhica.so (hand-written CUDA for sm_100a + the C ABI) in-tree with nvcc."""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(CSRC, "_obj")
+LIB = os.path.join(HERE, "libhica.so")
+SOURCES = ["hica_api.cu", "hica_p1_distance.cu", "hica_p1_linkage.cu", "hica_p1_rank.cu", "hica_p1_cuts.cu",
+           "hica_p2_score.cu"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+              "-fmad=false",  # numpy/scipy/numba on x86-64 do not contract a*b+c; neither may we
+              "-Xcompiler", "-fPIC", "-Xcompiler", "-O2"]
+
+
+def _nvcc() -> str:
+    for cand in (shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found; libhica.so cannot be built")
+
+
+def _stale(target: str, deps) -> bool:
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    nvcc = _nvcc()
+    os.makedirs(OBJ, exist_ok=True)
+    headers = [os.path.join(CSRC, "hica_common.cuh"), os.path.join(HERE, "..", "include", "hica.h")]
+    objs, jobs = [], []
+    for src in SOURCES:
+        s = os.path.join(CSRC, src)
+        o = os.path.join(OBJ, src.replace(".cu", ".o"))
+        objs.append(o)
+        if force or _stale(o, [s] + headers):
+            jobs.append([nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o])
+
+    def run(cmd):
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("nvcc failed: %s\n%s\n%s" % (" ".join(cmd), r.stdout, r.stderr))
+        if verbose:
+            sys.stderr.write(r.stderr)
+
+    with ThreadPoolExecutor(max_workers=6) as ex:
+        list(ex.map(run, jobs))
+    if force or jobs or _stale(LIB, objs):
+        run([nvcc, "-shared", "-o", LIB] + objs + ["-lcudart"])
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,182 @@
+// hica_api.cu - handle lifetime, uploads, error plumbing.
+#include <stdarg.h>
+#include <stdio.h>
+
+#include "hica_common.cuh"
+
+static thread_local std::string g_create_error;
+
+int hica_set_error(hica_ctx *h, int code, const char *fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (h) h->err = buf;
+    else g_create_error = buf;
+    return code;
+}
+
+extern "C" int hica_version(void) { return 100; }
+
+extern "C" const char *hica_last_error(hica_handle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+extern "C" int64_t hica_launch_count(hica_handle h) { return h ? h->launches : -1; }
+
+extern "C" int hica_get_timers(hica_handle h, double *ms)
+{
+    if (!h || !ms) return HICA_ERR_ARG;
+    for (int i = 0; i < HICA_T_COUNT; i++) ms[i] = h->timers[i];
+    return HICA_OK;
+}
+
+extern "C" int hica_create(int device, hica_handle *out)
+{
+    if (!out) return HICA_ERR_ARG;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return hica_set_error(nullptr, HICA_ERR_CUDA, "no CUDA device available (%s); libhica has no CPU fallback",
+                              e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if (device < 0 || device >= count)
+        return hica_set_error(nullptr, HICA_ERR_ARG, "device %d out of range (have %d)", device, count);
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) return hica_set_error(nullptr, HICA_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    if (prop.major < 10)
+        return hica_set_error(nullptr, HICA_ERR_CUDA, "device %d is sm_%d%d; libhica is built for sm_100a only", device,
+                              prop.major, prop.minor);
+    hica_ctx *h = new hica_ctx();
+    h->device = device;
+    h->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess) {
+        delete h;
+        return hica_set_error(nullptr, HICA_ERR_CUDA, "stream/event creation failed");
+    }
+    cudaMalloc((void **)&h->misc_d, 4096 * sizeof(int32_t));
+    cudaMallocHost((void **)&h->misc_h, 4096 * sizeof(int32_t));
+    cudaMalloc((void **)&h->red_d, 4096 * 16);
+    cudaMallocHost((void **)&h->red_h, 64);
+    *out = h;
+    return HICA_OK;
+}
+
+static void free_p1(hica_ctx *h)
+{
+    cudaFree(h->A); h->A = nullptr;
+    cudaFree(h->s_pair); h->s_pair = nullptr;
+    cudaFree(h->s_seq); h->s_seq = nullptr;
+    cudaFree(h->W); h->W = nullptr;
+    cudaFree(h->order); h->order = nullptr;
+    cudaFree(h->pos); h->pos = nullptr;
+    cudaFree(h->R); h->R = nullptr;
+    cudaFree(h->Zraw); h->Zraw = nullptr;
+    cudaFree(h->size_d); h->size_d = nullptr;
+    cudaFree(h->chain_d); h->chain_d = nullptr;
+    cudaFree(h->x_d); h->x_d = nullptr;
+    cudaFree(h->sig_d); h->sig_d = nullptr;
+    cudaFree(h->q_d); h->q_d = nullptr;
+    cudaFree(h->plan_d); h->plan_d = nullptr; h->plan_n = 0;
+    h->have_s_pair = h->have_s_seq = h->have_W = h->have_order = false;
+    h->rank_bytes = 0;
+    h->n = h->ld = 0;
+    h->A_is_distance = false;
+}
+
+extern "C" int hica_destroy(hica_handle h)
+{
+    if (!h) return HICA_OK;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    if (h->g_is_A) h->G = nullptr;
+    free_p1(h);
+    cudaFree(h->G);
+    cudaFree(h->S);
+    cudaFree(h->St);
+    cudaFree(h->seg_ptr);
+    cudaFree(h->seg_bins);
+    cudaFree(h->p2_buf);
+    cudaFree(h->scores);
+    cudaFree(h->tr_d);
+    cudaFree(h->misc_d);
+    cudaFreeHost(h->misc_h);
+    cudaFree(h->red_d);
+    cudaFreeHost(h->red_h);
+    cudaEventDestroy(h->ev0);
+    cudaEventDestroy(h->ev1);
+    cudaStreamDestroy(h->stream);
+    delete h;
+    return HICA_OK;
+}
+
+static int p1_alloc(hica_ctx *h, int64_t n)
+{
+    if (n < 2) return hica_set_error(h, HICA_ERR_ARG, "n must be >= 2 (got %lld)", (long long)n);
+    if (h->g_is_A) { h->G = nullptr; h->g_is_A = false; h->gn = 0; }
+    if (h->n != n) {
+        free_p1(h);
+        h->n = n;
+        h->ld = (n + 15) / 16 * 16;
+        int rc;
+        if ((rc = hica_realloc(h, &h->A, n * n))) return rc;
+        if ((rc = hica_realloc(h, &h->s_pair, n))) return rc;
+        if ((rc = hica_realloc(h, &h->s_seq, n))) return rc;
+        if ((rc = hica_realloc(h, &h->order, n))) return rc;
+        if ((rc = hica_realloc(h, &h->pos, n))) return rc;
+        if ((rc = hica_realloc(h, &h->x_d, n + 16))) return rc;
+        if ((rc = hica_realloc(h, &h->sig_d, n + 16))) return rc;
+        if ((rc = hica_realloc(h, &h->q_d, 4 * (n + 16)))) return rc;
+    }
+    h->have_s_pair = h->have_s_seq = h->have_W = h->have_order = false;
+    h->rank_bytes = 0;
+    h->A_is_distance = false;
+    return HICA_OK;
+}
+
+extern "C" int hica_p1_upload(hica_handle h, const double *A_host, int64_t n)
+{
+    HICA_CHECK_HANDLE(h);
+    if (!A_host) return hica_set_error(h, HICA_ERR_ARG, "A_host is NULL");
+    int rc = p1_alloc(h, n);
+    if (rc) return rc;
+    hica_timer t(h, HICA_T_UPLOAD);
+    HICA_CUDA(cudaMemcpyAsync(h->A, A_host, sizeof(double) * n * n, cudaMemcpyHostToDevice, h->stream));
+    t.stop();
+    HICA_CUDA(cudaStreamSynchronize(h->stream));
+    return HICA_OK;
+}
+
+extern "C" int hica_p1_upload_device(hica_handle h, const double *A_dev, int64_t n)
+{
+    HICA_CHECK_HANDLE(h);
+    if (!A_dev) return hica_set_error(h, HICA_ERR_ARG, "A_dev is NULL");
+    int rc = p1_alloc(h, n);
+    if (rc) return rc;
+    hica_timer t(h, HICA_T_UPLOAD);
+    HICA_CUDA(cudaMemcpyAsync(h->A, A_dev, sizeof(double) * n * n, cudaMemcpyDeviceToDevice, h->stream));
+    t.stop();
+    HICA_CUDA(cudaStreamSynchronize(h->stream));
+    return HICA_OK;
+}
+
+extern "C" int hica_p1_get_pairwise_row_sums(hica_handle h, double *s_host)
+{
+    HICA_CHECK_HANDLE(h);
+    if (!h->have_s_pair) return hica_set_error(h, HICA_ERR_STATE, "call hica_p1_distance first");
+    HICA_CUDA(cudaMemcpyAsync(s_host, h->s_pair, sizeof(double) * h->n, cudaMemcpyDeviceToHost, h->stream));
+    HICA_CUDA(cudaStreamSynchronize(h->stream));
+    return HICA_OK;
+}
+
+extern "C" int hica_p1_get_row_sums(hica_handle h, double *s_host)
+{
+    HICA_CHECK_HANDLE(h);
+    if (!h->have_s_seq) return hica_set_error(h, HICA_ERR_STATE, "row sums not set; call hica_p1_set_row_sums first");
+    HICA_CUDA(cudaMemcpyAsync(s_host, h->s_seq, sizeof(double) * h->n, cudaMemcpyDeviceToHost, h->stream));
+    HICA_CUDA(cudaStreamSynchronize(h->stream));
+    return HICA_OK;
+}

@@ -1,0 +1,195 @@
+// hica_common.cuh - handle layout and small device helpers shared by the
+// translation units of libhica.so.  sm_100a only.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/hica.h"
+
+struct hica_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    int64_t launches = 0;
+    double timers[HICA_T_COUNT] = {0};
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int sm_count = 148;
+
+    // ---- Part 1 state ---------------------------------------------------
+    int64_t n = 0;           // bins
+    int64_t ld = 0;          // leading dimension of W (n rounded up to 16)
+    double *A = nullptr;     // n x n ICE matrix, row-major, ld = n
+    double *s_pair = nullptr;  // numpy-pairwise row sums (distance transform)
+    double *s_seq = nullptr;   // left-to-right row sums (binList[i].rowSum)
+    bool have_s_pair = false, have_s_seq = false;
+    double *W = nullptr;       // mirrored working matrix for linkage, n x ld
+    bool have_W = false;
+    bool A_is_distance = false;  // hica_p1_upload_distance: A holds D, not ICE
+    int32_t *order = nullptr;    // current row/col order (leaves), n
+    int32_t *pos = nullptr;      // inverse of order
+    bool have_order = false;
+    void *R = nullptr;           // rank matrix n x n, uint16 (n <= 65535) or int32
+    int rank_bytes = 0;          // 2 or 4, 0 = none
+    // linkage scratch
+    double *Zraw = nullptr;      // (n-1) x 4 raw merges (device)
+    int32_t *size_d = nullptr;   // cluster sizes
+    int32_t *chain_d = nullptr;  // per-CTA chain copies
+    // cuts scratch
+    int32_t *x_d = nullptr;      // window counts
+    uint8_t *sig_d = nullptr;
+    int32_t *misc_d = nullptr;   // small result buffer (device)
+    int32_t *misc_h = nullptr;   // pinned mirror
+    int64_t *q_d = nullptr;      // query buffer for hypergeom batches
+    int64_t scratch_n = 0;
+    // pairwise-sum plan (leaf table + combine tree) for rows of length plan_n
+    int32_t *plan_d = nullptr;
+    int64_t plan_n = 0;
+    int plan_m = 0, plan_levels = 0;
+
+    // ---- Part 2 state ---------------------------------------------------
+    double *G = nullptr;   // genome matrix (owned unless g_is_A)
+    int64_t gn = 0;
+    bool g_is_A = false;
+    double *S = nullptr;   // selected sub-matrix L x L
+    int32_t L = 0;
+    int64_t S_cap = 0;
+    int32_t *seg_ptr = nullptr, *seg_bins = nullptr;
+    int32_t nseg = 0, seg_total = 0;
+    std::vector<int32_t> seg_ptr_h, seg_bins_h;
+    double *St = nullptr;  // transpose of S (coalesced access to the short diagonals)
+    void *p2_buf = nullptr;  // candidate / order staging
+    int64_t p2_buf_cap = 0;
+    double *scores = nullptr;
+    int64_t scores_cap = 0;
+    double *tr_d = nullptr;  // traces scratch
+    int64_t tr_cap = 0;
+    void *red_d = nullptr;   // argmax partials
+    void *red_h = nullptr;   // pinned
+};
+
+// ---- error plumbing --------------------------------------------------------
+int hica_set_error(hica_ctx *h, int code, const char *fmt, ...);
+
+#define HICA_CUDA(call)                                                                     \
+    do {                                                                                    \
+        cudaError_t e__ = (call);                                                           \
+        if (e__ != cudaSuccess)                                                             \
+            return hica_set_error(h, HICA_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, \
+                                  cudaGetErrorString(e__));                                 \
+    } while (0)
+
+#define HICA_CHECK_HANDLE(h)                   \
+    do {                                       \
+        if (!(h)) return HICA_ERR_ARG;         \
+        cudaSetDevice((h)->device);            \
+    } while (0)
+
+#define HICA_LAUNCHED(h) ((h)->launches++)
+
+struct hica_timer {
+    hica_ctx *h;
+    int slot;
+    hica_timer(hica_ctx *h_, int slot_) : h(h_), slot(slot_) { cudaEventRecord(h->ev0, h->stream); }
+    void stop()
+    {
+        cudaEventRecord(h->ev1, h->stream);
+        cudaEventSynchronize(h->ev1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+        h->timers[slot] = ms;
+    }
+};
+
+template <typename T>
+static inline int hica_realloc(hica_ctx *h, T **p, int64_t count)
+{
+    if (*p) { cudaFree(*p); *p = nullptr; }
+    if (count <= 0) return HICA_OK;
+    cudaError_t e = cudaMalloc((void **)p, sizeof(T) * (size_t)count);
+    if (e != cudaSuccess) {
+        *p = nullptr;
+        return hica_set_error(h, HICA_ERR_NOMEM, "cudaMalloc(%lld bytes): %s",
+                              (long long)(sizeof(T) * (size_t)count), cudaGetErrorString(e));
+    }
+    return HICA_OK;
+}
+
+// ---- device helpers ----------------------------------------------------------
+#ifdef __CUDACC__
+
+// L2-coherent (L1-bypassing) loads for data written by other SMs in the same kernel.
+__device__ __forceinline__ double ld_cg_f64(const double *p)
+{
+    double v;
+    asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ double2 ld_cg_f64x2(const double *p)
+{
+    double2 v;
+    asm volatile("ld.global.cg.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ int ld_cg_s32(const int *p)
+{
+    int v;
+    asm volatile("ld.global.cg.s32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+// streaming (evict-first) 128-bit load / store for once-touched data
+__device__ __forceinline__ double2 ld_stream_f64x2(const double *p)
+{
+    double2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void st_stream_f64x2(double *p, double2 v)
+{
+    asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y));
+}
+
+// numpy pairwise summation, one thread, arbitrary stride (DOUBLE_pairwise_sum).
+// Used where a whole sum is owned by one thread (diagonal traces); the row-sum
+// kernel uses a cooperative version of the same tree.
+__device__ inline double pairwise_sum_thread(const double *a, int64_t n, int64_t stride)
+{
+    if (n < 8) {
+        double res = 0.;
+        for (int64_t i = 0; i < n; i++) res = __dadd_rn(res, a[i * stride]);
+        return res;
+    }
+    if (n <= 128) {
+        double r[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) r[j] = a[j * stride];
+        int64_t i;
+        for (i = 8; i < n - (n % 8); i += 8) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) r[j] = __dadd_rn(r[j], a[(i + j) * stride]);
+        }
+        double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                               __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+        for (; i < n; i++) res = __dadd_rn(res, a[i * stride]);
+        return res;
+    }
+    int64_t n2 = n / 2;
+    n2 -= n2 % 8;
+    return __dadd_rn(pairwise_sum_thread(a, n2, stride), pairwise_sum_thread(a + n2 * stride, n - n2, stride));
+}
+
+// (1 - a/s) + 1, the distance transform of convertMatrix (:147); no contraction.
+__device__ __forceinline__ double dist_transform(double a, double s)
+{
+    return __dadd_rn(__dsub_rn(1.0, __ddiv_rn(a, s)), 1.0);
+}
+// rowSum * (1 - (d - 1)), the similarity transform (:149)
+__device__ __forceinline__ double sim_transform(double d, double rs)
+{
+    return __dmul_rn(rs, __dsub_rn(1.0, __dsub_rn(d, 1.0)));
+}
+
+#endif  // __CUDACC__

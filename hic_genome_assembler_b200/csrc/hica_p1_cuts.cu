@@ -1,0 +1,528 @@
+// hica_p1_cuts.cu - K6/K7: windowed rank counts, hypergeometric decisions and
+// the two cut-index searches that drive them.
+//
+// Replaces hyper_geom (scaffoldToChromosomes.py:352-368),
+// get_sliding_window_distance_metrics (:370-411),
+// find_matrix_pvalue_breakpoints (:413-511),
+// pre_process_all_matrix_breakpoints (:513-551) and
+// filter_noisy_breakpoints (:553-727).
+//
+// The reference calls scipy.stats.hypergeom.sf once per row (0.8 ms each).  The
+// test only ever uses the DECISION "sf(x-1; M, n, N) < psig", and sf is
+// monotone in x, so the device computes, per (M, n, N), the critical count
+// x* = min{x : sf(x-1) < psig} from the hypergeometric pmf (lgamma at one
+// anchor + exact ratio recurrence, summed from the far tail inwards) and
+// compares integer counts against it.  Decisions whose tail probability lies
+// within a relative 1e-7 of psig are reported as "ambiguous" (the restatement
+// agrees with Boost's hypergeom sf to ~1e-10 relative).
+#include <limits.h>
+#include <math.h>
+
+#include <algorithm>
+#include <map>
+#include <set>
+
+#include "hica_common.cuh"
+
+namespace {
+
+constexpr double HICA_MARGIN = 1e-7;
+constexpr double LOG_TINY = -700.0;
+
+__device__ __forceinline__ double lchoose(double a, double b)
+{
+    return lgamma(a + 1.0) - lgamma(b + 1.0) - lgamma(a - b + 1.0);
+}
+
+struct HypParams {
+    long long M, n, N, kmin, kmax;
+    double lden;  // log C(M, N)
+};
+
+__device__ __forceinline__ double hyp_logpmf(const HypParams &p, long long k)
+{
+    return lchoose((double)p.n, (double)k) + lchoose((double)(p.M - p.n), (double)(p.N - k)) - p.lden;
+}
+
+__device__ __forceinline__ bool hyp_valid(long long M, long long n, long long N)
+{
+    return M > 0 && n >= 0 && N >= 0 && n <= M && N <= M;  // scipy hypergeom._argcheck
+}
+
+// largest k in [klo, kmax] with logpmf(k) >= LOG_TINY, assuming logpmf is
+// non-increasing on [klo, kmax]; returns klo-1 if none.
+__device__ long long hyp_tail_start(const HypParams &p, long long klo)
+{
+    if (hyp_logpmf(p, p.kmax) >= LOG_TINY) return p.kmax;
+    if (hyp_logpmf(p, klo) < LOG_TINY) return klo - 1;
+    long long a = klo, b = p.kmax;  // invariant: lp(a) >= tiny, lp(b) < tiny
+    while (b - a > 1) {
+        long long mid = a + (b - a) / 2;
+        if (hyp_logpmf(p, mid) >= LOG_TINY) a = mid; else b = mid;
+    }
+    return a;
+}
+
+// critical count x* = min{ x : P[X >= x] < psig }.  x >= x*  <=>  sf(x-1) < psig.
+// amb is set when a tail sum adjacent to the threshold is within the margin.
+__device__ long long hyp_critical(long long M, long long n, long long N, double psig, bool *amb)
+{
+    *amb = false;
+    HypParams p;
+    p.M = M; p.n = n; p.N = N;
+    p.kmin = max(0ll, N + n - M);
+    p.kmax = min(n, N);
+    if (!(psig > 0.0)) return LLONG_MAX;        // nothing is < psig
+    if (psig > 1.0) return LLONG_MIN;           // everything is
+    p.lden = lchoose((double)M, (double)N);
+    // mode of the pmf; the pmf is non-increasing above it
+    long long mode = (long long)floor(((double)n + 1.0) * ((double)N + 1.0) / ((double)M + 2.0));
+    mode = min(max(mode, p.kmin), p.kmax);
+    long long k = hyp_tail_start(p, mode);
+    double tail = 0.0, prev_tail = 0.0;
+    if (k >= mode) {
+        double pm = exp(hyp_logpmf(p, k));
+        for (; k >= p.kmin; k--) {
+            prev_tail = tail;
+            tail += pm;
+            if (tail >= psig) {
+                if (fabs(tail - psig) <= HICA_MARGIN * psig || fabs(prev_tail - psig) <= HICA_MARGIN * psig) *amb = true;
+                return k + 1;
+            }
+            // pmf(k-1) = pmf(k) * k (M-n-N+k) / ((n-k+1)(N-k+1))
+            double num = (double)k * (double)(M - n - N + k);
+            double den = (double)(n - k + 1) * (double)(N - k + 1);
+            pm = pm * (num / den);
+        }
+    }
+    // numerically the whole support sums to < psig only if psig ~ 1
+    *amb = true;
+    return p.kmin + 1;
+}
+
+// decision for one explicit query: 1 if sf(x-1; M, n, N) < psig else 0; NaN -> nan_value; |2 if ambiguous
+__device__ int hyp_less(long long x, long long M, long long n, long long N, double psig, int nan_value)
+{
+    if (!hyp_valid(M, n, N)) return nan_value;
+    long long kmin = max(0ll, N + n - M), kmax = min(n, N);
+    if (x <= kmin) return 1.0 < psig ? 1 : 0;
+    if (x > kmax) return 0.0 < psig ? 1 : 0;
+    bool amb;
+    long long xc = hyp_critical(M, n, N, psig, &amb);
+    int r = (x >= xc) ? 1 : 0;
+    if (amb && (x == xc || x == xc - 1)) r |= 2;
+    return r;
+}
+
+// ---------------------------------------------------------------------------
+template <typename RankT>
+__global__ void __launch_bounds__(128) k_window_counts(const RankT *__restrict__ R, int64_t n, int64_t start,
+                                                       int32_t *__restrict__ x)
+{
+    // row i = start + 1 + blockIdx.x, c = i - start
+    const int64_t c = (int64_t)blockIdx.x + 1, i = start + c;
+    const RankT *row = R + i * n;
+    int cnt = 0;
+    for (int64_t k = threadIdx.x; k < c; k += blockDim.x) {
+        int64_t v = row[k];
+        cnt += (v >= start && v <= i);
+    }
+    __shared__ int part[4];
+    for (int d = 16; d >= 1; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        x[c] = part[0] + part[1] + part[2] + part[3];
+        if (blockIdx.x == 0) x[0] = 0;
+    }
+}
+
+template <typename RankT>
+__global__ void __launch_bounds__(128) k_filter_counts(const RankT *__restrict__ R, int64_t n, int64_t start,
+                                                       int64_t cut, int32_t *__restrict__ x)
+{
+    const int64_t ii = start + blockIdx.x;
+    const int64_t local = cut - start;
+    const RankT *row = R + ii * n;
+    int cnt = 0;
+    for (int64_t k = threadIdx.x; k < local; k += blockDim.x) {
+        int64_t v = row[k];
+        cnt += (v >= start && v <= cut);
+    }
+    __shared__ int part[4];
+    for (int d = 16; d >= 1; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) x[blockIdx.x] = part[0] + part[1] + part[2] + part[3];
+}
+
+// mode 0: sig[c] for c in [1, Lw): n = N = c; NaN -> 1.   sig[0] = 0.
+__global__ void k_sig_mode0(const int32_t *__restrict__ x, int64_t Lw, long long M, double psig,
+                            uint8_t *__restrict__ sig, int32_t *__restrict__ misc)
+{
+    int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= Lw) return;
+    int s = 0;
+    if (c > 0) {
+        int r = hyp_less(x[c], M, c, c, psig, 1);
+        s = r & 1;
+        if (r & 2) atomicAdd(&misc[3], 1);
+    }
+    sig[c] = (uint8_t)s;
+    if (s) atomicAdd(&misc[0], 1);
+}
+
+// mode 1: all rows share (M, local, local): one critical value.
+__global__ void k_crit_single(long long M, long long n, long long N, double psig, int32_t *__restrict__ misc)
+{
+    bool amb = false;
+    long long xc;
+    if (!hyp_valid(M, n, N)) xc = LLONG_MAX;  // NaN -> not significant
+    else xc = hyp_critical(M, n, N, psig, &amb);
+    // clamp into int32 range for the compare kernel
+    misc[4] = xc > INT_MAX ? INT_MAX : (xc < INT_MIN ? INT_MIN : (int)xc);
+    misc[5] = amb ? 1 : 0;
+}
+
+__global__ void k_sig_mode1(const int32_t *__restrict__ x, int64_t rows, int64_t Lw, int valid, long long kmin,
+                            long long kmax, double psig, uint8_t *__restrict__ sig, int32_t *__restrict__ misc)
+{
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= Lw) return;
+    int s = 0;
+    if (r < rows) {
+        long long xv = x[r];
+        if (!valid) s = 0;  // NaN p-value: `pval < psig` is False (:633-636)
+        else if (xv <= kmin) s = 1.0 < psig;
+        else if (xv > kmax) s = 0.0 < psig;
+        else {
+            s = xv >= misc[4];
+            if (misc[5] && (xv == misc[4] || xv == (long long)misc[4] - 1)) atomicAdd(&misc[3], 1);
+        }
+    }
+    sig[r] = (uint8_t)s;
+}
+
+// break signal of get_sliding_window_distance_metrics with w == min_size:
+// b[t] == w  <=>  sig[t..t+w) all 1 and sig[t+w..t+2w) all 0 (full right half).
+__global__ void k_break_hits(const uint8_t *__restrict__ sig, int64_t Lw, int w, int32_t *__restrict__ misc)
+{
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= Lw - w || t + 2 * (int64_t)w > Lw) return;
+    int a = 0, b = 0;
+    for (int k = 0; k < w; k++) { a += sig[t + k]; b += sig[t + w + k]; }
+    if (a - b == w) {
+        atomicMin(&misc[1], (int)t);
+        atomicAdd(&misc[2], 1);
+    }
+}
+
+// filter stage: for every interval [bounds[j-1] or start, bounds[j]) sum the row
+// significances and run the second hypergeometric test (:648-666).
+__global__ void k_filter_intervals(const uint8_t *__restrict__ sig, int64_t start, const int64_t *__restrict__ bounds,
+                                   int nb, long long M, long long local, double psig, int32_t *__restrict__ flags,
+                                   int32_t *__restrict__ misc)
+{
+    int j = blockIdx.x;  // one warp per interval
+    if (j >= nb) return;
+    // fc_prev (:643-655) is `start` for the first bound and the previous bound afterwards;
+    // an interval whose bound equals fc_prev is skipped.
+    const int64_t hi = bounds[j];
+    const int64_t lo = (j == 0) ? start : max(start, bounds[j - 1]);
+    int flag = 0;
+    if (hi > lo) {
+        int cnt = 0;
+        for (int64_t r = lo - start + threadIdx.x; r < hi - start; r += 32) cnt += sig[r];
+        for (int d = 16; d >= 1; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
+        if (threadIdx.x == 0) {
+            int r = hyp_less(cnt, M, local, hi - lo, psig, 0);
+            flag = r & 1;
+            if (r & 2) atomicAdd(&misc[3], 1);
+        }
+    }
+    if (threadIdx.x == 0) flags[j] = flag;
+}
+
+template <typename F>
+int with_rank(hica_ctx *h, F f)
+{
+    if (h->rank_bytes == 2) return f((const uint16_t *)h->R);
+    if (h->rank_bytes == 4) return f((const int32_t *)h->R);
+    return hica_set_error(h, HICA_ERR_STATE, "no rank matrix (hica_p1_rank / hica_p1_set_rank)");
+}
+
+int reset_misc(hica_ctx *h)
+{
+    h->misc_h[0] = 0; h->misc_h[1] = INT_MAX; h->misc_h[2] = 0; h->misc_h[3] = 0; h->misc_h[4] = 0; h->misc_h[5] = 0;
+    HICA_CUDA(cudaMemcpyAsync(h->misc_d, h->misc_h, 6 * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    return HICA_OK;
+}
+
+int fetch_misc(hica_ctx *h, int count)
+{
+    HICA_CUDA(cudaMemcpyAsync(h->misc_h, h->misc_d, count * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    HICA_CUDA(cudaStreamSynchronize(h->stream));
+    return HICA_OK;
+}
+
+// window counts for `start` into x_d[0 .. n-start)
+int run_window_counts(hica_ctx *h, int64_t start)
+{
+    const int64_t n = h->n, Lw = n - start;
+    if (Lw <= 1) {
+        HICA_CUDA(cudaMemsetAsync(h->x_d, 0, sizeof(int32_t), h->stream));
+        return HICA_OK;
+    }
+    return with_rank(h, [&](auto *R) {
+        k_window_counts<<<(unsigned)(Lw - 1), 128, 0, h->stream>>>(R, n, start, h->x_d);
+        HICA_LAUNCHED(h);
+        HICA_CUDA(cudaGetLastError());
+        return (int)HICA_OK;
+    });
+}
+
+// mode-0 significance for world size M -> sig_d, misc[0] = sum, misc[3] += ambiguous
+int run_sig_mode0(hica_ctx *h, int64_t Lw, int64_t M, double psig)
+{
+    k_sig_mode0<<<(unsigned)((Lw + 127) / 128), 128, 0, h->stream>>>(h->x_d, Lw, M, psig, h->sig_d, h->misc_d);
+    HICA_LAUNCHED(h);
+    HICA_CUDA(cudaGetLastError());
+    return HICA_OK;
+}
+
+// mode-1 significance for (start, cut) -> sig_d[0 .. n-start)
+int run_sig_mode1(hica_ctx *h, int64_t start, int64_t cut, int64_t M, double psig)
+{
+    const int64_t n = h->n, Lw = n - start;
+    const int64_t MD = n / 5;
+    const int64_t rows = std::min<int64_t>(Lw, MD + 1);
+    const int64_t local = cut - start;
+    int rc = with_rank(h, [&](auto *R) {
+        k_filter_counts<<<(unsigned)rows, 128, 0, h->stream>>>(R, n, start, cut, h->x_d);
+        HICA_LAUNCHED(h);
+        HICA_CUDA(cudaGetLastError());
+        return (int)HICA_OK;
+    });
+    if (rc) return rc;
+    const bool valid = M > 0 && local >= 0 && local <= M;
+    long long kmin = valid ? std::max<long long>(0, 2 * local - M) : 0, kmax = valid ? local : -1;
+    k_crit_single<<<1, 1, 0, h->stream>>>(M, local, local, psig, h->misc_d);
+    HICA_LAUNCHED(h);
+    k_sig_mode1<<<(unsigned)((Lw + 127) / 128), 128, 0, h->stream>>>(h->x_d, rows, Lw, valid ? 1 : 0, kmin, kmax, psig,
+                                                                     h->sig_d, h->misc_d);
+    HICA_LAUNCHED(h);
+    HICA_CUDA(cudaGetLastError());
+    return HICA_OK;
+}
+
+// find_matrix_pvalue_breakpoints (:413-511): returns the leftmost relative cut
+// offset (or -1) and the number of hits.
+int find_breakpoints(hica_ctx *h, int64_t start, int64_t min_size, int64_t world, double psig, int64_t *first_cut,
+                     int64_t *n_hits, int64_t *amb)
+{
+    const int64_t n = h->n, Lw = n - start;
+    int64_t M = world;
+    int64_t ws = min_size;
+    int break_sig = 0, loop_count = 0;
+    int rc = run_window_counts(h, start);
+    if (rc) return rc;
+    *first_cut = -1;
+    *n_hits = 0;
+    for (;;) {
+        for (;;) {
+            if ((rc = reset_misc(h))) return rc;
+            if ((rc = run_sig_mode0(h, Lw, M, psig))) return rc;
+            if ((rc = fetch_misc(h, 4))) return rc;
+            *amb += h->misc_h[3];
+            loop_count++;
+            if (((double)h->misc_h[0] / (double)Lw) >= .9) M = (int64_t)(M - start);
+            else break_sig = 1;
+            if (break_sig == 1 || loop_count >= 5) break;
+        }
+        // sliding window with window size ws, compared against min_size (:487-488)
+        if (ws == min_size && ws < Lw) {
+            if ((rc = reset_misc(h))) return rc;
+            k_break_hits<<<(unsigned)((Lw + 255) / 256), 256, 0, h->stream>>>(h->sig_d, Lw, (int)ws, h->misc_d);
+            HICA_LAUNCHED(h);
+            HICA_CUDA(cudaGetLastError());
+            if ((rc = fetch_misc(h, 4))) return rc;
+            if (h->misc_h[2] > 0) {
+                *first_cut = (int64_t)h->misc_h[1] + min_size;
+                *n_hits = h->misc_h[2];
+                return HICA_OK;
+            }
+        }
+        // a window narrower than min_size can never reach a difference of min_size,
+        // but the reference still re-evaluates the significances (which may shrink M).
+        ws -= 1;
+        if (ws == 0) return HICA_OK;
+    }
+}
+
+}  // namespace
+
+extern "C" int hica_p1_window_sig(hica_handle h, int64_t start, int64_t cut, int64_t M, double psig, int mode,
+                                  uint8_t *sig_host, int64_t *x_host, int64_t *ambiguous)
+{
+    HICA_CHECK_HANDLE(h);
+    if (!h->rank_bytes) return hica_set_error(h, HICA_ERR_STATE, "no rank matrix");
+    const int64_t n = h->n;
+    if (start < 0 || start >= n) return hica_set_error(h, HICA_ERR_ARG, "start out of range");
+    const int64_t Lw = n - start;
+    int rc;
+    int64_t nx = Lw;
+    if ((rc = reset_misc(h))) return rc;
+    if (mode == 0) {
+        if ((rc = run_window_counts(h, start))) return rc;
+        if ((rc = run_sig_mode0(h, Lw, M, psig))) return rc;
+    } else if (mode == 1) {
+        if (cut < start || cut >= n) return hica_set_error(h, HICA_ERR_ARG, "cut out of range");
+        if ((rc = run_sig_mode1(h, start, cut, M, psig))) return rc;
+        nx = std::min<int64_t>(Lw, n / 5 + 1);
+    } else return hica_set_error(h, HICA_ERR_ARG, "mode must be 0 or 1");
+    if ((rc = fetch_misc(h, 6))) return rc;
+    if (ambiguous) *ambiguous = h->misc_h[3];
+    if (sig_host) HICA_CUDA(cudaMemcpyAsync(sig_host, h->sig_d, Lw, cudaMemcpyDeviceToHost, h->stream));
+    if (x_host) {
+        std::vector<int32_t> tmp(nx);
+        HICA_CUDA(cudaMemcpyAsync(tmp.data(), h->x_d, nx * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+        HICA_CUDA(cudaStreamSynchronize(h->stream));
+        for (int64_t k = 0; k < Lw; k++) x_host[k] = k < nx ? tmp[k] : 0;
+    }
+    HICA_CUDA(cudaStreamSynchronize(h->stream));
+    return HICA_OK;
+}
+
+extern "C" int hica_p1_breakpoints(hica_handle h, int64_t min_size, double min_frac, int64_t *cuts_host,
+                                   int64_t capacity, int64_t *n_cuts, int64_t *ambiguous)
+{
+    HICA_CHECK_HANDLE(h);
+    if (!h->rank_bytes) return hica_set_error(h, HICA_ERR_STATE, "no rank matrix");
+    if (!n_cuts) return hica_set_error(h, HICA_ERR_ARG, "n_cuts is NULL");
+    if (min_size < 1) return hica_set_error(h, HICA_ERR_ARG, "min_size must be >= 1");
+    hica_timer t(h, HICA_T_BREAKPOINTS);
+    const int64_t n = h->n;
+    const int64_t stop_ind = (int64_t)((double)n - ((double)n * min_frac));
+    int64_t ind = 0, count = 0, amb = 0;
+    *n_cuts = 0;
+    if (min_frac == 1.0) { t.stop(); return HICA_OK; }
+    for (;;) {
+        int64_t first = -1, hits = 0;
+        int rc = find_breakpoints(h, ind, min_size, n - ind, .05, &first, &hits, &amb);
+        if (rc) return rc;
+        if (hits == 0) break;
+        ind += first;
+        if (count < capacity && cuts_host) cuts_host[count] = ind;
+        count++;
+        if (ind >= stop_ind || (n - ind) <= min_size) break;
+    }
+    *n_cuts = count;
+    if (ambiguous) *ambiguous = amb;
+    t.stop();
+    if (count > capacity) return hica_set_error(h, HICA_ERR_ARG, "cuts capacity %lld too small for %lld cuts",
+                                                (long long)capacity, (long long)count);
+    return HICA_OK;
+}
+
+extern "C" int hica_p1_filter(hica_handle h, const int64_t *cuts_in, int64_t n_in, double psig, int64_t *cuts_out,
+                              int64_t *n_out, int64_t *ambiguous)
+{
+    HICA_CHECK_HANDLE(h);
+    if (!h->rank_bytes) return hica_set_error(h, HICA_ERR_STATE, "no rank matrix");
+    if (!n_out) return hica_set_error(h, HICA_ERR_ARG, "n_out is NULL");
+    *n_out = 0;
+    if (n_in == 0) return HICA_OK;
+    if (n_in > 4000) return hica_set_error(h, HICA_ERR_ARG, "more than 4000 cut indices");
+    hica_timer t(h, HICA_T_FILTER);
+    const int64_t n = h->n;
+    for (int64_t i = 0; i < n_in; i++)
+        if (cuts_in[i] < 0 || cuts_in[i] >= n) return hica_set_error(h, HICA_ERR_ARG, "cut index out of range");
+    const int64_t max_rounds = 10 * n_in;
+    std::vector<int64_t> altered(cuts_in, cuts_in + n_in);
+    std::set<int64_t> prev_filtered, filtered;
+    int64_t amb = 0;
+    int32_t *flags_d = h->misc_d + 16;
+    int32_t *flags_h = h->misc_h + 16;
+    for (;;) {
+        int64_t start = 0;
+        filtered.clear();
+        int64_t round_count = 0;
+        for (;;) {
+            if (round_count >= max_rounds) break;
+            const int64_t M = n - start;
+            int noise_found = 0;
+            size_t keep_from = 0;
+            const int nb = (int)altered.size();
+            HICA_CUDA(cudaMemcpyAsync(h->q_d, altered.data(), sizeof(int64_t) * nb, cudaMemcpyHostToDevice, h->stream));
+            for (size_t i = 0; i < altered.size(); i++) {
+                const int64_t c = altered[i];
+                const int64_t local = c - start;
+                int rc;
+                if ((rc = reset_misc(h))) return rc;
+                if (local < 0) return hica_set_error(h, HICA_ERR_ARG, "cut indices must be ascending");
+                if ((rc = run_sig_mode1(h, start, c, M, psig))) return rc;
+                k_filter_intervals<<<nb, 32, 0, h->stream>>>(h->sig_d, start, h->q_d, nb, M, local, psig, flags_d,
+                                                             h->misc_d);
+                HICA_LAUNCHED(h);
+                HICA_CUDA(cudaGetLastError());
+                if ((rc = fetch_misc(h, 16 + nb))) return rc;
+                amb += h->misc_h[3];
+                int right_most_ind = -1;
+                for (int j = 0; j < nb; j++) if (flags_h[j]) right_most_ind = j;
+                if (right_most_ind >= 0) {
+                    start = altered[right_most_ind];
+                    filtered.insert(start);
+                    noise_found = 1;
+                    keep_from = (size_t)right_most_ind;
+                    break;
+                }
+                filtered.insert(c);
+            }
+            round_count++;
+            if (!noise_found) break;
+            altered.erase(altered.begin(), altered.begin() + keep_from);
+        }
+        if (prev_filtered != filtered) {
+            altered.assign(filtered.begin(), filtered.end());
+            prev_filtered = filtered;
+        } else break;
+    }
+    int64_t k = 0;
+    for (int64_t v : filtered) cuts_out[k++] = v;
+    *n_out = k;
+    if (ambiguous) *ambiguous = amb;
+    t.stop();
+    return HICA_OK;
+}
+
+__global__ void k_hyp_batch(const int64_t *x, const int64_t *M, const int64_t *n, const int64_t *N, int64_t count,
+                            double psig, uint8_t *out)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) out[i] = (uint8_t)hyp_less(x[i], M[i], n[i], N[i], psig, 0);
+}
+
+extern "C" int hica_hypergeom_less(hica_handle h, const int64_t *x, const int64_t *M, const int64_t *n,
+                                   const int64_t *N, int64_t count, double psig, uint8_t *out)
+{
+    HICA_CHECK_HANDLE(h);
+    if (count <= 0) return HICA_OK;
+    int64_t *buf = nullptr;
+    uint8_t *o = nullptr;
+    int rc = hica_realloc(h, &buf, 4 * count);
+    if (rc) return rc;
+    if ((rc = hica_realloc(h, &o, count))) { cudaFree(buf); return rc; }
+    cudaMemcpyAsync(buf, x, 8 * count, cudaMemcpyHostToDevice, h->stream);
+    cudaMemcpyAsync(buf + count, M, 8 * count, cudaMemcpyHostToDevice, h->stream);
+    cudaMemcpyAsync(buf + 2 * count, n, 8 * count, cudaMemcpyHostToDevice, h->stream);
+    cudaMemcpyAsync(buf + 3 * count, N, 8 * count, cudaMemcpyHostToDevice, h->stream);
+    k_hyp_batch<<<(unsigned)((count + 127) / 128), 128, 0, h->stream>>>(buf, buf + count, buf + 2 * count,
+                                                                        buf + 3 * count, count, psig, o);
+    HICA_LAUNCHED(h);
+    cudaMemcpyAsync(out, o, count, cudaMemcpyDeviceToHost, h->stream);
+    cudaError_t e = cudaStreamSynchronize(h->stream);
+    cudaFree(buf);
+    cudaFree(o);
+    if (e != cudaSuccess) return hica_set_error(h, HICA_ERR_CUDA, "hypergeom batch: %s", cudaGetErrorString(e));
+    return HICA_OK;
+}

@@ -1,0 +1,382 @@
+// hica_p1_linkage.cu - K2/K3: nearest-neighbour-chain UPGMA on the mirrored
+// working matrix, then merge sorting / relabelling / leaf order.
+//
+// Replaces scipy.cluster.hierarchy.average(condensed) -> _hierarchy.nn_chain
+// (scaffoldToChromosomes.py:197) and dendrogram(count_sort='ascending',
+// get_leaves=True) (:204).
+//
+// The merge sequence is inherently serial (each merge's heights depend on the
+// previous updates, and fp64 rounding makes the result depend on the exact
+// merge order), so the whole chain runs inside ONE persistent kernel executed
+// by ONE thread-block cluster: every nearest-neighbour search is a contiguous
+// row of W split over the CTAs of the cluster, reduced with warp shuffles ->
+// shared memory -> distributed shared memory, and one cluster barrier per
+// search.  The matrix never leaves HBM/L2; the host sees only the (n-1) x 4
+// merge list.
+//
+// Exact tie rules of scipy's nn_chain that are reproduced here:
+//   * an empty chain restarts at the lowest live index;
+//   * neighbours are scanned in ascending index with strict '<';
+//   * the minimum is seeded with the previous chain element, which therefore
+//     wins ties;
+//   * the merged pair is ordered x < y, the union lives in slot y;
+//   * d(i, x u y) = (nx*d(i,x) + ny*d(i,y)) / (nx+ny), no FMA;
+//   * merges are then STABLY sorted by height and relabelled by union-find
+//     (smaller root first, new id = n + k).
+#include <cooperative_groups.h>
+#include <limits.h>
+#include <math.h>
+
+#include <algorithm>
+#include <numeric>
+
+#include "hica_common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace {
+
+constexpr int NN_THREADS = 512;
+constexpr int NN_WARPS = NN_THREADS / 32;
+constexpr int NN_MAX_CLUSTER = 16;
+
+struct Cand {
+    double v;
+    int i;  // comparison index: -1 for the previous chain element, else column
+};
+
+__device__ __forceinline__ bool cand_less(double v, int i, double bv, int bi)
+{
+    return v < bv || (v == bv && i < bi);
+}
+
+__device__ __forceinline__ void cand_min_shfl(double &v, int &i, int delta)
+{
+    double ov = __shfl_xor_sync(0xffffffffu, v, delta);
+    int oi = __shfl_xor_sync(0xffffffffu, i, delta);
+    if (cand_less(ov, oi, v, i)) { v = ov; i = oi; }
+}
+
+template <bool CHAIN_SMEM>
+__global__ void __launch_bounds__(NN_THREADS, 1)
+k_nn_chain(double *__restrict__ W, const int n, const int64_t ld, int32_t *__restrict__ size_g,
+           int32_t *__restrict__ chain_g, double *__restrict__ Zraw)
+{
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    const int nranks = (int)cluster.num_blocks();
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    extern __shared__ __align__(16) unsigned char smem[];
+    // layout: slots[2][NN_MAX_CLUSTER] | wpart[NN_WARPS] | alive words | chain (optional)
+    Cand *slots = reinterpret_cast<Cand *>(smem);
+    Cand *wpart = slots + 2 * NN_MAX_CLUSTER;
+    uint32_t *alive = reinterpret_cast<uint32_t *>(wpart + NN_WARPS);
+    const int nwords = (int)((ld + 31) / 32);
+    int32_t *chain = CHAIN_SMEM ? reinterpret_cast<int32_t *>(alive + nwords) : chain_g + (int64_t)rank * n;
+
+    for (int w = tid; w < nwords; w += NN_THREADS) {
+        int base = w * 32;
+        uint32_t bits = 0;
+        if (base + 32 <= n) bits = 0xffffffffu;
+        else if (base < n) bits = (1u << (n - base)) - 1u;
+        alive[w] = bits;
+    }
+    // column slice of this CTA (even bounds so that 16-byte loads stay aligned)
+    int per = (n + nranks - 1) / nranks;
+    per = (per + 1) & ~1;
+    const int lo = min(n, rank * per), hi = min(n, lo + per);
+    __syncthreads();
+    cluster.sync();
+
+    int len = 0;         // chain length
+    int top = -1, second = -1;  // chain[len-1], chain[len-2] (register copies, identical in every thread)
+    int first_alive = 0;
+    int parity = 0;
+    int pend_x = -1, pend_y = -1, pend_sz = 0;  // deferred size update (rank 0, thread 0)
+
+    for (int k = 0; k < n - 1; k++) {
+        if (len == 0) {
+            while (!((alive[first_alive >> 5] >> (first_alive & 31)) & 1u)) first_alive++;
+            top = first_alive;
+            second = -1;
+            if (tid == 0) chain[0] = top;
+            len = 1;
+        }
+        double gv;
+        int y;
+        for (;;) {
+            const int x = top;
+            const int yprev = (len > 1) ? second : -2;
+            // ---- nearest-neighbour scan of row x over this CTA's slice ----
+            if (rank == 0 && tid == 0 && pend_x >= 0) {  // sizes of the previous merge, see below
+                size_g[pend_x] = 0;
+                size_g[pend_y] = pend_sz;
+                pend_x = -1;
+            }
+            const double *row = W + (int64_t)x * ld;
+            double bv = INFINITY;
+            int bi = INT_MAX;
+            for (int c = lo + 2 * tid; c < hi; c += 2 * NN_THREADS) {
+                double2 v = ld_cg_f64x2(row + c);
+                uint32_t bits = alive[c >> 5] >> (c & 31);  // c even: bit0 -> c, bit1 -> c+1
+                if ((bits & 1u) && c != x) {
+                    int ci = (c == yprev) ? -1 : c;
+                    if (cand_less(v.x, ci, bv, bi)) { bv = v.x; bi = ci; }
+                }
+                if ((bits & 2u) && c + 1 != x) {
+                    int ci = (c + 1 == yprev) ? -1 : c + 1;
+                    if (cand_less(v.y, ci, bv, bi)) { bv = v.y; bi = ci; }
+                }
+            }
+#pragma unroll
+            for (int d = 16; d >= 1; d >>= 1) cand_min_shfl(bv, bi, d);
+            if (lane == 0) { wpart[warp].v = bv; wpart[warp].i = bi; }
+            __syncthreads();
+            if (warp == 0) {
+                double v2 = INFINITY;
+                int i2 = INT_MAX;
+                if (lane < NN_WARPS) { v2 = wpart[lane].v; i2 = wpart[lane].i; }
+#pragma unroll
+                for (int d = NN_WARPS / 2; d >= 1; d >>= 1) cand_min_shfl(v2, i2, d);
+                if (lane < nranks) {
+                    Cand *remote = cluster.map_shared_rank(slots, lane);
+                    remote[parity * NN_MAX_CLUSTER + rank].v = v2;
+                    remote[parity * NN_MAX_CLUSTER + rank].i = i2;
+                }
+            }
+            cluster.sync();
+            gv = INFINITY;
+            int gi = INT_MAX;
+            for (int r = 0; r < nranks; r++) {
+                Cand cnd = slots[parity * NN_MAX_CLUSTER + r];
+                if (cand_less(cnd.v, cnd.i, gv, gi)) { gv = cnd.v; gi = cnd.i; }
+            }
+            parity ^= 1;
+            y = (gi == -1) ? yprev : gi;
+            if (len > 1 && y == yprev) break;
+            // push y
+            if (tid == 0) chain[len] = y;
+            second = top;
+            top = y;
+            len++;
+        }
+        // ---- merge top (x) and second (y) -------------------------------
+        int x = top;
+        len -= 2;
+        if (x > y) { int t = x; x = y; y = t; }
+        const int nx = ld_cg_s32(size_g + x), ny = ld_cg_s32(size_g + y);
+        const double dnx = (double)nx, dny = (double)ny, dsum = (double)(nx + ny);
+        const double *rowx = W + (int64_t)x * ld;
+        double *rowy = W + (int64_t)y * ld;
+        for (int c = lo + 2 * tid; c < hi; c += 2 * NN_THREADS) {
+            uint32_t bits = alive[c >> 5] >> (c & 31);
+            bool u0 = (bits & 1u) && c != x && c != y;
+            bool u1 = (bits & 2u) && c + 1 != x && c + 1 != y;
+            if (!(u0 || u1)) continue;
+            double2 vx = ld_cg_f64x2(rowx + c), vy = ld_cg_f64x2(rowy + c);
+            if (u0) {
+                double v = __ddiv_rn(__dadd_rn(__dmul_rn(dnx, vx.x), __dmul_rn(dny, vy.x)), dsum);
+                rowy[c] = v;
+                W[(int64_t)c * ld + y] = v;
+            }
+            if (u1) {
+                double v = __ddiv_rn(__dadd_rn(__dmul_rn(dnx, vx.y), __dmul_rn(dny, vy.y)), dsum);
+                rowy[c + 1] = v;
+                W[(int64_t)(c + 1) * ld + y] = v;
+            }
+        }
+        if (rank == 0 && tid == 0) {
+            Zraw[4 * (int64_t)k + 0] = (double)x;
+            Zraw[4 * (int64_t)k + 1] = (double)y;
+            Zraw[4 * (int64_t)k + 2] = gv;
+            Zraw[4 * (int64_t)k + 3] = dsum;
+            // size_g is still being read by the other CTAs of this merge: publish
+            // the new sizes only after the cluster barrier below (before the next
+            // scan's barrier, which orders it ahead of the next size read).
+            pend_x = x;
+            pend_y = y;
+            pend_sz = nx + ny;
+        }
+        __syncthreads();  // every thread is done reading alive[] for this merge
+        if (tid == 0) alive[x >> 5] &= ~(1u << (x & 31));
+        // restore the register copies of the chain top
+        if (len >= 1) {
+            top = chain[len - 1];
+            second = (len >= 2) ? chain[len - 2] : -1;
+        }
+        cluster.sync();  // W updates (incl. scattered column y) visible cluster-wide
+    }
+    // flush the last pending size update for completeness
+    if (rank == 0 && tid == 0 && pend_x >= 0) {
+        size_g[pend_x] = 0;
+        size_g[pend_y] = pend_sz;
+    }
+}
+
+__global__ void k_fill_i32(int32_t *p, int64_t n, int32_t v)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+__global__ void k_inverse_perm(const int32_t *order, int32_t *pos, int64_t n)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) pos[order[i]] = (int32_t)i;
+}
+
+// ---- host: stable sort by height, union-find relabel, leaf order ------------
+int64_t uf_find(std::vector<int64_t> &parent, int64_t x)
+{
+    int64_t r = x;
+    while (parent[r] != r) r = parent[r];
+    while (parent[x] != r) {
+        int64_t nx = parent[x];
+        parent[x] = r;
+        x = nx;
+    }
+    return r;
+}
+
+void label_and_order(const std::vector<double> &raw, int64_t n, std::vector<double> &Z, std::vector<int32_t> &leaves)
+{
+    const int64_t m = n - 1;
+    std::vector<int64_t> idx(m);
+    std::iota(idx.begin(), idx.end(), 0);
+    std::stable_sort(idx.begin(), idx.end(), [&](int64_t a, int64_t b) { return raw[4 * a + 2] < raw[4 * b + 2]; });
+    std::vector<int64_t> parent(2 * n - 1), sz(2 * n - 1, 0);
+    std::iota(parent.begin(), parent.end(), 0);
+    for (int64_t i = 0; i < n; i++) sz[i] = 1;
+    Z.resize(4 * m);
+    int64_t next = n;
+    for (int64_t k = 0; k < m; k++) {
+        const double *r = &raw[4 * idx[k]];
+        int64_t a = uf_find(parent, (int64_t)r[0]), b = uf_find(parent, (int64_t)r[1]);
+        if (a > b) std::swap(a, b);
+        Z[4 * k + 0] = (double)a;
+        Z[4 * k + 1] = (double)b;
+        Z[4 * k + 2] = r[2];
+        parent[a] = parent[b] = next;
+        sz[next] = sz[a] + sz[b];
+        Z[4 * k + 3] = (double)sz[next];
+        next++;
+    }
+    // pre-order walk; the child with fewer leaves first, Z[i,0] first on equal counts
+    leaves.clear();
+    leaves.reserve(n);
+    std::vector<int64_t> stack;
+    stack.push_back(2 * n - 2);
+    while (!stack.empty()) {
+        int64_t c = stack.back();
+        stack.pop_back();
+        if (c < n) { leaves.push_back((int32_t)c); continue; }
+        int64_t a = (int64_t)Z[4 * (c - n)], b = (int64_t)Z[4 * (c - n) + 1];
+        if (sz[a] > sz[b]) std::swap(a, b);
+        stack.push_back(b);
+        stack.push_back(a);
+    }
+}
+
+template <bool CHAIN_SMEM>
+int launch_nn_chain(hica_ctx *h, int cluster_size, size_t smem_bytes)
+{
+    auto kern = k_nn_chain<CHAIN_SMEM>;
+    HICA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+    if (cluster_size > 8) HICA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(cluster_size);
+    cfg.blockDim = dim3(NN_THREADS);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = h->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cluster_size;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int max_clusters = 0;
+    cudaError_t e = cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg);
+    if (e != cudaSuccess || max_clusters < 1) {
+        cudaGetLastError();
+        return -1;  // caller retries with a smaller cluster
+    }
+    int n32 = (int)h->n;
+    HICA_CUDA(cudaLaunchKernelEx(&cfg, kern, h->W, n32, h->ld, h->size_d, h->chain_d, h->Zraw));
+    HICA_LAUNCHED(h);
+    return HICA_OK;
+}
+
+}  // namespace
+
+int hica_set_order_internal(hica_ctx *h, const int32_t *order_host)
+{
+    const int64_t n = h->n;
+    HICA_CUDA(cudaMemcpyAsync(h->order, order_host, sizeof(int32_t) * n, cudaMemcpyHostToDevice, h->stream));
+    k_inverse_perm<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->order, h->pos, n);
+    HICA_LAUNCHED(h);
+    HICA_CUDA(cudaGetLastError());
+    HICA_CUDA(cudaStreamSynchronize(h->stream));
+    h->have_order = true;
+    h->rank_bytes = 0;  // any rank matrix refers to the previous order
+    return HICA_OK;
+}
+
+extern "C" int hica_p1_set_order(hica_handle h, const int32_t *order)
+{
+    HICA_CHECK_HANDLE(h);
+    if (!h->A) return hica_set_error(h, HICA_ERR_STATE, "no matrix uploaded");
+    if (!order) return hica_set_error(h, HICA_ERR_ARG, "order is NULL");
+    std::vector<char> seen(h->n, 0);
+    for (int64_t i = 0; i < h->n; i++) {
+        if (order[i] < 0 || order[i] >= h->n || seen[order[i]])
+            return hica_set_error(h, HICA_ERR_ARG, "order is not a permutation of 0..n-1 (entry %lld)", (long long)i);
+        seen[order[i]] = 1;
+    }
+    return hica_set_order_internal(h, order);
+}
+
+extern "C" int hica_p1_linkage(hica_handle h, double *Z_host, int32_t *leaves_host)
+{
+    HICA_CHECK_HANDLE(h);
+    if (!h->have_W) return hica_set_error(h, HICA_ERR_STATE, "call hica_p1_distance (or upload_distance) first");
+    const int64_t n = h->n;
+    if (n > 0x7fffffff) return hica_set_error(h, HICA_ERR_ARG, "n too large");
+    int rc;
+    if (!h->Zraw && (rc = hica_realloc(h, &h->Zraw, 4 * (n - 1)))) return rc;
+    if (!h->size_d && (rc = hica_realloc(h, &h->size_d, n))) return rc;
+
+    const int nwords = (int)((h->ld + 31) / 32);
+    size_t base_smem = sizeof(Cand) * (2 * NN_MAX_CLUSTER + NN_WARPS) + sizeof(uint32_t) * nwords;
+    size_t chain_smem = sizeof(int32_t) * (size_t)n;
+    bool chain_in_smem = base_smem + chain_smem <= 200 * 1024;
+    if (!chain_in_smem && !h->chain_d && (rc = hica_realloc(h, &h->chain_d, (int64_t)NN_MAX_CLUSTER * n))) return rc;
+
+    hica_timer t(h, HICA_T_LINKAGE);
+    k_fill_i32<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->size_d, n, 1);
+    HICA_LAUNCHED(h);
+    int launched = -1;
+    for (int cs = NN_MAX_CLUSTER; cs >= 1 && launched != HICA_OK; cs >>= 1) {
+        launched = chain_in_smem ? launch_nn_chain<true>(h, cs, base_smem + chain_smem)
+                                 : launch_nn_chain<false>(h, cs, base_smem);
+        if (launched > 0) return launched;  // a real error
+    }
+    if (launched != HICA_OK) return hica_set_error(h, HICA_ERR_CUDA, "no cluster configuration could be launched");
+    HICA_CUDA(cudaGetLastError());
+    t.stop();
+    h->have_W = false;  // W has been consumed
+
+    std::vector<double> raw(4 * (n - 1));
+    HICA_CUDA(cudaMemcpyAsync(raw.data(), h->Zraw, sizeof(double) * raw.size(), cudaMemcpyDeviceToHost, h->stream));
+    HICA_CUDA(cudaStreamSynchronize(h->stream));
+    hica_timer t2(h, HICA_T_LEAFORDER);
+    std::vector<double> Z;
+    std::vector<int32_t> leaves;
+    label_and_order(raw, n, Z, leaves);
+    if (Z_host) std::copy(Z.begin(), Z.end(), Z_host);
+    if (leaves_host) std::copy(leaves.begin(), leaves.end(), leaves_host);
+    rc = hica_set_order_internal(h, leaves.data());
+    t2.stop();
+    return rc;
+}

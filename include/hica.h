@@ -1,0 +1,183 @@
+/*
+ * hica.h - C ABI of libhica.so, the B200-native (sm_100a) replacement for the
+ * contact-map scoring hot path of AO33/HiC_Genome_Assembler.
+ *
+ * The reference has no FFI or plugin API of its own (it is 100 % Python and
+ * calls numpy/scipy/numba in-process).  The boundary is therefore the set of
+ * module-level functions its two pipelines call on the hot path
+ * (SURVEY.md section 8b); every entry point below names the reference
+ * function/lines it replaces (paths relative to /root/reference/HIC_ASSEMBLER/).
+ * INTEGRATION.md shows the ctypes stub that rebinds those functions.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on error; the message is
+ *     available from hica_last_error(h) (or hica_last_error(NULL) for
+ *     hica_create failures);
+ *   - the caller owns all host buffers (C-contiguous, must outlive the call);
+ *     the library owns all device memory behind the opaque handle;
+ *   - calls are synchronous with respect to the host: when a function returns
+ *     its host outputs are valid;
+ *   - one handle per GPU; a handle is not re-entrant;
+ *   - there is NO CPU fallback: without a CUDA device hica_create fails.
+ */
+#ifndef HICA_H
+#define HICA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct hica_ctx *hica_handle;
+
+#define HICA_OK 0
+#define HICA_ERR_CUDA 1
+#define HICA_ERR_ARG 2
+#define HICA_ERR_STATE 3
+#define HICA_ERR_NOMEM 4
+
+/* ---- lifetime ----------------------------------------------------------- */
+int hica_version(void);
+int hica_create(int device, hica_handle *out);
+int hica_destroy(hica_handle h);
+const char *hica_last_error(hica_handle h);
+/* number of kernel launches issued through this handle so far */
+int64_t hica_launch_count(hica_handle h);
+/* Wall-clock independent stage timers: CUDA-event milliseconds of the last
+ * call of each stage (index = HICA_T_*), measured on the handle's stream. */
+enum {
+    HICA_T_UPLOAD = 0, HICA_T_DISTANCE, HICA_T_LINKAGE, HICA_T_LEAFORDER, HICA_T_RANK,
+    HICA_T_BREAKPOINTS, HICA_T_FILTER, HICA_T_P2_SCORE, HICA_T_COUNT
+};
+int hica_get_timers(hica_handle h, double *ms /* HICA_T_COUNT */);
+
+/* ---- Part 1: ICE matrix -> leaf order -> cut indices ---------------------- */
+
+/* Copy the dense n x n ICE matrix (after removeRows, scaffoldToChromosomes.py
+ * :1116-1118) to the device.  A_host may be pageable or pinned. */
+int hica_p1_upload(hica_handle h, const double *A_host, int64_t n);
+
+/* Same, but the matrix is already in device memory (row-major, ld = n). The
+ * library copies it; the caller keeps ownership of A_dev. */
+int hica_p1_upload_device(hica_handle h, const double *A_dev, int64_t n);
+
+/* binList[i].rowSum (removeRows, :134: builtin left-to-right sum).  Pass the
+ * host values the reference computed, or NULL to compute them on the device in
+ * the same left-to-right order. */
+int hica_p1_set_row_sums(hica_handle h, const double *row_sum_host_or_null);
+
+/* convertMatrix(distance=True) :138-147 + squareform :194: numpy-pairwise row
+ * sums, then the mirrored working matrix W[i][j] = W[j][i] = (1 - A_ij/s_i) + 1
+ * (i < j) that the linkage consumes. */
+int hica_p1_distance(hica_handle h);
+
+/* The full asymmetric D (what convertMatrix(distance=True) returns), n x n. */
+int hica_p1_get_distance(hica_handle h, double *D_host);
+/* The numpy-pairwise row sums s_i used by the distance transform. */
+int hica_p1_get_pairwise_row_sums(hica_handle h, double *s_host);
+int hica_p1_get_row_sums(hica_handle h, double *row_sum_host);
+
+/* Replace the working matrix by the strict upper triangle of a caller-supplied
+ * square matrix D (the seam averageClusterNodes(adjacencyMatrix, ...) :187 when
+ * it is handed a matrix that did not come from hica_p1_distance). */
+int hica_p1_upload_distance(hica_handle h, const double *D_host, int64_t n);
+
+/* averageClusterNodes :187-208 = hierarchy.average (nn_chain, stable sort by
+ * height, union-find relabel) + dendrogram(count_sort='ascending') leaf order.
+ * Z_host: (n-1) x 4 doubles or NULL; leaves_host: n int32 or NULL.  The leaf
+ * order also becomes the handle's current row/column order. */
+int hica_p1_linkage(hica_handle h, double *Z_host, int32_t *leaves_host);
+
+/* Set the row/column order explicitly (readDengrogramLeavesFromFile :222,
+ * reorderMatrix :157-163 by indirection). */
+int hica_p1_set_order(hica_handle h, const int32_t *order);
+
+/* Materialise reordered matrices for the Python seams:
+ *   what = 0: D[:, o][o]              (reorderMatrix :161)
+ *   what = 1: S = rowSum*(1-(D-1))    (convertMatrix(similarity=True) :148-149) */
+int hica_p1_get_reordered(hica_handle h, int what, double *out_host);
+
+/* numpy.argsort(S, axis=1)[:, ::-1] :1132 on the device; ties resolve as a
+ * stable ascending sort reversed (descending column index). */
+int hica_p1_rank(hica_handle h);
+int hica_p1_get_rank(hica_handle h, int64_t *R_host);
+/* Seam input: an argsorted matrix computed elsewhere (n x n int64). */
+int hica_p1_set_rank(hica_handle h, const int64_t *R_host, int64_t n);
+
+/* One evaluation of the per-row significance vector.
+ *   mode 0: find_matrix_pvalue_breakpoints :446-469 - rows i in (start, n),
+ *           c = i-start, x = #{k<c : start <= R[i][k] <= i},
+ *           sig = !(sf(x-1; M, c, c) >= psig)            (NaN -> 1)
+ *           out arrays have n-start entries, entry 0 = 0.
+ *   mode 1: filter_noisy_breakpoints :617-636 with cut index `cut` - rows
+ *           ii in [start, n), x = #{k<cut-start : start <= R[ii][k] <= cut},
+ *           sig = sf(x-1; M, local, local) < psig        (NaN -> 0), rows
+ *           beyond start + int(n/5) are 0.
+ * sig_host / x_host may be NULL.  *ambiguous receives the number of decisions
+ * whose p-value lies within the library's safety margin of psig. */
+int hica_p1_window_sig(hica_handle h, int64_t start, int64_t cut, int64_t M, double psig, int mode,
+                       uint8_t *sig_host, int64_t *x_host, int64_t *ambiguous);
+
+/* pre_process_all_matrix_breakpoints :513-551 (first-stage psig is the literal
+ * .05 as in the reference, :535). */
+int hica_p1_breakpoints(hica_handle h, int64_t min_size, double min_frac,
+                        int64_t *cuts_host, int64_t capacity, int64_t *n_cuts, int64_t *ambiguous);
+
+/* filter_noisy_breakpoints :553-727. */
+int hica_p1_filter(hica_handle h, const int64_t *cuts_in, int64_t n_in, double psig,
+                   int64_t *cuts_out, int64_t *n_out, int64_t *ambiguous);
+
+/* P(X >= x) decisions `sf(x-1; M, n, N) < psig` for a batch of scalar queries
+ * (hyper_geom :352-368); out[i] = 1/0, or 2 when inside the safety margin. */
+int hica_hypergeom_less(hica_handle h, const int64_t *x, const int64_t *M, const int64_t *n,
+                        const int64_t *N, int64_t count, double psig, uint8_t *out);
+
+/* ---- Part 2: ordering score over candidate batches ------------------------ */
+
+/* The genome (or chromosome) contact matrix of orderGenome :607 (raw ICE
+ * values).  n x n doubles. */
+int hica_p2_upload(hica_handle h, const double *G_host, int64_t n);
+/* Use the Part1 matrix already resident in this handle. */
+int hica_p2_use_p1_matrix(hica_handle h);
+
+/* giveNewAdjMat :297-308: select the working sub-matrix S = G[ix_(idx, idx)]
+ * (device-side gather).  Subsequent segment/bin indices refer to S. */
+int hica_p2_select(hica_handle h, const int32_t *idx, int32_t L);
+
+/* Scaffolds as segments of S: seg_ptr has nseg+1 entries into seg_bins, which
+ * lists each scaffold's bin indices in "+" (ascending bin id) reading order. */
+int hica_p2_set_segments(hica_handle h, const int32_t *seg_ptr, const int32_t *seg_bins, int32_t nseg);
+
+/* total = sum_k numpy.trace(M, offset=k) (orderGenome.py:343, 448, 506) for the
+ * matrix laid out by `cand` (nslots entries, each (segment << 1) | flip). */
+int hica_p2_total(hica_handle h, const int32_t *cand, int32_t nslots, double *total);
+
+/* costFunction_numba :184-191 over a batch of explicit candidates: cands is
+ * B x nslots, each entry (segment << 1) | flip.  Returns the first strict
+ * maximum above `carried` (best_idx = -1 when none), exactly the accept rule of
+ * :349, :464, :535.  scores_or_null receives all B scores when non-NULL. */
+int hica_p2_score_candidates(hica_handle h, const int32_t *cands, int64_t B, int32_t nslots,
+                             double total, double carried, double *best, int64_t *best_idx,
+                             double *scores_or_null);
+
+/* Window enumeration on the device (bruteForceBestScore :432-473 and one window
+ * of scanOrdering :513-541): the candidate with index c in [cand_lo, cand_hi)
+ * is base[0:win_start] + arrangement(c) + base[win_start+win_n:], where
+ * arrangement(c) places window scaffold order_table[c / n_orients][j] with
+ * orientation orient_table[c % n_orients][j] (0 = '+', 1 = '-') at window slot
+ * j.  base is nslots entries of (segment << 1) | flip.  best_idx is absolute. */
+int hica_p2_score_window(hica_handle h, const int32_t *base, int32_t nslots, int32_t win_start, int32_t win_n,
+                         const uint8_t *order_table, int32_t n_orders, const uint8_t *orient_table,
+                         int32_t n_orients, int64_t cand_lo, int64_t cand_hi, double total, double carried,
+                         double *best, int64_t *best_idx, double *scores_or_null);
+
+/* Explicit bin orders (B x L int32 into S): the most general form, used by
+ * tests and by the costFunction_numba seam. */
+int hica_p2_score_orders(hica_handle h, const int32_t *orders, int64_t B, int32_t L, double total,
+                         double carried, double *best, int64_t *best_idx, double *scores_or_null);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HICA_H */

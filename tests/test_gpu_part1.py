@@ -1,0 +1,154 @@
+"""GPU parity of the Part1 kernels against the oracle (bit-exact)."""
+import numpy as np
+import pytest
+
+import hica_oracle as O
+import c_oracle as CO
+from hic_genome_assembler_b200.synth import make_genome
+
+pytestmark = pytest.mark.gpu
+
+
+def _rand_sym(n, seed, tie=False):
+    rng = np.random.RandomState(seed)
+    A = rng.rand(n, n) * 10
+    A = np.triu(A, 1)
+    if tie:
+        A[rng.rand(n, n) < 0.6] = 0.0
+    A = A + A.T + np.eye(n) * 1e-3
+    return A
+
+
+@pytest.mark.parametrize("n", [2, 3, 7, 8, 9, 31, 64, 65, 127, 128, 129, 130, 200, 257, 1000, 1031, 2049])
+def test_row_sums_and_distance(hica, n):
+    A = _rand_sym(n, n)
+    hica.p1_upload(A)
+    hica.p1_set_row_sums(None)
+    hica.p1_distance()
+    assert np.array_equal(hica.p1_get_pairwise_row_sums(), O.pairwise_row_sums(A))
+    assert np.array_equal(hica.p1_get_row_sums(), O.sequential_row_sums(A))
+    assert np.array_equal(hica.p1_get_distance(), O.convert_distance(A))
+
+
+@pytest.mark.parametrize("n,tie", [(2, False), (3, False), (5, False), (17, True), (40, False), (70, True),
+                                   (150, False), (333, True), (1000, False), (1500, True)])
+def test_linkage_bitwise(hica, n, tie):
+    A = _rand_sym(n, 100 + n, tie)
+    D = O.convert_distance(A)
+    Z_ref, leaves_ref = O.average_cluster_leaves(D)
+    hica.p1_upload(A)
+    hica.p1_distance()
+    Z, leaves = hica.p1_linkage()
+    assert np.array_equal(Z, Z_ref)
+    assert list(leaves) == list(leaves_ref)
+
+
+def test_linkage_from_distance_matrix(hica):
+    A = _rand_sym(90, 5)
+    D = O.convert_distance(A)
+    Z_ref, leaves_ref = O.average_cluster_leaves(D)
+    hica.p1_upload_distance(D)
+    Z, leaves = hica.p1_linkage()
+    assert np.array_equal(Z, Z_ref) and list(leaves) == list(leaves_ref)
+
+
+@pytest.mark.parametrize("n", [5, 33, 200, 700])
+def test_reorder_similarity_rank(hica, n):
+    A = _rand_sym(n, 7 * n)
+    rs = O.sequential_row_sums(A)
+    D = O.convert_distance(A)
+    _, leaves = O.average_cluster_leaves(D)
+    Dp = O.reorder(D, leaves)
+    S = O.convert_similarity(Dp, rs[np.asarray(leaves)])
+    hica.p1_upload(A)
+    hica.p1_set_row_sums(rs)
+    hica.p1_distance()
+    hica.p1_set_order(leaves)
+    assert np.array_equal(hica.p1_get_reordered(0), Dp)
+    assert np.array_equal(hica.p1_get_reordered(1), S)
+    hica.p1_rank()
+    R = hica.p1_get_rank()
+    assert np.array_equal(R, O.rank_matrix_stable(S))
+    # tie-free input: identical to numpy's default (unstable) argsort as well
+    assert np.array_equal(R, O.rank_matrix(S))
+
+
+def test_rank_with_ties_is_stable_reversed(hica):
+    n = 64
+    A = _rand_sym(n, 3, tie=True)
+    A = np.round(A, 1)
+    np.fill_diagonal(A, 1.0)
+    rs = O.sequential_row_sums(A)
+    hica.p1_upload(A)
+    hica.p1_set_row_sums(rs)
+    hica.p1_distance()
+    order = np.random.RandomState(0).permutation(n)
+    hica.p1_set_order(order)
+    hica.p1_rank()
+    S = O.convert_similarity(O.reorder(O.convert_distance(A), order), rs[order])
+    assert np.array_equal(hica.p1_get_rank(), O.rank_matrix_stable(S))
+
+
+@pytest.mark.parametrize("n,nc,spc,seed", [(60, 3, 4, 1), (200, 5, 6, 2), (400, 8, 8, 7), (640, 8, 10, 11)])
+def test_cut_indices_end_to_end(hica, n, nc, spc, seed):
+    g = make_genome(n, n_chrom=nc, seed=seed, scaffolds_per_chrom=spc)
+    A = g.A.numpy()
+    ref = O.part1_cut_indices(A, min_size=5, min_frac=0.0, psig=.05)
+    hica.p1_upload(A)
+    hica.p1_set_row_sums(None)
+    hica.p1_distance()
+    Z, leaves = hica.p1_linkage()
+    assert np.array_equal(Z, ref["Z"]) and list(leaves) == list(ref["leaves"])
+    hica.p1_rank()
+    assert np.array_equal(hica.p1_get_rank(), ref["R"])
+    init, amb0 = hica.p1_breakpoints(5, 0.0)
+    assert init == ref["initial_cuts"]
+    cuts, amb1 = hica.p1_filter(init, .05)
+    assert cuts == ref["cuts"]
+    assert amb0 == 0 and amb1 == 0
+
+
+@pytest.mark.parametrize("start", [0, 37, 150])
+def test_window_significance_vectors(hica, start):
+    g = make_genome(300, n_chrom=5, seed=3, scaffolds_per_chrom=5)
+    A = g.A.numpy()
+    ref = O.part1_cut_indices(A, min_frac=0.0)
+    R = ref["R"]
+    hica.p1_set_rank(R) if False else None
+    hica.p1_upload(A); hica.p1_set_row_sums(None); hica.p1_distance(); hica.p1_linkage(); hica.p1_rank()
+    n = 300
+    for M in (n - start, n - 2 * start, 40, 0, -5):
+        sig, x, amb = hica.p1_window_sig(start, M, .05, 0)
+        xr = O.window_counts(R, start)
+        assert np.array_equal(x, xr)
+        assert np.array_equal(sig, O.window_significance(xr, M, .05)), M
+    for cut in (start + 1, start + 20, start + 77):
+        sig, x, amb = hica.p1_window_sig(start, n - start, .05, 1, cut=cut)
+        assert np.array_equal(sig, O.filter_row_significance(R, start, cut, .05))
+
+
+def test_set_rank_seam_and_filter(hica):
+    g = make_genome(400, n_chrom=8, seed=7, scaffolds_per_chrom=8)
+    ref = O.part1_cut_indices(g.A.numpy(), min_frac=0.0)
+    from hic_genome_assembler_b200._lib import Handle
+    h2 = Handle(0)
+    h2.p1_set_rank(ref["R"])
+    init, _ = h2.p1_breakpoints(5, 0.0)
+    assert init == ref["initial_cuts"]
+    cuts, _ = h2.p1_filter(init, .05)
+    assert cuts == ref["cuts"]
+    h2.close()
+
+
+def test_hypergeom_decisions_match_scipy(hica):
+    rng = np.random.RandomState(0)
+    M = rng.randint(1, 4000, size=20000)
+    n = (rng.rand(20000) * (M + 1)).astype(np.int64)
+    N = (rng.rand(20000) * (M + 1)).astype(np.int64)
+    lo = np.maximum(0, N + n - M)
+    hi = np.minimum(n, N)
+    x = lo + (rng.rand(20000) * (hi - lo + 2)).astype(np.int64)
+    out = hica.hypergeom_less(x, M, n, N, .05)
+    ref = (O.hyper_geom(x, M, n, N) < .05).astype(np.uint8)
+    assert (out & 2).sum() == 0
+    assert np.array_equal(out & 1, ref)
