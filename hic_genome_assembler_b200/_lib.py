@@ -21,7 +21,7 @@ ABI_SYMBOLS = (
     "hica_version", "hica_create", "hica_destroy", "hica_last_error", "hica_launch_count", "hica_get_timers",
     "hica_p1_upload", "hica_p1_upload_device", "hica_p1_set_row_sums", "hica_p1_distance", "hica_p1_get_distance",
     "hica_p1_get_pairwise_row_sums", "hica_p1_get_row_sums", "hica_p1_upload_distance", "hica_p1_linkage",
-    "hica_p1_set_order", "hica_p1_get_reordered", "hica_p1_rank", "hica_p1_get_rank", "hica_p1_set_rank",
+    "hica_p1_set_order", "hica_p1_get_reordered", "hica_p1_rank", "hica_p1_upload_similarity", "hica_p1_get_rank", "hica_p1_set_rank",
     "hica_p1_window_sig", "hica_p1_breakpoints", "hica_p1_filter", "hica_hypergeom_less",
     "hica_p2_upload", "hica_p2_use_p1_matrix", "hica_p2_select", "hica_p2_set_segments", "hica_p2_total",
     "hica_p2_score_candidates", "hica_p2_score_window", "hica_p2_score_orders",
@@ -65,6 +65,7 @@ def load_library():
     L.hica_p1_set_order.argtypes = [vp, vp]
     L.hica_p1_get_reordered.argtypes = [vp, C.c_int, vp]
     L.hica_p1_rank.argtypes = [vp]
+    L.hica_p1_upload_similarity.argtypes = [vp, vp, i64]
     L.hica_p1_get_rank.argtypes = [vp, vp]
     L.hica_p1_set_rank.argtypes = [vp, vp, i64]
     L.hica_p1_window_sig.argtypes = [vp, i64, i64, i64, dbl, C.c_int, vp, vp, vp]
@@ -151,6 +152,11 @@ class Handle:
         D = _c(D, np.float64)
         self.n = D.shape[0]
         self._check(self._L.hica_p1_upload_distance(self._h, _ptr(D), self.n))
+
+    def p1_upload_similarity(self, S: np.ndarray):
+        S = _c(S, np.float64)
+        self.n = S.shape[0]
+        self._check(self._L.hica_p1_upload_similarity(self._h, _ptr(S), self.n))
 
     def p1_set_row_sums(self, rs: Optional[np.ndarray] = None):
         rs = None if rs is None else _c(rs, np.float64)

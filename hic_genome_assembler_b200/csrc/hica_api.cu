@@ -84,7 +84,7 @@ static void free_p1(hica_ctx *h)
     h->have_s_pair = h->have_s_seq = h->have_W = h->have_order = false;
     h->rank_bytes = 0;
     h->n = h->ld = 0;
-    h->A_is_distance = false;
+    h->A_kind = 0;
 }
 
 extern "C" int hica_destroy(hica_handle h)
@@ -133,7 +133,7 @@ static int p1_alloc(hica_ctx *h, int64_t n)
     }
     h->have_s_pair = h->have_s_seq = h->have_W = h->have_order = false;
     h->rank_bytes = 0;
-    h->A_is_distance = false;
+    h->A_kind = 0;
     return HICA_OK;
 }
 

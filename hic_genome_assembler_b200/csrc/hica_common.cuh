@@ -28,7 +28,7 @@ struct hica_ctx {
     bool have_s_pair = false, have_s_seq = false;
     double *W = nullptr;       // mirrored working matrix for linkage, n x ld
     bool have_W = false;
-    bool A_is_distance = false;  // hica_p1_upload_distance: A holds D, not ICE
+    int A_kind = 0;  // 0: ICE contacts; 1: distance matrix D (hica_p1_upload_distance); 2: similarity S (hica_p1_upload_similarity)
     int32_t *order = nullptr;    // current row/col order (leaves), n
     int32_t *pos = nullptr;      // inverse of order
     bool have_order = false;

@@ -251,7 +251,7 @@ extern "C" int hica_p1_set_row_sums(hica_handle h, const double *rs)
     if (rs) {
         HICA_CUDA(cudaMemcpyAsync(h->s_seq, rs, sizeof(double) * h->n, cudaMemcpyHostToDevice, h->stream));
     } else {
-        if (h->A_is_distance) return hica_set_error(h, HICA_ERR_STATE, "row sums of a distance matrix must be supplied");
+        if (h->A_kind != 0) return hica_set_error(h, HICA_ERR_STATE, "row sums of a distance/similarity matrix must be supplied");
         int64_t blocks = (h->n + 63) / 64;
         k_rowsum_sequential<<<(unsigned)blocks, 64, 0, h->stream>>>(h->A, h->n, h->s_seq);
         HICA_LAUNCHED(h);
@@ -266,7 +266,7 @@ extern "C" int hica_p1_distance(hica_handle h)
 {
     HICA_CHECK_HANDLE(h);
     if (!h->A) return hica_set_error(h, HICA_ERR_STATE, "no matrix uploaded");
-    if (h->A_is_distance) return hica_set_error(h, HICA_ERR_STATE, "handle holds a distance matrix already");
+    if (h->A_kind != 0) return hica_set_error(h, HICA_ERR_STATE, "handle holds a distance/similarity matrix, not ICE contacts");
     const int64_t n = h->n;
     int rc = ensure_plan(h, n);
     if (rc) return rc;
@@ -313,7 +313,7 @@ extern "C" int hica_p1_upload_distance(hica_handle h, const double *D_host, int6
     HICA_CHECK_HANDLE(h);
     int rc = hica_p1_upload(h, D_host, n);
     if (rc) return rc;
-    h->A_is_distance = true;
+    h->A_kind = 1;
     if (!h->W && (rc = hica_realloc(h, &h->W, n * h->ld))) return rc;
     unsigned T = (unsigned)((n + 63) / 64);
     k_build_W<false><<<dim3(T, T), 256, 0, h->stream>>>(h->A, n, nullptr, h->W, h->ld);

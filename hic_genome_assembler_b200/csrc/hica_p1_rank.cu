@@ -48,12 +48,12 @@ k_rank_rows(const double *__restrict__ A, int64_t n, const double *__restrict__ 
     const int64_t i = blockIdx.x;
     const int64_t a = order[i];
     const double sp = is_distance ? 1.0 : s_pair[a];
-    const double rs = s_seq[a];
+    const double rs = is_distance == 2 ? 1.0 : s_seq[a];
     const double *row = A + a * n;
     for (int b = threadIdx.x; b < P; b += T) {
         if (b < n) {
             double d = is_distance ? row[b] : dist_transform(row[b], sp);
-            keys[b] = order_key(sim_transform(d, rs));
+            keys[b] = order_key(is_distance == 2 ? d : sim_transform(d, rs));
             pay[b] = (PayT)pos[b];
         } else {
             keys[b] = 0ull;  // pads sort last
@@ -92,12 +92,12 @@ __global__ void __launch_bounds__(256) k_reordered(const double *__restrict__ A,
     const int64_t i = blockIdx.x;
     const int64_t a = order[i];
     const double sp = is_distance ? 1.0 : s_pair[a];
-    const double rs = what ? s_seq[a] : 0.0;
+    const double rs = (what && is_distance != 2) ? s_seq[a] : 0.0;
     const double *row = A + a * n;
     for (int64_t j = threadIdx.x; j < n; j += blockDim.x) {
         double v = row[order[j]];
         double d = is_distance ? v : dist_transform(v, sp);
-        out[i * n + j] = what ? sim_transform(d, rs) : d;
+        out[i * n + j] = (what && is_distance != 2) ? sim_transform(d, rs) : d;
     }
 }
 
@@ -108,8 +108,8 @@ extern "C" int hica_p1_rank(hica_handle h)
     HICA_CHECK_HANDLE(h);
     if (!h->A) return hica_set_error(h, HICA_ERR_STATE, "no matrix uploaded");
     if (!h->have_order) return hica_set_error(h, HICA_ERR_STATE, "no order set (hica_p1_linkage / hica_p1_set_order)");
-    if (!h->have_s_seq) return hica_set_error(h, HICA_ERR_STATE, "row sums not set (hica_p1_set_row_sums)");
-    if (!h->A_is_distance && !h->have_s_pair) return hica_set_error(h, HICA_ERR_STATE, "call hica_p1_distance first");
+    if (h->A_kind != 2 && !h->have_s_seq) return hica_set_error(h, HICA_ERR_STATE, "row sums not set (hica_p1_set_row_sums)");
+    if (h->A_kind == 0 && !h->have_s_pair) return hica_set_error(h, HICA_ERR_STATE, "call hica_p1_distance first");
     const int64_t n = h->n;
     int P = 1;
     while (P < n) P <<= 1;
@@ -125,7 +125,7 @@ extern "C" int hica_p1_rank(hica_handle h)
     int threads = std::min(1024, std::max(32, P / 2));
     hica_timer t(h, HICA_T_RANK);
     k_rank_rows<uint16_t><<<(unsigned)n, threads, smem, h->stream>>>(h->A, n, h->s_pair, h->s_seq, h->order, h->pos,
-                                                                     h->A_is_distance ? 1 : 0, P, (uint16_t *)h->R);
+                                                                     h->A_kind, P, (uint16_t *)h->R);
     HICA_LAUNCHED(h);
     HICA_CUDA(cudaGetLastError());
     t.stop();
@@ -198,14 +198,14 @@ extern "C" int hica_p1_get_reordered(hica_handle h, int what, double *out_host)
 {
     HICA_CHECK_HANDLE(h);
     if (!h->A || !h->have_order) return hica_set_error(h, HICA_ERR_STATE, "matrix and order required");
-    if (!h->A_is_distance && !h->have_s_pair) return hica_set_error(h, HICA_ERR_STATE, "call hica_p1_distance first");
-    if (what == 1 && !h->have_s_seq) return hica_set_error(h, HICA_ERR_STATE, "row sums not set");
+    if (h->A_kind == 0 && !h->have_s_pair) return hica_set_error(h, HICA_ERR_STATE, "call hica_p1_distance first");
+    if (what == 1 && h->A_kind != 2 && !h->have_s_seq) return hica_set_error(h, HICA_ERR_STATE, "row sums not set");
     if (what != 0 && what != 1) return hica_set_error(h, HICA_ERR_ARG, "what must be 0 or 1");
     const int64_t n = h->n;
     double *out = nullptr;
     int rc = hica_realloc(h, &out, n * n);
     if (rc) return rc;
-    k_reordered<<<(unsigned)n, 256, 0, h->stream>>>(h->A, n, h->s_pair, h->s_seq, h->order, h->A_is_distance ? 1 : 0,
+    k_reordered<<<(unsigned)n, 256, 0, h->stream>>>(h->A, n, h->s_pair, h->s_seq, h->order, h->A_kind,
                                                    what, out);
     HICA_LAUNCHED(h);
     cudaError_t e = cudaGetLastError();
@@ -214,4 +214,19 @@ extern "C" int hica_p1_get_reordered(hica_handle h, int what, double *out_host)
     cudaFree(out);
     if (e != cudaSuccess) return hica_set_error(h, HICA_ERR_CUDA, "get_reordered: %s", cudaGetErrorString(e));
     return HICA_OK;
+}
+
+// defined in hica_api.cu / hica_p1_linkage.cu
+extern "C" int hica_p1_upload(hica_handle h, const double *A_host, int64_t n);
+int hica_set_order_internal(hica_ctx *h, const int32_t *order_host);
+
+extern "C" int hica_p1_upload_similarity(hica_handle h, const double *S_host, int64_t n)
+{
+    HICA_CHECK_HANDLE(h);
+    int rc = hica_p1_upload(h, S_host, n);
+    if (rc) return rc;
+    h->A_kind = 2;
+    std::vector<int32_t> ident(n);
+    for (int64_t i = 0; i < n; i++) ident[i] = (int32_t)i;
+    return hica_set_order_internal(h, ident.data());
 }

@@ -307,7 +307,7 @@ extern "C" int hica_p2_upload(hica_handle h, const double *G_host, int64_t n)
 extern "C" int hica_p2_use_p1_matrix(hica_handle h)
 {
     HICA_CHECK_HANDLE(h);
-    if (!h->A || h->A_is_distance) return hica_set_error(h, HICA_ERR_STATE, "no ICE matrix resident from Part1");
+    if (!h->A || h->A_kind != 0) return hica_set_error(h, HICA_ERR_STATE, "no ICE matrix resident from Part1");
     if (!h->g_is_A && h->G) cudaFree(h->G);
     h->G = h->A;
     h->gn = h->n;

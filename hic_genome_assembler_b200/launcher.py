@@ -1,0 +1,140 @@
+"""Drop-in launcher: run the UNCHANGED reference entry point with its hot path on the GPU.
+
+    python -m hic_genome_assembler_b200.launcher --reference-dir /path/to/HIC_ASSEMBLER \
+        -part1 -part2 -config hicAssembler_config.txt
+
+The reference has no plugin API; its pipelines call module-level functions through module globals
+(e.g. orderChromosome -> bruteForceBestScore, orderGenome.py:575).  The launcher imports the reference's
+own modules from ``--reference-dir``, rebinds the hot-path functions of SURVEY.md section 8(b) to the
+libhica-backed implementations in :mod:`.part1` / :mod:`.part2`, and then executes ``run_hicAssembler.py``
+with the remaining command line.  Config file, output files and formats are the reference's own code.
+
+No reference file is modified or copied.  There is no CPU fallback: without libhica.so and a CUDA
+device the launcher fails at start-up.
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import os
+import runpy
+import sys
+import types
+
+from ._lib import Handle
+from .part1 import Seams as Part1Seams
+from .part2 import _Seams as Part2Seams
+
+_OPTIONAL = ("hmmlearn", "hmmlearn.hmm", "community", "matplotlib", "matplotlib.pyplot", "matplotlib.colors",
+             "matplotlib.patches", "xarray")
+
+
+def _stub_missing_optional_modules(verbose=True):
+    """hmmlearn / python-louvain / matplotlib / xarray are imported by the reference at module import
+    (scaffoldToChromosomes.py:10,14,17; plotContactMaps.py:5-8) but are off the hot path.  When one is
+    not installed an empty stand-in lets the import succeed; plotting then becomes a no-op."""
+    stubbed = []
+    for name in _OPTIONAL:
+        if name in sys.modules:
+            continue
+        try:
+            importlib.import_module(name)
+        except Exception:
+            m = types.ModuleType(name)
+            sys.modules[name] = m
+            if "." in name:
+                setattr(sys.modules[name.split(".")[0]], name.split(".")[1], m)
+            stubbed.append(name)
+    if stubbed and verbose:
+        print("[hica launcher] optional modules not installed, stubbed: " + ", ".join(stubbed))
+    return stubbed
+
+
+class _NumpyShim(types.ModuleType):
+    """Stands in for the name ``numpy`` inside scaffoldToChromosomes only: forwards everything to numpy
+    except ``argsort(S, axis=1)`` on the similarity matrix (:1132), which runs on the device."""
+
+    def __init__(self, real, seams: Part1Seams):
+        super().__init__("numpy")
+        self.__dict__["_real"] = real
+        self.__dict__["_seams"] = seams
+
+    def __getattr__(self, name):
+        return getattr(self.__dict__["_real"], name)
+
+    def argsort(self, a, axis=-1, *args, **kwargs):
+        real = self.__dict__["_real"]
+        if axis == 1 and not args and not kwargs and getattr(a, "ndim", 0) == 2 and a.shape[0] == a.shape[1] \
+                and a.shape[0] > 1:
+            return _DescendingRank(self.__dict__["_seams"].argsort_desc(a))
+        return real.argsort(a, axis, *args, **kwargs)
+
+
+class _DescendingRank:
+    """Result of the shimmed argsort: the reference immediately takes ``[:, ::-1]`` of it."""
+
+    def __init__(self, R_desc):
+        self._R = R_desc
+
+    def __getitem__(self, key):
+        if isinstance(key, tuple) and len(key) == 2 and key[0] == slice(None) and key[1] == slice(None, None, -1):
+            return self._R
+        return self._R[:, ::-1][key]
+
+    def __array__(self, dtype=None, copy=None):
+        out = self._R[:, ::-1]
+        return out.astype(dtype) if dtype is not None else out
+
+
+def install(reference_dir: str, device: int = 0, no_plots: bool = False):
+    """Import the reference modules from ``reference_dir`` and rebind their hot-path functions.
+    Returns (handle, part1 module, part2 module)."""
+    reference_dir = os.path.abspath(reference_dir)
+    if not os.path.isfile(os.path.join(reference_dir, "run_hicAssembler.py")):
+        raise FileNotFoundError("run_hicAssembler.py not found in %s" % reference_dir)
+    stubbed = _stub_missing_optional_modules()
+    if reference_dir not in sys.path:
+        sys.path.insert(0, reference_dir)
+    h = Handle(device)  # fails loudly without libhica.so / a GPU
+    plot = importlib.import_module("plotContactMaps")
+    if no_plots or any(s.startswith("matplotlib") or s == "xarray" for s in stubbed):
+        plot.plotContactMap = lambda *a, **k: None
+    part1 = importlib.import_module("scaffoldToChromosomes")
+    part2 = importlib.import_module("orderGenome")
+
+    s1 = Part1Seams(h)
+    part1.convertMatrix = s1.convertMatrix
+    part1.averageClusterNodes = s1.averageClusterNodes
+    part1.reorderMatrix = s1.reorderMatrix
+    part1.pre_process_all_matrix_breakpoints = s1.pre_process_all_matrix_breakpoints
+    part1.filter_noisy_breakpoints = s1.filter_noisy_breakpoints
+    part1.numpy = _NumpyShim(part1.numpy, s1)
+
+    s2 = Part2Seams(h)
+    part2.costFunction_numba = s2.costFunction_numba
+    part2.bruteForceBestScore = s2.bruteForceBestScore
+    part2.checkAllScores = s2.checkAllScores
+    part2.scanOrdering = s2.scanOrdering
+    return h, part1, part2
+
+
+def main(argv=None):
+    ap = argparse.ArgumentParser(add_help=False)
+    ap.add_argument("--reference-dir", required=True)
+    ap.add_argument("--device", type=int, default=0)
+    ap.add_argument("--no-plots", action="store_true")
+    ns, rest = ap.parse_known_args(argv)
+    h, _, _ = install(ns.reference_dir, ns.device, ns.no_plots)
+    script = os.path.join(os.path.abspath(ns.reference_dir), "run_hicAssembler.py")
+    old_argv = sys.argv
+    sys.argv = [script] + rest
+    try:
+        runpy.run_path(script, run_name="__main__")
+    finally:
+        sys.argv = old_argv
+        print("[hica launcher] kernels launched: %d" % h.launches)
+        h.close()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,216 @@
+"""Host side of Part1 (scaffoldToChromosomes.py): the device pipeline and the
+seam functions with the reference's signatures.
+
+``run_part1`` drives the C ABI from a dense ICE matrix in host memory to
+``(leaves, cut indices)`` - the timing boundary of SURVEY.md 8(d).  The
+``Seams`` class holds drop-in replacements for the reference's module-level
+functions (same names, arguments and return conventions); matrices returned to
+Python are ``numpy.matrix`` objects tagged with the device state they mirror,
+so that a following seam call can skip the re-upload.
+"""
+from __future__ import annotations
+
+import time
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from ._lib import Handle
+
+
+def run_part1(h: Handle, A: np.ndarray, min_size: int = 5, min_frac: float = .05, psig: float = .05,
+              row_sums: Optional[np.ndarray] = None, want_Z: bool = False) -> dict:
+    """scaffoldToChromosomes.runPipeline :1116-1134 without file I/O and plots:
+    distance transform -> UPGMA -> leaf order -> similarity rank -> breakpoints -> noise filter."""
+    h.p1_upload(A)
+    return run_part1_resident(h, min_size, min_frac, psig, row_sums, want_Z)
+
+
+def run_part1_resident(h: Handle, min_size: int = 5, min_frac: float = .05, psig: float = .05,
+                       row_sums: Optional[np.ndarray] = None, want_Z: bool = False) -> dict:
+    """Same, for a matrix that is already on the device (p1_upload / p1_upload_device)."""
+    h.p1_set_row_sums(row_sums)
+    h.p1_distance()
+    Z, leaves = h.p1_linkage(want_Z=want_Z)
+    h.p1_rank()
+    init, amb0 = h.p1_breakpoints(min_size, min_frac)
+    cuts, amb1 = h.p1_filter(init, psig)
+    return dict(Z=Z, leaves=leaves, initial_cuts=init, cuts=cuts, ambiguous=amb0 + amb1)
+
+
+# --------------------------------------------------------------------------- #
+# bin -> scaffold -> chromosome group assignment (scaffoldToChromosomes.py:945-1100)
+# --------------------------------------------------------------------------- #
+
+
+def chromosome_groups(cuts: Sequence[int], leaves: Sequence[int], bin_ids: Sequence[int],
+                      scaffold_of_bin: Sequence[str], scaffold_size_bp: Dict[str, int],
+                      percent_to_assign: float = 51.) -> List[List[Tuple[int, str]]]:
+    """In-memory restatement of writeBinGroupingsToFile (:945-962) -> assessChromosomeClustering
+    (:1038-1077) -> writeChromosomeGroupingsToFile (:1079-1100): split the dendrogram order at the cut
+    indices, assign a scaffold to a group when >= 51 % of its bins fall in it, sort groups by bp size.
+    ``bin_ids`` / ``scaffold_of_bin`` are in matrix (pre-reorder) index order."""
+    order = list(leaves)
+    bounds = [0] + list(cuts) + [len(order)]
+    bin_groups = [[order[k] for k in range(bounds[g], bounds[g + 1])] for g in range(len(bounds) - 1)]
+    # all bins of every scaffold, sorted by bin id (:1047-1056)
+    per_scaf: Dict[str, List[int]] = {}
+    for grp in bin_groups:
+        for i in grp:
+            per_scaf.setdefault(scaffold_of_bin[i], []).append(int(bin_ids[i]))
+    for s in per_scaf:
+        per_scaf[s].sort()
+    final = []
+    for grp in bin_groups:
+        counts: Dict[str, int] = {}
+        for i in grp:
+            counts[scaffold_of_bin[i]] = counts.get(scaffold_of_bin[i], 0) + 1
+        nodes: List[Tuple[int, str]] = []
+        for s, c in counts.items():  # dict order = first appearance, as in the reference
+            pct = round((float(c) / float(len(per_scaf[s]))) * 100., 2)
+            if pct >= percent_to_assign:
+                nodes += [(b, s) for b in per_scaf[s]]
+        if nodes:
+            final.append(nodes)
+    sizes = [sum(scaffold_size_bp[s] for s in dict.fromkeys(nm for _, nm in grp)) for grp in final]
+    ranked = sorted(zip(final, sizes), key=lambda p: p[1], reverse=True)
+    return [g for g, _ in ranked]
+
+
+# --------------------------------------------------------------------------- #
+# seams
+# --------------------------------------------------------------------------- #
+
+
+class DeviceBackedMatrix(np.matrix):
+    """numpy.matrix that remembers which device state it mirrors."""
+
+    _hica_tag = None
+
+    def __array_finalize__(self, obj):
+        np.matrix.__array_finalize__(self, obj)
+        self._hica_tag = None  # views / copies are plain host data
+
+
+def _tag(M: np.ndarray, tag) -> DeviceBackedMatrix:
+    out = np.asmatrix(M).view(DeviceBackedMatrix)
+    out._hica_tag = tag
+    return out
+
+
+class Seams:
+    """Replacements for the module-level functions of scaffoldToChromosomes.py on the hot path."""
+
+    def __init__(self, h: Handle):
+        self.h = h
+        self._epoch = 0
+
+    def _fresh(self, kind):
+        self._epoch += 1
+        return (kind, self._epoch)
+
+    def _is_current(self, M, kind) -> bool:
+        tag = getattr(M, "_hica_tag", None)
+        return tag is not None and tag == (kind, self._epoch)
+
+    # convertMatrix(adjacencyMatrix, binList, distance=True, similarity=False) :138-155
+    def convertMatrix(self, adjacencyMatrix, binList, distance=True, similarity=False):
+        t0 = time.time()
+        h = self.h
+        if distance == True:  # noqa: E712 - the reference compares with == True
+            A = np.ascontiguousarray(np.asarray(adjacencyMatrix, dtype=np.float64))
+            h.p1_upload(A)
+            h.p1_set_row_sums(np.asarray([b.rowSum for b in binList], dtype=np.float64))
+            h.p1_distance()
+            out = _tag(h.p1_get_distance(), self._fresh("D"))
+        elif similarity == True:  # noqa: E712
+            rs = np.asarray([b.rowSum for b in binList], dtype=np.float64)
+            if self._is_current(adjacencyMatrix, "Dperm"):
+                # reordered distance matrix of the resident ICE matrix: row sums follow the reordered binList
+                order = self._order
+                full = np.empty(h.n)
+                full[np.asarray(order)] = rs
+                h.p1_set_row_sums(full)
+                out = _tag(h.p1_get_reordered(1), self._fresh("S"))
+            else:
+                D = np.ascontiguousarray(np.asarray(adjacencyMatrix, dtype=np.float64))
+                h.p1_upload_distance(D)
+                h.p1_set_row_sums(rs)
+                h.p1_set_order(np.arange(D.shape[0], dtype=np.int32))
+                self._order = list(range(D.shape[0]))
+                out = _tag(h.p1_get_reordered(1), self._fresh("S"))
+        else:
+            out = np.asmatrix(adjacencyMatrix)
+        print("Time to convert matrix " + str(time.time() - t0))
+        return out
+
+    # averageClusterNodes(adjacencyMatrix, nodeLabels, noPlot=True) :187-208
+    def averageClusterNodes(self, adjacencyMatrix, nodeLabels, noPlot=True):
+        t0 = time.time()
+        h = self.h
+        if not self._is_current(adjacencyMatrix, "D"):
+            h.p1_upload_distance(np.ascontiguousarray(np.asarray(adjacencyMatrix, dtype=np.float64)))
+            self._fresh("Dhost")
+        Z, leaves = h.p1_linkage(want_Z=True)
+        leaves = [int(v) for v in leaves]
+        self._order = leaves
+        # a linkage consumes W; the D tag stays valid for reorderMatrix
+        print("Time to cluster " + str(time.time() - t0))
+        return {"leaves": leaves, "ivl": [nodeLabels[i] for i in leaves], "Z": Z}
+
+    # reorderMatrix(matrix, binList, newOrder) :157-163
+    def reorderMatrix(self, matrix, binList, newOrder):
+        h = self.h
+        order = [int(v) for v in newOrder]
+        tag = getattr(matrix, "_hica_tag", None)
+        if tag is not None and tag[1] == self._epoch and tag[0] in ("D", "Dhost"):
+            h.p1_set_order(np.asarray(order, dtype=np.int32))
+            self._order = order
+            out = _tag(h.p1_get_reordered(0), self._fresh("Dperm"))
+        else:
+            # a matrix that is not the resident one: upload it as is and gather on the device
+            h.p1_upload_distance(np.ascontiguousarray(np.asarray(matrix, dtype=np.float64)))
+            self._fresh("Dhost")
+            h.p1_set_order(np.asarray(order, dtype=np.int32))
+            self._order = order
+            out = _tag(h.p1_get_reordered(0), self._fresh("Dperm"))
+        return out, [binList[i] for i in order]
+
+    # numpy.argsort(adjMat, axis=1)[:, ::-1] :1132 (bound through the module's `numpy` name)
+    def argsort_desc(self, S) -> np.ndarray:
+        h = self.h
+        if not self._is_current(S, "S"):
+            h.p1_upload_similarity(np.ascontiguousarray(np.asarray(S, dtype=np.float64)))
+            self._fresh("Shost")
+        h.p1_rank()
+        R = h.p1_get_rank()
+        self._rank_key = (R.__array_interface__["data"][0], R.shape)  # the device already holds this R
+        return R
+
+    def _ensure_rank(self, argsorted_mat):
+        R = np.asarray(argsorted_mat)
+        key = (R.__array_interface__["data"][0], R.shape)
+        if getattr(self, "_rank_key", None) != key:
+            self.h.p1_set_rank(np.ascontiguousarray(R, dtype=np.int64))
+            self._rank_key = key
+
+    # pre_process_all_matrix_breakpoints(argsorted_mat, min_size=5, min_frac=.05, psig=.05) :513-551
+    def pre_process_all_matrix_breakpoints(self, argsorted_mat, min_size=5, min_frac=.05, psig=.05):
+        self._ensure_rank(argsorted_mat)
+        cuts, amb = self.h.p1_breakpoints(int(min_size), float(min_frac))
+        if amb:
+            print("- WARNING - {} hypergeometric decisions fell within 1e-7 of the significance level".format(amb))
+        print("- Breakpoints found {}".format(len(cuts)))
+        return cuts
+
+    # filter_noisy_breakpoints(argsorted_mat, original_inds, psig=.05) :553-727
+    def filter_noisy_breakpoints(self, argsorted_mat, original_inds, psig=.05):
+        if len(original_inds) == 0:
+            return []
+        self._ensure_rank(argsorted_mat)
+        cuts, amb = self.h.p1_filter([int(v) for v in original_inds], float(psig))
+        if amb:
+            print("- WARNING - {} hypergeometric decisions fell within 1e-7 of the significance level".format(amb))
+        print("- Original cut indices {}".format(list(original_inds)))
+        print("- Filtered cut indices {}".format(cuts))
+        return cuts

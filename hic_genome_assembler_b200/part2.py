@@ -1,0 +1,351 @@
+"""Host side of Part2 (orderGenome.py): candidate enumeration and search control.
+
+The arithmetic (gather + ordering score + first-strict-maximum) runs in
+libhica's CUDA kernels; this module mirrors the reference's interface for the
+path - same function names, argument meaning and accept rules - and turns each
+search loop into ONE batched device call:
+
+  reference loop (orderGenome.py)                 device call
+  ---------------------------------------------   ---------------------------
+  bruteForceBestScore :432-473  (n!/2 * 2^n)      hica_p2_score_window
+  checkAllScores      :332-372  (2(k+1))          hica_p2_score_candidates
+  scanOrdering window :513-541  (60 * 32 at 5)    hica_p2_score_window
+
+A chromosome's contact matrix is gathered ONCE on the device
+(hica_p2_select); every candidate is a signed permutation of scaffold
+segments of that matrix, so no permuted matrix is ever materialised.
+"""
+from __future__ import annotations
+
+import functools
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from ._lib import Handle
+
+# --------------------------------------------------------------------------- #
+# enumeration order of the reference (orderGenome.py:374-430)
+# --------------------------------------------------------------------------- #
+
+
+def _swap_order_permutations(symbols: Sequence) -> List[tuple]:
+    """Every arrangement of ``symbols`` in the order the reference's recursive
+    swap generator emits them (:381-394); duplicates are kept."""
+    work = list(symbols)
+    n = len(work)
+    found: List[tuple] = []
+    # explicit stack instead of recursion: frame = (depth k, next swap index i)
+    stack = [[0, 0]]
+    while stack:
+        k, i = stack[-1]
+        if k == n:
+            found.append(tuple(work))
+            stack.pop()
+            if stack:
+                kk, ii = stack[-1]
+                work[kk], work[ii - 1] = work[ii - 1], work[kk]  # undo the swap that led here
+            continue
+        if i == n:
+            stack.pop()
+            if stack:
+                kk, ii = stack[-1]
+                work[kk], work[ii - 1] = work[ii - 1], work[kk]
+            continue
+        work[k], work[i] = work[i], work[k]
+        stack[-1][1] = i + 1
+        stack.append([k + 1, k + 1])
+    return found
+
+
+@functools.lru_cache(maxsize=None)
+def order_table(n: int) -> np.ndarray:
+    """(n!/2, n) uint8: index permutations that survive removeReverseDuplicates
+    (:396-411) - of every {p, reversed(p)} pair the first one enumerated."""
+    kept, seen = [], set()
+    for p in _swap_order_permutations(range(n)):
+        r = p[::-1]
+        if r in seen:
+            seen.discard(r)
+            continue
+        seen.add(p)
+        kept.append(p)
+    return np.asarray(kept, dtype=np.uint8).reshape(len(kept), n)
+
+
+@functools.lru_cache(maxsize=None)
+def orient_table(n: int) -> np.ndarray:
+    """(2^n, n) uint8, 0 = '+', 1 = '-': plusMinusPerms (:413-430)."""
+    seq = [tuple([0] * n)]
+    for i in range(n):
+        seq.extend(_swap_order_permutations([0] * i + [1] * (n - i)))
+    uniq = list(dict.fromkeys(seq))
+    return np.asarray(uniq, dtype=np.uint8).reshape(len(uniq), n)
+
+
+def calc_possible_perms(n: int) -> float:
+    import math
+    return math.factorial(n) * (2 ** n) / 2
+
+
+# --------------------------------------------------------------------------- #
+# device-resident chromosome
+# --------------------------------------------------------------------------- #
+
+
+class Scaf:
+    """A scaffold of the chromosome being ordered: ``bins`` = bin ids in '+'
+    (ascending id) reading order, ``seg`` = segment index on the device."""
+
+    __slots__ = ("name", "bins", "orientation", "seg")
+
+    def __init__(self, name, bins, orientation="+", seg=-1):
+        self.name = name
+        self.bins = list(bins)
+        self.orientation = orientation
+        self.seg = seg
+
+    def entry(self, orientation: Optional[str] = None) -> int:
+        o = self.orientation if orientation is None else orientation
+        return (self.seg << 1) | (1 if o == "-" else 0)
+
+
+def _flip(o: str) -> str:
+    return "-" if o == "+" else "+"
+
+
+STATS = {"candidates": 0, "bin_pairs": 0, "calls": 0}
+
+
+def _account(n_cand: int, scafs) -> None:
+    L = sum(len(s.bins) for s in scafs)
+    STATS["candidates"] += int(n_cand)
+    STATS["bin_pairs"] += int(n_cand) * (L * (L - 1) // 2)
+    STATS["calls"] += 1
+
+
+class DeviceChromosome:
+    """One chromosome group resident on the GPU: its sub-matrix gathered from
+    the genome matrix and its scaffolds registered as segments."""
+
+    def __init__(self, h: Handle, genome_index_of_bin: Dict[int, int], scafs: Sequence[Scaf]):
+        self.h = h
+        self.scafs = list(scafs)
+        idx, ptr, local = [], [0], []
+        for s_i, s in enumerate(self.scafs):
+            s.seg = s_i
+            for b in s.bins:
+                local.append(len(idx))
+                idx.append(genome_index_of_bin[b])
+            ptr.append(len(idx))
+        h.p2_select(np.asarray(idx, dtype=np.int32))
+        h.p2_set_segments(np.asarray(ptr, dtype=np.int32), np.asarray(local, dtype=np.int32))
+
+    # -- the three searches -------------------------------------------------
+    def total(self, layout: Sequence[Scaf]) -> float:
+        return self.h.p2_total([s.entry() for s in layout])
+
+    def brute_force(self, layout: List[Scaf]):
+        """bruteForceBestScore (:432-473) -> (order idx tuple, orientation tuple of '+'/'-', cost).
+        ``layout`` is the pulled scaffold list in its current state."""
+        n = len(layout)
+        orders, orients = order_table(n), orient_table(n)
+        total = self.total(layout)
+        if total == 0:
+            return tuple(int(v) for v in orders[0]), tuple("-" if v else "+" for v in orients[0]), 0.0
+        base = [s.entry() for s in layout]
+        best, idx, _ = self.h.p2_score_window(base, 0, n, orders, orients, total, 0.0)
+        _account(orders.shape[0] * orients.shape[0], layout)
+        if idx < 0:
+            raise RuntimeError("no ordering scored above 0 (the reference would fail on 'NA' here)")
+        oi, ri = divmod(idx, orients.shape[0])
+        return tuple(int(v) for v in orders[oi]), tuple("-" if v else "+" for v in orients[ri]), best
+
+    def insert_best(self, ordered: List[Scaf], new: Scaf) -> Tuple[List[Scaf], float]:
+        """checkAllScores (:332-372): 2(k+1) candidates, orientation alternating
+        with the insertion index exactly as the reference's in-place flips do."""
+        k = len(ordered)
+        total = self.total(ordered + [new])
+        base = [s.entry() for s in ordered]
+        o0 = new.orientation
+        cands, tried = [], []
+        for i in range(k + 1):
+            first = o0 if i % 2 == 0 else _flip(o0)
+            for o in (first, _flip(first)):
+                cands.append(base[:i] + [new.entry(o)] + base[i:])
+                tried.append((i, o))
+        best, idx, _ = self.h.p2_score_candidates(np.asarray(cands, dtype=np.int32), total, 0.0)
+        _account(len(cands), ordered + [new])
+        pos, orient = (0, "+") if idx < 0 else tried[idx]
+        new.orientation = orient
+        ordered.insert(pos, new)
+        return ordered, (best if idx >= 0 else 0.0)
+
+    def scan(self, ordered: List[Scaf], best_cost: float, scan: int) -> Tuple[List[Scaf], float, int]:
+        """scanOrdering (:495-549): sliding window, carried best cost, rounds to a fixed point."""
+        total = self.total(ordered)
+        orders, orients = order_table(scan), orient_table(scan)
+        rounds = 0
+        while True:
+            improved = False
+            for i in range(0, len(ordered) - scan + 1):
+                base = [s.entry() for s in ordered]
+                best, idx, _ = self.h.p2_score_window(base, i, scan, orders, orients, total, best_cost)
+                _account(orders.shape[0] * orients.shape[0], ordered)
+                if idx >= 0:
+                    oi, ri = divmod(idx, orients.shape[0])
+                    window = ordered[i:i + scan]
+                    arranged = []
+                    for j in range(scan):
+                        s = window[int(orders[oi][j])]
+                        s.orientation = "-" if orients[ri][j] else "+"
+                        arranged.append(s)
+                    ordered[i:i + scan] = arranged
+                    best_cost = best
+                    improved = True
+            rounds += 1
+            if not improved:
+                break
+        return ordered, best_cost, rounds
+
+
+def order_chromosome(h: Handle, genome_index_of_bin: Dict[int, int], nodes: Sequence[Tuple[int, str]],
+                     n_scaffolds: int = 6, scan: int = 5):
+    """orderChromosome (:551-586) for one chromosome group; the genome matrix must
+    already be resident (Handle.p2_upload / p2_use_p1_matrix).
+    Returns ([(scaffold name, '+'/'-'), ...], best cost, scan rounds)."""
+    if n_scaffolds >= 9:
+        n_scaffolds = 8
+    if scan > n_scaffolds:
+        scan = n_scaffolds
+    by_name: Dict[str, Scaf] = {}
+    for b, nm in nodes:
+        if nm not in by_name:
+            by_name[nm] = Scaf(nm, [])
+    for b, nm in nodes:
+        by_name[nm].bins.append(b)
+    for s in by_name.values():
+        s.bins.sort()
+    pool = sorted(by_name.values(), key=lambda s: len(s.bins), reverse=True)
+    chrom = DeviceChromosome(h, genome_index_of_bin, pool)
+    ordered, pool = pool[:n_scaffolds], pool[n_scaffolds:]
+    od, orr, _ = chrom.brute_force(ordered)
+    for si, o in zip(od, orr):
+        ordered[si].orientation = o
+    ordered = [ordered[si] for si in od]
+    best_cost = 0.0
+    # orderRemainderScaffolds (:475-493) is a do-while: with nothing left to place the last
+    # brute-forced scaffold is still popped and re-inserted.
+    while True:
+        if pool:
+            ordered.append(pool.pop(0))
+        new = ordered.pop(-1)
+        ordered, best_cost = chrom.insert_best(ordered, new)
+        if not pool:
+            break
+    rounds = 0
+    if len(ordered) > n_scaffolds:
+        ordered, best_cost, rounds = chrom.scan(ordered, best_cost, scan)
+    return [(s.name, s.orientation) for s in ordered], best_cost, rounds
+
+
+def order_genome(h: Handle, G: Optional[np.ndarray], bin_ids: Sequence[int],
+                 chrom_groups: Sequence[Sequence[Tuple[int, str]]], n_scaffolds: int = 6, scan: int = 5,
+                 chrom_subset: Optional[Sequence[int]] = None):
+    """orderGenome (:591-628) without plotting.  ``G`` = genome matrix in ``bin_ids`` order (None: already
+    resident).  ``chrom_subset`` restricts the work to some groups (multi-GPU sharding: chromosomes are
+    independent, :608-611).  Returns {group index: [(name, orientation), ...]}."""
+    if G is not None:
+        h.p2_upload(G)
+    index_of = {int(b): i for i, b in enumerate(bin_ids)}
+    out = {}
+    for ci, group in enumerate(chrom_groups):
+        if chrom_subset is not None and ci not in chrom_subset:
+            continue
+        out[ci] = order_chromosome(h, index_of, group, n_scaffolds, scan)
+    return out
+
+
+# --------------------------------------------------------------------------- #
+# seams with the reference signatures (duck-typed on orderGenome.Scaffold)
+# --------------------------------------------------------------------------- #
+
+
+class _Seams:
+    """Callable replacements for the module-level functions of orderGenome.py; the launcher binds them
+    into the loaded reference module.  They operate on the reference's own Scaffold objects
+    (``name``, ``binList``, ``orientation``, ``flipOrientation()``)."""
+
+    def __init__(self, h: Handle):
+        self.h = h
+        self._genome_key = None
+
+    # costFunction_numba(matrix, total) :184-191
+    def costFunction_numba(self, matrix, total):
+        M = np.ascontiguousarray(np.asarray(matrix, dtype=np.float64))
+        n = M.shape[0]
+        self.h.p2_upload(M)
+        self._genome_key = None
+        self.h.p2_select(np.arange(n, dtype=np.int32))
+        _, _, sc = self.h.p2_score_orders(np.arange(n, dtype=np.int32)[None, :], float(total), 0.0, want_scores=True)
+        return float(sc[0])
+
+    @staticmethod
+    def _plus_bins(sObj):
+        return list(sObj.binList) if sObj.orientation == "+" else list(sObj.binList)[::-1]
+
+    @staticmethod
+    def _set_orientation(sObj, o):
+        if sObj.orientation != o:
+            sObj.flipOrientation()
+
+    def _resident_matrix(self, matrix, orderDict, sObjs) -> DeviceChromosome:
+        M = np.ascontiguousarray(np.asarray(matrix, dtype=np.float64))
+        self.h.p2_upload(M)
+        self._genome_key = None
+        scafs = [Scaf(s.name, self._plus_bins(s), s.orientation) for s in sObjs]
+        # every row of `matrix` is addressed through orderDict (binID -> row)
+        return DeviceChromosome(self.h, dict(orderDict), scafs), scafs
+
+    # bruteForceBestScore(sObjList, scaffDict, matrix, orderDict) :432-473
+    def bruteForceBestScore(self, sObjList, scaffDict, matrix, orderDict):
+        chrom, scafs = self._resident_matrix(matrix, orderDict, sObjList)
+        names = [s.name for s in sObjList]
+        od, orr, cost = chrom.brute_force(scafs)
+        n = len(names)
+        # leave the shared Scaffold objects in the state of the LAST candidate, as the reference's loop does
+        last_o, last_r = order_table(n)[-1], orient_table(n)[-1]
+        if cost != 0.0 or chrom.total(scafs) != 0:
+            for j in range(n):
+                self._set_orientation(scaffDict[names[int(last_o[j])]], "-" if last_r[j] else "+")
+        return [names[i] for i in od], list(orr), cost
+
+    # checkAllScores(adjMat, orderDict, orderedScaffs, scaffToCheck) :332-372
+    def checkAllScores(self, adjMat, orderDict, orderedScaffs, scaffToCheck):
+        chrom, scafs = self._resident_matrix(adjMat, orderDict, list(orderedScaffs) + [scaffToCheck])
+        ordered, new = scafs[:-1], scafs[-1]
+        ordered, best = chrom.insert_best(ordered, new)
+        pos = ordered.index(new)
+        self._set_orientation(scaffToCheck, new.orientation)
+        orderedScaffs.insert(pos, scaffToCheck)
+        return orderedScaffs, best
+
+    # scanOrdering(orderedScaffolds, scaffoldDict, orderDict, matrix, binList, bestCost, scanScaffolds=5) :495-549
+    def scanOrdering(self, orderedScaffolds, scaffoldDict, orderDict, matrix, binList, bestCost, scanScaffolds=5):
+        M = np.asarray(matrix)
+        key = (M.__array_interface__["data"][0], M.shape)
+        if key != self._genome_key:
+            self.h.p2_upload(np.ascontiguousarray(M, dtype=np.float64))
+            self._genome_key = key
+        index_of = {b.ID: i for i, b in enumerate(binList)}
+        scafs = [Scaf(s.name, self._plus_bins(s), s.orientation) for s in orderedScaffolds]
+        chrom = DeviceChromosome(self.h, index_of, scafs)
+        ordered, best, rounds = chrom.scan(scafs, float(bestCost), int(scanScaffolds))
+        out = []
+        for s in ordered:
+            ref = scaffoldDict[s.name]
+            self._set_orientation(ref, s.orientation)
+            out.append(ref)
+        print("Sliding window conversion after " + str(rounds) + " rounds")
+        print("Best cost at the end of the final step = " + str(best))
+        return out, best

@@ -101,6 +101,9 @@ int hica_p1_get_reordered(hica_handle h, int what, double *out_host);
 /* numpy.argsort(S, axis=1)[:, ::-1] :1132 on the device; ties resolve as a
  * stable ascending sort reversed (descending column index). */
 int hica_p1_rank(hica_handle h);
+/* Seam input for :1132 when the similarity matrix S was computed elsewhere: upload it as is (identity
+ * order); hica_p1_rank then sorts its rows directly. */
+int hica_p1_upload_similarity(hica_handle h, const double *S_host, int64_t n);
 int hica_p1_get_rank(hica_handle h, int64_t *R_host);
 /* Seam input: an argsorted matrix computed elsewhere (n x n int64). */
 int hica_p1_set_rank(hica_handle h, const int64_t *R_host, int64_t n);

@@ -509,6 +509,29 @@ def ordering_cost(M: np.ndarray, total: float) -> float:
     return cost
 
 
+_numba_cost = None
+
+
+def ordering_cost_numba(M: np.ndarray, total: float) -> float:
+    """The same loop compiled with numba's nopython JIT, exactly as the reference runs it
+    (orderGenome.py:183-191); used for CPU-baseline timing and as a cross-check of ``ordering_cost``."""
+    global _numba_cost
+    if _numba_cost is None:
+        from numba import jit
+        from numpy import trace as np_trace
+
+        @jit(nopython=True)
+        def _cost(matrix, total):
+            cum, cost = 0., 0.
+            for i in range(1, len(matrix)):
+                cum += np_trace(matrix, offset=i)
+                cost += (cum / total / float(i))
+            return cost
+
+        _numba_cost = _cost
+    return float(_numba_cost(np.ascontiguousarray(M, dtype=np.float64), float(total)))
+
+
 def ordering_cost_of(M: np.ndarray, order: Sequence[int], total: float) -> float:
     """cost of M[ix_(order, order)] (orderGenome.py:348, 463, 534)."""
     o = np.asarray(order, dtype=np.int64)
