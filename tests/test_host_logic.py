@@ -1,0 +1,57 @@
+"""CPU: host-side logic of the product package (no GPU needed)."""
+import os
+
+import numpy as np
+
+import hica_oracle as O
+from hic_genome_assembler_b200 import part1, part2
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_enumeration_tables_match_reference_order():
+    # orders documented in SURVEY.md 3.2 (measured by calling the reference)
+    t3 = ["".join("ABC"[i] for i in r) for r in part2.order_table(3)]
+    assert t3 == ["ABC", "ACB", "BAC"]
+    t4 = ["".join("ABCD"[i] for i in r) for r in part2.order_table(4)]
+    assert t4 == "ABCD ABDC ACBD ACDB ADCB ADBC BACD BADC BCAD BDAC CBAD CABD".split()
+    o3 = ["".join("-" if v else "+" for v in r) for r in part2.orient_table(3)]
+    assert o3 == "+++ --- +-- -+- --+ ++- +-+ -++".split()
+    o4 = ["".join("-" if v else "+" for v in r) for r in part2.orient_table(4)]
+    assert o4 == "++++ ---- +--- -+-- --+- ---+ ++-- +-+- +--+ -++- -+-+ --++ +++- ++-+ +-++ -+++".split()
+    for n, cnt in [(5, 1920), (6, 23040), (7, 322560)]:
+        assert part2.order_table(n).shape[0] * part2.orient_table(n).shape[0] == cnt == part2.calc_possible_perms(n)
+    for n in range(1, 7):
+        assert [tuple(int(v) for v in r) for r in part2.order_table(n)] == O.order_candidates(n)
+        assert [tuple("-" if v else "+" for v in r) for r in part2.orient_table(n)] == O.orient_candidates(n)
+
+
+def _read_groups(path):
+    groups, cur = [], None
+    for line in open(path):
+        line = line.rstrip("\n")
+        if line.startswith("#"):
+            cur = []
+            groups.append(cur)
+        else:
+            cur.append(line.split("\t"))
+    return groups
+
+
+def test_chromosome_groups_match_reference_files():
+    """binGroups.txt (cuts applied to the dendrogram order) -> chromosomeGroups.txt, both written by the reference."""
+    d = os.path.join(G, "pipeline_320")
+    bin_groups = _read_groups(os.path.join(d, "out", "binGroups.txt"))
+    want = _read_groups(os.path.join(d, "out", "chromosomeGroups.txt"))
+    bed = [l.rstrip("\n").split("\t") for l in open(os.path.join(d, "in", "synth_abs.bed"))]
+    bin_ids = [int(c[3]) for c in bed]
+    scaf = [c[0] for c in bed]
+    sizes = {l.split("\t")[0]: int(l.split("\t")[1]) for l in open(os.path.join(d, "in", "synth.sizes"))}
+    row_of = {b: i for i, b in enumerate(bin_ids)}
+    leaves, cuts = [], []
+    for g in bin_groups:
+        leaves += [row_of[int(c[0])] for c in g]
+        cuts.append(len(leaves))
+    cuts = cuts[:-1]
+    got = part1.chromosome_groups(cuts, leaves, bin_ids, scaf, sizes)
+    assert [[[str(b), s] for b, s in g] for g in got] == want
