@@ -43,6 +43,7 @@ def parse_args():
     ap.add_argument("--impl", default="hica", choices=["hica", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--part1-only", action="store_true")
+    ap.add_argument("--p2-host-loop", action="store_true", help="Part2 through per-call host loops (exact scoring of every candidate)")
     return ap.parse_args()
 
 
@@ -124,17 +125,23 @@ def gpu_step(h, wl, args, source, rank, world, dist):
     t1 = time.perf_counter()
     tm1 = h.timers()
     out = {"leaves": res["leaves"], "cuts": res["cuts"], "initial_cuts": res["initial_cuts"],
-           "ambiguous": res["ambiguous"], "t_part1": t1 - t0, "timers_p1": tm1}
+           "ambiguous": res["ambiguous"], "t_part1": t1 - t0, "timers_p1": tm1, "linkage_stats": h.linkage_stats()}
     p2_pairs, p2_cands, p2_calls, kernel_ms_p2 = 0, 0, 0, 0.0
     orderings = {}
     if not args.part1_only:
         groups = part1.chromosome_groups(res["cuts"], res["leaves"], wl["bin_ids"], wl["scaffold_of_bin"], wl["sizes"])
         h.p2_use_p1_matrix()
         index_of = {int(b): i for i, b in enumerate(wl["bin_ids"])}
-        part2.STATS.update(candidates=0, bin_pairs=0, calls=0)
+        part2.STATS.update(candidates=0, bin_pairs=0, calls=0, exact=0)
         mine = [ci for ci in range(len(groups)) if ci % world == rank]
-        for ci in mine:
-            orderings[ci] = part2.order_chromosome(h, index_of, groups[ci], 6, 5)
+        if args.p2_host_loop:
+            for ci in mine:
+                orderings[ci] = part2.order_chromosome(h, index_of, groups[ci], 6, 5)
+        elif mine:
+            got, cost, rounds, stats = part2.order_groups_device(h, index_of, [groups[ci] for ci in mine], 6, 5)
+            for k, ci in enumerate(mine):
+                orderings[ci] = (got[k], float(cost[k]), int(rounds[k]))
+            out["p2_exact"] = part2.STATS.get("exact", 0)
         p2_pairs, p2_cands, p2_calls = part2.STATS["bin_pairs"], part2.STATS["candidates"], part2.STATS["calls"]
         out["n_groups"] = len(groups)
     t2 = time.perf_counter()
@@ -318,9 +325,9 @@ def main():
                    "sharding": "Part1 replicated per rank, Part2 chromosomes round-robin over ranks" if world > 1 else "1 GPU"},
         "seconds": {"part1": last["t_part1"], "part2": last["t_part2"], "total": last["t_total"],
                     "e2e_total": secs_e2e / args.steps},
-        "stage_ms_part1": tm,
+        "stage_ms_part1": tm, "linkage_stats": last["linkage_stats"],
         "work": {"part1_bin_pairs": p1_pairs, "part2_bin_pairs": p2_pairs, "part2_candidates": p2_cands,
-                 "part2_device_calls": p2_calls, "cuts": len(last["cuts"]), "groups": last.get("n_groups"),
+                 "part2_device_calls": p2_calls, "part2_exact_rescored": last.get("p2_exact"), "cuts": len(last["cuts"]), "groups": last.get("n_groups"),
                  "ambiguous_decisions": last["ambiguous"]},
         "e2e": {"value": e2e_value, "unit": "bin-pairs/s", "h2d_bytes_per_step": int(8 * n * n),
                 "d2h_bytes_per_step": int(32 * (n - 1) + 4 * n + 8 * len(last["cuts"]) + 24 * max(1, p2_calls))},

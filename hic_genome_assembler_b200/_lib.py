@@ -19,12 +19,13 @@ T_NAMES = ("upload", "distance", "linkage", "leaforder", "rank", "breakpoints", 
 # every symbol include/hica.h declares (checked by tests/test_abi.py)
 ABI_SYMBOLS = (
     "hica_version", "hica_create", "hica_destroy", "hica_last_error", "hica_launch_count", "hica_get_timers",
+    "hica_linkage_stats",
     "hica_p1_upload", "hica_p1_upload_device", "hica_p1_set_row_sums", "hica_p1_distance", "hica_p1_get_distance",
     "hica_p1_get_pairwise_row_sums", "hica_p1_get_row_sums", "hica_p1_upload_distance", "hica_p1_linkage",
     "hica_p1_set_order", "hica_p1_get_reordered", "hica_p1_rank", "hica_p1_upload_similarity", "hica_p1_get_rank", "hica_p1_set_rank",
     "hica_p1_window_sig", "hica_p1_breakpoints", "hica_p1_filter", "hica_hypergeom_less",
     "hica_p2_upload", "hica_p2_use_p1_matrix", "hica_p2_select", "hica_p2_set_segments", "hica_p2_total",
-    "hica_p2_score_candidates", "hica_p2_score_window", "hica_p2_score_orders",
+    "hica_p2_score_candidates", "hica_p2_score_window", "hica_p2_score_orders", "hica_p2_order_groups",
 )
 
 _lib = None
@@ -80,6 +81,7 @@ def load_library():
     L.hica_p2_score_candidates.argtypes = [vp, vp, i64, i32, dbl, dbl, vp, vp, vp]
     L.hica_p2_score_window.argtypes = [vp, vp, i32, i32, i32, vp, i32, vp, i32, i64, i64, dbl, dbl, vp, vp, vp]
     L.hica_p2_score_orders.argtypes = [vp, vp, i64, i32, dbl, dbl, vp, vp, vp]
+    L.hica_p2_order_groups.argtypes = [vp, i32, vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, i32, vp, i32, vp, vp, vp, vp]
     _lib = L
     return L
 
@@ -135,6 +137,12 @@ class Handle:
         ms = np.zeros(len(T_NAMES))
         self._check(self._L.hica_get_timers(self._h, _ptr(ms)))
         return dict(zip(T_NAMES, ms.tolist()))
+
+    def linkage_stats(self) -> dict:
+        out = np.zeros(3, dtype=np.int64)
+        self._L.hica_linkage_stats.argtypes = [C.c_void_p, C.c_void_p]
+        self._check(self._L.hica_linkage_stats(self._h, _ptr(out)))
+        return {"searches": int(out[0]), "search_cycles": int(out[1]), "merge_cycles": int(out[2])}
 
     # -- Part 1 -----------------------------------------------------------
     def p1_upload(self, A: np.ndarray):
@@ -289,6 +297,34 @@ class Handle:
                                                  _ptr(rt), rt.shape[0], cand_lo, cand_hi, total, carried,
                                                  C.byref(best), C.byref(bi), _ptr(sc)))
         return best.value, bi.value, sc
+
+    def p2_order_groups(self, grp_ptr, seg_ptr, bin_rows, n_scaffolds: int, scan: int, brute_tables: dict,
+                        scan_tables: tuple):
+        """brute_tables: {k: (order_table(k), orient_table(k))} for every k in use; scan_tables: (orders, orients)."""
+        grp_ptr, seg_ptr, bin_rows = _c(grp_ptr, np.int32), _c(seg_ptr, np.int32), _c(bin_rows, np.int32)
+        ngroups = grp_ptr.size - 1
+        ob, rb, oo, ro = [], [], [0, 0], [0, 0]
+        for k in range(1, 9):
+            if k in brute_tables:
+                ob.append(_c(brute_tables[k][0], np.uint8).ravel())
+                rb.append(_c(brute_tables[k][1], np.uint8).ravel())
+            else:
+                ob.append(np.zeros(0, np.uint8))
+                rb.append(np.zeros(0, np.uint8))
+            oo.append(oo[-1] + ob[-1].size)
+            ro.append(ro[-1] + rb[-1].size)
+        ob, rb = np.concatenate(ob + [np.zeros(1, np.uint8)]), np.concatenate(rb + [np.zeros(1, np.uint8)])
+        oo, ro = _c(oo, np.int32), _c(ro, np.int32)
+        so, sr = _c(scan_tables[0], np.uint8), _c(scan_tables[1], np.uint8)
+        layout = np.empty(seg_ptr.size - 1, dtype=np.int32)
+        cost = np.empty(ngroups)
+        rounds = np.empty(ngroups, dtype=np.int32)
+        stats = np.zeros((ngroups, 4), dtype=np.int64)
+        self._check(self._L.hica_p2_order_groups(self._h, ngroups, _ptr(grp_ptr), _ptr(seg_ptr), _ptr(bin_rows),
+                                                 int(n_scaffolds), int(scan), _ptr(ob), _ptr(oo), _ptr(rb), _ptr(ro),
+                                                 _ptr(so), so.shape[0], _ptr(sr), sr.shape[0], _ptr(layout),
+                                                 _ptr(cost), _ptr(rounds), _ptr(stats)))
+        return layout, cost, rounds, stats
 
     def p2_score_orders(self, orders: np.ndarray, total: float, carried: float = 0.0, want_scores: bool = False):
         orders = _c(orders, np.int32)

@@ -24,6 +24,13 @@ extern "C" const char *hica_last_error(hica_handle h) { return h ? h->err.c_str(
 
 extern "C" int64_t hica_launch_count(hica_handle h) { return h ? h->launches : -1; }
 
+extern "C" int hica_linkage_stats(hica_handle h, int64_t *out3)
+{
+    if (!h || !out3) return HICA_ERR_ARG;
+    for (int i = 0; i < 3; i++) out3[i] = h->nn_stats[i];
+    return HICA_OK;
+}
+
 extern "C" int hica_get_timers(hica_handle h, double *ms)
 {
     if (!h || !ms) return HICA_ERR_ARG;

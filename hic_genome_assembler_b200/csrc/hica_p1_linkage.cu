@@ -60,7 +60,7 @@ __device__ __forceinline__ void cand_min_shfl(double &v, int &i, int delta)
 template <bool CHAIN_SMEM>
 __global__ void __launch_bounds__(NN_THREADS, 1)
 k_nn_chain(double *__restrict__ W, const int n, const int64_t ld, int32_t *__restrict__ size_g,
-           int32_t *__restrict__ chain_g, double *__restrict__ Zraw)
+           int32_t *__restrict__ chain_g, double *__restrict__ Zraw, long long *__restrict__ stats)
 {
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank();
@@ -95,7 +95,9 @@ k_nn_chain(double *__restrict__ W, const int n, const int64_t ld, int32_t *__res
     int parity = 0;
     int pend_x = -1, pend_y = -1, pend_sz = 0;  // deferred size update (rank 0, thread 0)
 
+    long long n_scans = 0, cyc_scan = 0, cyc_merge = 0;
     for (int k = 0; k < n - 1; k++) {
+        long long t_begin = clock64();
         if (len == 0) {
             while (!((alive[first_alive >> 5] >> (first_alive & 31)) & 1u)) first_alive++;
             top = first_alive;
@@ -153,6 +155,7 @@ k_nn_chain(double *__restrict__ W, const int n, const int64_t ld, int32_t *__res
                 if (cand_less(cnd.v, cnd.i, gv, gi)) { gv = cnd.v; gi = cnd.i; }
             }
             parity ^= 1;
+            n_scans++;
             y = (gi == -1) ? yprev : gi;
             if (len > 1 && y == yprev) break;
             // push y
@@ -162,6 +165,8 @@ k_nn_chain(double *__restrict__ W, const int n, const int64_t ld, int32_t *__res
             len++;
         }
         // ---- merge top (x) and second (y) -------------------------------
+        long long t_mid = clock64();
+        cyc_scan += t_mid - t_begin;
         int x = top;
         len -= 2;
         if (x > y) { int t = x; x = y; y = t; }
@@ -204,9 +209,15 @@ k_nn_chain(double *__restrict__ W, const int n, const int64_t ld, int32_t *__res
         if (len >= 1) {
             top = chain[len - 1];
             second = (len >= 2) ? chain[len - 2] : -1;
+            // the next search scans row `top`: pull this CTA's slice towards L2 while the barrier drains
+            const double *nrow = W + (int64_t)top * ld;
+            for (int c = lo + 16 * tid; c < hi; c += 16 * NN_THREADS)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(nrow + c));
         }
         cluster.sync();  // W updates (incl. scattered column y) visible cluster-wide
+        cyc_merge += clock64() - t_mid;
     }
+    if (rank == 0 && tid == 0 && stats) { stats[0] = n_scans; stats[1] = cyc_scan; stats[2] = cyc_merge; }
     // flush the last pending size update for completeness
     if (rank == 0 && tid == 0 && pend_x >= 0) {
         size_g[pend_x] = 0;
@@ -303,7 +314,8 @@ int launch_nn_chain(hica_ctx *h, int cluster_size, size_t smem_bytes)
         return -1;  // caller retries with a smaller cluster
     }
     int n32 = (int)h->n;
-    HICA_CUDA(cudaLaunchKernelEx(&cfg, kern, h->W, n32, h->ld, h->size_d, h->chain_d, h->Zraw));
+    HICA_CUDA(cudaLaunchKernelEx(&cfg, kern, h->W, n32, h->ld, h->size_d, h->chain_d, h->Zraw,
+                                 reinterpret_cast<long long *>(h->misc_d + 64)));
     HICA_LAUNCHED(h);
     return HICA_OK;
 }
@@ -370,6 +382,11 @@ extern "C" int hica_p1_linkage(hica_handle h, double *Z_host, int32_t *leaves_ho
     std::vector<double> raw(4 * (n - 1));
     HICA_CUDA(cudaMemcpyAsync(raw.data(), h->Zraw, sizeof(double) * raw.size(), cudaMemcpyDeviceToHost, h->stream));
     HICA_CUDA(cudaStreamSynchronize(h->stream));
+    {
+        long long st[3] = {0, 0, 0};
+        cudaMemcpy(st, h->misc_d + 64, sizeof(st), cudaMemcpyDeviceToHost);
+        h->nn_stats[0] = st[0]; h->nn_stats[1] = st[1]; h->nn_stats[2] = st[2];
+    }
     hica_timer t2(h, HICA_T_LEAFORDER);
     std::vector<double> Z;
     std::vector<int32_t> leaves;

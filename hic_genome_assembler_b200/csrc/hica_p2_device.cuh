@@ -1,0 +1,128 @@
+// hica_p2_device.cuh - device routines shared by the Part2 translation units:
+// building a candidate's bin order from scaffold segments and the bit-exact
+// ordering score of costFunction_numba (orderGenome.py:184-191).
+#pragma once
+
+#include "hica_common.cuh"
+
+#ifdef __CUDACC__
+
+// Build o[0..n) in shared memory from `nslots` slot entries ((segment << 1) | flip).
+//   entry(s)     -> slot entry of slot s (any callable)
+//   spos / sent  -> shared scratch of nslots+1 / nslots ints
+// All threads of the CTA must call; ends with __syncthreads().
+template <class EntryF>
+__device__ __forceinline__ void build_order_cta(const EntryF &entry, int nslots, const int32_t *__restrict__ seg_ptr,
+                                                const int32_t *__restrict__ seg_bins, int32_t *o, int32_t *spos,
+                                                int32_t *sent, int n)
+{
+    const int tid = threadIdx.x, T = blockDim.x;
+    for (int s = tid; s < nslots; s += T) sent[s] = entry(s);
+    __syncthreads();
+    if (tid == 0) {
+        int acc = 0;
+        for (int s = 0; s < nslots; s++) {
+            spos[s] = acc;
+            int seg = sent[s] >> 1;
+            acc += seg_ptr[seg + 1] - seg_ptr[seg];
+        }
+        spos[nslots] = acc;
+    }
+    __syncthreads();
+    for (int t = tid; t < n; t += T) {
+        int lo = 0, hi = nslots;  // last slot with spos <= t
+        while (hi - lo > 1) {
+            int mid = (lo + hi) >> 1;
+            if (spos[mid] <= t) lo = mid; else hi = mid;
+        }
+        int e = sent[lo], seg = e >> 1, off = t - spos[lo];
+        int b0 = seg_ptr[seg], len = seg_ptr[seg + 1] - b0;
+        o[t] = seg_bins[b0 + ((e & 1) ? (len - 1 - off) : off)];
+    }
+    __syncthreads();
+}
+
+// Bit-exact costFunction_numba of M = S[ix_(o, o)]:
+//   trace_k = ((M[0,k] + M[1,k+1]) + ...)            strictly top to bottom
+//   cum_k   = cum_{k-1} + trace_k ; cost += cum_k / total / k   strictly in k
+// Thread p owns diagonals p+1 and n-1-p (n terms in all).  The short diagonal
+// is read through the transpose St so that neighbouring threads touch
+// neighbouring addresses.  tr = shared scratch of n doubles.  Returns the cost
+// in thread 0 (other threads: undefined).  All threads of the CTA must call.
+__device__ __forceinline__ double exact_cost_cta(const double *__restrict__ S, const double *__restrict__ St, int L,
+                                                 const int32_t *o, int n, double total, double *tr)
+{
+    const int tid = threadIdx.x, T = blockDim.x;
+    const int npairs = n / 2;
+    for (int p = tid; p < npairs; p += T) {
+        const int k1 = p + 1, k2 = n - 1 - p;
+        const int len1 = n - k1;
+        double acc1 = 0.;
+#pragma unroll 4
+        for (int r = 0; r < len1; r++) acc1 = __dadd_rn(acc1, S[(int64_t)o[r] * L + o[r + k1]]);
+        tr[k1] = acc1;
+        if (k2 != k1) {
+            const int len2 = n - k2;
+            double acc2 = 0.;
+#pragma unroll 4
+            for (int t = 0; t < len2; t++) acc2 = __dadd_rn(acc2, St[(int64_t)o[t + k2] * L + o[t]]);
+            tr[k2] = acc2;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double cum = 0.;
+        for (int k = 1; k < n; k++) { cum = __dadd_rn(cum, tr[k]); tr[k] = cum; }
+    }
+    __syncthreads();
+    for (int k = 1 + tid; k < n; k += T) tr[k] = __ddiv_rn(__ddiv_rn(tr[k], total), (double)k);
+    __syncthreads();
+    double cost = 0.;
+    if (tid == 0)
+        for (int k = 1; k < n; k++) cost = __dadd_rn(cost, tr[k]);
+    __syncthreads();
+    return cost;
+}
+
+// numpy.trace over a gathered diagonal = numpy pairwise summation of f(0..n)
+template <class F>
+__device__ double pairwise_f(const F &f, int off, int n)
+{
+    if (n < 8) {
+        double res = 0.;
+        for (int i = 0; i < n; i++) res = __dadd_rn(res, f(off + i));
+        return res;
+    }
+    if (n <= 128) {
+        double r[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) r[j] = f(off + j);
+        int i;
+        for (i = 8; i < n - (n % 8); i += 8) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) r[j] = __dadd_rn(r[j], f(off + i + j));
+        }
+        double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                               __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+        for (; i < n; i++) res = __dadd_rn(res, f(off + i));
+        return res;
+    }
+    int n2 = n / 2;
+    n2 -= n2 % 8;
+    return __dadd_rn(pairwise_f(f, off, n2), pairwise_f(f, off + n2, n - n2));
+}
+
+// order-preserving map double -> uint64 (for atomicMax on scores)
+__device__ __forceinline__ unsigned long long f64_order_key(double v)
+{
+    long long b = __double_as_longlong(v);
+    unsigned long long u = (unsigned long long)b;
+    return (b < 0) ? ~u : (u | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double f64_from_order_key(unsigned long long k)
+{
+    unsigned long long u = (k & 0x8000000000000000ull) ? (k & 0x7fffffffffffffffull) : ~k;
+    return __longlong_as_double((long long)u);
+}
+
+#endif  // __CUDACC__

@@ -18,7 +18,7 @@
 
 #include <algorithm>
 
-#include "hica_common.cuh"
+#include "hica_p2_device.cuh"
 
 namespace {
 
@@ -59,6 +59,12 @@ __device__ __forceinline__ int slot_entry(const ScoreArgs &a, long long cand, in
     return (seg << 1) | (int)a.orient_table[ri * a.win_n + j];
 }
 
+struct SlotSrc {
+    const ScoreArgs *a;
+    long long cand;
+    __device__ int operator()(int s) const { return slot_entry(*a, cand, s); }
+};
+
 __global__ void __launch_bounds__(SC_THREADS) k_score(ScoreArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -66,72 +72,17 @@ __global__ void __launch_bounds__(SC_THREADS) k_score(ScoreArgs a)
     int32_t *o = reinterpret_cast<int32_t *>(tr + a.n);            // n
     int32_t *spos = o + a.n;                                       // nslots + 1
     int32_t *sent = spos + a.nslots + 1;                           // nslots
-    const int tid = threadIdx.x;
     const long long cand = blockIdx.x;
     const int n = a.n;
-
     if (a.src == SRC_ORDERS) {
         const int32_t *src = a.orders + cand * n;
-        for (int t = tid; t < n; t += SC_THREADS) o[t] = src[t];
+        for (int t = threadIdx.x; t < n; t += SC_THREADS) o[t] = src[t];
+        __syncthreads();
     } else {
-        for (int s = tid; s < a.nslots; s += SC_THREADS) sent[s] = slot_entry(a, cand, s);
-        __syncthreads();
-        if (tid == 0) {
-            int acc = 0;
-            for (int s = 0; s < a.nslots; s++) {
-                spos[s] = acc;
-                int seg = sent[s] >> 1;
-                acc += a.seg_ptr[seg + 1] - a.seg_ptr[seg];
-            }
-            spos[a.nslots] = acc;
-        }
-        __syncthreads();
-        for (int t = tid; t < n; t += SC_THREADS) {
-            int lo = 0, hi = a.nslots;  // last slot with spos <= t
-            while (hi - lo > 1) {
-                int mid = (lo + hi) >> 1;
-                if (spos[mid] <= t) lo = mid; else hi = mid;
-            }
-            int e = sent[lo], seg = e >> 1, off = t - spos[lo];
-            int b0 = a.seg_ptr[seg], len = a.seg_ptr[seg + 1] - b0;
-            o[t] = a.seg_bins[b0 + ((e & 1) ? (len - 1 - off) : off)];
-        }
+        build_order_cta(SlotSrc{&a, cand}, a.nslots, a.seg_ptr, a.seg_bins, o, spos, sent, n);
     }
-    __syncthreads();
-
-    // ---- traces: thread p owns diagonal k1 = p+1 (rows 0..n-k1-1) then k2 = n-1-p ----
-    const int npairs = n / 2;  // diagonals 1..n-1 -> ceil((n-1)/2) pairs
-    const int L = a.L;
-    for (int p = tid; p < npairs; p += SC_THREADS) {
-        const int k1 = p + 1, k2 = n - 1 - p;
-        const int len1 = n - k1;
-        double acc1 = 0., acc2 = 0.;
-        int r = 0;
-#pragma unroll 4
-        for (; r < len1; r++) acc1 = __dadd_rn(acc1, a.S[(int64_t)o[r] * L + o[r + k1]]);
-        tr[k1] = acc1;
-        if (k2 != k1) {
-            // diagonal k2 element t: S[o[t]][o[t+k2]] = St[o[t+k2]][o[t]]; adjacent threads -> adjacent t offsets
-            const int len2 = n - k2;
-#pragma unroll 4
-            for (int t = 0; t < len2; t++) acc2 = __dadd_rn(acc2, a.St[(int64_t)o[t + k2] * L + o[t]]);
-            tr[k2] = acc2;
-        }
-    }
-    __syncthreads();
-    // ---- cumulative sum over diagonals (sequential), divisions (parallel), final sum (sequential)
-    if (tid == 0) {
-        double cum = 0.;
-        for (int k = 1; k < n; k++) { cum = __dadd_rn(cum, tr[k]); tr[k] = cum; }
-    }
-    __syncthreads();
-    for (int k = 1 + tid; k < n; k += SC_THREADS) tr[k] = __ddiv_rn(__ddiv_rn(tr[k], a.total), (double)k);
-    __syncthreads();
-    if (tid == 0) {
-        double cost = 0.;
-        for (int k = 1; k < n; k++) cost = __dadd_rn(cost, tr[k]);
-        a.scores[cand] = cost;
-    }
+    double cost = exact_cost_cta(a.S, a.St, a.L, o, n, a.total, tr);
+    if (threadIdx.x == 0) a.scores[cand] = cost;
 }
 
 // first strict maximum above `carried` (sequential accept rule of :349/:464/:535)
@@ -179,34 +130,6 @@ __global__ void k_gather_sub(const double *__restrict__ G, int64_t gn, const int
         S[(int64_t)i * L + j] = v;
         St[(int64_t)j * L + i] = v;
     }
-}
-
-// numpy.trace(M, offset=k) for k = 1..n-1 on M = S[ix_(o, o)]: numpy pairwise over the diagonal
-template <class F>
-__device__ double pairwise_f(const F &f, int off, int n)
-{
-    if (n < 8) {
-        double res = 0.;
-        for (int i = 0; i < n; i++) res = __dadd_rn(res, f(off + i));
-        return res;
-    }
-    if (n <= 128) {
-        double r[8];
-#pragma unroll
-        for (int j = 0; j < 8; j++) r[j] = f(off + j);
-        int i;
-        for (i = 8; i < n - (n % 8); i += 8) {
-#pragma unroll
-            for (int j = 0; j < 8; j++) r[j] = __dadd_rn(r[j], f(off + i + j));
-        }
-        double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
-                               __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
-        for (; i < n; i++) res = __dadd_rn(res, f(off + i));
-        return res;
-    }
-    int n2 = n / 2;
-    n2 -= n2 % 8;
-    return __dadd_rn(pairwise_f(f, off, n2), pairwise_f(f, off + n2, n - n2));
 }
 
 __global__ void k_traces_pairwise(const double *__restrict__ S, int L, const int32_t *__restrict__ o, int n,

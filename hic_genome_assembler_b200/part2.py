@@ -249,6 +249,71 @@ def order_chromosome(h: Handle, genome_index_of_bin: Dict[int, int], nodes: Sequ
     return [(s.name, s.orientation) for s in ordered], best_cost, rounds
 
 
+def _pool(nodes: Sequence[Tuple[int, str]]) -> List[Scaf]:
+    """initiateBinsAndScaffolds (:256-281): bins ascending inside a scaffold, scaffolds by bin count
+    descending (stable: ties keep first-appearance order)."""
+    by_name: Dict[str, Scaf] = {}
+    for b, nm in nodes:
+        if nm not in by_name:
+            by_name[nm] = Scaf(nm, [])
+    for b, nm in nodes:
+        by_name[nm].bins.append(b)
+    for s in by_name.values():
+        s.bins.sort()
+    return sorted(by_name.values(), key=lambda s: len(s.bins), reverse=True)
+
+
+def order_groups_device(h: Handle, genome_index_of_bin: Dict[int, int],
+                        chrom_groups: Sequence[Sequence[Tuple[int, str]]], n_scaffolds: int = 6, scan: int = 5):
+    """orderGenome (:591-628) for all groups in ONE device call (hica_p2_order_groups): every chromosome runs its
+    brute force / insertion / scan on its own CUDA stream with device-side decisions.
+    Returns ([[(name, orientation), ...] per group], costs, rounds, stats)."""
+    if n_scaffolds >= 9:
+        n_scaffolds = 8
+    if scan > n_scaffolds:
+        scan = n_scaffolds
+    pools = [_pool(g) for g in chrom_groups]
+    grp_ptr, seg_ptr, rows = [0], [0], []
+    for pool in pools:
+        for s in pool:
+            rows.extend(genome_index_of_bin[b] for b in s.bins)
+            seg_ptr.append(len(rows))
+        grp_ptr.append(len(seg_ptr) - 1)
+    ks = sorted({min(n_scaffolds, len(p)) for p in pools})
+    brute = {k: (order_table(k), orient_table(k)) for k in ks}
+    layout, cost, rounds, stats = h.p2_order_groups(grp_ptr, seg_ptr, rows, n_scaffolds, scan, brute,
+                                                    (order_table(scan), orient_table(scan)))
+    out = []
+    for gi, pool in enumerate(pools):
+        ent = layout[grp_ptr[gi]:grp_ptr[gi + 1]]
+        out.append([(pool[e >> 1].name, "-" if (e & 1) else "+") for e in ent])
+        # algorithmic work = what the reference evaluates: candidates x L(L-1)/2 bin pairs each
+        lens = [len(s.bins) for s in pool]
+        k = min(n_scaffolds, len(pool))
+        pairs = lambda n: n * (n - 1) // 2  # noqa: E731
+        nb = sum(lens[:k])
+        cand = order_table(k).shape[0] * orient_table(k).shape[0] if nb >= 2 else 0
+        work = cand * pairs(nb)
+        placed, bins, first = k, nb, True
+        while first or placed < len(pool):
+            first = False
+            if placed < len(pool):
+                m, bins, placed = placed, bins + lens[placed], placed + 1
+            else:
+                m = placed - 1
+            cand += 2 * (m + 1)
+            work += 2 * (m + 1) * pairs(bins)
+        if len(pool) > n_scaffolds:
+            c = int(rounds[gi]) * (len(pool) - scan + 1) * order_table(scan).shape[0] * orient_table(scan).shape[0]
+            cand += c
+            work += c * pairs(sum(lens))
+        STATS["candidates"] += cand
+        STATS["bin_pairs"] += work
+        STATS["exact"] = STATS.get("exact", 0) + int(stats[gi, 1])
+    STATS["calls"] += 1
+    return out, cost, rounds, stats
+
+
 def order_genome(h: Handle, G: Optional[np.ndarray], bin_ids: Sequence[int],
                  chrom_groups: Sequence[Sequence[Tuple[int, str]]], n_scaffolds: int = 6, scan: int = 5,
                  chrom_subset: Optional[Sequence[int]] = None):

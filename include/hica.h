@@ -51,6 +51,8 @@ enum {
     HICA_T_BREAKPOINTS, HICA_T_FILTER, HICA_T_P2_SCORE, HICA_T_COUNT
 };
 int hica_get_timers(hica_handle h, double *ms /* HICA_T_COUNT */);
+/* counters of the last hica_p1_linkage: nearest-neighbour searches, SM cycles spent in searches, in merges */
+int hica_linkage_stats(hica_handle h, int64_t *out3);
 
 /* ---- Part 1: ICE matrix -> leaf order -> cut indices ---------------------- */
 
@@ -174,6 +176,27 @@ int hica_p2_score_window(hica_handle h, const int32_t *base, int32_t nslots, int
                          const uint8_t *order_table, int32_t n_orders, const uint8_t *orient_table,
                          int32_t n_orients, int64_t cand_lo, int64_t cand_hi, double total, double carried,
                          double *best, int64_t *best_idx, double *scores_or_null);
+
+/* orderGenome :591-628 / orderChromosome :551-586 for a batch of independent chromosome groups, entirely
+ * on the device (one CUDA stream per group; brute force, greedy insertion and the sliding-window scan are
+ * stream-ordered kernels whose accept/apply decisions are taken on the device).
+ *   grp_ptr   ngroups+1 offsets into the scaffold arrays; the scaffolds of a group are listed in the
+ *             reference's pool order (bin count descending, stable - initiateBinsAndScaffolds :279)
+ *   seg_ptr   total_scaffolds+1 offsets into bin_rows
+ *   bin_rows  genome-matrix row of every bin, each scaffold in '+' (ascending bin id) reading order
+ *   ord_*_tabs / ori_*_tabs: the reference's enumeration tables (orders after removeReverseDuplicates
+ *             :396-411, orientations of plusMinusPerms :413-430, 0 = '+', 1 = '-'); the brute-force tables
+ *             for k = 1..8 scaffolds are concatenated, table k occupying [off[k], off[k+1]) bytes
+ *             (rows of k entries; empty when unused), the scan tables have `scan` entries per row.
+ *   out_layout  total_scaffolds entries: per group the final order as (local scaffold index << 1) | flip
+ *   out_stats   ngroups x 4: closed-form candidate evaluations, exact re-scorings, 1 if the group's matrix
+ *               needed full exact scoring (negative/asymmetric entries), 1 if no ordering scored above 0 */
+int hica_p2_order_groups(hica_handle h, int32_t ngroups, const int32_t *grp_ptr, const int32_t *seg_ptr,
+                         const int32_t *bin_rows, int32_t n_scaffolds, int32_t scan,
+                         const uint8_t *ord_brute_tabs, const int32_t *ord_brute_off,
+                         const uint8_t *ori_brute_tabs, const int32_t *ori_brute_off,
+                         const uint8_t *ord_scan, int32_t n_ord_scan, const uint8_t *ori_scan, int32_t n_ori_scan,
+                         int32_t *out_layout, double *out_cost, int32_t *out_rounds, int64_t *out_stats);
 
 /* Explicit bin orders (B x L int32 into S): the most general form, used by
  * tests and by the costFunction_numba seam. */

@@ -51,3 +51,45 @@ def test_single_bin_scaffolds_orientation_parity(hica):
     got, cost, _ = part2.order_chromosome(hica, index_of, nodes, 6, 5)
     want, wcost = O.order_chromosome(A, index_of, nodes, 6, 5)
     assert got == want and cost == wcost
+
+
+@pytest.mark.parametrize("n,nc,spc,seed,nscaf,scan", [(400, 8, 8, 7, 4, 3), (300, 3, 12, 5, 5, 4), (240, 4, 9, 3, 6, 5),
+                                                     (200, 5, 3, 9, 6, 5), (120, 6, 1, 2, 6, 5)])
+def test_device_engine_matches_oracle(hica, n, nc, spc, seed, nscaf, scan):
+    """hica_p2_order_groups (all groups in one call, device-side decisions, closed-form filter + exact re-score)
+    must give the orderings and costs of the reference's exhaustive loops."""
+    g = make_genome(n, n_chrom=nc, seed=seed, scaffolds_per_chrom=spc)
+    A = g.A.numpy()
+    names = [g.scaffold_names[s] for s in g.scaffold_of_bin]
+    groups = []
+    for ch in range(nc):
+        groups.append([(i + 1, names[i]) for i in range(n) if g.true_chrom_of_bin[i] == ch])
+    index_of = {i + 1: i for i in range(n)}
+    hica.p2_upload(A)
+    got, cost, rounds, stats = part2.order_groups_device(hica, index_of, groups, nscaf, scan)
+    for gi, grp in enumerate(groups):
+        want, wcost = O.order_chromosome(A, index_of, grp, nscaf, scan)
+        assert got[gi] == want, gi
+        assert cost[gi] == wcost, gi
+    assert stats[:, 2].sum() == 0 and stats[:, 3].sum() == 0
+
+
+def test_device_engine_single_bin_scaffolds_and_asymmetric_matrix(hica):
+    rng = np.random.RandomState(4)
+    n = 40
+    pos = np.arange(n)
+    A = 100.0 / (1.0 + np.abs(pos[:, None] - pos[None, :])) * np.exp(0.1 * rng.randn(n, n))
+    Asym = (A + A.T) / 2
+    sizes = [6, 5, 5, 4, 4, 3] + [1] * 13
+    nodes, b = [], 0
+    for si, sz in enumerate(sizes):
+        for _ in range(sz):
+            nodes.append((b + 1, "s%d" % si))
+            b += 1
+    index_of = {i + 1: i for i in range(n)}
+    for M, full in ((Asym, 0), (A, 1)):   # asymmetric input falls back to exact scoring of every candidate
+        hica.p2_upload(M)
+        got, cost, rounds, stats = part2.order_groups_device(hica, index_of, [nodes], 6, 5)
+        want, wcost = O.order_chromosome(M, index_of, nodes, 6, 5)
+        assert got[0] == want and cost[0] == wcost
+        assert stats[0, 2] == full
