@@ -26,6 +26,7 @@
 #include <cooperative_groups.h>
 #include <limits.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <numeric>
@@ -225,6 +226,12 @@ k_nn_chain(double *__restrict__ W, const int n, const int64_t ld, int32_t *__res
     }
 }
 
+}  // namespace
+
+#include "hica_p1_nnchain2.cuh"
+
+namespace {
+
 __global__ void k_fill_i32(int32_t *p, int64_t n, int32_t v)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -289,15 +296,17 @@ void label_and_order(const std::vector<double> &raw, int64_t n, std::vector<doub
     }
 }
 
-template <bool CHAIN_SMEM>
+template <bool CHAIN_SMEM, int VERSION>
 int launch_nn_chain(hica_ctx *h, int cluster_size, size_t smem_bytes)
 {
-    auto kern = k_nn_chain<CHAIN_SMEM>;
+    auto kern = VERSION == 2 ? nn2::k_nn_chain2<CHAIN_SMEM> : k_nn_chain<CHAIN_SMEM>;
     HICA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
     if (cluster_size > 8) HICA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(cluster_size);
-    cfg.blockDim = dim3(NN_THREADS);
+    int nn2_threads = 512;  // measured on B200 at N=16k: 161 ms @128, 127 ms @256, 110 ms @512 threads per CTA
+    if (const char *e = getenv("HICA_NN_THREADS")) nn2_threads = std::max(32, std::min(512, atoi(e) / 32 * 32));
+    cfg.blockDim = dim3(VERSION == 2 ? nn2_threads : NN_THREADS);
     cfg.dynamicSmemBytes = smem_bytes;
     cfg.stream = h->stream;
     cudaLaunchAttribute attr[1];
@@ -357,21 +366,30 @@ extern "C" int hica_p1_linkage(hica_handle h, double *Z_host, int32_t *leaves_ho
     if (n > 0x7fffffff) return hica_set_error(h, HICA_ERR_ARG, "n too large");
     int rc;
     if (!h->Zraw && (rc = hica_realloc(h, &h->Zraw, 4 * (n - 1)))) return rc;
-    if (!h->size_d && (rc = hica_realloc(h, &h->size_d, n))) return rc;
+    if (!h->size_d && (rc = hica_realloc(h, &h->size_d, (int64_t)NN_MAX_CLUSTER * n))) return rc;
+    const char *ver_env = getenv("HICA_NN_KERNEL");
+    const int version = (ver_env && ver_env[0] == '1') ? 1 : 2;
 
     const int nwords = (int)((h->ld + 31) / 32);
-    size_t base_smem = sizeof(Cand) * (2 * NN_MAX_CLUSTER + NN_WARPS) + sizeof(uint32_t) * nwords;
+    size_t base_smem = version == 2 ? nn2::base_smem(nwords)
+                                    : sizeof(Cand) * (2 * NN_MAX_CLUSTER + NN_WARPS) + sizeof(uint32_t) * nwords;
     size_t chain_smem = sizeof(int32_t) * (size_t)n;
     bool chain_in_smem = base_smem + chain_smem <= 200 * 1024;
     if (!chain_in_smem && !h->chain_d && (rc = hica_realloc(h, &h->chain_d, (int64_t)NN_MAX_CLUSTER * n))) return rc;
 
     hica_timer t(h, HICA_T_LINKAGE);
-    k_fill_i32<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->size_d, n, 1);
+    k_fill_i32<<<(unsigned)((NN_MAX_CLUSTER * n + 255) / 256), 256, 0, h->stream>>>(h->size_d, NN_MAX_CLUSTER * n, 1);
     HICA_LAUNCHED(h);
     int launched = -1;
-    for (int cs = NN_MAX_CLUSTER; cs >= 1 && launched != HICA_OK; cs >>= 1) {
-        launched = chain_in_smem ? launch_nn_chain<true>(h, cs, base_smem + chain_smem)
-                                 : launch_nn_chain<false>(h, cs, base_smem);
+    int cs_max = NN_MAX_CLUSTER;
+    if (const char *e = getenv("HICA_NN_CLUSTER")) cs_max = std::max(1, std::min(NN_MAX_CLUSTER, atoi(e)));
+    for (int cs = cs_max; cs >= 1 && launched != HICA_OK; cs >>= 1) {
+        if (version == 2)
+            launched = chain_in_smem ? launch_nn_chain<true, 2>(h, cs, base_smem + chain_smem)
+                                     : launch_nn_chain<false, 2>(h, cs, base_smem);
+        else
+            launched = chain_in_smem ? launch_nn_chain<true, 1>(h, cs, base_smem + chain_smem)
+                                     : launch_nn_chain<false, 1>(h, cs, base_smem);
         if (launched > 0) return launched;  // a real error
     }
     if (launched != HICA_OK) return hica_set_error(h, HICA_ERR_CUDA, "no cluster configuration could be launched");
@@ -383,9 +401,9 @@ extern "C" int hica_p1_linkage(hica_handle h, double *Z_host, int32_t *leaves_ho
     HICA_CUDA(cudaMemcpyAsync(raw.data(), h->Zraw, sizeof(double) * raw.size(), cudaMemcpyDeviceToHost, h->stream));
     HICA_CUDA(cudaStreamSynchronize(h->stream));
     {
-        long long st[3] = {0, 0, 0};
+        long long st[6] = {0, 0, 0, 0, 0, 0};
         cudaMemcpy(st, h->misc_d + 64, sizeof(st), cudaMemcpyDeviceToHost);
-        h->nn_stats[0] = st[0]; h->nn_stats[1] = st[1]; h->nn_stats[2] = st[2];
+        for (int i = 0; i < 6; i++) h->nn_stats[i] = st[i];
     }
     hica_timer t2(h, HICA_T_LEAFORDER);
     std::vector<double> Z;

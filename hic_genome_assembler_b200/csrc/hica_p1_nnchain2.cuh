@@ -1,0 +1,253 @@
+// hica_p1_nnchain2.cuh - second-generation NN-chain kernel (included by hica_p1_linkage.cu).
+//
+// Same algorithm and tie rules as k_nn_chain (see hica_p1_linkage.cu); what changes is the cost of one
+// nearest-neighbour search, which is pure latency:
+//   * 4 warps per CTA, every thread keeps up to four 16-byte loads of the row in flight;
+//   * the (value, index) minimum is taken with redux.sync on an order-preserving 64-bit key
+//     (3 warp reductions instead of 5 shuffle rounds of 3 shuffles each);
+//   * the cross-CTA exchange of a SEARCH no longer uses the hardware cluster barrier: every CTA pushes its
+//     partial result into every peer's shared memory as three 8-byte words that each carry a sequence
+//     number (the LL idiom: an 8-byte store is atomic), and readers spin on their LOCAL shared memory.
+//     Searches only read W, so no memory fence is needed there.  The fenced cluster barrier remains once
+//     per MERGE, where W is written;
+//   * cluster sizes live in per-CTA private copies, which removes the deferred-write hazard.
+#pragma once
+
+namespace nn2 {
+
+constexpr int MAX_THREADS = 512;
+constexpr int MAX_WARPS = MAX_THREADS / 32;
+constexpr int MAX_CLUSTER = 16;
+constexpr unsigned NONE = 0xffffffffu;
+
+struct Best {
+    unsigned hi, lo, ic;  // order key (hi, lo) of the distance; ic = 0 for the previous chain element, else column + 1
+};
+
+__device__ __forceinline__ Best warp_best(Best b)
+{
+    const unsigned mh = __reduce_min_sync(0xffffffffu, b.hi);
+    const unsigned ml = __reduce_min_sync(0xffffffffu, b.hi == mh ? b.lo : NONE);
+    const unsigned mi = __reduce_min_sync(0xffffffffu, (b.hi == mh && b.lo == ml) ? b.ic : NONE);
+    Best r;
+    r.hi = mh; r.lo = ml; r.ic = mi;
+    return r;
+}
+
+__device__ __forceinline__ void consider(Best &b, double v, unsigned ic)
+{
+    long long bits = __double_as_longlong(v);
+    unsigned long long u = (unsigned long long)bits;
+    u = (bits < 0) ? ~u : (u | 0x8000000000000000ull);
+    if (v != v) return;  // NaN never wins ('dist < current_min' is false)
+    const unsigned hi = (unsigned)(u >> 32), lo = (unsigned)u;
+    if (hi < b.hi || (hi == b.hi && (lo < b.lo || (lo == b.lo && ic < b.ic)))) { b.hi = hi; b.lo = lo; b.ic = ic; }
+}
+
+__device__ __forceinline__ double key_to_double(unsigned hi, unsigned lo)
+{
+    unsigned long long k = ((unsigned long long)hi << 32) | lo;
+    unsigned long long u = (k & 0x8000000000000000ull) ? (k & 0x7fffffffffffffffull) : ~k;
+    return __longlong_as_double((long long)u);
+}
+
+struct Slot {
+    unsigned long long w[4];  // {payload | seq << 32} x 3, one pad word
+};
+
+__device__ __forceinline__ unsigned long long ld_volatile_shared_u64(const unsigned long long *p)
+{
+    unsigned long long v;
+    unsigned a = (unsigned)__cvta_generic_to_shared(p);
+    asm volatile("ld.volatile.shared.u64 %0, [%1];" : "=l"(v) : "r"(a));
+    return v;
+}
+
+template <bool CHAIN_SMEM>
+__global__ void __launch_bounds__(MAX_THREADS, 1)
+k_nn_chain2(double *__restrict__ W, const int n, const int64_t ld, int32_t *__restrict__ size_g,
+            int32_t *__restrict__ chain_g, double *__restrict__ Zraw, long long *__restrict__ stats)
+{
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    const int nranks = (int)cluster.num_blocks();
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int T = blockDim.x, nwarps = T >> 5;
+
+    extern __shared__ __align__(16) unsigned char smem[];
+    Slot *slots = reinterpret_cast<Slot *>(smem);                       // [2][MAX_CLUSTER]
+    unsigned *wb = reinterpret_cast<unsigned *>(slots + 2 * MAX_CLUSTER);  // [2][WARPS][4]
+    uint32_t *alive = reinterpret_cast<uint32_t *>(wb + 2 * MAX_WARPS * 4);
+    const int nwords = (int)((ld + 31) / 32);
+    int32_t *chain = CHAIN_SMEM ? reinterpret_cast<int32_t *>(alive + nwords) : chain_g + (int64_t)rank * n;
+    int32_t *size = size_g + (int64_t)rank * n;  // private copy of the cluster sizes
+
+    for (int i = tid; i < 2 * MAX_CLUSTER * 4; i += T) reinterpret_cast<unsigned long long *>(slots)[i] = 0ull;
+    for (int w = tid; w < nwords; w += T) {
+        int base = w * 32;
+        uint32_t bits = 0;
+        if (base + 32 <= n) bits = 0xffffffffu;
+        else if (base < n) bits = (1u << (n - base)) - 1u;
+        alive[w] = bits;
+    }
+    int per = (n + nranks - 1) / nranks;
+    per = (per + 1) & ~1;
+    const int lo = min(n, rank * per), hi = min(n, lo + per);
+    __syncthreads();
+    cluster.sync();
+
+    int len = 0, top = -1, second = -1, first_alive = 0;
+    unsigned seq = 0;
+    long long n_scans = 0, cyc_scan = 0, cyc_merge = 0, cyc_load = 0, cyc_red = 0, cyc_poll = 0;
+
+    for (int k = 0; k < n - 1; k++) {
+        long long t_begin = clock64();
+        if (len == 0) {
+            while (!((alive[first_alive >> 5] >> (first_alive & 31)) & 1u)) first_alive++;
+            top = first_alive;
+            second = -1;
+            if (tid == 0) chain[0] = top;
+            len = 1;
+        }
+        double gv;
+        int y;
+        for (;;) {
+            const int x = top;
+            const int yprev = (len > 1) ? second : -2;
+            seq++;
+            const int par = seq & 1;
+            const long long ts0 = clock64();
+            const double *row = W + (int64_t)x * ld;
+            Best b;
+            b.hi = NONE; b.lo = NONE; b.ic = NONE;
+            for (int c0 = lo + 2 * tid; c0 < hi; c0 += 8 * T) {
+                double2 v[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int c = c0 + 2 * T * u;
+                    if (c < hi) v[u] = ld_cg_f64x2(row + c);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int c = c0 + 2 * T * u;
+                    if (c < hi) {
+                        const uint32_t bits = alive[c >> 5] >> (c & 31);
+                        if ((bits & 1u) && c != x) consider(b, v[u].x, c == yprev ? 0u : (unsigned)c + 1u);
+                        if ((bits & 2u) && c + 1 != x) consider(b, v[u].y, c + 1 == yprev ? 0u : (unsigned)c + 2u);
+                    }
+                }
+            }
+            const long long ts1 = clock64();
+            b = warp_best(b);
+            if (lane == 0) {
+                unsigned *dst = wb + (par * MAX_WARPS + warp) * 4;
+                dst[0] = b.hi; dst[1] = b.lo; dst[2] = b.ic;
+            }
+            __syncthreads();
+            if (warp == 0) {
+                Best c;
+                c.hi = NONE; c.lo = NONE; c.ic = NONE;
+                if (lane < nwarps) {
+                    const unsigned *src = wb + (par * MAX_WARPS + lane) * 4;
+                    c.hi = src[0]; c.lo = src[1]; c.ic = src[2];
+                }
+                c = warp_best(c);
+                if (lane < nranks) {
+                    Slot *remote = cluster.map_shared_rank(slots, lane) + par * MAX_CLUSTER + rank;
+                    const unsigned long long tag = (unsigned long long)seq << 32;
+                    volatile unsigned long long *w = remote->w;
+                    w[0] = tag | c.lo;
+                    w[1] = tag | c.hi;
+                    w[2] = tag | c.ic;
+                }
+            }
+            const long long ts2 = clock64();
+            // every warp waits for the nranks partial results in its own CTA's shared memory
+            Best g;
+            g.hi = NONE; g.lo = NONE; g.ic = NONE;
+            {
+                const Slot *mine = slots + par * MAX_CLUSTER + (lane < nranks ? lane : 0);
+                bool ok;
+                unsigned long long w0, w1, w2;
+                do {
+                    w0 = ld_volatile_shared_u64(&mine->w[0]);
+                    w1 = ld_volatile_shared_u64(&mine->w[1]);
+                    w2 = ld_volatile_shared_u64(&mine->w[2]);
+                    ok = (lane >= nranks) ||
+                         ((unsigned)(w0 >> 32) == seq && (unsigned)(w1 >> 32) == seq && (unsigned)(w2 >> 32) == seq);
+                } while (!__all_sync(0xffffffffu, ok));
+                if (lane < nranks) { g.lo = (unsigned)w0; g.hi = (unsigned)w1; g.ic = (unsigned)w2; }
+            }
+            g = warp_best(g);
+            const long long ts3 = clock64();
+            cyc_load += ts1 - ts0; cyc_red += ts2 - ts1; cyc_poll += ts3 - ts2;
+            gv = key_to_double(g.hi, g.lo);
+            n_scans++;
+            y = (g.ic == 0u) ? yprev : (int)(g.ic - 1u);
+            if (len > 1 && y == yprev) break;
+            if (tid == 0) chain[len] = y;
+            second = top;
+            top = y;
+            len++;
+        }
+        // ---- merge ---------------------------------------------------------------------------------
+        long long t_mid = clock64();
+        cyc_scan += t_mid - t_begin;
+        int x = top;
+        len -= 2;
+        if (x > y) { int t = x; x = y; y = t; }
+        const int nx = size[x], ny = size[y];
+        const double dnx = (double)nx, dny = (double)ny, dsum = (double)(nx + ny);
+        const double *rowx = W + (int64_t)x * ld;
+        double *rowy = W + (int64_t)y * ld;
+        for (int c = lo + 2 * tid; c < hi; c += 2 * T) {
+            const uint32_t bits = alive[c >> 5] >> (c & 31);
+            const bool u0 = (bits & 1u) && c != x && c != y;
+            const bool u1 = (bits & 2u) && c + 1 != x && c + 1 != y;
+            if (!(u0 || u1)) continue;
+            const double2 vx = ld_cg_f64x2(rowx + c), vy = ld_cg_f64x2(rowy + c);
+            if (u0) {
+                const double v = __ddiv_rn(__dadd_rn(__dmul_rn(dnx, vx.x), __dmul_rn(dny, vy.x)), dsum);
+                rowy[c] = v;
+                W[(int64_t)c * ld + y] = v;
+            }
+            if (u1) {
+                const double v = __ddiv_rn(__dadd_rn(__dmul_rn(dnx, vx.y), __dmul_rn(dny, vy.y)), dsum);
+                rowy[c + 1] = v;
+                W[(int64_t)(c + 1) * ld + y] = v;
+            }
+        }
+        if (rank == 0 && tid == 0) {
+            Zraw[4 * (int64_t)k + 0] = (double)x;
+            Zraw[4 * (int64_t)k + 1] = (double)y;
+            Zraw[4 * (int64_t)k + 2] = gv;
+            Zraw[4 * (int64_t)k + 3] = dsum;
+        }
+        __syncthreads();  // all threads have read alive[] and size[] for this merge
+        if (tid == 0) {
+            alive[x >> 5] &= ~(1u << (x & 31));
+            size[x] = 0;
+            size[y] = nx + ny;
+        }
+        if (len >= 1) {
+            top = chain[len - 1];
+            second = (len >= 2) ? chain[len - 2] : -1;
+            const double *nrow = W + (int64_t)top * ld;
+            for (int c = lo + 16 * tid; c < hi; c += 16 * T)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(nrow + c));
+        }
+        cluster.sync();  // W updates (incl. the scattered column y) visible cluster-wide; also a CTA barrier
+        cyc_merge += clock64() - t_mid;
+    }
+    if (rank == 0 && tid == 0 && stats) {
+        stats[0] = n_scans; stats[1] = cyc_scan; stats[2] = cyc_merge;
+        stats[3] = cyc_load; stats[4] = cyc_red; stats[5] = cyc_poll;
+    }
+}
+
+inline size_t base_smem(int nwords)
+{
+    return sizeof(Slot) * 2 * MAX_CLUSTER + sizeof(unsigned) * 2 * MAX_WARPS * 4 + sizeof(uint32_t) * nwords;
+}
+
+}  // namespace nn2

@@ -51,8 +51,9 @@ enum {
     HICA_T_BREAKPOINTS, HICA_T_FILTER, HICA_T_P2_SCORE, HICA_T_COUNT
 };
 int hica_get_timers(hica_handle h, double *ms /* HICA_T_COUNT */);
-/* counters of the last hica_p1_linkage: nearest-neighbour searches, SM cycles spent in searches, in merges */
-int hica_linkage_stats(hica_handle h, int64_t *out3);
+/* counters of the last hica_p1_linkage: nearest-neighbour searches, SM cycles spent in searches, in merges,
+ * and the search cycles split into row load / in-CTA reduction / cross-CTA exchange (6 values) */
+int hica_linkage_stats(hica_handle h, int64_t *out6);
 
 /* ---- Part 1: ICE matrix -> leaf order -> cut indices ---------------------- */
 
