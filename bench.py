@@ -324,7 +324,8 @@ def main():
                    "l2": "inputs (%.2f GB matrix) larger than L2; no explicit flush" % (8.0 * n * n / 1e9),
                    "sharding": "Part1 replicated per rank, Part2 chromosomes round-robin over ranks" if world > 1 else "1 GPU"},
         "seconds": {"part1": last["t_part1"], "part2": last["t_part2"], "total": last["t_total"],
-                    "e2e_total": secs_e2e / args.steps},
+                    "e2e_total": secs_e2e / args.steps, "e2e_part1": res_e2e[-1]["t_part1"],
+                    "e2e_part2": res_e2e[-1]["t_part2"], "e2e_upload_ms": res_e2e[-1]["timers_p1"]["upload"]},
         "stage_ms_part1": tm, "linkage_stats": last["linkage_stats"],
         "work": {"part1_bin_pairs": p1_pairs, "part2_bin_pairs": p2_pairs, "part2_candidates": p2_cands,
                  "part2_device_calls": p2_calls, "part2_exact_rescored": last.get("p2_exact"), "cuts": len(last["cuts"]), "groups": last.get("n_groups"),

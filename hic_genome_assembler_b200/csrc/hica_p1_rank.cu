@@ -16,71 +16,14 @@
 // kernel implements "stable ascending argsort, reversed": ties come out in
 // DESCENDING reordered column index.  The downstream window counts only depend
 // on the order when a tie group straddles a window boundary.
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "hica_common.cuh"
+#include "hica_p1_ranksort.cuh"
 
 namespace {
-
-__device__ __forceinline__ unsigned long long order_key(double v)
-{
-    long long b = __double_as_longlong(v);
-    unsigned long long u = (unsigned long long)b;
-    return (b < 0) ? ~u : (u | 0x8000000000000000ull);
-}
-
-// true when element (ka, pa) must precede (kb, pb) in the output
-__device__ __forceinline__ bool precedes(unsigned long long ka, uint32_t pa, unsigned long long kb, uint32_t pb)
-{
-    return ka > kb || (ka == kb && pa > pb);
-}
-
-template <typename PayT>
-__global__ void __launch_bounds__(1024, 1)
-k_rank_rows(const double *__restrict__ A, int64_t n, const double *__restrict__ s_pair,
-            const double *__restrict__ s_seq, const int32_t *__restrict__ order, const int32_t *__restrict__ pos,
-            int is_distance, int P, PayT *__restrict__ R)
-{
-    extern __shared__ __align__(16) unsigned char smem[];
-    unsigned long long *keys = reinterpret_cast<unsigned long long *>(smem);
-    PayT *pay = reinterpret_cast<PayT *>(keys + P);
-    const int T = blockDim.x;
-    const int64_t i = blockIdx.x;
-    const int64_t a = order[i];
-    const double sp = is_distance ? 1.0 : s_pair[a];
-    const double rs = is_distance == 2 ? 1.0 : s_seq[a];
-    const double *row = A + a * n;
-    for (int b = threadIdx.x; b < P; b += T) {
-        if (b < n) {
-            double d = is_distance ? row[b] : dist_transform(row[b], sp);
-            keys[b] = order_key(is_distance == 2 ? d : sim_transform(d, rs));
-            pay[b] = (PayT)pos[b];
-        } else {
-            keys[b] = 0ull;  // pads sort last
-            pay[b] = (PayT)0;
-        }
-    }
-    __syncthreads();
-    for (int k = 2; k <= P; k <<= 1) {
-        for (int j = k >> 1; j >= 1; j >>= 1) {
-            for (int p = threadIdx.x; p < (P >> 1); p += T) {
-                int lo = ((p & ~(j - 1)) << 1) | (p & (j - 1));
-                int hi = lo | j;
-                unsigned long long ka = keys[lo], kb = keys[hi];
-                uint32_t pa = pay[lo], pb = pay[hi];
-                bool fwd = (lo & k) == 0;  // this block ends up in final (descending) order
-                bool swap = fwd ? precedes(kb, pb, ka, pa) : precedes(ka, pa, kb, pb);
-                if (swap) {
-                    keys[lo] = kb; keys[hi] = ka;
-                    pay[lo] = (PayT)pb; pay[hi] = (PayT)pa;
-                }
-            }
-            __syncthreads();
-        }
-    }
-    PayT *out = R + i * n;
-    for (int b = threadIdx.x; b < n; b += T) out[b] = pay[b];
-}
 
 // out[i][j] = f(A[o[i]][o[j]]): what = 0 -> D, what = 1 -> S
 __global__ void __launch_bounds__(256) k_reordered(const double *__restrict__ A, int64_t n,
@@ -103,6 +46,62 @@ __global__ void __launch_bounds__(256) k_reordered(const double *__restrict__ A,
 
 }  // namespace
 
+template <typename PayT, int MAXT>
+static int rank_rows(hica_ctx *h, int q, int64_t P)
+{
+    using namespace ranksort;
+    const int64_t n = h->n;
+    const int CP = 1 << q;
+    const int64_t nchunks = P / CP;
+    const int threads = CP / EPT;
+    const size_t smem = (size_t)(CP + (CP >> 4)) * (8 + sizeof(PayT));
+    HICA_CUDA(cudaFuncSetAttribute(k_rank_chunk<PayT, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ChunkArgs a = {};
+    a.A = h->A; a.n = n; a.s_pair = h->s_pair; a.s_seq = h->s_seq; a.order = h->order; a.pos = h->pos;
+    a.kind = h->A_kind; a.q = q; a.P = P; a.R = h->R;
+    if (nchunks == 1) {
+        a.mode = 0; a.write_final = 1;
+        for (int64_t r0 = 0; r0 < n; r0 += 65535) {
+            a.row0 = r0;
+            k_rank_chunk<PayT, MAXT><<<dim3(1, (unsigned)std::min<int64_t>(65535, n - r0)), threads, smem, h->stream>>>(a);
+            HICA_LAUNCHED(h);
+        }
+        HICA_CUDA(cudaGetLastError());
+        return HICA_OK;
+    }
+    // multi-chunk rows: chunk sort -> global strides -> chunk merge, in row batches that bound the scratch
+    const int64_t per_row = P * (int64_t)(8 + sizeof(PayT));
+    int64_t rows_b = std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(n, 65535), (6ll << 30) / per_row));
+    unsigned long long *sk = nullptr;
+    PayT *sp = nullptr;
+    int rc = hica_realloc(h, &sk, rows_b * P);
+    if (rc) return rc;
+    if ((rc = hica_realloc(h, &sp, rows_b * P))) { cudaFree(sk); return rc; }
+    a.sk = sk; a.sp = sp;
+    for (int64_t r0 = 0; r0 < n; r0 += rows_b) {
+        const int64_t rows = std::min(rows_b, n - r0);
+        a.row0 = r0; a.mode = 0; a.write_final = 0;
+        k_rank_chunk<PayT, MAXT><<<dim3((unsigned)nchunks, (unsigned)rows), threads, smem, h->stream>>>(a);
+        HICA_LAUNCHED(h);
+        for (long long kp = 2ll * CP; kp <= P; kp <<= 1) {
+            for (long long j = kp >> 1; j >= CP; j >>= 1) {
+                const int64_t work = (P >> 1) * rows;
+                k_rank_global_step<PayT><<<(unsigned)((work + 255) / 256), 256, 0, h->stream>>>(sk, sp, P, kp, j, rows);
+                HICA_LAUNCHED(h);
+            }
+            a.mode = 1; a.k_merge = kp; a.write_final = (kp == P) ? 1 : 0;
+            k_rank_chunk<PayT, MAXT><<<dim3((unsigned)nchunks, (unsigned)rows), threads, smem, h->stream>>>(a);
+            HICA_LAUNCHED(h);
+        }
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(sk);
+    cudaFree(sp);
+    if (e != cudaSuccess) return hica_set_error(h, HICA_ERR_CUDA, "rank: %s", cudaGetErrorString(e));
+    return HICA_OK;
+}
+
 extern "C" int hica_p1_rank(hica_handle h)
 {
     HICA_CHECK_HANDLE(h);
@@ -111,23 +110,21 @@ extern "C" int hica_p1_rank(hica_handle h)
     if (h->A_kind != 2 && !h->have_s_seq) return hica_set_error(h, HICA_ERR_STATE, "row sums not set (hica_p1_set_row_sums)");
     if (h->A_kind == 0 && !h->have_s_pair) return hica_set_error(h, HICA_ERR_STATE, "call hica_p1_distance first");
     const int64_t n = h->n;
-    int P = 1;
-    while (P < n) P <<= 1;
-    if (P > 16384)
-        return hica_set_error(h, HICA_ERR_ARG, "rank: n = %lld needs the multi-chunk sort (n <= 16384 supported)",
-                              (long long)n);
-    const int bytes = 2;  // n <= 16384 < 65536
+    int64_t P = 512;
+    int lg = 9;
+    while (P < n) { P <<= 1; lg++; }
+    int qmax = 14;  // measured at N=16k on B200: q=14 (1024 thr, some spills) 29 ms, q=13 (512 thr, 2 chunks/row) 47 ms
+    if (const char *e = getenv("HICA_RANK_Q")) qmax = std::max(9, std::min(14, atoi(e)));
+    const int q = std::min(lg, qmax);
+    const int bytes = n <= 65535 ? 2 : 4;
     if (h->R) { cudaFree(h->R); h->R = nullptr; }
     HICA_CUDA(cudaMalloc(&h->R, (size_t)n * n * bytes));
     h->rank_bytes = 0;
-    size_t smem = (size_t)P * (8 + bytes);
-    HICA_CUDA(cudaFuncSetAttribute(k_rank_rows<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int threads = std::min(1024, std::max(32, P / 2));
     hica_timer t(h, HICA_T_RANK);
-    k_rank_rows<uint16_t><<<(unsigned)n, threads, smem, h->stream>>>(h->A, n, h->s_pair, h->s_seq, h->order, h->pos,
-                                                                     h->A_kind, P, (uint16_t *)h->R);
-    HICA_LAUNCHED(h);
-    HICA_CUDA(cudaGetLastError());
+    int rc;
+    if (q == 14) rc = bytes == 2 ? rank_rows<uint16_t, 1024>(h, q, P) : rank_rows<uint32_t, 1024>(h, q, P);
+    else rc = bytes == 2 ? rank_rows<uint16_t, 512>(h, q, P) : rank_rows<uint32_t, 512>(h, q, P);
+    if (rc) return rc;
     t.stop();
     HICA_CUDA(cudaStreamSynchronize(h->stream));
     h->rank_bytes = bytes;

@@ -153,3 +153,24 @@ def test_hypergeom_decisions_match_scipy(hica):
     ref = (O.hyper_geom(x, M, n, N) < .05).astype(np.uint8)
     assert (out & 2).sum() == 0
     assert np.array_equal(out & 1, ref)
+
+
+@pytest.mark.parametrize("n,q", [(700, 9), (1100, 9), (1100, 10), (2049, 10), (3000, 11), (5000, 12), (5000, 14), (9000, 13)])
+def test_rank_multi_chunk_paths(hica, n, q, monkeypatch):
+    """Rows longer than one sort chunk: chunk sort -> global strides -> chunk merge (forced with small chunks)."""
+    monkeypatch.setenv("HICA_RANK_Q", str(q))
+    rng = np.random.RandomState(n + q)
+    S = rng.rand(n, n)
+    hica.p1_upload_similarity(S)
+    hica.p1_rank()
+    R = hica.p1_get_rank()
+    assert np.array_equal(R, O.rank_matrix_stable(S))
+
+
+def test_rank_with_heavy_ties_multi_chunk(hica, monkeypatch):
+    monkeypatch.setenv("HICA_RANK_Q", "9")
+    rng = np.random.RandomState(1)
+    S = np.round(rng.rand(900, 900), 1)
+    hica.p1_upload_similarity(S)
+    hica.p1_rank()
+    assert np.array_equal(hica.p1_get_rank(), O.rank_matrix_stable(S))
