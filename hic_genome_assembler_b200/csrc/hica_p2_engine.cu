@@ -1,28 +1,24 @@
 // hica_p2_engine.cu - orderChromosome (orderGenome.py:551-586) for a batch of
 // independent chromosome groups, entirely on the device.
 //
-// Every group gets its own CUDA stream; brute force (:432-473), greedy insertion
-// (:475-493 / :332-372) and the sliding-window scan (:495-549) are enqueued as
-// stream-ordered kernels whose decisions (accept / apply / converged) are taken
-// on the device, so the host never waits inside a chromosome and the groups
-// overlap on the GPU.
+// All groups advance in lock-step through the same sequence of phases - brute force (:432-473), the greedy
+// insertion steps (:475-493 / :332-372) and the sliding-window scan (:495-549) - and every kernel launch
+// covers ALL groups (blockIdx.y = group).  The accept / apply / converged decisions are taken on the device,
+// so the host only enqueues kernels and reads the converged flags once per batch of scan rounds.
 //
 // Window searches (brute force, scan windows) are two-phase:
 //   1. a closed-form score  cost = sum_{a<b} M[o_a,o_b] * w(b-a),
 //      w(d) = (H_{n-1} - H_{d-1}) / total   
-//      is evaluated for ALL candidates from scaffold-pair tables (the window's
-//      scaffolds against the fixed prefix/suffix bins and against each other,
-//      for every orientation and every set of scaffolds in between), ~20 table
-//      look-ups per candidate;
-//   2. every candidate within a relative 1e-10 of the best closed-form score (or
-//      of the carried best cost) is re-scored with the bit-exact numba-order
-//      kernel, and the reference's accept rule (first strict maximum above the
-//      carried cost) is applied to those exact scores.
-// The closed form differs from numba's summation order only by rounding
-// (<= ~3n ulp, 3e-13 relative at n = 800, for non-negative contacts), so the
-// exact winner is always inside the re-scored set; results are bit-identical
-// to scoring every candidate exactly.  Matrices with negative entries (for
-// which that bound does not hold) are re-scored in full.
+//      is evaluated for ALL candidates from scaffold-pair tables (the window's scaffolds against the fixed
+//      prefix/suffix bins and against each other, for every orientation and every set of scaffolds in
+//      between): m + m(m-1)/2 table look-ups per candidate;
+//   2. every candidate within a relative 1e-10 of the best closed-form score (or of the carried best cost)
+//      is re-scored with the bit-exact numba-order routine, and the reference's accept rule (first strict
+//      maximum above the carried cost) is applied to those exact scores.
+// The closed form differs from numba's summation order only by rounding (<= ~3n ulp, 3e-13 relative at
+// n = 800, for non-negative symmetric contacts), so the exact winner is always inside the re-scored set and
+// the result is bit-identical to scoring every candidate exactly.  Matrices with negative or asymmetric
+// entries (for which that bound does not hold) are detected at gather time and re-scored in full.
 #include <limits.h>
 #include <math.h>
 
@@ -39,43 +35,66 @@ constexpr double NEAR_TOL = 1e-10;
 struct GroupState {
     double total, best_cost, E_layout, rel0;
     unsigned long long amax_key;
-    int near_count, improved, converged, rounds, error, has_negative, skip, done_blocks;
-    long long n_exact, n_approx, n_kernels_unused;
+    int near_count, improved, converged, rounds, error, inexact, skip, done_blocks;
+    long long n_exact;
 };
 
 struct GroupDev {
     const double *S, *St;
-    int L, nseg;
-    const int32_t *seg_ptr, *seg_bins;
+    int L, nseg, k, scanning;
+    const int32_t *seg_ptr, *seg_bins, *cum;  // cum[j] = bins of the first j scaffolds in pool order
     int32_t *layout;
-    double *Wt;         // L + 1
-    double *tab_out;    // m*2 << m
-    double *tab_win;    // m*m*4 << m
-    double *rel;        // B_max
-    int32_t *near_id;   // B_max
-    double *near_score; // B_max
-    double *tr;         // L + 1
+    double *Wt, *tab_out, *tab_win, *rel, *near_score, *tr;
+    int32_t *near_id;
     GroupState *st;
 };
 
+struct Tables {  // enumeration tables per window width m (device pointers)
+    const uint8_t *ord[9], *ori[9];
+    int n_ord[9], n_ori[9];
+};
+
+enum { PH_BRUTE = 0, PH_INSERT = 1, PH_SCAN = 2 };
+struct Phase { int kind, step, m_scan; };
+
+struct PhaseParams { int active, nslots, n, ws, m; };
+
+__device__ __forceinline__ PhaseParams phase_params(const GroupDev &g, const Phase &ph)
+{
+    PhaseParams p;
+    if (ph.kind == PH_BRUTE) {
+        p.nslots = g.k; p.n = g.cum[g.k]; p.ws = 0; p.m = g.k;
+        p.active = p.n >= 2;
+    } else if (ph.kind == PH_INSERT) {
+        const int steps = max(1, g.nseg - g.k);
+        const int mbase = g.nseg > g.k ? g.k + ph.step : g.k - 1;  // nothing left: pop and re-insert the last one
+        p.nslots = mbase + 1; p.n = g.cum[min(p.nslots, g.nseg)]; p.ws = 0; p.m = mbase;
+        p.active = ph.step < steps;
+    } else {
+        p.nslots = g.nseg; p.n = g.L; p.ws = ph.step; p.m = ph.m_scan;
+        p.active = g.scanning && ph.step + ph.m_scan <= g.nseg && !g.st->converged;
+    }
+    return p;
+}
+
 // ---------------------------------------------------------------------------
 // candidate sources
-struct SrcLayout {  // the current layout itself (nslots entries)
+struct SrcLayout {
     const int32_t *layout;
     __device__ int operator()(int s) const { return layout[s]; }
 };
 struct SrcWindow {  // layout with window [ws, ws+m) rearranged by candidate (oi, ri)
     const int32_t *layout;
     int ws, m;
-    const uint8_t *ord, *ori;  // rows of the tables for this candidate
+    const uint8_t *ord, *ori;
     __device__ int operator()(int s) const
     {
         if (s < ws || s >= ws + m) return layout[s];
-        int j = s - ws;
+        const int j = s - ws;
         return ((layout[ws + ord[j]] >> 1) << 1) | (int)ori[j];
     }
 };
-struct SrcInsert {  // layout[0..m) with layout[m] inserted at slot i with orientation o
+struct SrcInsert {  // layout[0..m) with the new entry inserted at slot i
     const int32_t *layout;
     int i, newentry;
     __device__ int operator()(int s) const { return s < i ? layout[s] : (s == i ? newentry : layout[s - 1]); }
@@ -85,11 +104,11 @@ struct SmemPlan {
     double *tr;
     int32_t *o, *spos, *sent;
 };
-__device__ __forceinline__ SmemPlan carve(unsigned char *smem, int n, int nslots)
+__device__ __forceinline__ SmemPlan carve(unsigned char *smem, int n_tr, int n, int nslots)
 {
     SmemPlan p;
     p.tr = reinterpret_cast<double *>(smem);
-    p.o = reinterpret_cast<int32_t *>(p.tr + n);
+    p.o = reinterpret_cast<int32_t *>(p.tr + n_tr);
     p.spos = p.o + n;
     p.sent = p.spos + nslots + 1;
     return p;
@@ -97,16 +116,16 @@ __device__ __forceinline__ SmemPlan carve(unsigned char *smem, int n, int nslots
 size_t smem_bytes(int n, int nslots) { return sizeof(double) * n + sizeof(int32_t) * (n + 2 * nslots + 2); }
 
 // ---------------------------------------------------------------------------
-// total = sum_k numpy.trace(M, k) for the layout's first nslots slots (:343/:448/:506)
-__global__ void __launch_bounds__(128) k_g_total(GroupDev g, int nslots, int n)
+// total = sum_k numpy.trace(M, k) of the phase's layout (:343/:448/:506), then the weights of the closed form
+__global__ void __launch_bounds__(128) k_g_total(const GroupDev *gs, Phase ph, int want_weights)
 {
     extern __shared__ __align__(16) unsigned char smem[];
-    SmemPlan sp;  // no trace scratch here: o | spos | sent
-    sp.tr = nullptr;
-    sp.o = reinterpret_cast<int32_t *>(smem);
-    sp.spos = sp.o + n;
-    sp.sent = sp.spos + nslots + 1;
-    build_order_cta(SrcLayout{g.layout}, nslots, g.seg_ptr, g.seg_bins, sp.o, sp.spos, sp.sent, n);
+    const GroupDev &g = gs[blockIdx.y];
+    const PhaseParams pp = phase_params(g, ph);
+    if (!pp.active) return;
+    const int n = pp.n;
+    SmemPlan sp = carve(smem, 0, n, pp.nslots);
+    build_order_cta(SrcLayout{g.layout}, pp.nslots, g.seg_ptr, g.seg_bins, sp.o, sp.spos, sp.sent, n);
     const int k = blockIdx.x * blockDim.x + threadIdx.x + 1;
     if (k < n) {
         const int32_t *o = sp.o;
@@ -120,48 +139,52 @@ __global__ void __launch_bounds__(128) k_g_total(GroupDev g, int nslots, int n)
     __syncthreads();
     if (threadIdx.x == 0) last = (atomicAdd(&g.st->done_blocks, 1) == (int)gridDim.x - 1);
     __syncthreads();
-    if (last && threadIdx.x == 0) {
+    if (!last) return;
+    if (threadIdx.x == 0) {
         double t = 0.;
         for (int kk = 1; kk < n; kk++) t = __dadd_rn(t, ld_cg_f64(g.tr + kk));
         g.st->total = t;
         g.st->done_blocks = 0;
+        g.st->skip = (t == 0.0) ? 1 : 0;
+        if (want_weights) {  // w(d) = (sum_{j=d}^{n-1} 1/j) / total
+            double acc = 0.;
+            for (int d = n - 1; d >= 1; d--) {
+                acc += 1.0 / (double)d;
+                g.Wt[d] = acc / t;
+            }
+            g.Wt[0] = 0.;
+        }
     }
-}
-
-// w(d) = (sum_{j=d}^{n-1} 1/j) / total for the closed-form score
-__global__ void k_g_weights(GroupDev g, int n)
-{
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    const double total = g.st->total;
-    g.st->skip = (total == 0.0) ? 1 : 0;
-    double acc = 0.;
-    for (int d = n - 1; d >= 1; d--) {
-        acc += 1.0 / (double)d;
-        g.Wt[d] = acc / total;
-    }
-    g.Wt[0] = 0.;
 }
 
 // exact cost of the current layout -> E_layout (anchor of the closed-form scores)
-__global__ void __launch_bounds__(EX_THREADS) k_g_anchor(GroupDev g, int nslots, int n)
+__global__ void __launch_bounds__(EX_THREADS) k_g_anchor(const GroupDev *gs, Phase ph)
 {
     extern __shared__ __align__(16) unsigned char smem[];
-    if (g.st->skip) return;
-    SmemPlan sp = carve(smem, n, nslots);
-    build_order_cta(SrcLayout{g.layout}, nslots, g.seg_ptr, g.seg_bins, sp.o, sp.spos, sp.sent, n);
-    double c = exact_cost_cta(g.S, g.St, g.L, sp.o, n, g.st->total, sp.tr);
+    const GroupDev &g = gs[blockIdx.y];
+    const PhaseParams pp = phase_params(g, ph);
+    if (!pp.active || g.st->skip) return;
+    SmemPlan sp = carve(smem, pp.n, pp.n, pp.nslots);
+    build_order_cta(SrcLayout{g.layout}, pp.nslots, g.seg_ptr, g.seg_bins, sp.o, sp.spos, sp.sent, pp.n);
+    const double c = exact_cost_cta(g.S, g.St, g.L, sp.o, pp.n, g.st->total, sp.tr);
     if (threadIdx.x == 0) g.st->E_layout = c;
 }
 
 // ---------------------------------------------------------------------------
 // scaffold-pair tables for the window [ws, ws+m) of the current layout
-//   tab_out[((s*2+o) << m) | before]           : scaffold s (orientation o) vs all bins outside the window,
-//                                                 `before` = set of window scaffolds placed before s
+//   tab_out[((s*2+o) << m) | before]                : scaffold s (orientation o) against all bins outside the
+//                                                      window, `before` = window scaffolds placed before s
 //   tab_win[((((s*m+s2)*2+o)*2+o2) << m) | between] : s placed before s2 with the scaffolds `between` in between
-__global__ void __launch_bounds__(128) k_g_tables(GroupDev g, int nslots, int n, int ws, int m)
+__global__ void __launch_bounds__(128) k_g_tables(const GroupDev *gs, Phase ph)
 {
-    if (g.st->skip || g.st->converged) return;
-    __shared__ int wseg[8], wlen[8], woff[8];
+    const GroupDev &g = gs[blockIdx.y];
+    const PhaseParams pp = phase_params(g, ph);
+    if (!pp.active || g.st->skip) return;
+    const int m = pp.m, ws = pp.ws, nslots = pp.nslots;
+    const int n_out = (m * 2) << m, n_win = (m * m * 4) << m;
+    const int b = blockIdx.x;
+    if (b >= n_out + n_win) return;
+    __shared__ int wlen[8], woff[8];
     __shared__ int p0_s, wtot_s;
     __shared__ double red[4];
     const int tid = threadIdx.x;
@@ -171,7 +194,6 @@ __global__ void __launch_bounds__(128) k_g_tables(GroupDev g, int nslots, int n,
         int wt = 0;
         for (int j = 0; j < m; j++) {
             int sg = g.layout[ws + j] >> 1;
-            wseg[j] = sg;
             wlen[j] = g.seg_ptr[sg + 1] - g.seg_ptr[sg];
             woff[j] = g.seg_ptr[sg];
             wt += wlen[j];
@@ -180,8 +202,6 @@ __global__ void __launch_bounds__(128) k_g_tables(GroupDev g, int nslots, int n,
         wtot_s = wt;
     }
     __syncthreads();
-    const int n_out = (m * 2) << m;
-    const int b = blockIdx.x;
     const int full = (1 << m) - 1;
     const int L = g.L;
     double acc = 0.;
@@ -193,28 +213,25 @@ __global__ void __launch_bounds__(128) k_g_tables(GroupDev g, int nslots, int n,
         int q = 0;
         for (int j = 0; j < m; j++) if ((mask >> j) & 1) q += wlen[j];
         const int len = wlen[s], p0 = p0_s, wtot = wtot_s;
-        const int n_outside = n - wtot;
-        // outside position a -> bin: walk the layout slots; to stay cheap the outside bins are enumerated by slot
-        // (prefix slots [0, ws) then suffix slots [ws+m, nslots)), each thread strides over (slot-bin, t) pairs.
+        // outside bins by slot: prefix slots [0, ws) then suffix slots [ws+m, nslots)
         int pos = 0;
         for (int sl = 0; sl < nslots; sl++) {
             if (sl == ws) { sl = ws + m - 1; pos = p0 + wtot; continue; }
             const int e = g.layout[sl], sg = e >> 1, b0 = g.seg_ptr[sg], sl_len = g.seg_ptr[sg + 1] - b0;
             const int work = sl_len * len;
             for (int w = tid; w < work; w += blockDim.x) {
-                const int t = w / sl_len, u = w - t * sl_len;      // u: offset inside the outside scaffold
+                const int t = w / sl_len, u = w - t * sl_len;
                 const int abin = g.seg_bins[b0 + ((e & 1) ? (sl_len - 1 - u) : u)];
                 const int apos = pos + u;
                 const int bbin = g.seg_bins[woff[s] + t];
                 const int bpos = p0 + q + (o ? (len - 1 - t) : t);
                 const int d = apos < bpos ? bpos - apos : apos - bpos;
-                // the reference reads M[row of the earlier position][col of the later position]
+                // the reference reads M[row of the earlier position][column of the later position]
                 const double v = apos < bpos ? g.S[(int64_t)abin * L + bbin] : g.St[(int64_t)abin * L + bbin];
                 acc += v * g.Wt[d];
             }
             pos += sl_len;
         }
-        (void)n_outside;
     } else {
         int r = b - n_out;
         const int mask = r & full;
@@ -264,15 +281,19 @@ __device__ __forceinline__ double rel_of(const GroupDev &g, int m, const uint8_t
 }
 
 // closed-form score (relative to the constant terms) of every candidate of the window
-__global__ void __launch_bounds__(256) k_g_approx(GroupDev g, int ws, int m, const uint8_t *__restrict__ ord_t,
-                                                  const uint8_t *__restrict__ ori_t, int n_orients, long long B)
+__global__ void __launch_bounds__(256) k_g_approx(const GroupDev *gs, Phase ph, Tables tb)
 {
-    if (g.st->skip || g.st->converged) return;
+    const GroupDev &g = gs[blockIdx.y];
+    const PhaseParams pp = phase_params(g, ph);
+    if (!pp.active || g.st->skip) return;
+    const int m = pp.m, n_ori = tb.n_ori[m];
+    const long long B = (long long)tb.n_ord[m] * n_ori;
     const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if ((long long)blockIdx.x * blockDim.x >= B) return;
     double rel = -INFINITY;
     if (c < B) {
-        const int oi = (int)(c / n_orients), ri = (int)(c % n_orients);
-        rel = rel_of(g, m, ord_t + (size_t)oi * m, ori_t + (size_t)ri * m);
+        const int oi = (int)(c / n_ori), ri = (int)(c % n_ori);
+        rel = rel_of(g, m, tb.ord[m] + (size_t)oi * m, tb.ori[m] + (size_t)ri * m);
         g.rel[c] = rel;
     }
     double mx = rel;
@@ -280,59 +301,66 @@ __global__ void __launch_bounds__(256) k_g_approx(GroupDev g, int ws, int m, con
     if ((threadIdx.x & 31) == 0 && mx > -INFINITY) atomicMax(&g.st->amax_key, f64_order_key(mx));
     if (c == 0) {  // the current arrangement: identity order, current orientations
         uint8_t ido[8], idr[8];
-        for (int j = 0; j < m; j++) { ido[j] = (uint8_t)j; idr[j] = (uint8_t)(g.layout[ws + j] & 1); }
+        for (int j = 0; j < m; j++) { ido[j] = (uint8_t)j; idr[j] = (uint8_t)(g.layout[pp.ws + j] & 1); }
         g.st->rel0 = rel_of(g, m, ido, idr);
     }
 }
 
 // candidates that can still be the exact winner
-__global__ void __launch_bounds__(256) k_g_select(GroupDev g, long long B, int use_carried)
+__global__ void __launch_bounds__(256) k_g_select(const GroupDev *gs, Phase ph, Tables tb)
 {
+    const GroupDev &g = gs[blockIdx.y];
+    const PhaseParams pp = phase_params(g, ph);
     GroupState *st = g.st;
-    if (st->skip || st->converged) return;
+    if (!pp.active || st->skip) return;
+    const long long B = (long long)tb.n_ord[pp.m] * tb.n_ori[pp.m];
     const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= B) return;
     const double amax = st->E_layout + (f64_from_order_key(st->amax_key) - st->rel0);
-    const double carried = use_carried ? st->best_cost : 0.0;
+    const double carried = ph.kind == PH_SCAN ? st->best_cost : 0.0;
     const double scale = fmax(fabs(amax), fmax(fabs(carried), fabs(st->E_layout)));
     const double thr = fmax(amax, carried) - NEAR_TOL * scale;
     const double a = st->E_layout + (g.rel[c] - st->rel0);
-    if (st->has_negative || !(a < thr)) {
-        int slot = atomicAdd(&st->near_count, 1);
+    if (st->inexact || !(a < thr)) {
+        const int slot = atomicAdd(&st->near_count, 1);
         g.near_id[slot] = (int)c;
     }
 }
 
 // bit-exact re-scoring of the near list
-__global__ void __launch_bounds__(EX_THREADS) k_g_exact_near(GroupDev g, int nslots, int n, int ws, int m,
-                                                           const uint8_t *__restrict__ ord_t,
-                                                           const uint8_t *__restrict__ ori_t, int n_orients)
+__global__ void __launch_bounds__(EX_THREADS) k_g_exact_near(const GroupDev *gs, Phase ph, Tables tb)
 {
     extern __shared__ __align__(16) unsigned char smem[];
-    if (g.st->skip || g.st->converged) return;
-    SmemPlan sp = carve(smem, n, nslots);
+    const GroupDev &g = gs[blockIdx.y];
+    const PhaseParams pp = phase_params(g, ph);
+    if (!pp.active || g.st->skip) return;
     const int cnt = g.st->near_count;
+    if ((int)blockIdx.x >= cnt) return;
+    const int m = pp.m, n_ori = tb.n_ori[m];
+    SmemPlan sp = carve(smem, pp.n, pp.n, pp.nslots);
     const double total = g.st->total;
     for (int i = blockIdx.x; i < cnt; i += gridDim.x) {
         const int c = g.near_id[i];
-        const int oi = c / n_orients, ri = c % n_orients;
-        SrcWindow src{g.layout, ws, m, ord_t + (size_t)oi * m, ori_t + (size_t)ri * m};
-        build_order_cta(src, nslots, g.seg_ptr, g.seg_bins, sp.o, sp.spos, sp.sent, n);
-        double cost = exact_cost_cta(g.S, g.St, g.L, sp.o, n, total, sp.tr);
+        const int oi = c / n_ori, ri = c % n_ori;
+        SrcWindow src{g.layout, pp.ws, m, tb.ord[m] + (size_t)oi * m, tb.ori[m] + (size_t)ri * m};
+        build_order_cta(src, pp.nslots, g.seg_ptr, g.seg_bins, sp.o, sp.spos, sp.sent, pp.n);
+        const double cost = exact_cost_cta(g.S, g.St, g.L, sp.o, pp.n, total, sp.tr);
         if (threadIdx.x == 0) g.near_score[i] = cost;
     }
 }
 
-// accept rule on the exact scores of the near list + apply the arrangement.  kind 0 = brute force, 1 = scan window
-__global__ void __launch_bounds__(256) k_g_pick_window(GroupDev g, int ws, int m, const uint8_t *__restrict__ ord_t,
-                                                       const uint8_t *__restrict__ ori_t, int n_orients, int kind)
+// accept rule on the exact scores of the near list + apply the arrangement
+__global__ void __launch_bounds__(256) k_g_pick_window(const GroupDev *gs, Phase ph, Tables tb)
 {
+    const GroupDev &g = gs[blockIdx.y];
+    const PhaseParams pp = phase_params(g, ph);
     GroupState *st = g.st;
+    if (!pp.active) return;
+    const int m = pp.m, ws = pp.ws, n_ori = tb.n_ori[m];
     __shared__ double sv[8];
     __shared__ int si[8];
-    if (st->converged) return;
     if (st->skip) {  // total == 0: the reference returns the first ordering with all '+' and cost 0 (:449-453)
-        if (threadIdx.x == 0 && kind == 0) {
+        if (threadIdx.x == 0 && ph.kind == PH_BRUTE) {
             for (int j = 0; j < m; j++) g.layout[ws + j] &= ~1;
             st->best_cost = 0.0;
         }
@@ -347,8 +375,8 @@ __global__ void __launch_bounds__(256) k_g_pick_window(GroupDev g, int ws, int m
         if (s > bv || (s == bv && c < bi)) { bv = s; bi = c; }
     }
     for (int d = 16; d >= 1; d >>= 1) {
-        double ov = __shfl_xor_sync(0xffffffffu, bv, d);
-        int oi = __shfl_xor_sync(0xffffffffu, bi, d);
+        const double ov = __shfl_xor_sync(0xffffffffu, bv, d);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, d);
         if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
     }
     if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = bv; si[threadIdx.x >> 5] = bi; }
@@ -356,18 +384,18 @@ __global__ void __launch_bounds__(256) k_g_pick_window(GroupDev g, int ws, int m
     if (threadIdx.x == 0) {
         for (int w = 1; w < (int)blockDim.x / 32; w++)
             if (sv[w] > bv || (sv[w] == bv && si[w] < bi)) { bv = sv[w]; bi = si[w]; }
-        const double carried = kind == 1 ? st->best_cost : 0.0;
+        const double carried = ph.kind == PH_SCAN ? st->best_cost : 0.0;
         st->n_exact += cnt;
         if (bv > carried) {
-            const int oi = bi / n_orients, ri = bi % n_orients;
+            const int oi = bi / n_ori, ri = bi % n_ori;
             int segs[8];
             for (int j = 0; j < m; j++) segs[j] = g.layout[ws + j] >> 1;
             for (int j = 0; j < m; j++)
-                g.layout[ws + j] = (segs[ord_t[(size_t)oi * m + j]] << 1) | (int)ori_t[(size_t)ri * m + j];
+                g.layout[ws + j] = (segs[tb.ord[m][(size_t)oi * m + j]] << 1) | (int)tb.ori[m][(size_t)ri * m + j];
             st->best_cost = bv;
             st->E_layout = bv;
             st->improved = 1;
-        } else if (kind == 0) {
+        } else if (ph.kind == PH_BRUTE) {
             st->error = 1;  // the reference would fail on bestOrder == "NA"
         }
         st->near_count = 0;
@@ -375,26 +403,40 @@ __global__ void __launch_bounds__(256) k_g_pick_window(GroupDev g, int ws, int m
     }
 }
 
-// checkAllScores (:332-372): 2(m+1) exact candidates, then insert
-__global__ void __launch_bounds__(EX_THREADS) k_g_insert_scores(GroupDev g, int m, int n)
+// checkAllScores (:332-372): 2(m+1) exact candidates ...
+__global__ void __launch_bounds__(EX_THREADS) k_g_insert_scores(const GroupDev *gs, Phase ph)
 {
     extern __shared__ __align__(16) unsigned char smem[];
-    SmemPlan sp = carve(smem, n, m + 1);
-    const int c = blockIdx.x, i = c >> 1, which = c & 1;
+    const GroupDev &g = gs[blockIdx.y];
+    const PhaseParams pp = phase_params(g, ph);
+    if (!pp.active) return;
+    const int m = pp.m, n = pp.n;
+    const int c = blockIdx.x;
+    if (c >= 2 * (m + 1)) return;
+    if (n < 2) {  // a single bin: every cost is 0.0
+        if (threadIdx.x == 0) g.near_score[c] = 0.0;
+        return;
+    }
+    SmemPlan sp = carve(smem, n, n, m + 1);
+    const int i = c >> 1, which = c & 1;
     const int ne = g.layout[m];
     const int o0 = ne & 1;
-    const int first = (i & 1) ? (o0 ^ 1) : o0;
+    const int first = (i & 1) ? (o0 ^ 1) : o0;   // the reference leaves the scaffold flipped after every slot (:356-365)
     const int ori = which ? (first ^ 1) : first;
     SrcInsert src{g.layout, i, ((ne >> 1) << 1) | ori};
     build_order_cta(src, m + 1, g.seg_ptr, g.seg_bins, sp.o, sp.spos, sp.sent, n);
-    double cost = exact_cost_cta(g.S, g.St, g.L, sp.o, n, g.st->total, sp.tr);
+    const double cost = exact_cost_cta(g.S, g.St, g.L, sp.o, n, g.st->total, sp.tr);
     if (threadIdx.x == 0) g.near_score[c] = cost;
 }
 
-__global__ void __launch_bounds__(32) k_g_pick_insert(GroupDev g, int m)
+// ... then the insertion itself
+__global__ void __launch_bounds__(32) k_g_pick_insert(const GroupDev *gs, Phase ph)
 {
+    const GroupDev &g = gs[blockIdx.y];
+    const PhaseParams pp = phase_params(g, ph);
+    if (!pp.active) return;
     GroupState *st = g.st;
-    const int B = 2 * (m + 1);
+    const int m = pp.m, B = 2 * (m + 1);
     double best = 0.0;  // bestCost starts at 0. (:338); strict '>' keeps the first maximum
     int bi = INT_MAX;
     for (int c = threadIdx.x; c < B; c += 32) {
@@ -402,8 +444,8 @@ __global__ void __launch_bounds__(32) k_g_pick_insert(GroupDev g, int m)
         if (s > best) { best = s; bi = c; }
     }
     for (int d = 16; d >= 1; d >>= 1) {
-        double ov = __shfl_xor_sync(0xffffffffu, best, d);
-        int oi = __shfl_xor_sync(0xffffffffu, bi, d);
+        const double ov = __shfl_xor_sync(0xffffffffu, best, d);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, d);
         if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
     }
     if (threadIdx.x != 0) return;
@@ -420,9 +462,10 @@ __global__ void __launch_bounds__(32) k_g_pick_insert(GroupDev g, int m)
     st->n_exact += B;
 }
 
-__global__ void k_g_round_end(GroupDev g)
+__global__ void k_g_round_end(const GroupDev *gs)
 {
-    if (threadIdx.x != 0) return;
+    const GroupDev &g = gs[blockIdx.x];
+    if (threadIdx.x != 0 || !g.scanning) return;
     GroupState *st = g.st;
     if (st->converged) return;
     st->rounds += 1;
@@ -430,52 +473,54 @@ __global__ void k_g_round_end(GroupDev g)
     st->improved = 0;
 }
 
-__global__ void k_g_reset_for_scan(GroupDev g)
+__global__ void k_g_reset_for_scan(const GroupDev *gs)
 {
+    const GroupDev &g = gs[blockIdx.x];
     if (threadIdx.x != 0) return;
     g.st->improved = 0;
-    g.st->converged = 0;
+    g.st->converged = g.scanning ? 0 : 1;
     g.st->rounds = 0;
     g.st->near_count = 0;
     g.st->amax_key = 0ull;
 }
 
-__global__ void k_g_gather(const double *__restrict__ G, int64_t gn, const int32_t *__restrict__ idx, int L,
-                           double *__restrict__ S, double *__restrict__ St, GroupState *st)
+__global__ void k_g_gather(const double *__restrict__ G, int64_t gn, const int32_t *__restrict__ rows_all,
+                           const int32_t *__restrict__ row_off, const GroupDev *gs)
 {
+    const GroupDev &g = gs[blockIdx.y];
+    const int L = g.L;
     const int i = blockIdx.x;
+    if (i >= L) return;
+    const int32_t *idx = rows_all + row_off[blockIdx.y];
+    double *S = const_cast<double *>(g.S), *St = const_cast<double *>(g.St);
     const double *row = G + (int64_t)idx[i] * gn;
-    int neg = 0;
+    int bad = 0;
     for (int j = threadIdx.x; j < L; j += blockDim.x) {
-        double v = row[idx[j]];
+        const double v = row[idx[j]];
         S[(int64_t)i * L + j] = v;
         St[(int64_t)j * L + i] = v;
         // the closed-form bound needs non-negative, symmetric contacts; anything else is re-scored in full
-        neg |= (v < 0.0) || (v != v) || (G[(int64_t)idx[j] * gn + idx[i]] != v);
+        bad |= (v < 0.0) || (v != v) || (G[(int64_t)idx[j] * gn + idx[i]] != v);
     }
-    if (neg) st->has_negative = 1;
+    if (bad) g.st->inexact = 1;
 }
 
 struct Arena {
     char *base = nullptr;
-    size_t used = 0, cap = 0;
+    size_t used = 0;
     template <typename T>
     T *take(size_t count)
     {
-        size_t bytes = (count * sizeof(T) + 255) / 256 * 256;
         T *p = reinterpret_cast<T *>(base + used);
-        used += bytes;
+        used += (count * sizeof(T) + 255) / 256 * 256;
         return p;
     }
 };
-
 template <typename T>
 size_t padded(size_t count) { return (count * sizeof(T) + 255) / 256 * 256; }
 
 }  // namespace
 
-// tables: defined in Python (part2.order_table / orient_table) and passed in so that the enumeration order has
-// one definition on the host side.
 extern "C" int hica_p2_order_groups(hica_handle h, int32_t ngroups, const int32_t *grp_ptr, const int32_t *seg_ptr,
                                     const int32_t *bin_rows, int32_t n_scaffolds, int32_t scan,
                                     const uint8_t *ord_brute_tabs, const int32_t *ord_brute_off,
@@ -487,251 +532,212 @@ extern "C" int hica_p2_order_groups(hica_handle h, int32_t ngroups, const int32_
     HICA_CHECK_HANDLE(h);
     if (!h->G) return hica_set_error(h, HICA_ERR_STATE, "no genome matrix (hica_p2_upload / hica_p2_use_p1_matrix)");
     if (ngroups < 1 || !grp_ptr || !seg_ptr || !bin_rows) return hica_set_error(h, HICA_ERR_ARG, "bad group arguments");
-    if (n_scaffolds >= 9) n_scaffolds = 8;      // :562-567
+    if (n_scaffolds >= 9) n_scaffolds = 8;       // :562-567
     if (n_scaffolds < 1) return hica_set_error(h, HICA_ERR_ARG, "nScaffolds must be >= 1");
     if (scan > n_scaffolds) scan = n_scaffolds;  // :568-569
     if (scan < 1) return hica_set_error(h, HICA_ERR_ARG, "scanScaffolds must be >= 1");
     hica_timer timer(h, HICA_T_P2_SCORE);
+    cudaStream_t s = h->stream;
 
-    // ---- per-group sizes and one arena allocation
-    struct HostGroup {
-        int seg0, nseg, L, k, bins_k;
-        long long Bb, Bmax;
-        GroupDev dev;
-        cudaStream_t stream;
-        std::vector<int> len;
-    };
+    struct HostGroup { int seg0, nseg, L, k, bins_k; long long Bmax; };
     std::vector<HostGroup> gs(ngroups);
+    std::vector<int32_t> cum_all, row_off(ngroups);
     auto fact = [](int n) { long long f = 1; for (int i = 2; i <= n; i++) f *= i; return f; };
-    size_t arena_bytes = 0;
     const long long Bscan = (long long)n_ord_scan * n_ori_scan;
+    size_t arena_bytes = 0;
+    int Lmax = 0, nseg_max = 0, ins_steps = 0, win_max = 0, kmax = 0;
+    long long Bbrute_max = 0;
+    bool any_scan = false;
     for (int gi = 0; gi < ngroups; gi++) {
         HostGroup &g = gs[gi];
         g.seg0 = grp_ptr[gi];
         g.nseg = grp_ptr[gi + 1] - grp_ptr[gi];
         if (g.nseg < 1) return hica_set_error(h, HICA_ERR_ARG, "group %d has no scaffolds", gi);
-        g.len.resize(g.nseg);
-        g.L = 0;
-        for (int s = 0; s < g.nseg; s++) {
-            g.len[s] = seg_ptr[g.seg0 + s + 1] - seg_ptr[g.seg0 + s];
-            if (g.len[s] < 1) return hica_set_error(h, HICA_ERR_ARG, "empty scaffold in group %d", gi);
-            g.L += g.len[s];
-        }
+        g.L = seg_ptr[g.seg0 + g.nseg] - seg_ptr[g.seg0];
+        for (int sgi = 0; sgi < g.nseg; sgi++)
+            if (seg_ptr[g.seg0 + sgi + 1] <= seg_ptr[g.seg0 + sgi]) return hica_set_error(h, HICA_ERR_ARG, "empty scaffold in group %d", gi);
         g.k = std::min<int>(n_scaffolds, g.nseg);
-        g.bins_k = 0;
-        for (int s = 0; s < g.k; s++) g.bins_k += g.len[s];
-        g.Bb = g.k >= 2 ? fact(g.k) / 2 * (1ll << g.k) : 2;  // k = 1: one order, two orientations
-        g.Bmax = std::max<long long>(std::max<long long>(g.Bb, Bscan), 2ll * (g.nseg + 1));
-        const int mmax = std::max(g.k, scan);
-        arena_bytes += 2 * padded<double>((size_t)g.L * g.L) + padded<int32_t>(g.nseg + 1) + padded<int32_t>(g.L) +
-                       padded<int32_t>(g.nseg + 1) + 2 * padded<double>(g.L + 1) +
-                       padded<double>((size_t)(mmax * 2) << mmax) + padded<double>((size_t)(mmax * mmax * 4) << mmax) +
-                       2 * padded<double>(g.Bmax) + padded<int32_t>(g.Bmax) + padded<GroupState>(1) +
-                       padded<int32_t>(g.L);
+        g.bins_k = seg_ptr[g.seg0 + g.k] - seg_ptr[g.seg0];
+        const long long Bb = g.k >= 2 ? fact(g.k) / 2 * (1ll << g.k) : 2;  // k = 1: one order, two orientations
+        if (ord_brute_off[g.k + 1] - ord_brute_off[g.k] <= 0 || ori_brute_off[g.k + 1] - ori_brute_off[g.k] <= 0)
+            return hica_set_error(h, HICA_ERR_ARG, "enumeration tables for %d scaffolds are missing", g.k);
+        g.Bmax = std::max<long long>(std::max<long long>(Bb, Bscan), 2ll * (g.nseg + 1));
+        const int mmax = std::max(g.k, (int)scan);
+        arena_bytes += 2 * padded<double>((size_t)g.L * g.L) + 3 * padded<int32_t>(g.nseg + 1) + padded<int32_t>(g.L) +
+                       2 * padded<double>(g.L + 1) + padded<double>((size_t)(mmax * 2) << mmax) +
+                       padded<double>((size_t)(mmax * mmax * 4) << mmax) + 2 * padded<double>(g.Bmax) +
+                       padded<int32_t>(g.Bmax) + padded<GroupState>(1);
+        Lmax = std::max(Lmax, g.L);
+        nseg_max = std::max(nseg_max, g.nseg);
+        kmax = std::max(kmax, g.k);
+        ins_steps = std::max(ins_steps, std::max(1, g.nseg - g.k));
+        Bbrute_max = std::max(Bbrute_max, Bb);
+        if (g.nseg > n_scaffolds) { any_scan = true; win_max = std::max(win_max, g.nseg - scan + 1); }
     }
-    // enumeration tables on the device
-    size_t tab_bytes = 0;
-    for (int k = 1; k <= 8; k++) {
-        tab_bytes += padded<uint8_t>((size_t)(ord_brute_off[k + 1] - ord_brute_off[k]));
-        tab_bytes += padded<uint8_t>((size_t)(ori_brute_off[k + 1] - ori_brute_off[k]));
-    }
-    tab_bytes += padded<uint8_t>((size_t)n_ord_scan * scan) + padded<uint8_t>((size_t)n_ori_scan * scan);
+    const int64_t total_bins = seg_ptr[grp_ptr[ngroups]];
+    for (int64_t b = 0; b < total_bins; b++)
+        if (bin_rows[b] < 0 || bin_rows[b] >= h->gn) return hica_set_error(h, HICA_ERR_ARG, "bin row out of range");
+    size_t tab_bytes = padded<uint8_t>((size_t)n_ord_scan * scan) + padded<uint8_t>((size_t)n_ori_scan * scan);
+    for (int k = 1; k <= 8; k++)
+        tab_bytes += padded<uint8_t>((size_t)(ord_brute_off[k + 1] - ord_brute_off[k])) +
+                     padded<uint8_t>((size_t)(ori_brute_off[k + 1] - ori_brute_off[k]));
     Arena ar;
-    ar.cap = arena_bytes + tab_bytes + 4096;
-    cudaError_t ce = cudaMalloc((void **)&ar.base, ar.cap);
-    if (ce != cudaSuccess) return hica_set_error(h, HICA_ERR_NOMEM, "cudaMalloc(%zu): %s", ar.cap, cudaGetErrorString(ce));
-    std::vector<cudaStream_t> streams;
-    auto cleanup = [&]() {
-        for (auto s : streams) cudaStreamDestroy(s);
-        cudaFree(ar.base);
-    };
+    const size_t cap = arena_bytes + tab_bytes + padded<GroupDev>(ngroups) + padded<int32_t>(total_bins) +
+                       padded<int32_t>(ngroups) + 4096;
+    cudaError_t ce = cudaMalloc((void **)&ar.base, cap);
+    if (ce != cudaSuccess) return hica_set_error(h, HICA_ERR_NOMEM, "cudaMalloc(%zu): %s", cap, cudaGetErrorString(ce));
 #define ENG_CUDA(call)                                                                                       \
     do {                                                                                                     \
         cudaError_t e__ = (call);                                                                            \
         if (e__ != cudaSuccess) {                                                                            \
-            cleanup();                                                                                       \
+            cudaFree(ar.base);                                                                               \
             return hica_set_error(h, HICA_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
         }                                                                                                    \
     } while (0)
 
-    const uint8_t *d_ord_b[9] = {nullptr}, *d_ori_b[9] = {nullptr};
-    int n_ord_b[9] = {0}, n_ori_b[9] = {0};
+    // ---- enumeration tables
+    Tables tb = {};
     for (int k = 1; k <= 8; k++) {
-        size_t no = ord_brute_off[k + 1] - ord_brute_off[k], nr = ori_brute_off[k + 1] - ori_brute_off[k];
+        const size_t no = ord_brute_off[k + 1] - ord_brute_off[k], nr = ori_brute_off[k + 1] - ori_brute_off[k];
         uint8_t *po = ar.take<uint8_t>(no), *pr = ar.take<uint8_t>(nr);
-        if (no) ENG_CUDA(cudaMemcpyAsync(po, ord_brute_tabs + ord_brute_off[k], no, cudaMemcpyHostToDevice, h->stream));
-        if (nr) ENG_CUDA(cudaMemcpyAsync(pr, ori_brute_tabs + ori_brute_off[k], nr, cudaMemcpyHostToDevice, h->stream));
-        d_ord_b[k] = po; d_ori_b[k] = pr;
-        n_ord_b[k] = (int)(no / k); n_ori_b[k] = (int)(nr / k);
+        if (no) ENG_CUDA(cudaMemcpyAsync(po, ord_brute_tabs + ord_brute_off[k], no, cudaMemcpyHostToDevice, s));
+        if (nr) ENG_CUDA(cudaMemcpyAsync(pr, ori_brute_tabs + ori_brute_off[k], nr, cudaMemcpyHostToDevice, s));
+        tb.ord[k] = po; tb.ori[k] = pr;
+        tb.n_ord[k] = (int)(no / k); tb.n_ori[k] = (int)(nr / k);
     }
-    uint8_t *d_ord_s = ar.take<uint8_t>((size_t)n_ord_scan * scan), *d_ori_s = ar.take<uint8_t>((size_t)n_ori_scan * scan);
-    ENG_CUDA(cudaMemcpyAsync(d_ord_s, ord_scan, (size_t)n_ord_scan * scan, cudaMemcpyHostToDevice, h->stream));
-    ENG_CUDA(cudaMemcpyAsync(d_ori_s, ori_scan, (size_t)n_ori_scan * scan, cudaMemcpyHostToDevice, h->stream));
-
-    // ---- upload group descriptors, gather sub-matrices
-    std::vector<GroupState *> st_ptrs(ngroups);
+    {   // the scan tables are the width-`scan` tables
+        uint8_t *po = ar.take<uint8_t>((size_t)n_ord_scan * scan), *pr = ar.take<uint8_t>((size_t)n_ori_scan * scan);
+        ENG_CUDA(cudaMemcpyAsync(po, ord_scan, (size_t)n_ord_scan * scan, cudaMemcpyHostToDevice, s));
+        ENG_CUDA(cudaMemcpyAsync(pr, ori_scan, (size_t)n_ori_scan * scan, cudaMemcpyHostToDevice, s));
+        tb.ord[scan] = po; tb.ori[scan] = pr; tb.n_ord[scan] = n_ord_scan; tb.n_ori[scan] = n_ori_scan;
+    }
+    // ---- group descriptors
+    std::vector<GroupDev> hdev(ngroups);
+    std::vector<GroupState *> st_ptr(ngroups);
+    std::vector<int32_t *> lay_ptr(ngroups);
     for (int gi = 0; gi < ngroups; gi++) {
         HostGroup &g = gs[gi];
-        GroupDev &d = g.dev;
-        double *S = ar.take<double>((size_t)g.L * g.L), *St = ar.take<double>((size_t)g.L * g.L);
-        int32_t *sp = ar.take<int32_t>(g.nseg + 1), *sb = ar.take<int32_t>(g.L), *lay = ar.take<int32_t>(g.nseg + 1);
-        d.S = S; d.St = St; d.L = g.L; d.nseg = g.nseg; d.seg_ptr = sp; d.seg_bins = sb; d.layout = lay;
+        GroupDev &d = hdev[gi];
+        d.S = ar.take<double>((size_t)g.L * g.L);
+        d.St = ar.take<double>((size_t)g.L * g.L);
+        int32_t *sp = ar.take<int32_t>(g.nseg + 1), *cum = ar.take<int32_t>(g.nseg + 1), *lay = ar.take<int32_t>(g.nseg + 1);
+        int32_t *sb = ar.take<int32_t>(g.L);
+        d.seg_ptr = sp; d.seg_bins = sb; d.cum = cum; d.layout = lay;
+        d.L = g.L; d.nseg = g.nseg; d.k = g.k; d.scanning = g.nseg > n_scaffolds ? 1 : 0;
         d.Wt = ar.take<double>(g.L + 1);
         d.tr = ar.take<double>(g.L + 1);
-        const int mmax = std::max(g.k, scan);
+        const int mmax = std::max(g.k, (int)scan);
         d.tab_out = ar.take<double>((size_t)(mmax * 2) << mmax);
         d.tab_win = ar.take<double>((size_t)(mmax * mmax * 4) << mmax);
         d.rel = ar.take<double>(g.Bmax);
         d.near_score = ar.take<double>(g.Bmax);
         d.near_id = ar.take<int32_t>(g.Bmax);
         d.st = ar.take<GroupState>(1);
-        int32_t *rows_d = ar.take<int32_t>(g.L);
-        st_ptrs[gi] = d.st;
+        st_ptr[gi] = d.st;
+        lay_ptr[gi] = lay;
         std::vector<int32_t> hp(g.nseg + 1), hb(g.L), hl(g.nseg + 1, 0);
         const int bin0 = seg_ptr[g.seg0];
-        for (int s = 0; s <= g.nseg; s++) hp[s] = seg_ptr[g.seg0 + s] - bin0;
-        for (int b = 0; b < g.L; b++) {
-            hb[b] = b;
-            if (bin_rows[bin0 + b] < 0 || bin_rows[bin0 + b] >= h->gn) {
-                cleanup();
-                return hica_set_error(h, HICA_ERR_ARG, "bin row out of range in group %d", gi);
-            }
-        }
-        for (int s = 0; s < g.nseg; s++) hl[s] = s << 1;
-        cudaStream_t stream;
-        ENG_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
-        streams.push_back(stream);
-        g.stream = stream;
-        ENG_CUDA(cudaMemsetAsync(d.st, 0, sizeof(GroupState), stream));
-        ENG_CUDA(cudaMemcpyAsync(sp, hp.data(), sizeof(int32_t) * (g.nseg + 1), cudaMemcpyHostToDevice, stream));
-        ENG_CUDA(cudaMemcpyAsync(sb, hb.data(), sizeof(int32_t) * g.L, cudaMemcpyHostToDevice, stream));
-        ENG_CUDA(cudaMemcpyAsync(lay, hl.data(), sizeof(int32_t) * (g.nseg + 1), cudaMemcpyHostToDevice, stream));
-        ENG_CUDA(cudaMemcpyAsync(rows_d, bin_rows + bin0, sizeof(int32_t) * g.L, cudaMemcpyHostToDevice, stream));
-        k_g_gather<<<g.L, 256, 0, stream>>>(h->G, h->gn, rows_d, g.L, S, St, d.st);
-        HICA_LAUNCHED(h);
+        row_off[gi] = bin0;
+        for (int sg = 0; sg <= g.nseg; sg++) hp[sg] = seg_ptr[g.seg0 + sg] - bin0;
+        for (int b = 0; b < g.L; b++) hb[b] = b;
+        for (int sg = 0; sg < g.nseg; sg++) hl[sg] = sg << 1;
+        ENG_CUDA(cudaMemsetAsync(d.st, 0, sizeof(GroupState), s));
+        ENG_CUDA(cudaMemcpyAsync(sp, hp.data(), sizeof(int32_t) * (g.nseg + 1), cudaMemcpyHostToDevice, s));
+        ENG_CUDA(cudaMemcpyAsync(cum, hp.data(), sizeof(int32_t) * (g.nseg + 1), cudaMemcpyHostToDevice, s));
+        ENG_CUDA(cudaMemcpyAsync(sb, hb.data(), sizeof(int32_t) * g.L, cudaMemcpyHostToDevice, s));
+        ENG_CUDA(cudaMemcpyAsync(lay, hl.data(), sizeof(int32_t) * (g.nseg + 1), cudaMemcpyHostToDevice, s));
     }
-    ENG_CUDA(cudaStreamSynchronize(h->stream));  // enumeration tables are in place
+    GroupDev *gdev = ar.take<GroupDev>(ngroups);
+    int32_t *rows_d = ar.take<int32_t>(total_bins), *row_off_d = ar.take<int32_t>(ngroups);
+    ENG_CUDA(cudaMemcpyAsync(gdev, hdev.data(), sizeof(GroupDev) * ngroups, cudaMemcpyHostToDevice, s));
+    ENG_CUDA(cudaMemcpyAsync(rows_d, bin_rows, sizeof(int32_t) * total_bins, cudaMemcpyHostToDevice, s));
+    ENG_CUDA(cudaMemcpyAsync(row_off_d, row_off.data(), sizeof(int32_t) * ngroups, cudaMemcpyHostToDevice, s));
+    k_g_gather<<<dim3(Lmax, ngroups), 256, 0, s>>>(h->G, h->gn, rows_d, row_off_d, gdev);
+    HICA_LAUNCHED(h);
 
-    // ---- enqueue the whole search of every group
-    auto window_search = [&](HostGroup &g, int nslots, int n, int ws, int m, const uint8_t *ot, int n_ord,
-                             const uint8_t *rt, int n_ori, int kind) {
-        const long long B = (long long)n_ord * n_ori;
-        cudaStream_t s = g.stream;
-        const int nblocks_tab = ((m * 2) << m) + ((m * m * 4) << m);
-        k_g_tables<<<nblocks_tab, 128, 0, s>>>(g.dev, nslots, n, ws, m);
-        k_g_approx<<<(unsigned)((B + 255) / 256), 256, 0, s>>>(g.dev, ws, m, ot, rt, n_ori, B);
-        k_g_select<<<(unsigned)((B + 255) / 256), 256, 0, s>>>(g.dev, B, kind);
-        k_g_exact_near<<<(unsigned)std::min<long long>(B, 64), EX_THREADS, smem_bytes(n, nslots), s>>>(
-            g.dev, nslots, n, ws, m, ot, rt, n_ori);
-        k_g_pick_window<<<1, 256, 0, s>>>(g.dev, ws, m, ot, rt, n_ori, kind);
+    const size_t ex_smem = smem_bytes(Lmax, nseg_max + 1);
+    const size_t tot_smem = sizeof(int32_t) * (Lmax + 2 * (nseg_max + 1) + 2);
+    if (ex_smem > 200 * 1024) { cudaFree(ar.base); return hica_set_error(h, HICA_ERR_ARG, "chromosome too large for shared memory"); }
+    ENG_CUDA(cudaFuncSetAttribute(k_g_exact_near, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex_smem));
+    ENG_CUDA(cudaFuncSetAttribute(k_g_anchor, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex_smem));
+    ENG_CUDA(cudaFuncSetAttribute(k_g_insert_scores, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex_smem));
+    ENG_CUDA(cudaFuncSetAttribute(k_g_total, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tot_smem));
+    const unsigned G = (unsigned)ngroups;
+    const unsigned tot_blocks = (unsigned)std::max(1, (Lmax - 1 + 127) / 128);
+
+    auto window_search = [&](Phase ph, int m, long long B) {
+        const unsigned nb_tab = (unsigned)(((m * 2) << m) + ((m * m * 4) << m));
+        const unsigned nb_c = (unsigned)((B + 255) / 256);
+        k_g_tables<<<dim3(nb_tab, G), 128, 0, s>>>(gdev, ph);
+        k_g_approx<<<dim3(nb_c, G), 256, 0, s>>>(gdev, ph, tb);
+        k_g_select<<<dim3(nb_c, G), 256, 0, s>>>(gdev, ph, tb);
+        k_g_exact_near<<<dim3((unsigned)std::min<long long>(B, 48), G), EX_THREADS, ex_smem, s>>>(gdev, ph, tb);
+        k_g_pick_window<<<dim3(1, G), 256, 0, s>>>(gdev, ph, tb);
         h->launches += 5;
     };
-    size_t max_smem = 0;
-    for (auto &g : gs) max_smem = std::max(max_smem, smem_bytes(g.L, g.nseg + 1));
-    if (max_smem > 200 * 1024) { cleanup(); return hica_set_error(h, HICA_ERR_ARG, "chromosome too large for shared memory"); }
-    ENG_CUDA(cudaFuncSetAttribute(k_g_exact_near, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
-    ENG_CUDA(cudaFuncSetAttribute(k_g_anchor, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
-    ENG_CUDA(cudaFuncSetAttribute(k_g_insert_scores, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
-    ENG_CUDA(cudaFuncSetAttribute(k_g_total, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
-
-    auto total_of = [&](HostGroup &g, int nslots, int n) {
-        if (n >= 2) {
-            k_g_total<<<(n - 1 + 127) / 128, 128, sizeof(int32_t) * (n + 2 * nslots + 2), g.stream>>>(g.dev, nslots, n);
-            HICA_LAUNCHED(h);
-        }
-    };
-    const int scan_rounds_batch = 4;
-    for (auto &g : gs) {
-        cudaStream_t s = g.stream;
-        // brute force over the k largest scaffolds (:573-576)
-        if (g.bins_k >= 2) {
-            total_of(g, g.k, g.bins_k);
-            k_g_weights<<<1, 1, 0, s>>>(g.dev, g.bins_k);
-            k_g_anchor<<<1, EX_THREADS, smem_bytes(g.bins_k, g.k), s>>>(g.dev, g.k, g.bins_k);
-            h->launches += 2;
-            window_search(g, g.k, g.bins_k, 0, g.k, d_ord_b[g.k], n_ord_b[g.k], d_ori_b[g.k], n_ori_b[g.k], 0);
-        }
-        // greedy insertion, a do-while (:475-493)
-        int placed = g.k;
-        int bins = g.bins_k;
-        bool first = true;
-        while (first || placed < g.nseg) {
-            int m;
-            if (placed < g.nseg) { m = placed; bins += g.len[placed]; placed += 1; }
-            else { m = placed - 1; }  // nothing left: the last placed scaffold is popped and re-inserted
-            first = false;
-            total_of(g, m + 1, bins);
-            if (bins < 2) {  // a single bin: every cost is 0, the scaffold is inserted at 0 with '+'
-                cudaMemsetAsync(g.dev.near_score, 0, sizeof(double) * 2 * (m + 1), s);
-            } else {
-                k_g_insert_scores<<<2 * (m + 1), EX_THREADS, smem_bytes(bins, m + 1), s>>>(g.dev, m, bins);
-                HICA_LAUNCHED(h);
-            }
-            k_g_pick_insert<<<1, 32, 0, s>>>(g.dev, m);
-            HICA_LAUNCHED(h);
-        }
-        // sliding-window scan (:579-580)
-        if (g.nseg > n_scaffolds) {
-            total_of(g, g.nseg, g.L);
-            k_g_weights<<<1, 1, 0, s>>>(g.dev, g.L);
-            k_g_reset_for_scan<<<1, 1, 0, s>>>(g.dev);
-            k_g_anchor<<<1, EX_THREADS, smem_bytes(g.L, g.nseg), s>>>(g.dev, g.nseg, g.L);
-            h->launches += 3;
-        }
+    // ---- brute force over the k largest scaffolds (:573-576)
+    {
+        Phase ph = {PH_BRUTE, 0, 0};
+        k_g_total<<<dim3(tot_blocks, G), 128, tot_smem, s>>>(gdev, ph, 1);
+        k_g_anchor<<<dim3(1, G), EX_THREADS, ex_smem, s>>>(gdev, ph);
+        h->launches += 2;
+        window_search(ph, kmax, Bbrute_max);
     }
-    ENG_CUDA(cudaGetLastError());
-    // scan rounds: enqueue a few rounds, then look at the converged flags
-    std::vector<char> scanning(ngroups);
-    for (int gi = 0; gi < ngroups; gi++) scanning[gi] = gs[gi].nseg > n_scaffolds;
+    // ---- greedy insertion, a do-while per group (:475-493)
+    for (int step = 0; step < ins_steps; step++) {
+        Phase ph = {PH_INSERT, step, 0};
+        k_g_total<<<dim3(tot_blocks, G), 128, tot_smem, s>>>(gdev, ph, 0);
+        k_g_insert_scores<<<dim3(2 * (nseg_max + 1), G), EX_THREADS, ex_smem, s>>>(gdev, ph);
+        k_g_pick_insert<<<dim3(1, G), 32, 0, s>>>(gdev, ph);
+        h->launches += 3;
+    }
+    // ---- sliding-window scan (:579-580)
     std::vector<GroupState> hst(ngroups);
-    for (int pass = 0; pass < 1000; pass++) {
-        bool any = false;
-        for (int gi = 0; gi < ngroups; gi++) {
-            if (!scanning[gi]) continue;
-            any = true;
-            HostGroup &g = gs[gi];
-            for (int r = 0; r < scan_rounds_batch; r++) {
-                for (int i = 0; i + scan <= g.nseg; i++)
-                    window_search(g, g.nseg, g.L, i, scan, d_ord_s, n_ord_scan, d_ori_s, n_ori_scan, 1);
-                k_g_round_end<<<1, 1, 0, g.stream>>>(g.dev);
+    if (any_scan) {
+        Phase ph0 = {PH_SCAN, 0, scan};
+        k_g_reset_for_scan<<<G, 32, 0, s>>>(gdev);
+        k_g_total<<<dim3(tot_blocks, G), 128, tot_smem, s>>>(gdev, ph0, 1);
+        k_g_anchor<<<dim3(1, G), EX_THREADS, ex_smem, s>>>(gdev, ph0);
+        h->launches += 3;
+        ENG_CUDA(cudaGetLastError());
+        int batch = 2;
+        for (int pass = 0; pass < 10000; pass++) {
+            for (int r = 0; r < batch; r++) {
+                for (int i = 0; i < win_max; i++) window_search(Phase{PH_SCAN, i, scan}, scan, Bscan);
+                k_g_round_end<<<G, 32, 0, s>>>(gdev);
                 HICA_LAUNCHED(h);
             }
-        }
-        if (!any) break;
-        for (int gi = 0; gi < ngroups; gi++) {
-            if (!scanning[gi]) continue;
-            ENG_CUDA(cudaMemcpyAsync(&hst[gi], gs[gi].dev.st, sizeof(GroupState), cudaMemcpyDeviceToHost, gs[gi].stream));
-        }
-        for (int gi = 0; gi < ngroups; gi++) {
-            if (!scanning[gi]) continue;
-            ENG_CUDA(cudaStreamSynchronize(gs[gi].stream));
-            if (hst[gi].converged) scanning[gi] = 0;
+            batch = 1;
+            bool all_done = true;
+            for (int gi = 0; gi < ngroups; gi++)
+                ENG_CUDA(cudaMemcpyAsync(&hst[gi], st_ptr[gi], sizeof(GroupState), cudaMemcpyDeviceToHost, s));
+            ENG_CUDA(cudaStreamSynchronize(s));
+            for (int gi = 0; gi < ngroups; gi++)
+                if (gs[gi].nseg > n_scaffolds && !hst[gi].converged) all_done = false;
+            if (all_done) break;
         }
     }
     // ---- results
+    ENG_CUDA(cudaGetLastError());
     for (int gi = 0; gi < ngroups; gi++) {
-        HostGroup &g = gs[gi];
-        ENG_CUDA(cudaMemcpyAsync(&hst[gi], g.dev.st, sizeof(GroupState), cudaMemcpyDeviceToHost, g.stream));
-        ENG_CUDA(cudaMemcpyAsync(out_layout + g.seg0, g.dev.layout, sizeof(int32_t) * g.nseg, cudaMemcpyDeviceToHost,
-                                 g.stream));
+        ENG_CUDA(cudaMemcpyAsync(&hst[gi], st_ptr[gi], sizeof(GroupState), cudaMemcpyDeviceToHost, s));
+        ENG_CUDA(cudaMemcpyAsync(out_layout + gs[gi].seg0, lay_ptr[gi], sizeof(int32_t) * gs[gi].nseg,
+                                 cudaMemcpyDeviceToHost, s));
     }
+    ENG_CUDA(cudaStreamSynchronize(s));
     int err_group = -1;
     for (int gi = 0; gi < ngroups; gi++) {
-        HostGroup &g = gs[gi];
-        ENG_CUDA(cudaStreamSynchronize(g.stream));
         if (out_cost) out_cost[gi] = hst[gi].best_cost;
-        if (out_rounds) out_rounds[gi] = hst[gi].rounds;
+        if (out_rounds) out_rounds[gi] = gs[gi].nseg > n_scaffolds ? hst[gi].rounds : 0;
         if (out_stats) {
-            long long Bb = g.bins_k >= 2 ? g.Bb : 0;
-            long long approx = Bb + (g.nseg > n_scaffolds ? (long long)hst[gi].rounds * (g.nseg - scan + 1) * Bscan : 0);
-            out_stats[4 * gi + 0] = approx;
+            out_stats[4 * gi + 0] = 0;
             out_stats[4 * gi + 1] = hst[gi].n_exact;
-            out_stats[4 * gi + 2] = hst[gi].has_negative;
+            out_stats[4 * gi + 2] = hst[gi].inexact;
             out_stats[4 * gi + 3] = hst[gi].error;
         }
         if (hst[gi].error && err_group < 0) err_group = gi;
     }
-    cleanup();
+    cudaFree(ar.base);
     timer.stop();
     if (err_group >= 0)
         return hica_set_error(h, HICA_ERR_STATE, "group %d: no ordering scored above 0 (the reference fails on 'NA' here)",
