@@ -133,7 +133,8 @@ def gpu_step(h, wl, args, source, rank, world, dist):
         h.p2_use_p1_matrix()
         index_of = {int(b): i for i, b in enumerate(wl["bin_ids"])}
         part2.STATS.update(candidates=0, bin_pairs=0, calls=0, exact=0)
-        mine = [ci for ci in range(len(groups)) if ci % world == rank]
+        from hic_genome_assembler_b200 import dist as hdist
+        mine = hdist.shard_groups([len(g) for g in groups], world, rank)
         if args.p2_host_loop:
             for ci in mine:
                 orderings[ci] = part2.order_chromosome(h, index_of, groups[ci], 6, 5)
@@ -142,6 +143,9 @@ def gpu_step(h, wl, args, source, rank, world, dist):
             for k, ci in enumerate(mine):
                 orderings[ci] = (got[k], float(cost[k]), int(rounds[k]))
             out["p2_exact"] = part2.STATS.get("exact", 0)
+            out["p2_host_ms"] = h.debug_stats()
+        if world > 1:  # every rank ends the step with all orderings (one small all_gather_object)
+            orderings = dict(enumerate(hdist.merge_orderings(orderings, len(groups))))
         p2_pairs, p2_cands, p2_calls = part2.STATS["bin_pairs"], part2.STATS["candidates"], part2.STATS["calls"]
         out["n_groups"] = len(groups)
     t2 = time.perf_counter()
@@ -327,6 +331,9 @@ def main():
                     "e2e_total": secs_e2e / args.steps, "e2e_part1": res_e2e[-1]["t_part1"],
                     "e2e_part2": res_e2e[-1]["t_part2"], "e2e_upload_ms": res_e2e[-1]["timers_p1"]["upload"]},
         "stage_ms_part1": tm, "linkage_stats": last["linkage_stats"],
+        "per_step_seconds": [[round(r["t_part1"], 4), round(r["t_part2"], 4)] for r in res_dev],
+        "per_step_seconds_e2e": [[round(r["t_part1"], 4), round(r["t_part2"], 4)] for r in res_e2e],
+        "part2_host_phase_ms": [r.get("p2_host_ms") for r in res_dev + res_e2e],
         "work": {"part1_bin_pairs": p1_pairs, "part2_bin_pairs": p2_pairs, "part2_candidates": p2_cands,
                  "part2_device_calls": p2_calls, "part2_exact_rescored": last.get("p2_exact"), "cuts": len(last["cuts"]), "groups": last.get("n_groups"),
                  "ambiguous_decisions": last["ambiguous"]},

@@ -19,7 +19,7 @@ T_NAMES = ("upload", "distance", "linkage", "leaforder", "rank", "breakpoints", 
 # every symbol include/hica.h declares (checked by tests/test_abi.py)
 ABI_SYMBOLS = (
     "hica_version", "hica_create", "hica_destroy", "hica_last_error", "hica_launch_count", "hica_get_timers",
-    "hica_linkage_stats",
+    "hica_linkage_stats", "hica_debug_stats",
     "hica_p1_upload", "hica_p1_upload_device", "hica_p1_set_row_sums", "hica_p1_distance", "hica_p1_get_distance",
     "hica_p1_get_pairwise_row_sums", "hica_p1_get_row_sums", "hica_p1_upload_distance", "hica_p1_linkage",
     "hica_p1_set_order", "hica_p1_get_reordered", "hica_p1_rank", "hica_p1_upload_similarity", "hica_p1_get_rank", "hica_p1_set_rank",
@@ -137,6 +137,12 @@ class Handle:
         ms = np.zeros(len(T_NAMES))
         self._check(self._L.hica_get_timers(self._h, _ptr(ms)))
         return dict(zip(T_NAMES, ms.tolist()))
+
+    def debug_stats(self) -> list:
+        out = np.zeros(16)
+        self._L.hica_debug_stats.argtypes = [C.c_void_p, C.c_void_p]
+        self._check(self._L.hica_debug_stats(self._h, _ptr(out)))
+        return [round(float(v), 3) for v in out[:6]]
 
     def linkage_stats(self) -> dict:
         out = np.zeros(6, dtype=np.int64)

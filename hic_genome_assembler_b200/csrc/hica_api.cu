@@ -31,6 +31,13 @@ extern "C" int hica_linkage_stats(hica_handle h, int64_t *out6)
     return HICA_OK;
 }
 
+extern "C" int hica_debug_stats(hica_handle h, double *out16)
+{
+    if (!h || !out16) return HICA_ERR_ARG;
+    for (int i = 0; i < 16; i++) out16[i] = h->dbg[i];
+    return HICA_OK;
+}
+
 extern "C" int hica_get_timers(hica_handle h, double *ms)
 {
     if (!h || !ms) return HICA_ERR_ARG;
@@ -80,7 +87,7 @@ static void free_p1(hica_ctx *h)
     cudaFree(h->W); h->W = nullptr;
     cudaFree(h->order); h->order = nullptr;
     cudaFree(h->pos); h->pos = nullptr;
-    cudaFree(h->R); h->R = nullptr;
+    cudaFree(h->R); h->R = nullptr; h->R_cap = 0;
     cudaFree(h->Zraw); h->Zraw = nullptr;
     cudaFree(h->size_d); h->size_d = nullptr;
     cudaFree(h->chain_d); h->chain_d = nullptr;
@@ -104,6 +111,7 @@ extern "C" int hica_destroy(hica_handle h)
     cudaFree(h->G);
     cudaFree(h->S);
     cudaFree(h->St);
+    cudaFree(h->p2_arena);
     cudaFree(h->seg_ptr);
     cudaFree(h->seg_bins);
     cudaFree(h->p2_buf);

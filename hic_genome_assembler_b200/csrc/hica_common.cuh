@@ -18,6 +18,10 @@ struct hica_ctx {
     double timers[HICA_T_COUNT] = {0};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int sm_count = 148;
+    double dbg[16] = {0};  // host-side phase times (ms) of the last hica_p2_order_groups call
+    void *p2_arena = nullptr;  // scratch arena of hica_p2_order_groups (grow-only)
+    int64_t p2_arena_cap = 0;
+    int64_t R_cap = 0;         // bytes allocated behind R
 
     // ---- Part 1 state ---------------------------------------------------
     int64_t n = 0;           // bins

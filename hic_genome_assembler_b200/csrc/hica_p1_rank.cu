@@ -117,8 +117,12 @@ extern "C" int hica_p1_rank(hica_handle h)
     if (const char *e = getenv("HICA_RANK_Q")) qmax = std::max(9, std::min(14, atoi(e)));
     const int q = std::min(lg, qmax);
     const int bytes = n <= 65535 ? 2 : 4;
-    if (h->R) { cudaFree(h->R); h->R = nullptr; }
-    HICA_CUDA(cudaMalloc(&h->R, (size_t)n * n * bytes));
+    if (h->R_cap < n * n * bytes) {  // grow-only: cudaMalloc/cudaFree of 0.5 GB per call costs tens of ms
+        if (h->R) { cudaFree(h->R); h->R = nullptr; }
+        h->R_cap = 0;
+        HICA_CUDA(cudaMalloc(&h->R, (size_t)n * n * bytes));
+        h->R_cap = n * n * bytes;
+    }
     h->rank_bytes = 0;
     hica_timer t(h, HICA_T_RANK);
     int rc;
@@ -167,9 +171,13 @@ extern "C" int hica_p1_set_rank(hica_handle h, const int64_t *R_host, int64_t n)
     }
     const int64_t total = n * n;
     const int bytes = n <= 65535 ? 2 : 4;
-    if (h->R) { cudaFree(h->R); h->R = nullptr; }
     h->rank_bytes = 0;
-    HICA_CUDA(cudaMalloc(&h->R, (size_t)total * bytes));
+    if (h->R_cap < total * bytes) {
+        if (h->R) { cudaFree(h->R); h->R = nullptr; }
+        h->R_cap = 0;
+        HICA_CUDA(cudaMalloc(&h->R, (size_t)total * bytes));
+        h->R_cap = total * bytes;
+    }
     if (bytes == 2) {
         std::vector<uint16_t> tmp(total);
         for (int64_t k = 0; k < total; k++) {

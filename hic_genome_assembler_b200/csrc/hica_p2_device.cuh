@@ -52,34 +52,70 @@ __device__ __forceinline__ void build_order_cta(const EntryF &entry, int nslots,
 __device__ __forceinline__ double exact_cost_cta(const double *__restrict__ S, const double *__restrict__ St, int L,
                                                  const int32_t *o, int n, double total, double *tr)
 {
+    // The additions of one diagonal are a dependent chain (that IS the reference's order); what can overlap is
+    // the memory latency, so every thread keeps PF loads of its diagonal in flight ahead of the adds.
+    constexpr int PF = 16;
     const int tid = threadIdx.x, T = blockDim.x;
     const int npairs = n / 2;
     for (int p = tid; p < npairs; p += T) {
         const int k1 = p + 1, k2 = n - 1 - p;
         const int len1 = n - k1;
         double acc1 = 0.;
-#pragma unroll 4
-        for (int r = 0; r < len1; r++) acc1 = __dadd_rn(acc1, S[(int64_t)o[r] * L + o[r + k1]]);
+        int r = 0;
+        for (; r + PF <= len1; r += PF) {
+            double v[PF];
+#pragma unroll
+            for (int u = 0; u < PF; u++) v[u] = S[(int64_t)o[r + u] * L + o[r + u + k1]];
+#pragma unroll
+            for (int u = 0; u < PF; u++) acc1 = __dadd_rn(acc1, v[u]);
+        }
+        for (; r < len1; r++) acc1 = __dadd_rn(acc1, S[(int64_t)o[r] * L + o[r + k1]]);
         tr[k1] = acc1;
         if (k2 != k1) {
             const int len2 = n - k2;
             double acc2 = 0.;
-#pragma unroll 4
-            for (int t = 0; t < len2; t++) acc2 = __dadd_rn(acc2, St[(int64_t)o[t + k2] * L + o[t]]);
+            int t = 0;
+            for (; t + PF <= len2; t += PF) {
+                double v[PF];
+#pragma unroll
+                for (int u = 0; u < PF; u++) v[u] = St[(int64_t)o[t + u + k2] * L + o[t + u]];
+#pragma unroll
+                for (int u = 0; u < PF; u++) acc2 = __dadd_rn(acc2, v[u]);
+            }
+            for (; t < len2; t++) acc2 = __dadd_rn(acc2, St[(int64_t)o[t + k2] * L + o[t]]);
             tr[k2] = acc2;
         }
     }
     __syncthreads();
-    if (tid == 0) {
+    if (tid == 0) {  // running sum over the diagonals: sequential adds, shared-memory reads batched ahead of them
         double cum = 0.;
-        for (int k = 1; k < n; k++) { cum = __dadd_rn(cum, tr[k]); tr[k] = cum; }
+        int k = 1;
+        for (; k + 8 <= n; k += 8) {
+            double v[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) v[u] = tr[k + u];
+#pragma unroll
+            for (int u = 0; u < 8; u++) { cum = __dadd_rn(cum, v[u]); v[u] = cum; }
+#pragma unroll
+            for (int u = 0; u < 8; u++) tr[k + u] = v[u];
+        }
+        for (; k < n; k++) { cum = __dadd_rn(cum, tr[k]); tr[k] = cum; }
     }
     __syncthreads();
     for (int k = 1 + tid; k < n; k += T) tr[k] = __ddiv_rn(__ddiv_rn(tr[k], total), (double)k);
     __syncthreads();
     double cost = 0.;
-    if (tid == 0)
-        for (int k = 1; k < n; k++) cost = __dadd_rn(cost, tr[k]);
+    if (tid == 0) {
+        int k = 1;
+        for (; k + 8 <= n; k += 8) {
+            double v[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) v[u] = tr[k + u];
+#pragma unroll
+            for (int u = 0; u < 8; u++) cost = __dadd_rn(cost, v[u]);
+        }
+        for (; k < n; k++) cost = __dadd_rn(cost, tr[k]);
+    }
     __syncthreads();
     return cost;
 }

@@ -23,13 +23,14 @@
 #include <math.h>
 
 #include <algorithm>
+#include <chrono>
 #include <vector>
 
 #include "hica_p2_device.cuh"
 
 namespace {
 
-constexpr int EX_THREADS = 256;
+constexpr int EX_THREADS = 512;  // one pass over the n/2 diagonal pairs for n <= 1024
 constexpr double NEAR_TOL = 1e-10;
 
 struct GroupState {
@@ -52,6 +53,8 @@ struct GroupDev {
 struct Tables {  // enumeration tables per window width m (device pointers)
     const uint8_t *ord[9], *ori[9];
     int n_ord[9], n_ori[9];
+    const int32_t *valid_out[9], *valid_win[9];  // indices of the table entries that exist (set excludes s / s2)
+    int n_valid_out[9], n_valid_win[9];
 };
 
 enum { PH_BRUTE = 0, PH_INSERT = 1, PH_SCAN = 2 };
@@ -175,19 +178,20 @@ __global__ void __launch_bounds__(EX_THREADS) k_g_anchor(const GroupDev *gs, Pha
 //   tab_out[((s*2+o) << m) | before]                : scaffold s (orientation o) against all bins outside the
 //                                                      window, `before` = window scaffolds placed before s
 //   tab_win[((((s*m+s2)*2+o)*2+o2) << m) | between] : s placed before s2 with the scaffolds `between` in between
-__global__ void __launch_bounds__(128) k_g_tables(const GroupDev *gs, Phase ph)
+__global__ void __launch_bounds__(128) k_g_tables(const GroupDev *gs, Phase ph, Tables tb)
 {
+    extern __shared__ __align__(16) unsigned char smem[];
     const GroupDev &g = gs[blockIdx.y];
     const PhaseParams pp = phase_params(g, ph);
     if (!pp.active || g.st->skip) return;
-    const int m = pp.m, ws = pp.ws, nslots = pp.nslots;
-    const int n_out = (m * 2) << m, n_win = (m * m * 4) << m;
-    const int b = blockIdx.x;
-    if (b >= n_out + n_win) return;
+    const int m = pp.m, ws = pp.ws, nslots = pp.nslots, n = pp.n;
+    const int nvo = tb.n_valid_out[m], nvw = tb.n_valid_win[m];
+    const int bx = blockIdx.x;
+    if (bx >= nvo + (nvw + 3) / 4) return;
     __shared__ int wlen[8], woff[8];
     __shared__ int p0_s, wtot_s;
     __shared__ double red[4];
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
         int p0 = 0;
         for (int s = 0; s < ws; s++) { int sg = g.layout[s] >> 1; p0 += g.seg_ptr[sg + 1] - g.seg_ptr[sg]; }
@@ -204,58 +208,63 @@ __global__ void __launch_bounds__(128) k_g_tables(const GroupDev *gs, Phase ph)
     __syncthreads();
     const int full = (1 << m) - 1;
     const int L = g.L;
-    double acc = 0.;
-    double *dst;
-    if (b < n_out) {
+    if (bx < nvo) {
+        // ---- one (scaffold, orientation, set-before) entry against all bins outside the window ----------
+        const int b = tb.valid_out[m][bx];
         const int mask = b & full, o = (b >> m) & 1, s = b >> (m + 1);
-        dst = g.tab_out + b;
-        if ((mask >> s) & 1) return;
+        double *wt_s = reinterpret_cast<double *>(smem);             // n weights
+        int32_t *ord = reinterpret_cast<int32_t *>(wt_s + n);        // position -> bin of the current layout
+        int32_t *spos = ord + n, *sent = spos + nslots + 1;
+        for (int d = tid; d < n; d += blockDim.x) wt_s[d] = g.Wt[d];
+        build_order_cta(SrcLayout{g.layout}, nslots, g.seg_ptr, g.seg_bins, ord, spos, sent, n);
         int q = 0;
         for (int j = 0; j < m; j++) if ((mask >> j) & 1) q += wlen[j];
         const int len = wlen[s], p0 = p0_s, wtot = wtot_s;
-        // outside bins by slot: prefix slots [0, ws) then suffix slots [ws+m, nslots)
-        int pos = 0;
-        for (int sl = 0; sl < nslots; sl++) {
-            if (sl == ws) { sl = ws + m - 1; pos = p0 + wtot; continue; }
-            const int e = g.layout[sl], sg = e >> 1, b0 = g.seg_ptr[sg], sl_len = g.seg_ptr[sg + 1] - b0;
-            const int work = sl_len * len;
-            for (int w = tid; w < work; w += blockDim.x) {
-                const int t = w / sl_len, u = w - t * sl_len;
-                const int abin = g.seg_bins[b0 + ((e & 1) ? (sl_len - 1 - u) : u)];
-                const int apos = pos + u;
-                const int bbin = g.seg_bins[woff[s] + t];
+        const int n_outside = n - wtot;
+        const int32_t *sbins = g.seg_bins + woff[s];
+        double acc = 0.;
+        for (int a0 = tid; a0 < n_outside; a0 += blockDim.x) {
+            const int apos = a0 < p0 ? a0 : a0 + wtot;
+            const int abin = ord[apos];
+            // the reference reads M[row of the earlier position][column of the later one]; both branches walk a
+            // row of S / S^T so that neighbouring threads (neighbouring outside bins) touch neighbouring addresses
+            const double *base = (apos < p0 ? g.St : g.S) + abin;
+#pragma unroll 4
+            for (int t = 0; t < len; t++) {
                 const int bpos = p0 + q + (o ? (len - 1 - t) : t);
                 const int d = apos < bpos ? bpos - apos : apos - bpos;
-                // the reference reads M[row of the earlier position][column of the later position]
-                const double v = apos < bpos ? g.S[(int64_t)abin * L + bbin] : g.St[(int64_t)abin * L + bbin];
-                acc += v * g.Wt[d];
+                acc += base[(int64_t)sbins[t] * L] * wt_s[d];
             }
-            pos += sl_len;
         }
+        for (int d = 16; d >= 1; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+        if (lane == 0) red[warp] = acc;
+        __syncthreads();
+        if (tid == 0) g.tab_out[b] = (red[0] + red[1]) + (red[2] + red[3]);
     } else {
-        int r = b - n_out;
+        // ---- four (scaffold pair, orientations, set-between) entries per block, one per warp ----------------
+        const int j = (bx - nvo) * 4 + warp;
+        if (j >= nvw) return;
+        const int bw = tb.valid_win[m][j];
+        int r = bw;
         const int mask = r & full;
         r >>= m;
         const int o2 = r & 1, o = (r >> 1) & 1;
         r >>= 2;
         const int s2 = r % m, s = r / m;
-        dst = g.tab_win + (b - n_out);
-        if (s >= m || s == s2 || ((mask >> s) & 1) || ((mask >> s2) & 1)) return;
         int gap = 0;
-        for (int j = 0; j < m; j++) if ((mask >> j) & 1) gap += wlen[j];
+        for (int jj = 0; jj < m; jj++) if ((mask >> jj) & 1) gap += wlen[jj];
         const int len = wlen[s], len2 = wlen[s2];
         const int work = len * len2;
-        for (int w = tid; w < work; w += blockDim.x) {
+        double acc = 0.;
+        for (int w = lane; w < work; w += 32) {
             const int t = w / len2, t2 = w - t * len2;
             const int off = o ? (len - 1 - t) : t, off2 = o2 ? (len2 - 1 - t2) : t2;
             const int d = len - off + gap + off2;
             acc += g.S[(int64_t)g.seg_bins[woff[s] + t] * L + g.seg_bins[woff[s2] + t2]] * g.Wt[d];
         }
+        for (int d = 16; d >= 1; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+        if (lane == 0) g.tab_win[bw] = acc;
     }
-    for (int d = 16; d >= 1; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
-    if ((tid & 31) == 0) red[tid >> 5] = acc;
-    __syncthreads();
-    if (tid == 0) *dst = (red[0] + red[1]) + (red[2] + red[3]);
 }
 
 __device__ __forceinline__ double rel_of(const GroupDev &g, int m, const uint8_t *ord, const uint8_t *ori)
@@ -537,6 +546,9 @@ extern "C" int hica_p2_order_groups(hica_handle h, int32_t ngroups, const int32_
     if (scan > n_scaffolds) scan = n_scaffolds;  // :568-569
     if (scan < 1) return hica_set_error(h, HICA_ERR_ARG, "scanScaffolds must be >= 1");
     hica_timer timer(h, HICA_T_P2_SCORE);
+    using clk = std::chrono::steady_clock;
+    auto t_h0 = clk::now();
+    auto since = [&](clk::time_point t0) { return std::chrono::duration<double, std::milli>(clk::now() - t0).count(); };
     cudaStream_t s = h->stream;
 
     struct HostGroup { int seg0, nseg, L, k, bins_k; long long Bmax; };
@@ -583,16 +595,26 @@ extern "C" int hica_p2_order_groups(hica_handle h, int32_t ngroups, const int32_
                      padded<uint8_t>((size_t)(ori_brute_off[k + 1] - ori_brute_off[k]));
     Arena ar;
     const size_t cap = arena_bytes + tab_bytes + padded<GroupDev>(ngroups) + padded<int32_t>(total_bins) +
-                       padded<int32_t>(ngroups) + 4096;
-    cudaError_t ce = cudaMalloc((void **)&ar.base, cap);
-    if (ce != cudaSuccess) return hica_set_error(h, HICA_ERR_NOMEM, "cudaMalloc(%zu): %s", cap, cudaGetErrorString(ce));
+                       padded<int32_t>(ngroups) + (2u << 20);  // + the lists of existing table entries
+    h->dbg[0] = since(t_h0);  // host-side validation and sizing
+    auto t_h1 = clk::now();
+    // The arena is kept in the handle and only ever grows: cudaMalloc / cudaFree of a few hundred MB cost
+    // anywhere between 0.5 and 90 ms on B200 (measured), far more than the search itself.
+    if (h->p2_arena_cap < (int64_t)cap) {
+        if (h->p2_arena) cudaFree(h->p2_arena);
+        h->p2_arena = nullptr;
+        h->p2_arena_cap = 0;
+        cudaError_t ce = cudaMalloc(&h->p2_arena, cap);
+        if (ce != cudaSuccess) return hica_set_error(h, HICA_ERR_NOMEM, "cudaMalloc(%zu): %s", cap, cudaGetErrorString(ce));
+        h->p2_arena_cap = (int64_t)cap;
+    }
+    ar.base = (char *)h->p2_arena;
+    h->dbg[1] = since(t_h1);  // arena (re)allocation
 #define ENG_CUDA(call)                                                                                       \
     do {                                                                                                     \
         cudaError_t e__ = (call);                                                                            \
-        if (e__ != cudaSuccess) {                                                                            \
-            cudaFree(ar.base);                                                                               \
+        if (e__ != cudaSuccess)                                                                              \
             return hica_set_error(h, HICA_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
-        }                                                                                                    \
     } while (0)
 
     // ---- enumeration tables
@@ -610,6 +632,33 @@ extern "C" int hica_p2_order_groups(hica_handle h, int32_t ngroups, const int32_
         ENG_CUDA(cudaMemcpyAsync(po, ord_scan, (size_t)n_ord_scan * scan, cudaMemcpyHostToDevice, s));
         ENG_CUDA(cudaMemcpyAsync(pr, ori_scan, (size_t)n_ori_scan * scan, cudaMemcpyHostToDevice, s));
         tb.ord[scan] = po; tb.ori[scan] = pr; tb.n_ord[scan] = n_ord_scan; tb.n_ori[scan] = n_ori_scan;
+    }
+    // ---- lists of the table entries that exist, per window width in use
+    {
+        std::vector<int> widths;
+        for (auto &g : gs) widths.push_back(g.k);
+        widths.push_back(scan);
+        std::sort(widths.begin(), widths.end());
+        widths.erase(std::unique(widths.begin(), widths.end()), widths.end());
+        for (int m : widths) {
+            std::vector<int32_t> vo, vw;
+            const int full = (1 << m) - 1;
+            for (int b = 0; b < ((m * 2) << m); b++) {
+                const int mask = b & full, sidx = b >> (m + 1);
+                if (!((mask >> sidx) & 1)) vo.push_back(b);
+            }
+            for (int b = 0; b < ((m * m * 4) << m); b++) {
+                const int mask = b & full, r = b >> (m + 2), s2 = r % m, s1 = r / m;
+                if (s1 < m && s1 != s2 && !((mask >> s1) & 1) && !((mask >> s2) & 1)) vw.push_back(b);
+            }
+            int32_t *dvo = ar.take<int32_t>(std::max<size_t>(1, vo.size()));
+            int32_t *dvw = ar.take<int32_t>(std::max<size_t>(1, vw.size()));
+            if (!vo.empty()) ENG_CUDA(cudaMemcpyAsync(dvo, vo.data(), sizeof(int32_t) * vo.size(), cudaMemcpyHostToDevice, s));
+            if (!vw.empty()) ENG_CUDA(cudaMemcpyAsync(dvw, vw.data(), sizeof(int32_t) * vw.size(), cudaMemcpyHostToDevice, s));
+            ENG_CUDA(cudaStreamSynchronize(s));  // vo / vw are about to go out of scope
+            tb.valid_out[m] = dvo; tb.valid_win[m] = dvw;
+            tb.n_valid_out[m] = (int)vo.size(); tb.n_valid_win[m] = (int)vw.size();
+        }
     }
     // ---- group descriptors
     std::vector<GroupDev> hdev(ngroups);
@@ -657,24 +706,28 @@ extern "C" int hica_p2_order_groups(hica_handle h, int32_t ngroups, const int32_
 
     const size_t ex_smem = smem_bytes(Lmax, nseg_max + 1);
     const size_t tot_smem = sizeof(int32_t) * (Lmax + 2 * (nseg_max + 1) + 2);
-    if (ex_smem > 200 * 1024) { cudaFree(ar.base); return hica_set_error(h, HICA_ERR_ARG, "chromosome too large for shared memory"); }
+    if (ex_smem > 200 * 1024) return hica_set_error(h, HICA_ERR_ARG, "chromosome too large for shared memory");
     ENG_CUDA(cudaFuncSetAttribute(k_g_exact_near, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex_smem));
     ENG_CUDA(cudaFuncSetAttribute(k_g_anchor, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex_smem));
     ENG_CUDA(cudaFuncSetAttribute(k_g_insert_scores, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex_smem));
     ENG_CUDA(cudaFuncSetAttribute(k_g_total, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tot_smem));
+    const size_t tab_smem = sizeof(double) * Lmax + sizeof(int32_t) * (Lmax + 2 * (nseg_max + 1) + 2);
+    ENG_CUDA(cudaFuncSetAttribute(k_g_tables, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tab_smem));
     const unsigned G = (unsigned)ngroups;
     const unsigned tot_blocks = (unsigned)std::max(1, (Lmax - 1 + 127) / 128);
 
     auto window_search = [&](Phase ph, int m, long long B) {
-        const unsigned nb_tab = (unsigned)(((m * 2) << m) + ((m * m * 4) << m));
+        const unsigned nb_tab = (unsigned)(tb.n_valid_out[m] + (tb.n_valid_win[m] + 3) / 4);
         const unsigned nb_c = (unsigned)((B + 255) / 256);
-        k_g_tables<<<dim3(nb_tab, G), 128, 0, s>>>(gdev, ph);
+        k_g_tables<<<dim3(nb_tab, G), 128, tab_smem, s>>>(gdev, ph, tb);
         k_g_approx<<<dim3(nb_c, G), 256, 0, s>>>(gdev, ph, tb);
         k_g_select<<<dim3(nb_c, G), 256, 0, s>>>(gdev, ph, tb);
         k_g_exact_near<<<dim3((unsigned)std::min<long long>(B, 48), G), EX_THREADS, ex_smem, s>>>(gdev, ph, tb);
         k_g_pick_window<<<dim3(1, G), 256, 0, s>>>(gdev, ph, tb);
         h->launches += 5;
     };
+    h->dbg[2] = since(t_h1);  // ... + descriptor upload + gather enqueue
+    auto t_h2 = clk::now();
     // ---- brute force over the k largest scaffolds (:573-576)
     {
         Phase ph = {PH_BRUTE, 0, 0};
@@ -718,6 +771,8 @@ extern "C" int hica_p2_order_groups(hica_handle h, int32_t ngroups, const int32_
         }
     }
     // ---- results
+    h->dbg[3] = since(t_h2);  // enqueue + scan-round synchronisations
+    auto t_h3 = clk::now();
     ENG_CUDA(cudaGetLastError());
     for (int gi = 0; gi < ngroups; gi++) {
         ENG_CUDA(cudaMemcpyAsync(&hst[gi], st_ptr[gi], sizeof(GroupState), cudaMemcpyDeviceToHost, s));
@@ -737,7 +792,9 @@ extern "C" int hica_p2_order_groups(hica_handle h, int32_t ngroups, const int32_
         }
         if (hst[gi].error && err_group < 0) err_group = gi;
     }
-    cudaFree(ar.base);
+    h->dbg[4] = since(t_h3);  // result read-back
+    auto t_h4 = clk::now();
+    h->dbg[5] = since(t_h4);  // (the arena stays in the handle)
     timer.stop();
     if (err_group >= 0)
         return hica_set_error(h, HICA_ERR_STATE, "group %d: no ordering scored above 0 (the reference fails on 'NA' here)",
