@@ -35,8 +35,8 @@ def _stale(target: str, deps) -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = _nvcc()
     os.makedirs(OBJ, exist_ok=True)
-    headers = [os.path.join(CSRC, "hica_common.cuh"), os.path.join(CSRC, "hica_p2_device.cuh"),
-               os.path.join(HERE, "..", "include", "hica.h")]
+    headers = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith(".cuh")]
+    headers.append(os.path.join(HERE, "..", "include", "hica.h"))
     objs, jobs = [], []
     for src in SOURCES:
         s = os.path.join(CSRC, src)

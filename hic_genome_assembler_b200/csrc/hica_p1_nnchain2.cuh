@@ -77,7 +77,9 @@ k_nn_chain2(double *__restrict__ W, const int n, const int64_t ld, int32_t *__re
     extern __shared__ __align__(16) unsigned char smem[];
     Slot *slots = reinterpret_cast<Slot *>(smem);                       // [2][MAX_CLUSTER]
     unsigned *wb = reinterpret_cast<unsigned *>(slots + 2 * MAX_CLUSTER);  // [2][WARPS][4]
-    uint32_t *alive = reinterpret_cast<uint32_t *>(wb + 2 * MAX_WARPS * 4);
+    unsigned long long *patch = reinterpret_cast<unsigned long long *>(wb + 2 * MAX_WARPS * 4);  // [2], see (a) below
+    uint32_t *alive = reinterpret_cast<uint32_t *>(patch + 2);
+    if (tid < 2) patch[tid] = 0ull;
     const int nwords = (int)((ld + 31) / 32);
     int32_t *chain = CHAIN_SMEM ? reinterpret_cast<int32_t *>(alive + nwords) : chain_g + (int64_t)rank * n;
     int32_t *size = size_g + (int64_t)rank * n;  // private copy of the cluster sizes
@@ -96,19 +98,25 @@ k_nn_chain2(double *__restrict__ W, const int n, const int64_t ld, int32_t *__re
     __syncthreads();
     cluster.sync();
 
-    int len = 0, top = -1, second = -1, first_alive = 0;
+    // the chain starts at the lowest live index (scipy: first i with size[i] > 0)
+    int len = 1, top = 0, second = -1, first_alive = 0;
+    if (tid == 0) chain[0] = 0;
+    __syncthreads();
     unsigned seq = 0;
     long long n_scans = 0, cyc_scan = 0, cyc_merge = 0, cyc_load = 0, cyc_red = 0, cyc_poll = 0;
+    // Merges are not followed by a fenced cluster barrier.  Instead
+    //  (a) the ONE element of the next search row that the merge changes, W[next][y], is handed to the CTA
+    //      that scans column y through distributed shared memory (`patch`, tagged with the merge number);
+    //  (b) every thread fences its merge stores (membar.gl) AFTER it has issued the loads of the next search,
+    //      so the store-visibility latency hides behind the DRAM latency of those loads; a CTA posts its
+    //      search result only after that fence, and nobody starts the search after next before all posts
+    //      have arrived - which is the first point where another CTA can consume the merge's other stores.
+    int patch_col = -1;
+    unsigned patch_tag = 0;
+    bool fence_pending = false;
 
     for (int k = 0; k < n - 1; k++) {
         long long t_begin = clock64();
-        if (len == 0) {
-            while (!((alive[first_alive >> 5] >> (first_alive & 31)) & 1u)) first_alive++;
-            top = first_alive;
-            second = -1;
-            if (tid == 0) chain[0] = top;
-            len = 1;
-        }
         double gv;
         int y;
         for (;;) {
@@ -127,16 +135,34 @@ k_nn_chain2(double *__restrict__ W, const int n, const int64_t ld, int32_t *__re
                     const int c = c0 + 2 * T * u;
                     if (c < hi) v[u] = ld_cg_f64x2(row + c);
                 }
+                if (fence_pending) {  // (b): the loads above are in flight while the merge stores drain
+                    __threadfence();
+                    fence_pending = false;
+                }
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
                     const int c = c0 + 2 * T * u;
                     if (c < hi) {
+                        if (patch_col >= 0 && (patch_col >> 1) == (c >> 1)) {  // (a): take W[x][y] from the patch slot
+                            unsigned long long p0, p1;
+                            do {
+                                p0 = ld_volatile_shared_u64(&patch[0]);
+                                p1 = ld_volatile_shared_u64(&patch[1]);
+                            } while ((unsigned)(p0 >> 32) != patch_tag || (unsigned)(p1 >> 32) != patch_tag);
+                            const double pv = __longlong_as_double((long long)(((p1 & 0xffffffffull) << 32) | (p0 & 0xffffffffull)));
+                            if (patch_col == c) v[u].x = pv; else v[u].y = pv;
+                        }
                         const uint32_t bits = alive[c >> 5] >> (c & 31);
                         if ((bits & 1u) && c != x) consider(b, v[u].x, c == yprev ? 0u : (unsigned)c + 1u);
                         if ((bits & 2u) && c + 1 != x) consider(b, v[u].y, c + 1 == yprev ? 0u : (unsigned)c + 2u);
                     }
                 }
             }
+            if (fence_pending) {  // threads without columns in this slice
+                __threadfence();
+                fence_pending = false;
+            }
+            patch_col = -1;
             const long long ts1 = clock64();
             b = warp_best(b);
             if (lane == 0) {
@@ -196,6 +222,23 @@ k_nn_chain2(double *__restrict__ W, const int n, const int64_t ld, int32_t *__re
         int x = top;
         len -= 2;
         if (x > y) { int t = x; x = y; y = t; }
+        // the row the next search will scan: the new chain top, or the lowest live index if the chain is empty
+        int nxt, nxt2 = -1;
+        if (len >= 1) {
+            nxt = chain[len - 1];
+            if (len >= 2) nxt2 = chain[len - 2];
+        } else {
+            int fa = first_alive;
+            while (fa == x || !((alive[fa >> 5] >> (fa & 31)) & 1u)) fa++;  // y stays alive, so this terminates
+            first_alive = fa;
+            nxt = fa;
+        }
+        {   // pull this CTA's slice of that row towards L2 while the update runs
+            const double *nrow = W + (int64_t)nxt * ld;
+            for (int c = lo + 16 * tid; c < hi; c += 16 * T)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(nrow + c));
+        }
+        const unsigned tag = (unsigned)k + 1u;
         const int nx = size[x], ny = size[y];
         const double dnx = (double)nx, dny = (double)ny, dsum = (double)(nx + ny);
         const double *rowx = W + (int64_t)x * ld;
@@ -206,15 +249,25 @@ k_nn_chain2(double *__restrict__ W, const int n, const int64_t ld, int32_t *__re
             const bool u1 = (bits & 2u) && c + 1 != x && c + 1 != y;
             if (!(u0 || u1)) continue;
             const double2 vx = ld_cg_f64x2(rowx + c), vy = ld_cg_f64x2(rowy + c);
+            double vnext = 0.;
+            bool have_next = false;
             if (u0) {
                 const double v = __ddiv_rn(__dadd_rn(__dmul_rn(dnx, vx.x), __dmul_rn(dny, vy.x)), dsum);
                 rowy[c] = v;
                 W[(int64_t)c * ld + y] = v;
+                if (c == nxt) { vnext = v; have_next = true; }
             }
             if (u1) {
                 const double v = __ddiv_rn(__dadd_rn(__dmul_rn(dnx, vx.y), __dmul_rn(dny, vy.y)), dsum);
                 rowy[c + 1] = v;
                 W[(int64_t)(c + 1) * ld + y] = v;
+                if (c + 1 == nxt) { vnext = v; have_next = true; }
+            }
+            if (have_next) {  // (a): W[nxt][y] for the CTA that scans column y in the next search
+                const unsigned long long vb = (unsigned long long)__double_as_longlong(vnext);
+                volatile unsigned long long *p = cluster.map_shared_rank(patch, y / per);
+                p[0] = ((unsigned long long)tag << 32) | (vb & 0xffffffffull);
+                p[1] = ((unsigned long long)tag << 32) | (vb >> 32);
             }
         }
         if (rank == 0 && tid == 0) {
@@ -223,22 +276,23 @@ k_nn_chain2(double *__restrict__ W, const int n, const int64_t ld, int32_t *__re
             Zraw[4 * (int64_t)k + 2] = gv;
             Zraw[4 * (int64_t)k + 3] = dsum;
         }
-        __syncthreads();  // all threads have read alive[] and size[] for this merge
+        __syncthreads();  // all threads have read alive[], size[] and chain[] for this merge
         if (tid == 0) {
             alive[x >> 5] &= ~(1u << (x & 31));
             size[x] = 0;
             size[y] = nx + ny;
+            if (len == 0) chain[0] = nxt;
         }
-        if (len >= 1) {
-            top = chain[len - 1];
-            second = (len >= 2) ? chain[len - 2] : -1;
-            const double *nrow = W + (int64_t)top * ld;
-            for (int c = lo + 16 * tid; c < hi; c += 16 * T)
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(nrow + c));
-        }
-        cluster.sync();  // W updates (incl. the scattered column y) visible cluster-wide; also a CTA barrier
+        if (len == 0) len = 1;
+        top = nxt;
+        second = nxt2;
+        patch_col = (nxt != y) ? y : -1;
+        patch_tag = tag;
+        fence_pending = true;
+        __syncthreads();  // alive / size / chain updates visible to the whole CTA
         cyc_merge += clock64() - t_mid;
     }
+    cluster.sync();  // no CTA may exit while a peer can still write into its shared memory
     if (rank == 0 && tid == 0 && stats) {
         stats[0] = n_scans; stats[1] = cyc_scan; stats[2] = cyc_merge;
         stats[3] = cyc_load; stats[4] = cyc_red; stats[5] = cyc_poll;
@@ -247,7 +301,8 @@ k_nn_chain2(double *__restrict__ W, const int n, const int64_t ld, int32_t *__re
 
 inline size_t base_smem(int nwords)
 {
-    return sizeof(Slot) * 2 * MAX_CLUSTER + sizeof(unsigned) * 2 * MAX_WARPS * 4 + sizeof(uint32_t) * nwords;
+    return sizeof(Slot) * 2 * MAX_CLUSTER + sizeof(unsigned) * 2 * MAX_WARPS * 4 + 2 * sizeof(unsigned long long) +
+           sizeof(uint32_t) * nwords;
 }
 
 }  // namespace nn2
