@@ -53,8 +53,12 @@ def build_workload(n_bins, n_chrom, seed, device):
     g = make_genome(n_bins, n_chrom=n_chrom, seed=seed, device=device)
     names = [g.scaffold_names[s] for s in g.scaffold_of_bin]
     sizes = {nm: int(sz) for nm, sz in zip(g.scaffold_names, g.scaffold_sizes_bp)}
-    return dict(gen=g, A=g.A, bin_ids=np.arange(1, n_bins + 1), scaffold_of_bin=names, sizes=sizes,
-                resolution=g.resolution)
+    bin_ids = np.arange(1, n_bins + 1)
+    row_of = np.full(n_bins + 2, -1, dtype=np.int64)
+    row_of[bin_ids] = np.arange(n_bins)
+    return dict(gen=g, A=g.A, bin_ids=bin_ids, scaffold_of_bin=names, sizes=sizes, resolution=g.resolution,
+                scaffold_code=np.asarray(g.scaffold_of_bin, dtype=np.int64), scaffold_names=list(g.scaffold_names),
+                scaffold_sizes=[int(v) for v in g.scaffold_sizes_bp], row_of_bin_id=row_of)
 
 
 def workload_name(args):
@@ -129,12 +133,18 @@ def gpu_step(h, wl, args, source, rank, world, dist):
     p2_pairs, p2_cands, p2_calls, kernel_ms_p2 = 0, 0, 0, 0.0
     orderings = {}
     if not args.part1_only:
-        groups = part1.chromosome_groups(res["cuts"], res["leaves"], wl["bin_ids"], wl["scaffold_of_bin"], wl["sizes"])
+        if args.p2_host_loop:
+            groups = part1.chromosome_groups(res["cuts"], res["leaves"], wl["bin_ids"], wl["scaffold_of_bin"], wl["sizes"])
+            index_of = {int(b): i for i, b in enumerate(wl["bin_ids"])}
+        else:
+            groups = part1.chromosome_groups_compact(res["cuts"], res["leaves"], wl["bin_ids"], wl["scaffold_code"],
+                                                     wl["scaffold_names"], wl["scaffold_sizes"])
+            index_of = wl["row_of_bin_id"]
         h.p2_use_p1_matrix()
-        index_of = {int(b): i for i, b in enumerate(wl["bin_ids"])}
         part2.STATS.update(candidates=0, bin_pairs=0, calls=0, exact=0)
         from hic_genome_assembler_b200 import dist as hdist
-        mine = hdist.shard_groups([len(g) for g in groups], world, rank)
+        nbins = [len(g) if args.p2_host_loop else sum(len(ids) for _, ids in g) for g in groups]
+        mine = hdist.shard_groups(nbins, world, rank)
         if args.p2_host_loop:
             for ci in mine:
                 orderings[ci] = part2.order_chromosome(h, index_of, groups[ci], 6, 5)

@@ -22,6 +22,8 @@ struct hica_ctx {
     void *p2_arena = nullptr;  // scratch arena of hica_p2_order_groups (grow-only)
     int64_t p2_arena_cap = 0;
     int64_t R_cap = 0;         // bytes allocated behind R
+    void *cut_buf = nullptr;   // scratch of the batched noise filter (grow-only)
+    int64_t cut_buf_cap = 0;
 
     // ---- Part 1 state ---------------------------------------------------
     int64_t n = 0;           // bins

@@ -27,7 +27,10 @@
 namespace {
 
 constexpr double HICA_MARGIN = 1e-7;
-constexpr double LOG_TINY = -700.0;
+// The tail sum starts where the pmf has dropped to e^-80 ~ 2e-35: the mass beyond that point is ~30 orders
+// of magnitude below the 1e-7 * psig safety margin, and the recurrence is ~3x shorter than starting at the
+// edge of the double range.
+constexpr double LOG_TINY = -80.0;
 
 __device__ __forceinline__ double lchoose(double a, double b)
 {
@@ -243,6 +246,88 @@ __global__ void k_filter_intervals(const uint8_t *__restrict__ sig, int64_t star
     if (threadIdx.x == 0) flags[j] = flag;
 }
 
+// ---- batched filter stage: every cut of the current list at once (the host loop of :607-700 stops at the
+// first cut with a significant later interval, but the evaluations of one (start, list) are independent, so
+// they run as one set of launches and one read-back instead of one round trip per cut) -------------------
+template <typename RankT>
+__global__ void __launch_bounds__(128) k_fb_counts(const RankT *__restrict__ R, int64_t n, int64_t start,
+                                                   const int64_t *__restrict__ bounds, int64_t rows,
+                                                   int32_t *__restrict__ x)
+{
+    const int j = blockIdx.y;
+    const int64_t cut = bounds[j], local = cut - start;
+    const RankT *row = R + (start + blockIdx.x) * n;
+    int cnt = 0;
+    for (int64_t k = threadIdx.x; k < local; k += blockDim.x) {
+        int64_t v = row[k];
+        cnt += (v >= start && v <= cut);
+    }
+    __shared__ int part[4];
+    for (int d = 16; d >= 1; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) x[(int64_t)j * rows + blockIdx.x] = part[0] + part[1] + part[2] + part[3];
+}
+
+__global__ void k_fb_crit(int64_t start, const int64_t *__restrict__ bounds, int nb, long long M, double psig,
+                          int32_t *__restrict__ crit)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nb) return;
+    const long long local = bounds[j] - start;
+    bool amb = false;
+    long long xc = LLONG_MAX;  // invalid parameters: NaN p-value, `pval < psig` is False
+    if (hyp_valid(M, local, local)) xc = hyp_critical(M, local, local, psig, &amb);
+    crit[2 * j] = xc > INT_MAX ? INT_MAX : (xc < INT_MIN ? INT_MIN : (int)xc);
+    crit[2 * j + 1] = amb ? 1 : 0;
+}
+
+__global__ void k_fb_sig(const int32_t *__restrict__ x, int64_t rows, const int64_t *__restrict__ bounds, int nb,
+                         int64_t start, long long M, double psig, const int32_t *__restrict__ crit,
+                         uint8_t *__restrict__ sig, int32_t *__restrict__ misc)
+{
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= rows * nb) return;
+    const int j = (int)(idx / rows);
+    const long long local = bounds[j] - start;
+    const bool valid = hyp_valid(M, local, local);
+    int s = 0;
+    if (valid) {
+        const long long kmin = max(0ll, 2 * local - M), kmax = local, xv = x[idx];
+        if (xv <= kmin) s = 1.0 < psig;
+        else if (xv > kmax) s = 0.0 < psig;
+        else {
+            s = xv >= crit[2 * j];
+            if (crit[2 * j + 1] && (xv == crit[2 * j] || xv == (long long)crit[2 * j] - 1)) atomicAdd(&misc[3], 1);
+        }
+    }
+    sig[idx] = (uint8_t)s;
+}
+
+__global__ void k_fb_intervals(const uint8_t *__restrict__ sig, int64_t rows, int64_t start,
+                               const int64_t *__restrict__ bounds, int nb, const int64_t *__restrict__ eval_cuts,
+                               long long M, double psig, int32_t *__restrict__ flags, int32_t *__restrict__ misc)
+{
+    const int i = blockIdx.x, j = blockIdx.y;  // interval i of the whole list, evaluated for cut eval_cuts[j]
+    const int64_t hi = bounds[i];
+    const int64_t lo = (i == 0) ? start : max(start, bounds[i - 1]);
+    const long long local = eval_cuts[j] - start;
+    int flag = 0;
+    if (hi > lo) {
+        int cnt = 0;
+        const int64_t r1 = min(hi - start, rows);  // rows beyond start + int(n/5) are 0 (:622-626)
+        const uint8_t *sj = sig + (int64_t)j * rows;
+        for (int64_t r = lo - start + threadIdx.x; r < r1; r += 32) cnt += sj[r];
+        for (int d = 16; d >= 1; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
+        if (threadIdx.x == 0) {
+            int r = hyp_less(cnt, M, local, hi - lo, psig, 0);
+            flag = r & 1;
+            if (r & 2) atomicAdd(&misc[3], 1);
+        }
+    }
+    if (threadIdx.x == 0) flags[(int64_t)j * nb + i] = flag;
+}
+
 template <typename F>
 int with_rank(hica_ctx *h, F f)
 {
@@ -454,21 +539,63 @@ extern "C" int hica_p1_filter(hica_handle h, const int64_t *cuts_in, int64_t n_i
             size_t keep_from = 0;
             const int nb = (int)altered.size();
             HICA_CUDA(cudaMemcpyAsync(h->q_d, altered.data(), sizeof(int64_t) * nb, cudaMemcpyHostToDevice, h->stream));
-            for (size_t i = 0; i < altered.size(); i++) {
-                const int64_t c = altered[i];
-                const int64_t local = c - start;
+            for (int i = 0; i < nb; i++)
+                if (altered[i] < start) return hica_set_error(h, HICA_ERR_ARG, "cut indices must be ascending");
+            // The cuts of the list are evaluated a few at a time (one set of launches and one read-back per
+            // chunk): the loop usually stops at an early cut, so evaluating the whole list at once would waste
+            // far more work (later cuts have long windows) than the round trips it saves.
+            const int64_t Lw = n - start, rows = std::min<int64_t>(Lw, n / 5 + 1);
+            constexpr int CHUNK = 4;
+            std::vector<int32_t> all_flags((size_t)CHUNK * nb);
+            int chunk_lo = 0, chunk_hi = 0;  // cuts [chunk_lo, chunk_hi) of the list have flags in all_flags
+            auto eval_chunk = [&](int i0) -> int {
+                const int ne = std::min(CHUNK, nb - i0);
+                const int64_t need = (int64_t)ne * rows * 5 + (int64_t)ne * nb * 4 + (int64_t)ne * 8 + 1024;
+                if (h->cut_buf_cap < need) {
+                    if (h->cut_buf) cudaFree(h->cut_buf);
+                    h->cut_buf = nullptr;
+                    h->cut_buf_cap = 0;
+                    HICA_CUDA(cudaMalloc(&h->cut_buf, (size_t)need));
+                    h->cut_buf_cap = need;
+                }
+                char *base = (char *)h->cut_buf;
+                int32_t *fx = (int32_t *)base;
+                int32_t *fflags = (int32_t *)(base + (int64_t)ne * rows * 4);
+                int32_t *fcrit = fflags + (int64_t)ne * nb;
+                uint8_t *fsig = (uint8_t *)(fcrit + 2 * ne);
+                const int64_t *eval = h->q_d + i0;
                 int rc;
                 if ((rc = reset_misc(h))) return rc;
-                if (local < 0) return hica_set_error(h, HICA_ERR_ARG, "cut indices must be ascending");
-                if ((rc = run_sig_mode1(h, start, c, M, psig))) return rc;
-                k_filter_intervals<<<nb, 32, 0, h->stream>>>(h->sig_d, start, h->q_d, nb, M, local, psig, flags_d,
-                                                             h->misc_d);
-                HICA_LAUNCHED(h);
+                rc = with_rank(h, [&](auto *R) {
+                    k_fb_counts<<<dim3((unsigned)rows, (unsigned)ne), 128, 0, h->stream>>>(R, n, start, eval, rows, fx);
+                    HICA_LAUNCHED(h);
+                    return (int)HICA_OK;
+                });
+                if (rc) return rc;
+                k_fb_crit<<<1, 64, 0, h->stream>>>(start, eval, ne, M, psig, fcrit);
+                k_fb_sig<<<(unsigned)((rows * ne + 255) / 256), 256, 0, h->stream>>>(fx, rows, eval, ne, start, M, psig,
+                                                                                  fcrit, fsig, h->misc_d);
+                k_fb_intervals<<<dim3((unsigned)nb, (unsigned)ne), 32, 0, h->stream>>>(fsig, rows, start, h->q_d, nb, eval,
+                                                                                    M, psig, fflags, h->misc_d);
+                h->launches += 3;
                 HICA_CUDA(cudaGetLastError());
-                if ((rc = fetch_misc(h, 16 + nb))) return rc;
+                HICA_CUDA(cudaMemcpyAsync(all_flags.data(), fflags, sizeof(int32_t) * ne * nb, cudaMemcpyDeviceToHost,
+                                          h->stream));
+                if ((rc = fetch_misc(h, 6))) return rc;
                 amb += h->misc_h[3];
+                chunk_lo = i0;
+                chunk_hi = i0 + ne;
+                return HICA_OK;
+            };
+            for (size_t i = 0; i < altered.size(); i++) {
+                const int64_t c = altered[i];
+                if ((int)i >= chunk_hi) {
+                    int rc = eval_chunk((int)i);
+                    if (rc) return rc;
+                }
+                const int32_t *row_flags = all_flags.data() + (i - chunk_lo) * nb;
                 int right_most_ind = -1;
-                for (int j = 0; j < nb; j++) if (flags_h[j]) right_most_ind = j;
+                for (int j = 0; j < nb; j++) if (row_flags[j]) right_most_ind = j;
                 if (right_most_ind >= 0) {
                     start = altered[right_most_ind];
                     filtered.insert(start);

@@ -77,6 +77,46 @@ def chromosome_groups(cuts: Sequence[int], leaves: Sequence[int], bin_ids: Seque
     return [g for g, _ in ranked]
 
 
+def chromosome_groups_compact(cuts: Sequence[int], leaves: Sequence[int], bin_ids: np.ndarray,
+                             scaffold_code: np.ndarray, scaffold_names: Sequence[str],
+                             scaffold_size_bp: Sequence[int], percent_to_assign: float = 51.):
+    """Array form of :func:`chromosome_groups` for large N (no per-bin Python work): returns, per group,
+    ``[(scaffold name, sorted bin-id array), ...]`` in the order the reference lists the scaffolds (first
+    appearance inside the group), groups sorted by bp size.  ``scaffold_code[i]`` indexes ``scaffold_names`` /
+    ``scaffold_size_bp`` for matrix row i."""
+    n = len(leaves)
+    leaves = np.asarray(leaves, dtype=np.int64)
+    code = np.asarray(scaffold_code, dtype=np.int64)
+    bin_ids = np.asarray(bin_ids, dtype=np.int64)
+    S = len(scaffold_names)
+    gid = np.searchsorted(np.asarray(list(cuts), dtype=np.int64), np.arange(n), side="right")
+    code_o = code[leaves]
+    key = gid * S + code_o
+    uniq, first, counts = np.unique(key, return_index=True, return_counts=True)
+    total = np.bincount(code, minlength=S)
+    by_scaf = np.lexsort((bin_ids, code))            # bins of every scaffold, ascending bin id
+    start = np.concatenate([[0], np.cumsum(total)])
+    n_groups = len(cuts) + 1
+    order = np.lexsort((first, uniq // S))           # (group, first appearance)
+    final, sizes = [], []
+    pos = 0
+    for g in range(n_groups):
+        members, bp = [], 0
+        while pos < len(order) and uniq[order[pos]] // S == g:
+            s = int(uniq[order[pos]] % S)
+            c = int(counts[order[pos]])
+            pct = round((float(c) / float(total[s])) * 100., 2)
+            if pct >= percent_to_assign:
+                members.append((scaffold_names[s], bin_ids[by_scaf[start[s]:start[s + 1]]]))
+                bp += int(scaffold_size_bp[s])
+            pos += 1
+        if members:
+            final.append(members)
+            sizes.append(bp)
+    ranked = sorted(zip(final, sizes), key=lambda p: p[1], reverse=True)
+    return [g for g, _ in ranked]
+
+
 # --------------------------------------------------------------------------- #
 # seams
 # --------------------------------------------------------------------------- #

@@ -272,13 +272,31 @@ def order_groups_device(h: Handle, genome_index_of_bin: Dict[int, int],
         n_scaffolds = 8
     if scan > n_scaffolds:
         scan = n_scaffolds
-    pools = [_pool(g) for g in chrom_groups]
-    grp_ptr, seg_ptr, rows = [0], [0], []
+    compact = bool(chrom_groups) and bool(chrom_groups[0]) and isinstance(chrom_groups[0][0][1], np.ndarray)
+    if compact:
+        # groups from part1.chromosome_groups_compact: [(name, sorted bin-id array), ...]; the pool order of
+        # initiateBinsAndScaffolds is a stable sort by bin count, descending
+        pools = []
+        for g in chrom_groups:
+            scafs = [Scaf.__new__(Scaf) for _ in g]
+            for s, (nm, ids) in zip(scafs, g):
+                s.name, s.bins, s.orientation, s.seg = nm, ids, "+", -1
+            pools.append(sorted(scafs, key=lambda s: len(s.bins), reverse=True))
+        lookup = genome_index_of_bin if isinstance(genome_index_of_bin, np.ndarray) else None
+    else:
+        pools = [_pool(g) for g in chrom_groups]
+        lookup = None
+    grp_ptr, seg_ptr, rows, nrows = [0], [0], [], 0
     for pool in pools:
         for s in pool:
-            rows.extend(genome_index_of_bin[b] for b in s.bins)
-            seg_ptr.append(len(rows))
+            if lookup is not None:
+                rows.append(lookup[s.bins])
+            else:
+                rows.append(np.fromiter((genome_index_of_bin[int(b)] for b in s.bins), dtype=np.int64, count=len(s.bins)))
+            nrows += len(s.bins)
+            seg_ptr.append(nrows)
         grp_ptr.append(len(seg_ptr) - 1)
+    rows = np.concatenate(rows) if rows else np.zeros(0, dtype=np.int64)
     ks = sorted({min(n_scaffolds, len(p)) for p in pools})
     brute = {k: (order_table(k), orient_table(k)) for k in ks}
     layout, cost, rounds, stats = h.p2_order_groups(grp_ptr, seg_ptr, rows, n_scaffolds, scan, brute,

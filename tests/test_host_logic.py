@@ -55,3 +55,20 @@ def test_chromosome_groups_match_reference_files():
     cuts = cuts[:-1]
     got = part1.chromosome_groups(cuts, leaves, bin_ids, scaf, sizes)
     assert [[[str(b), s] for b, s in g] for g in got] == want
+
+
+def test_compact_groups_equal_tuple_groups():
+    rng = np.random.RandomState(3)
+    n, S = 900, 37
+    code = np.sort(rng.randint(0, S, size=n))           # bins of a scaffold are contiguous in file order
+    names = ["scaf_%d" % i for i in range(S)]
+    sizes = [int(1000 * (code == s).sum()) for s in range(S)]
+    bin_ids = rng.permutation(np.arange(1, n + 1))      # arbitrary ids
+    leaves = rng.permutation(n)
+    # make the dendrogram order mostly scaffold-contiguous so that groups are non-trivial
+    leaves = np.argsort(code + 0.3 * rng.rand(n), kind="stable")
+    cuts = [120, 121, 400, 650, 890]
+    want = part1.chromosome_groups(cuts, leaves, bin_ids, [names[c] for c in code], dict(zip(names, sizes)))
+    got = part1.chromosome_groups_compact(cuts, leaves, bin_ids, code, names, sizes)
+    flat = [[(int(b), nm) for nm, ids in g for b in ids] for g in got]
+    assert flat == want
