@@ -173,7 +173,7 @@ def cpu_baseline(wl, args, quick=False):
     import hica_oracle as O
     A = wl["A_host"]
     n = A.shape[0]
-    ns = min(n, 2400 if quick else 4000)
+    ns = min(n, 2400 if quick else 6000)
     sub = np.ascontiguousarray(A[:ns, :ns])
     t0 = time.perf_counter()
     rs = O.sequential_row_sums(sub)
@@ -204,7 +204,7 @@ def cpu_baseline(wl, args, quick=False):
     total = O.total_weight(M)
     rng = np.random.RandomState(0)
     O.ordering_cost_numba(M[:16, :16], 1.0)  # JIT warm-up outside the timed region
-    n_c = 200 if quick else 1500
+    n_c = 200 if quick else 5000
     t0 = time.perf_counter()
     for _ in range(n_c):
         o = np.arange(L)

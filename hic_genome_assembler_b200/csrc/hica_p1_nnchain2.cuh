@@ -186,6 +186,9 @@ k_nn_chain2(double *__restrict__ W, const int n, const int64_t ld, int32_t *__re
                     w[1] = tag | c.hi;
                     w[2] = tag | c.ic;
                 }
+                // (Tried: every CTA prefetching the whole row of its local winner into L2 during the exchange - the
+                // global winner is one of them.  Measured on B200: no gain in the load phase and +200 cycles in
+                // this one, 98.8 -> 105.6 ms at N = 16k; the row load is not what the search waits for.)
             }
             const long long ts2 = clock64();
             // every warp waits for the nranks partial results in its own CTA's shared memory

@@ -22,6 +22,7 @@
 
 #include "hica_common.cuh"
 #include "hica_p1_ranksort.cuh"
+#include "hica_p1_rankradix.cuh"
 
 namespace {
 
@@ -102,6 +103,32 @@ static int rank_rows(hica_ctx *h, int q, int64_t P)
     return HICA_OK;
 }
 
+template <int EPT, int RT>
+static int launch_radix(hica_ctx *h, rankradix::RadixArgs &a)
+{
+    const size_t smem = rankradix::smem_bytes(EPT, RT);
+    HICA_CUDA(cudaFuncSetAttribute(rankradix::k_rank_radix<EPT, RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    rankradix::k_rank_radix<EPT, RT><<<(unsigned)h->n, RT, smem, h->stream>>>(a);
+    HICA_LAUNCHED(h);
+    HICA_CUDA(cudaGetLastError());
+    return HICA_OK;
+}
+
+static int rank_rows_radix(hica_ctx *h)
+{
+    rankradix::RadixArgs a = {};
+    a.A = h->A; a.n = h->n; a.s_pair = h->s_pair; a.s_seq = h->s_seq; a.order = h->order; a.pos = h->pos;
+    a.kind = h->A_kind; a.R = h->R; a.row0 = 0;
+    const int64_t n = h->n;
+    // measured at N = 16k on B200: 1024 threads x 16 elements 16.7 ms, 512 x 32 17.4 ms (bitonic network: 29 ms)
+    const char *v = getenv("HICA_RANK_RADIX_THREADS");
+    const bool wide = !(v && atoi(v) == 512);
+    if (n <= 512 * 4) return launch_radix<4, 512>(h, a);
+    if (n <= 512 * 8) return launch_radix<8, 512>(h, a);
+    if (n <= 512 * 16) return wide ? launch_radix<8, 1024>(h, a) : launch_radix<16, 512>(h, a);
+    return wide ? launch_radix<16, 1024>(h, a) : launch_radix<32, 512>(h, a);
+}
+
 extern "C" int hica_p1_rank(hica_handle h)
 {
     HICA_CHECK_HANDLE(h);
@@ -126,8 +153,15 @@ extern "C" int hica_p1_rank(hica_handle h)
     h->rank_bytes = 0;
     hica_timer t(h, HICA_T_RANK);
     int rc;
-    if (q == 14) rc = bytes == 2 ? rank_rows<uint16_t, 1024>(h, q, P) : rank_rows<uint32_t, 1024>(h, q, P);
-    else rc = bytes == 2 ? rank_rows<uint16_t, 512>(h, q, P) : rank_rows<uint32_t, 512>(h, q, P);
+    const char *algo = getenv("HICA_RANK_ALGO");
+    if (n <= 16384 && !(algo && algo[0] == 'b')) {
+        // rows that fit one CTA's shared memory: stable LSD radix sort (hica_p1_rankradix.cuh)
+        rc = rank_rows_radix(h);
+    } else {
+        // longer rows (or HICA_RANK_ALGO=bitonic): chunked bitonic network with global merge steps
+        if (q == 14) rc = bytes == 2 ? rank_rows<uint16_t, 1024>(h, q, P) : rank_rows<uint32_t, 1024>(h, q, P);
+        else rc = bytes == 2 ? rank_rows<uint16_t, 512>(h, q, P) : rank_rows<uint32_t, 512>(h, q, P);
+    }
     if (rc) return rc;
     t.stop();
     HICA_CUDA(cudaStreamSynchronize(h->stream));

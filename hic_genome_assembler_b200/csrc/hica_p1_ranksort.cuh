@@ -34,30 +34,29 @@ __device__ __forceinline__ void cex(unsigned long long &ka, uint32_t &pa, unsign
 }
 
 // thread-local step: register index bit JB pairs e and e | (1 << JB)
-template <int JB, class IdxF>
-__device__ __forceinline__ void step_regs(unsigned long long (&k)[EPT], uint32_t (&p)[EPT], long long kphase, const IdxF &gidx)
+// fwd_mask: bit e = element e lies in a block that is sorted in the final direction during this merge phase
+// (computed once per phase and layout, not per compare-exchange).
+template <int JB>
+__device__ __forceinline__ void step_regs(unsigned long long (&k)[EPT], uint32_t (&p)[EPT], unsigned fwd_mask)
 {
 #pragma unroll
     for (int e = 0; e < EPT; e++) {
         if ((e >> JB) & 1) continue;
-        const bool fwd = (gidx(e) & kphase) == 0;
-        cex(k[e], p[e], k[e | (1 << JB)], p[e | (1 << JB)], fwd);
+        cex(k[e], p[e], k[e | (1 << JB)], p[e | (1 << JB)], (fwd_mask >> e) & 1u);
     }
 }
 
 // lane-shuffle step: partner lane = lane ^ lmask; i_am_low: my elements sit at the lower index of every pair
-template <class IdxF>
 __device__ __forceinline__ void step_shfl(unsigned long long (&k)[EPT], uint32_t (&p)[EPT], int lmask, bool i_am_low,
-                                          long long kphase, const IdxF &gidx)
+                                          unsigned fwd_mask)
 {
 #pragma unroll
     for (int e = 0; e < EPT; e++) {
         const unsigned long long ok = __shfl_xor_sync(0xffffffffu, k[e], lmask);
         const uint32_t op = __shfl_xor_sync(0xffffffffu, p[e], lmask);
-        const bool fwd = (gidx(e) & kphase) == 0;
-        const bool want_first = (i_am_low == fwd);  // keep the element that precedes
+        const bool want_first = (i_am_low == (bool)((fwd_mask >> e) & 1u));  // keep the element that precedes
         const bool mine_first = precedes(k[e], p[e], ok, op);
-        if (mine_first != want_first && !(k[e] == ok && p[e] == op)) { k[e] = ok; p[e] = op; }
+        if (mine_first != want_first) { k[e] = ok; p[e] = op; }  // equal elements: a no-op either way
     }
 }
 
@@ -146,28 +145,44 @@ __global__ void __launch_bounds__(MAXT, 1) k_rank_chunk(ChunkArgs a)
 #pragma unroll
         for (int e = 0; e < EPT; e++) { skeys[pad(idxB(e))] = k[e]; spay[pad(idxB(e))] = (PayT)p[e]; }
     };
+    // direction masks: bit e set <=> the element's global index has bit `kp` clear (its block ends up in final order)
+    auto maskA = [&](long long kp) -> unsigned {
+        if (kp >= EPT) return ((gA(0) & kp) == 0) ? 0xffffu : 0u;  // the same for all 16 elements of a thread
+        unsigned m = 0;
+#pragma unroll
+        for (int e = 0; e < EPT; e++) m |= ((gA(e) & kp) == 0 ? 1u : 0u) << e;
+        return m;
+    };
+    auto maskB = [&](long long kp) -> unsigned {
+        unsigned m = 0;
+#pragma unroll
+        for (int e = 0; e < EPT; e++) m |= ((gB(e) & kp) == 0 ? 1u : 0u) << e;
+        return m;
+    };
     // strides 256 .. 1 of phase kp in layout A (jmax = largest stride to run, <= 256)
     auto low_steps = [&](long long kp, int jmax) {
+        const unsigned fm = maskA(kp);
         for (int s = 4; s >= 0; s--) {
             const int j = 16 << s;
             if (j > jmax) continue;
-            step_shfl(k, p, 1 << s, ((lane >> s) & 1) == 0, kp, gA);
+            step_shfl(k, p, 1 << s, ((lane >> s) & 1) == 0, fm);
         }
-        if (jmax >= 8) step_regs<3>(k, p, kp, gA);
-        if (jmax >= 4) step_regs<2>(k, p, kp, gA);
-        if (jmax >= 2) step_regs<1>(k, p, kp, gA);
-        step_regs<0>(k, p, kp, gA);
+        if (jmax >= 8) step_regs<3>(k, p, fm);
+        if (jmax >= 4) step_regs<2>(k, p, fm);
+        if (jmax >= 2) step_regs<1>(k, p, fm);
+        step_regs<0>(k, p, fm);
     };
     // strides jmax .. 512 of phase kp in layout B (jmax >= 512)
     auto high_steps = [&](long long kp, int jmax) {
+        const unsigned fm = maskB(kp);
         for (int b = r - 1; b >= 0; b--) {
             const int j = 512 << b;
             if (j > jmax) continue;
-            if (b == 4) step_shfl(k, p, 1, (lane & 1) == 0, kp, gB);
-            else if (b == 3) step_regs<3>(k, p, kp, gB);
-            else if (b == 2) step_regs<2>(k, p, kp, gB);
-            else if (b == 1) step_regs<1>(k, p, kp, gB);
-            else step_regs<0>(k, p, kp, gB);
+            if (b == 4) step_shfl(k, p, 1, (lane & 1) == 0, fm);
+            else if (b == 3) step_regs<3>(k, p, fm);
+            else if (b == 2) step_regs<2>(k, p, fm);
+            else if (b == 1) step_regs<1>(k, p, fm);
+            else step_regs<0>(k, p, fm);
         }
     };
 
