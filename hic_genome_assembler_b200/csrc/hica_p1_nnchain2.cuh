@@ -75,6 +75,10 @@ k_nn_chain2(double *__restrict__ W, const int n, const int64_t ld, int32_t *__re
     const int T = blockDim.x, nwarps = T >> 5;
 
     extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ unsigned gres[8];
+    // every warp spins on the result slots itself; letting only warp 0 poll and broadcasting through a CTA
+    // barrier was measured slower on B200 (101.2 vs 95.8 ms at N = 16k)
+    constexpr bool POLL_ALL = true;
     Slot *slots = reinterpret_cast<Slot *>(smem);                       // [2][MAX_CLUSTER]
     unsigned *wb = reinterpret_cast<unsigned *>(slots + 2 * MAX_CLUSTER);  // [2][WARPS][4]
     unsigned long long *patch = reinterpret_cast<unsigned long long *>(wb + 2 * MAX_WARPS * 4);  // [2], see (a) below
@@ -107,10 +111,10 @@ k_nn_chain2(double *__restrict__ W, const int n, const int64_t ld, int32_t *__re
     // Merges are not followed by a fenced cluster barrier.  Instead
     //  (a) the ONE element of the next search row that the merge changes, W[next][y], is handed to the CTA
     //      that scans column y through distributed shared memory (`patch`, tagged with the merge number);
-    //  (b) every thread fences its merge stores (membar.gl) AFTER it has issued the loads of the next search,
-    //      so the store-visibility latency hides behind the DRAM latency of those loads; a CTA posts its
-    //      search result only after that fence, and nobody starts the search after next before all posts
-    //      have arrived - which is the first point where another CTA can consume the merge's other stores.
+    //  (b) every thread fences its merge stores (membar.gl) only AFTER it has loaded and scanned its slice of
+    //      the next search row, so the store-visibility latency hides behind that row load; a CTA posts its
+    //      search result only after the fence, and nobody starts the search after next before all posts have
+    //      arrived - which is the first point where another CTA can consume the merge's other stores.
     int patch_col = -1;
     unsigned patch_tag = 0;
     bool fence_pending = false;
@@ -135,10 +139,6 @@ k_nn_chain2(double *__restrict__ W, const int n, const int64_t ld, int32_t *__re
                     const int c = c0 + 2 * T * u;
                     if (c < hi) v[u] = ld_cg_f64x2(row + c);
                 }
-                if (fence_pending) {  // (b): the loads above are in flight while the merge stores drain
-                    __threadfence();
-                    fence_pending = false;
-                }
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
                     const int c = c0 + 2 * T * u;
@@ -158,13 +158,13 @@ k_nn_chain2(double *__restrict__ W, const int n, const int64_t ld, int32_t *__re
                     }
                 }
             }
-            if (fence_pending) {  // threads without columns in this slice
-                __threadfence();
-                fence_pending = false;
-            }
             patch_col = -1;
             const long long ts1 = clock64();
             b = warp_best(b);
+            if (fence_pending) {  // (b): the merge stores have had a whole row load + scan to drain by now
+                asm volatile("fence.acq_rel.cluster;" ::: "memory");  // all consumers are CTAs of this cluster
+                fence_pending = false;
+            }
             if (lane == 0) {
                 unsigned *dst = wb + (par * MAX_WARPS + warp) * 4;
                 dst[0] = b.hi; dst[1] = b.lo; dst[2] = b.ic;
@@ -194,7 +194,7 @@ k_nn_chain2(double *__restrict__ W, const int n, const int64_t ld, int32_t *__re
             // every warp waits for the nranks partial results in its own CTA's shared memory
             Best g;
             g.hi = NONE; g.lo = NONE; g.ic = NONE;
-            {
+            if (POLL_ALL || warp == 0) {
                 const Slot *mine = slots + par * MAX_CLUSTER + (lane < nranks ? lane : 0);
                 bool ok;
                 unsigned long long w0, w1, w2;
@@ -206,8 +206,13 @@ k_nn_chain2(double *__restrict__ W, const int n, const int64_t ld, int32_t *__re
                          ((unsigned)(w0 >> 32) == seq && (unsigned)(w1 >> 32) == seq && (unsigned)(w2 >> 32) == seq);
                 } while (!__all_sync(0xffffffffu, ok));
                 if (lane < nranks) { g.lo = (unsigned)w0; g.hi = (unsigned)w1; g.ic = (unsigned)w2; }
+                g = warp_best(g);
+                if (!POLL_ALL && lane == 0) { gres[par * 4 + 0] = g.hi; gres[par * 4 + 1] = g.lo; gres[par * 4 + 2] = g.ic; }
             }
-            g = warp_best(g);
+            if (!POLL_ALL) {  // only warp 0 spins on the slots; the others wait at the barrier and read the result
+                __syncthreads();
+                g.hi = gres[par * 4 + 0]; g.lo = gres[par * 4 + 1]; g.ic = gres[par * 4 + 2];
+            }
             const long long ts3 = clock64();
             cyc_load += ts1 - ts0; cyc_red += ts2 - ts1; cyc_poll += ts3 - ts2;
             gv = key_to_double(g.hi, g.lo);
