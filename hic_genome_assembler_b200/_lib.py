@@ -145,11 +145,12 @@ class Handle:
         return [round(float(v), 3) for v in out[:6]]
 
     def linkage_stats(self) -> dict:
-        out = np.zeros(6, dtype=np.int64)
+        out = np.zeros(8, dtype=np.int64)
         self._L.hica_linkage_stats.argtypes = [C.c_void_p, C.c_void_p]
         self._check(self._L.hica_linkage_stats(self._h, _ptr(out)))
         return {"searches": int(out[0]), "search_cycles": int(out[1]), "merge_cycles": int(out[2]),
-                "load_cycles": int(out[3]), "reduce_cycles": int(out[4]), "exchange_cycles": int(out[5])}
+                "load_cycles": int(out[3]), "reduce_cycles": int(out[4]), "exchange_cycles": int(out[5]),
+                "cached_searches": int(out[6])}
 
     # -- Part 1 -----------------------------------------------------------
     def p1_upload(self, A: np.ndarray):

@@ -24,10 +24,10 @@ extern "C" const char *hica_last_error(hica_handle h) { return h ? h->err.c_str(
 
 extern "C" int64_t hica_launch_count(hica_handle h) { return h ? h->launches : -1; }
 
-extern "C" int hica_linkage_stats(hica_handle h, int64_t *out6)
+extern "C" int hica_linkage_stats(hica_handle h, int64_t *out8)
 {
-    if (!h || !out6) return HICA_ERR_ARG;
-    for (int i = 0; i < 6; i++) out6[i] = h->nn_stats[i];
+    if (!h || !out8) return HICA_ERR_ARG;
+    for (int i = 0; i < 8; i++) out8[i] = h->nn_stats[i];
     return HICA_OK;
 }
 

@@ -44,7 +44,7 @@ struct hica_ctx {
     double *Zraw = nullptr;      // (n-1) x 4 raw merges (device)
     int32_t *size_d = nullptr;   // cluster sizes
     int32_t *chain_d = nullptr;  // per-CTA chain copies
-    long long nn_stats[6] = {0, 0, 0, 0, 0, 0};  // searches, cycles in searches, cycles in merges (last linkage)
+    long long nn_stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // searches, cycles in searches, cycles in merges (last linkage)
     // cuts scratch
     int32_t *x_d = nullptr;      // window counts
     uint8_t *sig_d = nullptr;

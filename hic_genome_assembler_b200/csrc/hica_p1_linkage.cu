@@ -229,6 +229,7 @@ k_nn_chain(double *__restrict__ W, const int n, const int64_t ld, int32_t *__res
 }  // namespace
 
 #include "hica_p1_nnchain2.cuh"
+#include "hica_p1_nnchain3.cuh"
 
 namespace {
 
@@ -329,6 +330,40 @@ int launch_nn_chain(hica_ctx *h, int cluster_size, size_t smem_bytes)
     return HICA_OK;
 }
 
+// k_nn_chain3: the kernel with the nearest-neighbour cache (n <= 65,534 and the cache must fit in shared memory)
+template <bool CHAIN_SMEM>
+int launch_nn_chain3(hica_ctx *h, int cluster_size, const double *nn0_val, const int32_t *nn0_idx)
+{
+    auto kern = nn3::k_nn_chain3<CHAIN_SMEM>;
+    const int n32 = (int)h->n;
+    const size_t smem_bytes = nn3::make_layout(n32, h->ld, nn3::slice_len(n32, cluster_size), CHAIN_SMEM).total;
+    if (smem_bytes > 227 * 1024) return -1;
+    HICA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+    if (cluster_size > 8) HICA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(cluster_size);
+    cfg.blockDim = dim3(nn3::MAX_THREADS);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = h->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cluster_size;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int max_clusters = 0;
+    cudaError_t e = cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg);
+    if (e != cudaSuccess || max_clusters < 1) {
+        cudaGetLastError();
+        return -1;  // caller retries with a smaller cluster
+    }
+    HICA_CUDA(cudaLaunchKernelEx(&cfg, kern, h->W, n32, h->ld, h->size_d, h->chain_d, h->Zraw,
+                                 reinterpret_cast<long long *>(h->misc_d + 64), nn0_val, nn0_idx));
+    HICA_LAUNCHED(h);
+    return HICA_OK;
+}
+
 }  // namespace
 
 int hica_set_order_internal(hica_ctx *h, const int32_t *order_host)
@@ -368,21 +403,37 @@ extern "C" int hica_p1_linkage(hica_handle h, double *Z_host, int32_t *leaves_ho
     if (!h->Zraw && (rc = hica_realloc(h, &h->Zraw, 4 * (n - 1)))) return rc;
     if (!h->size_d && (rc = hica_realloc(h, &h->size_d, (int64_t)NN_MAX_CLUSTER * n))) return rc;
     const char *ver_env = getenv("HICA_NN_KERNEL");
-    const int version = (ver_env && ver_env[0] == '1') ? 1 : 2;
+    int version = 3;  // 3: NN cache (default), 2: every search in full, 1: first-generation kernel
+    if (ver_env && ver_env[0] >= '1' && ver_env[0] <= '3') version = ver_env[0] - '0';
+    if (n > nn3::MAX_N || n < 2) version = std::min(version, 2);
 
     const int nwords = (int)((h->ld + 31) / 32);
-    size_t base_smem = version == 2 ? nn2::base_smem(nwords)
+    size_t base_smem = version >= 2 ? nn2::base_smem(nwords)
                                     : sizeof(Cand) * (2 * NN_MAX_CLUSTER + NN_WARPS) + sizeof(uint32_t) * nwords;
     size_t chain_smem = sizeof(int32_t) * (size_t)n;
     bool chain_in_smem = base_smem + chain_smem <= 200 * 1024;
-    if (!chain_in_smem && !h->chain_d && (rc = hica_realloc(h, &h->chain_d, (int64_t)NN_MAX_CLUSTER * n))) return rc;
+    if (!h->chain_d && (rc = hica_realloc(h, &h->chain_d, (int64_t)NN_MAX_CLUSTER * n))) return rc;
 
     hica_timer t(h, HICA_T_LINKAGE);
     k_fill_i32<<<(unsigned)((NN_MAX_CLUSTER * n + 255) / 256), 256, 0, h->stream>>>(h->size_d, NN_MAX_CLUSTER * n, 1);
     HICA_LAUNCHED(h);
+    HICA_CUDA(cudaMemsetAsync(h->misc_d + 64, 0, 24 * sizeof(long long), h->stream));
     int launched = -1;
     int cs_max = NN_MAX_CLUSTER;
     if (const char *e = getenv("HICA_NN_CLUSTER")) cs_max = std::max(1, std::min(NN_MAX_CLUSTER, atoi(e)));
+    if (version == 3) {
+        // nearest neighbour of every row, all SMs; q_d is free until the cut search
+        double *nn0_val = reinterpret_cast<double *>(h->q_d);
+        int32_t *nn0_idx = reinterpret_cast<int32_t *>(nn0_val + n);
+        nn3::k_nn_init<<<(unsigned)n, 256, 0, h->stream>>>(h->W, (int)n, h->ld, nn0_val, nn0_idx);
+        HICA_LAUNCHED(h);
+        for (int cs = cs_max; cs >= 1 && launched != HICA_OK; cs >>= 1) {
+            launched = launch_nn_chain3<true>(h, cs, nn0_val, nn0_idx);
+            if (launched < 0) launched = launch_nn_chain3<false>(h, cs, nn0_val, nn0_idx);
+            if (launched > 0) return launched;  // a real error
+        }
+        if (launched != HICA_OK) version = 2;  // the cache does not fit: every search in full
+    }
     for (int cs = cs_max; cs >= 1 && launched != HICA_OK; cs >>= 1) {
         if (version == 2)
             launched = chain_in_smem ? launch_nn_chain<true, 2>(h, cs, base_smem + chain_smem)
@@ -401,9 +452,16 @@ extern "C" int hica_p1_linkage(hica_handle h, double *Z_host, int32_t *leaves_ho
     HICA_CUDA(cudaMemcpyAsync(raw.data(), h->Zraw, sizeof(double) * raw.size(), cudaMemcpyDeviceToHost, h->stream));
     HICA_CUDA(cudaStreamSynchronize(h->stream));
     {
-        long long st[6] = {0, 0, 0, 0, 0, 0};
+        long long st[24] = {0};
         cudaMemcpy(st, h->misc_d + 64, sizeof(st), cudaMemcpyDeviceToHost);
-        for (int i = 0; i < 6; i++) h->nn_stats[i] = st[i];
+        for (int i = 0; i < 8; i++) h->nn_stats[i] = st[i];
+        if (getenv("HICA_NN_DEBUG"))
+            fprintf(stderr, "[hica nn] full %lld cached %lld slow %lld | per full search: wb %lld fence %lld sync %lld post %lld | "
+                    "after-merge polls %lld x %lld | per merge: loop %lld s1 %lld inval %lld s2 %lld\n",
+                    st[0], st[6], st[7], st[8] / std::max(1ll, st[0]), st[9] / std::max(1ll, st[0]),
+                    st[10] / std::max(1ll, st[0]), st[11] / std::max(1ll, st[0]), st[13], st[12] / std::max(1ll, st[13]),
+                    st[14] / std::max<long long>(1, n - 1), st[15] / std::max<long long>(1, n - 1),
+                    st[16] / std::max<long long>(1, n - 1), st[17] / std::max<long long>(1, n - 1));
     }
     hica_timer t2(h, HICA_T_LEAFORDER);
     std::vector<double> Z;

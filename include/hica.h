@@ -52,8 +52,9 @@ enum {
 };
 int hica_get_timers(hica_handle h, double *ms /* HICA_T_COUNT */);
 /* counters of the last hica_p1_linkage: nearest-neighbour searches, SM cycles spent in searches, in merges,
- * and the search cycles split into row load / in-CTA reduction / cross-CTA exchange (6 values) */
-int hica_linkage_stats(hica_handle h, int64_t *out6);
+ * the search cycles split into row load / in-CTA reduction / cross-CTA exchange, searches answered from the
+ * nearest-neighbour cache, reserved (8 values; "searches" counts the ones done in full) */
+int hica_linkage_stats(hica_handle h, int64_t *out8);
 /* host-side phase times (ms) of the last hica_p2_order_groups call: sizing, arena cudaMalloc, setup, enqueue +
  * round synchronisation, read-back, cudaFree (16 slots, the rest reserved) */
 int hica_debug_stats(hica_handle h, double *out16);
