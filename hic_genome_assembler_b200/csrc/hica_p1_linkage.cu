@@ -330,11 +330,11 @@ int launch_nn_chain(hica_ctx *h, int cluster_size, size_t smem_bytes)
     return HICA_OK;
 }
 
-// k_nn_chain3: the kernel with the nearest-neighbour cache (n <= 65,534 and the cache must fit in shared memory)
-template <bool CHAIN_SMEM>
-int launch_nn_chain3(hica_ctx *h, int cluster_size, const double *nn0_val, const int32_t *nn0_idx)
+// k_nn_chain3: nearest-neighbour cache + fused merge/search (n <= 32,767 and the cache must fit in shared memory)
+template <bool CHAIN_SMEM, bool STATS>
+int launch_nn_chain3(hica_ctx *h, int cluster_size, const double *nn0_val, const uint32_t *nn0_ent, unsigned flags)
 {
-    auto kern = nn3::k_nn_chain3<CHAIN_SMEM>;
+    auto kern = nn3::k_nn_chain3<CHAIN_SMEM, STATS>;
     const int n32 = (int)h->n;
     const size_t smem_bytes = nn3::make_layout(n32, h->ld, nn3::slice_len(n32, cluster_size), CHAIN_SMEM).total;
     if (smem_bytes > 227 * 1024) return -1;
@@ -342,7 +342,9 @@ int launch_nn_chain3(hica_ctx *h, int cluster_size, const double *nn0_val, const
     if (cluster_size > 8) HICA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(cluster_size);
-    cfg.blockDim = dim3(nn3::MAX_THREADS);
+    int threads = nn3::MAX_THREADS;
+    if (const char *e = getenv("HICA_NN_THREADS")) threads = std::max(64, std::min(nn3::MAX_THREADS, atoi(e) / 32 * 32));
+    cfg.blockDim = dim3(threads);
     cfg.dynamicSmemBytes = smem_bytes;
     cfg.stream = h->stream;
     cudaLaunchAttribute attr[1];
@@ -358,8 +360,8 @@ int launch_nn_chain3(hica_ctx *h, int cluster_size, const double *nn0_val, const
         cudaGetLastError();
         return -1;  // caller retries with a smaller cluster
     }
-    HICA_CUDA(cudaLaunchKernelEx(&cfg, kern, h->W, n32, h->ld, h->size_d, h->chain_d, h->Zraw,
-                                 reinterpret_cast<long long *>(h->misc_d + 64), nn0_val, nn0_idx));
+    HICA_CUDA(cudaLaunchKernelEx(&cfg, kern, h->W, n32, h->ld, h->chain_d, h->Zraw,
+                                 reinterpret_cast<long long *>(h->misc_d + 64), nn0_val, nn0_ent, flags));
     HICA_LAUNCHED(h);
     return HICA_OK;
 }
@@ -417,19 +419,25 @@ extern "C" int hica_p1_linkage(hica_handle h, double *Z_host, int32_t *leaves_ho
     hica_timer t(h, HICA_T_LINKAGE);
     k_fill_i32<<<(unsigned)((NN_MAX_CLUSTER * n + 255) / 256), 256, 0, h->stream>>>(h->size_d, NN_MAX_CLUSTER * n, 1);
     HICA_LAUNCHED(h);
-    HICA_CUDA(cudaMemsetAsync(h->misc_d + 64, 0, 24 * sizeof(long long), h->stream));
+    HICA_CUDA(cudaMemsetAsync(h->misc_d + 64, 0, 144 * sizeof(long long), h->stream));
     int launched = -1;
     int cs_max = NN_MAX_CLUSTER;
     if (const char *e = getenv("HICA_NN_CLUSTER")) cs_max = std::max(1, std::min(NN_MAX_CLUSTER, atoi(e)));
     if (version == 3) {
         // nearest neighbour of every row, all SMs; q_d is free until the cut search
         double *nn0_val = reinterpret_cast<double *>(h->q_d);
-        int32_t *nn0_idx = reinterpret_cast<int32_t *>(nn0_val + n);
-        nn3::k_nn_init<<<(unsigned)n, 256, 0, h->stream>>>(h->W, (int)n, h->ld, nn0_val, nn0_idx);
+        uint32_t *nn0_ent = reinterpret_cast<uint32_t *>(nn0_val + n);
+        nn3::k_nn_init<<<(unsigned)n, 256, 0, h->stream>>>(h->W, (int)n, h->ld, nn0_val, nn0_ent);
         HICA_LAUNCHED(h);
+        const bool dbg = getenv("HICA_NN_DEBUG") != nullptr;
+        unsigned flags = 0;
+        if (const char *e = getenv("HICA_NN_FLAGS")) flags = (unsigned)atoi(e);
         for (int cs = cs_max; cs >= 1 && launched != HICA_OK; cs >>= 1) {
-            launched = launch_nn_chain3<true>(h, cs, nn0_val, nn0_idx);
-            if (launched < 0) launched = launch_nn_chain3<false>(h, cs, nn0_val, nn0_idx);
+            launched = dbg ? launch_nn_chain3<true, true>(h, cs, nn0_val, nn0_ent, flags)
+                           : launch_nn_chain3<true, false>(h, cs, nn0_val, nn0_ent, flags);
+            if (launched < 0)
+                launched = dbg ? launch_nn_chain3<false, true>(h, cs, nn0_val, nn0_ent, flags)
+                               : launch_nn_chain3<false, false>(h, cs, nn0_val, nn0_ent, flags);
             if (launched > 0) return launched;  // a real error
         }
         if (launched != HICA_OK) version = 2;  // the cache does not fit: every search in full
@@ -452,16 +460,21 @@ extern "C" int hica_p1_linkage(hica_handle h, double *Z_host, int32_t *leaves_ho
     HICA_CUDA(cudaMemcpyAsync(raw.data(), h->Zraw, sizeof(double) * raw.size(), cudaMemcpyDeviceToHost, h->stream));
     HICA_CUDA(cudaStreamSynchronize(h->stream));
     {
-        long long st[24] = {0};
+        long long st[144] = {0};
         cudaMemcpy(st, h->misc_d + 64, sizeof(st), cudaMemcpyDeviceToHost);
         for (int i = 0; i < 8; i++) h->nn_stats[i] = st[i];
-        if (getenv("HICA_NN_DEBUG"))
-            fprintf(stderr, "[hica nn] full %lld cached %lld slow %lld | per full search: wb %lld fence %lld sync %lld post %lld | "
-                    "after-merge polls %lld x %lld | per merge: loop %lld s1 %lld inval %lld s2 %lld\n",
-                    st[0], st[6], st[7], st[8] / std::max(1ll, st[0]), st[9] / std::max(1ll, st[0]),
-                    st[10] / std::max(1ll, st[0]), st[11] / std::max(1ll, st[0]), st[13], st[12] / std::max(1ll, st[13]),
-                    st[14] / std::max<long long>(1, n - 1), st[15] / std::max<long long>(1, n - 1),
-                    st[16] / std::max<long long>(1, n - 1), st[17] / std::max<long long>(1, n - 1));
+        if (getenv("HICA_NN_DEBUG")) {
+            const long long nf = std::max(1ll, st[8]);
+            fprintf(stderr, "[hica nn] fused %lld full %lld cached %lld slow %lld; cycles search %lld merge+fused %lld\n",
+                    st[8], st[9], st[6], st[7], st[1], st[2]);
+            for (int r = 0; r < 16; r++) {
+                const long long *rs = st + 16 + 8 * r;
+                if (!rs[6]) continue;
+                fprintf(stderr, "[hica nn] rank %2d per fused step: load %lld compute %lld reduce+barrier %lld post %lld poll %lld | "
+                        "search phase %lld total %lld\n", r, rs[0] / nf, rs[1] / nf, rs[2] / nf, rs[3] / nf, rs[4] / nf,
+                        rs[5] / nf, (rs[5] + rs[6]) / nf);
+            }
+        }
     }
     hica_timer t2(h, HICA_T_LEAFORDER);
     std::vector<double> Z;
