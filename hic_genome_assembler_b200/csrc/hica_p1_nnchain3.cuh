@@ -22,9 +22,10 @@
 //     FUSED with the merge: rows x, y and the next row are loaded together; the one element of the next row
 //     that the merge changes is recomputed locally from W[next][x] and W[next][y] (bit-identical: W is a
 //     mirror); the minimum of the NEW row y - computed element by element anyway - is reduced alongside, so
-//     the merged cluster enters the cache for free.  One CTA barrier, one fence (issued by the posting warp
-//     after the barrier, the grid-sync idiom) and one exchange per merge; cluster sizes and the alive mask are
-//     updated after that barrier by every thread (same values), which removes the merge's own two barriers.
+//     the merged cluster enters the cache for free.  One exchange per merge (see exchange() for the barriers
+//     and the fence); cluster sizes and the alive mask are updated after its barrier by every thread (same
+//     values), which removes the merge's own two barriers.  (A single fence by the posting warp after the
+//     barrier - the grid-sync idiom - was measured slower than every thread fencing its own stores: 78 vs 75 ms.)
 //  4. Everything a thread reads outside a barrier it has written itself: chain[], ent[], size16[], alive[] and
 //     mexact[] are written by ALL threads of the CTA with identical values.
 //
@@ -513,11 +514,13 @@ k_nn_chain3(double *__restrict__ W, const int n, const int64_t ld, int32_t *__re
                         if (!(scan_next && cc == nxt)) W[(int64_t)cc * ld + y] = v;
                         consider_t(b2, v, (unsigned)cc + 1u);
                         // row cc of the cache: its only changed element is column y
-                        const unsigned e = ent[cc];
-                        const unsigned j = e & 0xffffu;
-                        if (j != 0xffffu && (int)j != x && (int)j != y && (unsigned)size16[j] == ((e >> 16) & 0x7fffu)) {
-                            const double me = mexact[cc - lo];
-                            if (v < me || v == me) {
+                        // (v <= recorded minimum is tested first: it is almost never true, and then the entry need
+                        // not even be looked at; mexact of an expired entry is stale, which only costs the look)
+                        const double me = mexact[cc - lo];
+                        if (v <= me) {
+                            const unsigned e = ent[cc];
+                            const unsigned j = e & 0xffffu;
+                            if (j != 0xffffu && (int)j != x && (int)j != y && (unsigned)size16[j] == ((e >> 16) & 0x7fffu)) {
                                 const int q = atomicAdd(qcnt, 1);
                                 if (q < LIST_CAP) { list_c[q] = (unsigned)cc | (v == me ? 0x80000000u : 0u); list_v[q] = v; }
                             }

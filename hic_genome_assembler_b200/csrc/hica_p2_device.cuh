@@ -45,9 +45,9 @@ __device__ __forceinline__ void build_order_cta(const EntryF &entry, int nslots,
 // Bit-exact costFunction_numba of M = S[ix_(o, o)]:
 //   trace_k = ((M[0,k] + M[1,k+1]) + ...)            strictly top to bottom
 //   cum_k   = cum_{k-1} + trace_k ; cost += cum_k / total / k   strictly in k
-// Thread p owns diagonals p+1 and n-1-p (n terms in all).  The short diagonal
-// is read through the transpose St so that neighbouring threads touch
-// neighbouring addresses.  tr = shared scratch of n doubles.  Returns the cost
+// Thread p owns diagonals p+1 and n-1-p (n terms in all).  At a given step the
+// lanes of a warp read one row of S at consecutive columns (coalesced wherever
+// the order is locally contiguous).  tr = shared scratch of n doubles.  Returns the cost
 // in thread 0 (other threads: undefined).  All threads of the CTA must call.
 __device__ __forceinline__ double exact_cost_cta(const double *__restrict__ S, const double *__restrict__ St, int L,
                                                  const int32_t *o, int n, double total, double *tr)
@@ -78,11 +78,11 @@ __device__ __forceinline__ double exact_cost_cta(const double *__restrict__ S, c
             for (; t + PF <= len2; t += PF) {
                 double v[PF];
 #pragma unroll
-                for (int u = 0; u < PF; u++) v[u] = St[(int64_t)o[t + u + k2] * L + o[t + u]];
+                for (int u = 0; u < PF; u++) v[u] = S[(int64_t)o[t + u] * L + o[t + u + k2]];
 #pragma unroll
                 for (int u = 0; u < PF; u++) acc2 = __dadd_rn(acc2, v[u]);
             }
-            for (; t < len2; t++) acc2 = __dadd_rn(acc2, St[(int64_t)o[t + k2] * L + o[t]]);
+            for (; t < len2; t++) acc2 = __dadd_rn(acc2, S[(int64_t)o[t] * L + o[t + k2]]);
             tr[k2] = acc2;
         }
     }

@@ -143,21 +143,34 @@ __global__ void __launch_bounds__(128) k_g_total(const GroupDev *gs, Phase ph, i
     if (threadIdx.x == 0) last = (atomicAdd(&g.st->done_blocks, 1) == (int)gridDim.x - 1);
     __syncthreads();
     if (!last) return;
+    __shared__ double t_s;
+    __shared__ double chunk_s[128];
     if (threadIdx.x == 0) {
         double t = 0.;
         for (int kk = 1; kk < n; kk++) t = __dadd_rn(t, ld_cg_f64(g.tr + kk));
         g.st->total = t;
         g.st->done_blocks = 0;
         g.st->skip = (t == 0.0) ? 1 : 0;
-        if (want_weights) {  // w(d) = (sum_{j=d}^{n-1} 1/j) / total
-            double acc = 0.;
-            for (int d = n - 1; d >= 1; d--) {
-                acc += 1.0 / (double)d;
-                g.Wt[d] = acc / t;
-            }
-            g.Wt[0] = 0.;
-        }
+        t_s = t;
     }
+    if (!want_weights) return;
+    // w(d) = (sum_{j=d}^{n-1} 1/j) / total, d = 1..n-1: only the closed-form (approximate) scores use it, so the
+    // suffix sums are taken chunk-wise by all threads
+    __syncthreads();
+    const double t = t_s;
+    const int T = blockDim.x, per = (n - 1 + T - 1) / T;
+    const int d_lo = 1 + threadIdx.x * per, d_hi = min(n, d_lo + per);
+    double own = 0.;
+    for (int d = d_hi - 1; d >= d_lo; d--) own += 1.0 / (double)d;
+    chunk_s[threadIdx.x] = own;
+    __syncthreads();
+    double acc = 0.;
+    for (int w = threadIdx.x + 1; w < T; w++) acc += chunk_s[w];
+    for (int d = d_hi - 1; d >= d_lo; d--) {
+        acc += 1.0 / (double)d;
+        g.Wt[d] = acc / t;
+    }
+    if (threadIdx.x == 0) g.Wt[0] = 0.;
 }
 
 // exact cost of the current layout -> E_layout (anchor of the closed-form scores)
@@ -412,7 +425,161 @@ __global__ void __launch_bounds__(256) k_g_pick_window(const GroupDev *gs, Phase
     }
 }
 
-// checkAllScores (:332-372): 2(m+1) exact candidates ...
+// ---------------------------------------------------------------------------
+// checkAllScores (:332-372): the pool's next scaffold s (Ls bins) is tried in every slot i = 0..m of the placed
+// layout (P bins) in both orientations - 2(m+1) candidates, each a full costFunction of n = P + Ls bins in the
+// reference.  Same two-phase scheme as the window search.  With w(d) of this step's n and total,
+//     cost(i, ori) = const + F(p_i) + X(i, ori)
+//     F(p)  = sum_{a < p <= b} M[a][b] (w(b - a + Ls) - w(b - a))      placed pairs pushed apart by the insert
+//     X     = sum_{t in s, a placed} M[.][.] w(|pos_t - pos_a|)         new scaffold against the placed bins
+// (pairs inside s, and placed pairs that do not straddle p, are the same for every candidate).
+// F(p_i) = sum_{a < p_i} D[a] with  D[a] = sum_{b >= end(a)} g(a, b) - sum_{b < start(a)} g(b, a),  start/end = the
+// bounds of the scaffold that holds position a: a pair in different scaffolds counts +1 while only its left end
+// is left of p, which is exactly "straddles p".  So one pass over the placed matrix gives all m+1 values of F.
+// Candidates within NEAR_TOL of the best closed-form score (made absolute by the closed-form cost of candidate 0) are
+// re-scored bit-exactly and the reference's rule (first maximum, strictly above 0.) is applied to those.
+struct InsertCand { int i, ori; };
+__device__ __forceinline__ InsertCand insert_cand(int c, int ne)
+{
+    InsertCand r;
+    r.i = c >> 1;
+    const int o0 = ne & 1;
+    const int first = (r.i & 1) ? (o0 ^ 1) : o0;  // the reference leaves the scaffold flipped after every slot (:356-365)
+    r.ori = (c & 1) ? (first ^ 1) : first;
+    return r;
+}
+
+// D[a] for every placed position (INS_ROWS per CTA, one warp per row at a time) -> tab_out[a].  The last CTA
+// computes the anchor instead: the closed-form cost of candidate 0 in full (any summation order), which turns
+// the relative scores into absolute ones for the tolerance test.
+constexpr int INS_ROWS = 64;
+__global__ void __launch_bounds__(256) k_g_ins_rows(const GroupDev *gs, Phase ph)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ double red[8];
+    const GroupDev &g = gs[blockIdx.y];
+    const PhaseParams pp = phase_params(g, ph);
+    if (!pp.active || g.st->inexact) return;  // negative / asymmetric contacts: every candidate is scored exactly
+    const int m = pp.m, n = pp.n;
+    if (n < 2) return;
+    const int ne = g.layout[m];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const double *Wt = g.Wt;
+    if (blockIdx.x == gridDim.x - 1) {  // candidate 0: slot 0, the scaffold's current orientation
+        SmemPlan sp = carve(smem, 0, n, m + 1);
+        SrcInsert src{g.layout, 0, ne};
+        build_order_cta(src, m + 1, g.seg_ptr, g.seg_bins, sp.o, sp.spos, sp.sent, n);
+        const int32_t *o = sp.o;
+        double acc = 0.;
+        for (int k = 1 + warp; k < n; k += 8) {  // one warp per diagonal: lanes read one row each, the sum is any-order
+            double tr = 0.;
+            for (int r = lane; r < n - k; r += 32) tr += g.S[(int64_t)o[r] * g.L + o[r + k]];
+            acc += tr * Wt[k];
+        }
+        for (int d = 16; d >= 1; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+        if (lane == 0) red[warp] = acc;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double c0 = 0.;
+            for (int w = 0; w < 8; w++) c0 += red[w];
+            g.st->E_layout = c0;
+        }
+        return;
+    }
+    const int seg = ne >> 1;
+    const int Ls = g.seg_ptr[seg + 1] - g.seg_ptr[seg], P = n - Ls;
+    if (m < 1 || (int)(blockIdx.x * INS_ROWS) >= P) return;
+    SmemPlan sp = carve(smem, 0, n, m + 1);
+    build_order_cta(SrcLayout{g.layout}, m, g.seg_ptr, g.seg_bins, sp.o, sp.spos, sp.sent, P);
+    const int32_t *o = sp.o;
+    for (int a = blockIdx.x * INS_ROWS + warp; a < min(P, (int)(blockIdx.x + 1) * INS_ROWS); a += 8) {
+        int lo = 0, hi = m;  // slot that holds position a
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (sp.spos[mid] <= a) lo = mid; else hi = mid;
+        }
+        const int start = sp.spos[lo], end = sp.spos[lo + 1];
+        const double *Srow = g.S + (int64_t)o[a] * g.L, *Trow = g.St + (int64_t)o[a] * g.L;
+        double acc = 0.;
+        for (int b = end + lane; b < P; b += 32) acc += Srow[o[b]] * (Wt[b - a + Ls] - Wt[b - a]);
+        for (int b = lane; b < start; b += 32) acc -= Trow[o[b]] * (Wt[a - b + Ls] - Wt[a - b]);
+        for (int d = 16; d >= 1; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+        if (lane == 0) g.tab_out[a] = acc;
+    }
+}
+
+// closed-form score of every candidate (relative to the constant terms)
+__global__ void __launch_bounds__(128) k_g_ins_rel(const GroupDev *gs, Phase ph)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ double red[4];
+    const GroupDev &g = gs[blockIdx.y];
+    const PhaseParams pp = phase_params(g, ph);
+    if (!pp.active || g.st->inexact) return;
+    const int m = pp.m, n = pp.n, c = blockIdx.x;
+    if (n < 2 || c >= 2 * (m + 1)) return;
+    const int ne = g.layout[m], seg = ne >> 1;
+    const int b0 = g.seg_ptr[seg], Ls = g.seg_ptr[seg + 1] - b0, P = n - Ls;
+    SmemPlan sp = carve(smem, 0, n, m + 1);
+    if (m >= 1) build_order_cta(SrcLayout{g.layout}, m, g.seg_ptr, g.seg_bins, sp.o, sp.spos, sp.sent, P);
+    const InsertCand cd = insert_cand(c, ne);
+    const int p = (m >= 1) ? sp.spos[cd.i] : 0;
+    const int32_t *o = sp.o;
+    const double *Wt = g.Wt;
+    const int L = g.L;
+    double acc = 0.;
+    for (int a = threadIdx.x; a < p; a += blockDim.x) acc += g.tab_out[a];
+    for (int a = threadIdx.x; a < P; a += blockDim.x) {
+        const int oa = o[a];
+        if (a < p) {
+            const double *Srow = g.S + (int64_t)oa * L;
+            for (int t = 0; t < Ls; t++) {
+                const int nb = g.seg_bins[b0 + (cd.ori ? (Ls - 1 - t) : t)];
+                acc += Srow[nb] * Wt[p + t - a];
+            }
+        } else {
+            const double *Trow = g.St + (int64_t)oa * L;  // St[oa][nb] = S[nb][oa]
+            for (int t = 0; t < Ls; t++) {
+                const int nb = g.seg_bins[b0 + (cd.ori ? (Ls - 1 - t) : t)];
+                acc += Trow[nb] * Wt[a + Ls - p - t];
+            }
+        }
+    }
+    for (int d = 16; d >= 1; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double rel = 0.;
+        for (int w = 0; w < (int)blockDim.x / 32; w++) rel += red[w];
+        g.rel[c] = rel;
+        atomicMax(&g.st->amax_key, f64_order_key(rel));
+        if (c == 0) g.st->rel0 = rel;
+    }
+}
+
+// candidates that can still be the exact winner
+__global__ void __launch_bounds__(128) k_g_ins_select(const GroupDev *gs, Phase ph)
+{
+    const GroupDev &g = gs[blockIdx.y];
+    const PhaseParams pp = phase_params(g, ph);
+    if (!pp.active) return;
+    GroupState *st = g.st;
+    const int B = 2 * (pp.m + 1);
+    const bool all = st->inexact || pp.n < 2;
+    const double amax = st->E_layout + (f64_from_order_key(st->amax_key) - st->rel0);
+    const double scale = fmax(fabs(amax), fabs(st->E_layout));
+    const double thr = fmax(amax, 0.0) - NEAR_TOL * scale;  // bestCost starts at 0. (:338)
+    for (int c = threadIdx.x; c < B; c += blockDim.x) {
+        bool near = all;
+        if (!all) {
+            const double a = st->E_layout + (g.rel[c] - st->rel0);
+            near = !(a < thr);
+        }
+        if (near) g.near_id[atomicAdd(&st->near_count, 1)] = c;
+    }
+}
+
+// bit-exact re-scoring of the near list
 __global__ void __launch_bounds__(EX_THREADS) k_g_insert_scores(const GroupDev *gs, Phase ph)
 {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -420,22 +587,22 @@ __global__ void __launch_bounds__(EX_THREADS) k_g_insert_scores(const GroupDev *
     const PhaseParams pp = phase_params(g, ph);
     if (!pp.active) return;
     const int m = pp.m, n = pp.n;
-    const int c = blockIdx.x;
-    if (c >= 2 * (m + 1)) return;
-    if (n < 2) {  // a single bin: every cost is 0.0
-        if (threadIdx.x == 0) g.near_score[c] = 0.0;
-        return;
-    }
+    const int cnt = g.st->near_count;
+    if ((int)blockIdx.x >= cnt) return;
     SmemPlan sp = carve(smem, n, n, m + 1);
-    const int i = c >> 1, which = c & 1;
     const int ne = g.layout[m];
-    const int o0 = ne & 1;
-    const int first = (i & 1) ? (o0 ^ 1) : o0;   // the reference leaves the scaffold flipped after every slot (:356-365)
-    const int ori = which ? (first ^ 1) : first;
-    SrcInsert src{g.layout, i, ((ne >> 1) << 1) | ori};
-    build_order_cta(src, m + 1, g.seg_ptr, g.seg_bins, sp.o, sp.spos, sp.sent, n);
-    const double cost = exact_cost_cta(g.S, g.St, g.L, sp.o, n, g.st->total, sp.tr);
-    if (threadIdx.x == 0) g.near_score[c] = cost;
+    for (int i = blockIdx.x; i < cnt; i += gridDim.x) {
+        const int c = g.near_id[i];
+        if (n < 2) {  // a single bin: every cost is 0.0
+            if (threadIdx.x == 0) g.near_score[i] = 0.0;
+            continue;
+        }
+        const InsertCand cd = insert_cand(c, ne);
+        SrcInsert src{g.layout, cd.i, ((ne >> 1) << 1) | cd.ori};
+        build_order_cta(src, m + 1, g.seg_ptr, g.seg_bins, sp.o, sp.spos, sp.sent, n);
+        const double cost = exact_cost_cta(g.S, g.St, g.L, sp.o, n, g.st->total, sp.tr);
+        if (threadIdx.x == 0) g.near_score[i] = cost;
+    }
 }
 
 // ... then the insertion itself
@@ -445,12 +612,13 @@ __global__ void __launch_bounds__(32) k_g_pick_insert(const GroupDev *gs, Phase 
     const PhaseParams pp = phase_params(g, ph);
     if (!pp.active) return;
     GroupState *st = g.st;
-    const int m = pp.m, B = 2 * (m + 1);
+    const int m = pp.m, cnt = st->near_count;
     double best = 0.0;  // bestCost starts at 0. (:338); strict '>' keeps the first maximum
     int bi = INT_MAX;
-    for (int c = threadIdx.x; c < B; c += 32) {
-        const double s = g.near_score[c];
-        if (s > best) { best = s; bi = c; }
+    for (int i = threadIdx.x; i < cnt; i += 32) {
+        const double s = g.near_score[i];
+        const int c = g.near_id[i];
+        if (s > best || (s == best && bi != INT_MAX && c < bi)) { best = s; bi = c; }
     }
     for (int d = 16; d >= 1; d >>= 1) {
         const double ov = __shfl_xor_sync(0xffffffffu, best, d);
@@ -461,14 +629,16 @@ __global__ void __launch_bounds__(32) k_g_pick_insert(const GroupDev *gs, Phase 
     const int ne = g.layout[m];
     int pos = 0, ori = 0;
     if (bi != INT_MAX) {
-        pos = bi >> 1;
-        const int o0 = ne & 1, first = (pos & 1) ? (o0 ^ 1) : o0;
-        ori = (bi & 1) ? (first ^ 1) : first;
+        const InsertCand cd = insert_cand(bi, ne);
+        pos = cd.i;
+        ori = cd.ori;
     }
     for (int s = m; s > pos; s--) g.layout[s] = g.layout[s - 1];
     g.layout[pos] = ((ne >> 1) << 1) | ori;
     st->best_cost = best;
-    st->n_exact += B;
+    st->n_exact += cnt;
+    st->near_count = 0;
+    st->amax_key = 0ull;
 }
 
 __global__ void k_g_round_end(const GroupDev *gs)
@@ -710,6 +880,8 @@ extern "C" int hica_p2_order_groups(hica_handle h, int32_t ngroups, const int32_
     ENG_CUDA(cudaFuncSetAttribute(k_g_exact_near, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex_smem));
     ENG_CUDA(cudaFuncSetAttribute(k_g_anchor, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex_smem));
     ENG_CUDA(cudaFuncSetAttribute(k_g_insert_scores, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex_smem));
+    ENG_CUDA(cudaFuncSetAttribute(k_g_ins_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tot_smem));
+    ENG_CUDA(cudaFuncSetAttribute(k_g_ins_rel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tot_smem));
     ENG_CUDA(cudaFuncSetAttribute(k_g_total, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tot_smem));
     const size_t tab_smem = sizeof(double) * Lmax + sizeof(int32_t) * (Lmax + 2 * (nseg_max + 1) + 2);
     ENG_CUDA(cudaFuncSetAttribute(k_g_tables, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tab_smem));
@@ -739,10 +911,14 @@ extern "C" int hica_p2_order_groups(hica_handle h, int32_t ngroups, const int32_
     // ---- greedy insertion, a do-while per group (:475-493)
     for (int step = 0; step < ins_steps; step++) {
         Phase ph = {PH_INSERT, step, 0};
-        k_g_total<<<dim3(tot_blocks, G), 128, tot_smem, s>>>(gdev, ph, 0);
-        k_g_insert_scores<<<dim3(2 * (nseg_max + 1), G), EX_THREADS, ex_smem, s>>>(gdev, ph);
+        const unsigned nb_c = 2 * (unsigned)(nseg_max + 1);
+        k_g_total<<<dim3(tot_blocks, G), 128, tot_smem, s>>>(gdev, ph, 1);
+        k_g_ins_rows<<<dim3((unsigned)((Lmax + INS_ROWS - 1) / INS_ROWS) + 1, G), 256, tot_smem, s>>>(gdev, ph);
+        k_g_ins_rel<<<dim3(nb_c, G), 128, tot_smem, s>>>(gdev, ph);
+        k_g_ins_select<<<dim3(1, G), 128, 0, s>>>(gdev, ph);
+        k_g_insert_scores<<<dim3(std::min(nb_c, 16u), G), EX_THREADS, ex_smem, s>>>(gdev, ph);
         k_g_pick_insert<<<dim3(1, G), 32, 0, s>>>(gdev, ph);
-        h->launches += 3;
+        h->launches += 6;
     }
     // ---- sliding-window scan (:579-580)
     std::vector<GroupState> hst(ngroups);
