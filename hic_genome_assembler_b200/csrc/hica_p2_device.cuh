@@ -17,16 +17,27 @@ __device__ __forceinline__ void build_order_cta(const EntryF &entry, int nslots,
                                                 int32_t *sent, int n)
 {
     const int tid = threadIdx.x, T = blockDim.x;
-    for (int s = tid; s < nslots; s += T) sent[s] = entry(s);
+    // slot lengths are fetched by all threads at once (a serial walk would chain nslots global-load latencies),
+    // then warp 0 turns them into start positions with a shuffle scan
+    for (int s = tid; s < nslots; s += T) {
+        const int e = entry(s), seg = e >> 1;
+        sent[s] = e;
+        spos[s + 1] = seg_ptr[seg + 1] - seg_ptr[seg];
+    }
     __syncthreads();
-    if (tid == 0) {
-        int acc = 0;
-        for (int s = 0; s < nslots; s++) {
-            spos[s] = acc;
-            int seg = sent[s] >> 1;
-            acc += seg_ptr[seg + 1] - seg_ptr[seg];
+    if (tid < 32) {
+        int carry = 0;
+        for (int base = 0; base < nslots; base += 32) {
+            const int s = base + tid;
+            int v = (s < nslots) ? spos[s + 1] : 0;
+            for (int d = 1; d < 32; d <<= 1) {
+                const int u = __shfl_up_sync(0xffffffffu, v, d);
+                if (tid >= d) v += u;
+            }
+            if (s < nslots) spos[s + 1] = carry + v;
+            carry += __shfl_sync(0xffffffffu, v, 31);
         }
-        spos[nslots] = acc;
+        if (tid == 0) spos[0] = 0;
     }
     __syncthreads();
     for (int t = tid; t < n; t += T) {

@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(128) k_g_total(const GroupDev *gs, Phase ph, i
 }
 
 // exact cost of the current layout -> E_layout (anchor of the closed-form scores)
-__global__ void __launch_bounds__(EX_THREADS) k_g_anchor(const GroupDev *gs, Phase ph)
+__global__ void __launch_bounds__(EX_THREADS, 1) k_g_anchor(const GroupDev *gs, Phase ph)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const GroupDev &g = gs[blockIdx.y];
@@ -350,7 +350,7 @@ __global__ void __launch_bounds__(256) k_g_select(const GroupDev *gs, Phase ph, 
 }
 
 // bit-exact re-scoring of the near list
-__global__ void __launch_bounds__(EX_THREADS) k_g_exact_near(const GroupDev *gs, Phase ph, Tables tb)
+__global__ void __launch_bounds__(EX_THREADS, 1) k_g_exact_near(const GroupDev *gs, Phase ph, Tables tb)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const GroupDev &g = gs[blockIdx.y];
@@ -580,7 +580,7 @@ __global__ void __launch_bounds__(128) k_g_ins_select(const GroupDev *gs, Phase 
 }
 
 // bit-exact re-scoring of the near list
-__global__ void __launch_bounds__(EX_THREADS) k_g_insert_scores(const GroupDev *gs, Phase ph)
+__global__ void __launch_bounds__(EX_THREADS, 1) k_g_insert_scores(const GroupDev *gs, Phase ph)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const GroupDev &g = gs[blockIdx.y];

@@ -65,7 +65,7 @@ struct SlotSrc {
     __device__ int operator()(int s) const { return slot_entry(*a, cand, s); }
 };
 
-__global__ void __launch_bounds__(SC_THREADS) k_score(ScoreArgs a)
+__global__ void __launch_bounds__(SC_THREADS, 1) k_score(ScoreArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     double *tr = reinterpret_cast<double *>(smem);                 // n
