@@ -32,6 +32,10 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 
+# DRAM bytes of one linkage-kernel launch measured with `ncu --set full` (bins -> bytes); see profiles/
+NCU_DRAM_BYTES = {16000: 4.95e9}
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -351,9 +355,11 @@ def main():
                 "d2h_bytes_per_step": int(32 * (n - 1) + 4 * n + 8 * len(last["cuts"]) + 24 * max(1, p2_calls))},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "k_nn_chain (linkage, latency-bound)", "achieved": achieved,
-                     "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                     "per_kernel": kernels},
+        "roofline": {"bound": "hbm", "kernel": "nn3::k_nn_chain3 (linkage: one 16-CTA cluster, latency-bound chain)",
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": NCU_DRAM_BYTES.get(n), "traffic_source": "profiles/r01_ncu_full_summary.txt (ncu --set full, "
+                     "dram__bytes_read.sum + dram__bytes_write.sum per launch)" if n in NCU_DRAM_BYTES else None,
+                     "alg_bytes_per_launch": link_bytes, "peak_source": peak_src, "per_kernel": kernels},
     }
     if not args.no_cpu_baseline:
         wl["p2_pairs_full"] = p2_pairs
