@@ -56,19 +56,18 @@ __device__ __forceinline__ void build_order_cta(const EntryF &entry, int nslots,
 // Bit-exact costFunction_numba of M = S[ix_(o, o)]:
 //   trace_k = ((M[0,k] + M[1,k+1]) + ...)            strictly top to bottom
 //   cum_k   = cum_{k-1} + trace_k ; cost += cum_k / total / k   strictly in k
-// Thread p owns diagonals p+1 and n-1-p (n terms in all).  At a given step the
-// lanes of a warp read one row of S at consecutive columns (coalesced wherever
-// the order is locally contiguous).  tr = shared scratch of n doubles.  Returns the cost
-// in thread 0 (other threads: undefined).  All threads of the CTA must call.
-__device__ __forceinline__ double exact_cost_cta(const double *__restrict__ S, const double *__restrict__ St, int L,
-                                                 const int32_t *o, int n, double total, double *tr)
+// Pair p of diagonals = (p+1, n-1-p): n terms in all, one thread each.  At a given step the lanes of a warp read
+// one row of S at consecutive columns (coalesced wherever the order is locally contiguous).
+//
+// exact_gather_diagonals: the trace sums of the pairs [p_begin, p_end) -> dst[k] (shared memory, possibly a
+// peer CTA's).  The additions of one diagonal are a dependent chain (that IS the reference's order); what can
+// overlap is the memory latency, so every thread keeps PF loads of its diagonal in flight ahead of the adds.
+template <int PF>
+__device__ __forceinline__ void exact_gather_diagonals(const double *__restrict__ S, int L, const int32_t *o, int n,
+                                                       double *dst, int p_begin, int p_end)
 {
-    // The additions of one diagonal are a dependent chain (that IS the reference's order); what can overlap is
-    // the memory latency, so every thread keeps PF loads of its diagonal in flight ahead of the adds.
-    constexpr int PF = 16;
     const int tid = threadIdx.x, T = blockDim.x;
-    const int npairs = n / 2;
-    for (int p = tid; p < npairs; p += T) {
+    for (int p = p_begin + tid; p < p_end; p += T) {
         const int k1 = p + 1, k2 = n - 1 - p;
         const int len1 = n - k1;
         double acc1 = 0.;
@@ -81,7 +80,7 @@ __device__ __forceinline__ double exact_cost_cta(const double *__restrict__ S, c
             for (int u = 0; u < PF; u++) acc1 = __dadd_rn(acc1, v[u]);
         }
         for (; r < len1; r++) acc1 = __dadd_rn(acc1, S[(int64_t)o[r] * L + o[r + k1]]);
-        tr[k1] = acc1;
+        dst[k1] = acc1;
         if (k2 != k1) {
             const int len2 = n - k2;
             double acc2 = 0.;
@@ -94,10 +93,16 @@ __device__ __forceinline__ double exact_cost_cta(const double *__restrict__ S, c
                 for (int u = 0; u < PF; u++) acc2 = __dadd_rn(acc2, v[u]);
             }
             for (; t < len2; t++) acc2 = __dadd_rn(acc2, S[(int64_t)o[t] * L + o[t + k2]]);
-            tr[k2] = acc2;
+            dst[k2] = acc2;
         }
     }
-    __syncthreads();
+}
+
+// exact_cost_finish: tr[1..n) holds the trace sums; the sequential part.  Returns the cost in thread 0 (other
+// threads: undefined).  All threads of the CTA must call.
+__device__ __forceinline__ double exact_cost_finish(double *tr, int n, double total)
+{
+    const int tid = threadIdx.x, T = blockDim.x;
     if (tid == 0) {  // running sum over the diagonals: sequential adds, shared-memory reads batched ahead of them
         double cum = 0.;
         int k = 1;
@@ -129,6 +134,16 @@ __device__ __forceinline__ double exact_cost_cta(const double *__restrict__ S, c
     }
     __syncthreads();
     return cost;
+}
+
+// one CTA does it all.  tr = shared scratch of n doubles.
+__device__ __forceinline__ double exact_cost_cta(const double *__restrict__ S, const double *__restrict__ St, int L,
+                                                 const int32_t *o, int n, double total, double *tr)
+{
+    (void)St;
+    exact_gather_diagonals<16>(S, L, o, n, tr, 0, n / 2);
+    __syncthreads();
+    return exact_cost_finish(tr, n, total);
 }
 
 // numpy.trace over a gathered diagonal = numpy pairwise summation of f(0..n)

@@ -19,6 +19,7 @@
 // n = 800, for non-negative symmetric contacts), so the exact winner is always inside the re-scored set and
 // the result is bit-identical to scoring every candidate exactly.  Matrices with negative or asymmetric
 // entries (for which that bound does not hold) are detected at gather time and re-scored in full.
+#include <cooperative_groups.h>
 #include <limits.h>
 #include <math.h>
 
@@ -31,6 +32,27 @@
 namespace {
 
 constexpr int EX_THREADS = 512;  // one pass over the n/2 diagonal pairs for n <= 1024
+constexpr int EX_SPLIT = 4;      // CTAs (one cluster) that share one exact score
+namespace cg = cooperative_groups;
+
+// Exact cost of one candidate by a cluster of EX_SPLIT CTAs: the pairs of diagonals are dealt out in contiguous
+// ranges, every CTA writes its trace sums straight into CTA 0's shared memory (DSMEM), CTA 0 runs the
+// sequential part.  One score is a chain of n dependent additions per thread whatever the split, but with a
+// quarter of the threads per SM the loads come back faster and 32 of them can be kept in flight per thread.
+// Returns true in CTA 0 (cost valid in its thread 0).  Every thread of every CTA of the cluster must call.
+__device__ __forceinline__ bool exact_cost_cluster(const double *__restrict__ S, int L, const int32_t *o, int n,
+                                                   double total, double *tr, double &cost)
+{
+    cg::cluster_group cl = cg::this_cluster();
+    const int part = (int)cl.block_rank(), nparts = (int)cl.num_blocks();
+    const int npairs = n / 2, per = (npairs + nparts - 1) / nparts;
+    exact_gather_diagonals<32>(S, L, o, n, cl.map_shared_rank(tr, 0), min(npairs, part * per),
+                               min(npairs, (part + 1) * per));
+    cl.sync();  // every trace sum has landed in CTA 0
+    if (part == 0) cost = exact_cost_finish(tr, n, total);
+    cl.sync();  // CTA 0 is done with tr: the next candidate may overwrite it
+    return part == 0;
+}
 constexpr double NEAR_TOL = 1e-10;
 
 struct GroupState {
@@ -242,11 +264,18 @@ __global__ void __launch_bounds__(128) k_g_tables(const GroupDev *gs, Phase ph, 
             // the reference reads M[row of the earlier position][column of the later one]; both branches walk a
             // row of S / S^T so that neighbouring threads (neighbouring outside bins) touch neighbouring addresses
             const double *base = (apos < p0 ? g.St : g.S) + abin;
-#pragma unroll 4
-            for (int t = 0; t < len; t++) {
-                const int bpos = p0 + q + (o ? (len - 1 - t) : t);
-                const int d = apos < bpos ? bpos - apos : apos - bpos;
-                acc += base[(int64_t)sbins[t] * L] * wt_s[d];
+            // 8 contacts in flight per thread: the loop is a chain of L2 round trips otherwise
+            for (int t0 = 0; t0 < len; t0 += 8) {
+                double v[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) v[k] = (t0 + k < len) ? base[(int64_t)sbins[t0 + k] * L] : 0.;
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const int t = min(t0 + k, len - 1);
+                    const int bpos = p0 + q + (o ? (len - 1 - t) : t);
+                    const int d = apos < bpos ? bpos - apos : apos - bpos;
+                    acc += v[k] * wt_s[d];
+                }
             }
         }
         for (int d = 16; d >= 1; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
@@ -269,11 +298,21 @@ __global__ void __launch_bounds__(128) k_g_tables(const GroupDev *gs, Phase ph, 
         const int len = wlen[s], len2 = wlen[s2];
         const int work = len * len2;
         double acc = 0.;
-        for (int w = lane; w < work; w += 32) {
-            const int t = w / len2, t2 = w - t * len2;
-            const int off = o ? (len - 1 - t) : t, off2 = o2 ? (len2 - 1 - t2) : t2;
-            const int d = len - off + gap + off2;
-            acc += g.S[(int64_t)g.seg_bins[woff[s] + t] * L + g.seg_bins[woff[s2] + t2]] * g.Wt[d];
+        for (int w0 = lane; w0 < work; w0 += 4 * 32) {  // 4 contacts in flight per lane
+            double v[4], wv[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int w = w0 + 32 * k;
+                v[k] = 0.; wv[k] = 0.;
+                if (w < work) {
+                    const int t = w / len2, t2 = w - t * len2;
+                    const int off = o ? (len - 1 - t) : t, off2 = o2 ? (len2 - 1 - t2) : t2;
+                    v[k] = g.S[(int64_t)g.seg_bins[woff[s] + t] * L + g.seg_bins[woff[s2] + t2]];
+                    wv[k] = g.Wt[len - off + gap + off2];
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++) acc += v[k] * wv[k];
         }
         for (int d = 16; d >= 1; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
         if (lane == 0) g.tab_win[bw] = acc;
@@ -350,24 +389,26 @@ __global__ void __launch_bounds__(256) k_g_select(const GroupDev *gs, Phase ph, 
 }
 
 // bit-exact re-scoring of the near list
-__global__ void __launch_bounds__(EX_THREADS, 1) k_g_exact_near(const GroupDev *gs, Phase ph, Tables tb)
+__global__ void __cluster_dims__(EX_SPLIT, 1, 1) __launch_bounds__(EX_THREADS, 1)
+k_g_exact_near(const GroupDev *gs, Phase ph, Tables tb)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const GroupDev &g = gs[blockIdx.y];
     const PhaseParams pp = phase_params(g, ph);
     if (!pp.active || g.st->skip) return;
     const int cnt = g.st->near_count;
-    if ((int)blockIdx.x >= cnt) return;
+    const int slot = blockIdx.x / EX_SPLIT, nslots_grid = gridDim.x / EX_SPLIT;  // one cluster per slot
+    if (slot >= cnt) return;
     const int m = pp.m, n_ori = tb.n_ori[m];
     SmemPlan sp = carve(smem, pp.n, pp.n, pp.nslots);
     const double total = g.st->total;
-    for (int i = blockIdx.x; i < cnt; i += gridDim.x) {
+    for (int i = slot; i < cnt; i += nslots_grid) {
         const int c = g.near_id[i];
         const int oi = c / n_ori, ri = c % n_ori;
         SrcWindow src{g.layout, pp.ws, m, tb.ord[m] + (size_t)oi * m, tb.ori[m] + (size_t)ri * m};
         build_order_cta(src, pp.nslots, g.seg_ptr, g.seg_bins, sp.o, sp.spos, sp.sent, pp.n);
-        const double cost = exact_cost_cta(g.S, g.St, g.L, sp.o, pp.n, total, sp.tr);
-        if (threadIdx.x == 0) g.near_score[i] = cost;
+        double cost = 0.;
+        if (exact_cost_cluster(g.S, g.L, sp.o, pp.n, total, sp.tr, cost) && threadIdx.x == 0) g.near_score[i] = cost;
     }
 }
 
@@ -436,7 +477,7 @@ __global__ void __launch_bounds__(256) k_g_pick_window(const GroupDev *gs, Phase
 // F(p_i) = sum_{a < p_i} D[a] with  D[a] = sum_{b >= end(a)} g(a, b) - sum_{b < start(a)} g(b, a),  start/end = the
 // bounds of the scaffold that holds position a: a pair in different scaffolds counts +1 while only its left end
 // is left of p, which is exactly "straddles p".  So one pass over the placed matrix gives all m+1 values of F.
-// Candidates within NEAR_TOL of the best closed-form score (made absolute by the closed-form cost of candidate 0) are
+// Candidates within NEAR_TOL (relative to an upper bound of any score) of the best closed-form score are
 // re-scored bit-exactly and the reference's rule (first maximum, strictly above 0.) is applied to those.
 struct InsertCand { int i, ori; };
 __device__ __forceinline__ InsertCand insert_cand(int c, int ne)
@@ -449,14 +490,11 @@ __device__ __forceinline__ InsertCand insert_cand(int c, int ne)
     return r;
 }
 
-// D[a] for every placed position (INS_ROWS per CTA, one warp per row at a time) -> tab_out[a].  The last CTA
-// computes the anchor instead: the closed-form cost of candidate 0 in full (any summation order), which turns
-// the relative scores into absolute ones for the tolerance test.
-constexpr int INS_ROWS = 64;
+// D[a] for every placed position (INS_ROWS per CTA, one warp per row at a time) -> tab_out[a].
+constexpr int INS_ROWS = 16;
 __global__ void __launch_bounds__(256) k_g_ins_rows(const GroupDev *gs, Phase ph)
 {
     extern __shared__ __align__(16) unsigned char smem[];
-    __shared__ double red[8];
     const GroupDev &g = gs[blockIdx.y];
     const PhaseParams pp = phase_params(g, ph);
     if (!pp.active || g.st->inexact) return;  // negative / asymmetric contacts: every candidate is scored exactly
@@ -465,27 +503,6 @@ __global__ void __launch_bounds__(256) k_g_ins_rows(const GroupDev *gs, Phase ph
     const int ne = g.layout[m];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const double *Wt = g.Wt;
-    if (blockIdx.x == gridDim.x - 1) {  // candidate 0: slot 0, the scaffold's current orientation
-        SmemPlan sp = carve(smem, 0, n, m + 1);
-        SrcInsert src{g.layout, 0, ne};
-        build_order_cta(src, m + 1, g.seg_ptr, g.seg_bins, sp.o, sp.spos, sp.sent, n);
-        const int32_t *o = sp.o;
-        double acc = 0.;
-        for (int k = 1 + warp; k < n; k += 8) {  // one warp per diagonal: lanes read one row each, the sum is any-order
-            double tr = 0.;
-            for (int r = lane; r < n - k; r += 32) tr += g.S[(int64_t)o[r] * g.L + o[r + k]];
-            acc += tr * Wt[k];
-        }
-        for (int d = 16; d >= 1; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
-        if (lane == 0) red[warp] = acc;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            double c0 = 0.;
-            for (int w = 0; w < 8; w++) c0 += red[w];
-            g.st->E_layout = c0;
-        }
-        return;
-    }
     const int seg = ne >> 1;
     const int Ls = g.seg_ptr[seg + 1] - g.seg_ptr[seg], P = n - Ls;
     if (m < 1 || (int)(blockIdx.x * INS_ROWS) >= P) return;
@@ -501,7 +518,9 @@ __global__ void __launch_bounds__(256) k_g_ins_rows(const GroupDev *gs, Phase ph
         const int start = sp.spos[lo], end = sp.spos[lo + 1];
         const double *Srow = g.S + (int64_t)o[a] * g.L, *Trow = g.St + (int64_t)o[a] * g.L;
         double acc = 0.;
+#pragma unroll 4
         for (int b = end + lane; b < P; b += 32) acc += Srow[o[b]] * (Wt[b - a + Ls] - Wt[b - a]);
+#pragma unroll 4
         for (int b = lane; b < start; b += 32) acc -= Trow[o[b]] * (Wt[a - b + Ls] - Wt[a - b]);
         for (int d = 16; d >= 1; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
         if (lane == 0) g.tab_out[a] = acc;
@@ -566,21 +585,21 @@ __global__ void __launch_bounds__(128) k_g_ins_select(const GroupDev *gs, Phase 
     GroupState *st = g.st;
     const int B = 2 * (pp.m + 1);
     const bool all = st->inexact || pp.n < 2;
-    const double amax = st->E_layout + (f64_from_order_key(st->amax_key) - st->rel0);
-    const double scale = fmax(fabs(amax), fabs(st->E_layout));
-    const double thr = fmax(amax, 0.0) - NEAR_TOL * scale;  // bestCost starts at 0. (:338)
+    // The closed form differs from the exact score by a few n ulp of the score itself, and no score exceeds
+    // H_{n-1} = sum_{k<n} 1/k (the traces add up to total, and w(k) <= w(1) = H_{n-1} / total): the tolerance
+    // is taken relative to that bound, which needs no absolute anchor.  Whether the best score beats the
+    // initial bestCost of 0. (:338) is decided on the exact scores in k_g_pick_insert.
+    const double hn = g.Wt[1] * st->total;  // w(1) = H_{n-1} / total
+    const double thr = f64_from_order_key(st->amax_key) - NEAR_TOL * hn;
     for (int c = threadIdx.x; c < B; c += blockDim.x) {
-        bool near = all;
-        if (!all) {
-            const double a = st->E_layout + (g.rel[c] - st->rel0);
-            near = !(a < thr);
-        }
+        const bool near = all || !(g.rel[c] < thr);
         if (near) g.near_id[atomicAdd(&st->near_count, 1)] = c;
     }
 }
 
 // bit-exact re-scoring of the near list
-__global__ void __launch_bounds__(EX_THREADS, 1) k_g_insert_scores(const GroupDev *gs, Phase ph)
+__global__ void __cluster_dims__(EX_SPLIT, 1, 1) __launch_bounds__(EX_THREADS, 1)
+k_g_insert_scores(const GroupDev *gs, Phase ph)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const GroupDev &g = gs[blockIdx.y];
@@ -588,10 +607,11 @@ __global__ void __launch_bounds__(EX_THREADS, 1) k_g_insert_scores(const GroupDe
     if (!pp.active) return;
     const int m = pp.m, n = pp.n;
     const int cnt = g.st->near_count;
-    if ((int)blockIdx.x >= cnt) return;
+    const int slot = blockIdx.x / EX_SPLIT, nslots_grid = gridDim.x / EX_SPLIT;  // one cluster per slot
+    if (slot >= cnt) return;
     SmemPlan sp = carve(smem, n, n, m + 1);
     const int ne = g.layout[m];
-    for (int i = blockIdx.x; i < cnt; i += gridDim.x) {
+    for (int i = slot; i < cnt; i += nslots_grid) {
         const int c = g.near_id[i];
         if (n < 2) {  // a single bin: every cost is 0.0
             if (threadIdx.x == 0) g.near_score[i] = 0.0;
@@ -600,8 +620,8 @@ __global__ void __launch_bounds__(EX_THREADS, 1) k_g_insert_scores(const GroupDe
         const InsertCand cd = insert_cand(c, ne);
         SrcInsert src{g.layout, cd.i, ((ne >> 1) << 1) | cd.ori};
         build_order_cta(src, m + 1, g.seg_ptr, g.seg_bins, sp.o, sp.spos, sp.sent, n);
-        const double cost = exact_cost_cta(g.S, g.St, g.L, sp.o, n, g.st->total, sp.tr);
-        if (threadIdx.x == 0) g.near_score[i] = cost;
+        double cost = 0.;
+        if (exact_cost_cluster(g.S, g.L, sp.o, n, g.st->total, sp.tr, cost) && threadIdx.x == 0) g.near_score[i] = cost;
     }
 }
 
@@ -888,14 +908,33 @@ extern "C" int hica_p2_order_groups(hica_handle h, int32_t ngroups, const int32_
     const unsigned G = (unsigned)ngroups;
     const unsigned tot_blocks = (unsigned)std::max(1, (Lmax - 1 + 127) / 128);
 
+    // HICA_P2_PROFILE=1: CUDA events between the launches, summed per kernel and printed to stderr (diagnostic)
+    const bool prof = getenv("HICA_P2_PROFILE") != nullptr;
+    static const char *knames[] = {"(start)", "k_g_total", "k_g_anchor", "k_g_tables", "k_g_approx", "k_g_select",
+                                   "k_g_exact_near", "k_g_pick_window", "k_g_ins_rows", "k_g_ins_rel", "k_g_ins_select",
+                                   "k_g_insert_scores", "k_g_pick_insert", "other"};
+    std::vector<std::pair<int, cudaEvent_t>> marks;
+    auto mark = [&](int id) {
+        if (!prof) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, s);
+        marks.push_back({id, e});
+    };
+    mark(0);
     auto window_search = [&](Phase ph, int m, long long B) {
         const unsigned nb_tab = (unsigned)(tb.n_valid_out[m] + (tb.n_valid_win[m] + 3) / 4);
         const unsigned nb_c = (unsigned)((B + 255) / 256);
         k_g_tables<<<dim3(nb_tab, G), 128, tab_smem, s>>>(gdev, ph, tb);
+        mark(3);
         k_g_approx<<<dim3(nb_c, G), 256, 0, s>>>(gdev, ph, tb);
+        mark(4);
         k_g_select<<<dim3(nb_c, G), 256, 0, s>>>(gdev, ph, tb);
-        k_g_exact_near<<<dim3((unsigned)std::min<long long>(B, 48), G), EX_THREADS, ex_smem, s>>>(gdev, ph, tb);
+        mark(5);
+        k_g_exact_near<<<dim3((unsigned)std::min<long long>(B, 32) * EX_SPLIT, G), EX_THREADS, ex_smem, s>>>(gdev, ph, tb);
+        mark(6);
         k_g_pick_window<<<dim3(1, G), 256, 0, s>>>(gdev, ph, tb);
+        mark(7);
         h->launches += 5;
     };
     h->dbg[2] = since(t_h1);  // ... + descriptor upload + gather enqueue
@@ -904,7 +943,9 @@ extern "C" int hica_p2_order_groups(hica_handle h, int32_t ngroups, const int32_
     {
         Phase ph = {PH_BRUTE, 0, 0};
         k_g_total<<<dim3(tot_blocks, G), 128, tot_smem, s>>>(gdev, ph, 1);
+        mark(1);
         k_g_anchor<<<dim3(1, G), EX_THREADS, ex_smem, s>>>(gdev, ph);
+        mark(2);
         h->launches += 2;
         window_search(ph, kmax, Bbrute_max);
     }
@@ -913,11 +954,17 @@ extern "C" int hica_p2_order_groups(hica_handle h, int32_t ngroups, const int32_
         Phase ph = {PH_INSERT, step, 0};
         const unsigned nb_c = 2 * (unsigned)(nseg_max + 1);
         k_g_total<<<dim3(tot_blocks, G), 128, tot_smem, s>>>(gdev, ph, 1);
-        k_g_ins_rows<<<dim3((unsigned)((Lmax + INS_ROWS - 1) / INS_ROWS) + 1, G), 256, tot_smem, s>>>(gdev, ph);
+        mark(1);
+        k_g_ins_rows<<<dim3((unsigned)((Lmax + INS_ROWS - 1) / INS_ROWS), G), 256, tot_smem, s>>>(gdev, ph);
+        mark(8);
         k_g_ins_rel<<<dim3(nb_c, G), 128, tot_smem, s>>>(gdev, ph);
+        mark(9);
         k_g_ins_select<<<dim3(1, G), 128, 0, s>>>(gdev, ph);
-        k_g_insert_scores<<<dim3(std::min(nb_c, 16u), G), EX_THREADS, ex_smem, s>>>(gdev, ph);
+        mark(10);
+        k_g_insert_scores<<<dim3(std::min(nb_c, 8u) * EX_SPLIT, G), EX_THREADS, ex_smem, s>>>(gdev, ph);
+        mark(11);
         k_g_pick_insert<<<dim3(1, G), 32, 0, s>>>(gdev, ph);
+        mark(12);
         h->launches += 6;
     }
     // ---- sliding-window scan (:579-580)
@@ -925,8 +972,11 @@ extern "C" int hica_p2_order_groups(hica_handle h, int32_t ngroups, const int32_
     if (any_scan) {
         Phase ph0 = {PH_SCAN, 0, scan};
         k_g_reset_for_scan<<<G, 32, 0, s>>>(gdev);
+        mark(13);
         k_g_total<<<dim3(tot_blocks, G), 128, tot_smem, s>>>(gdev, ph0, 1);
+        mark(1);
         k_g_anchor<<<dim3(1, G), EX_THREADS, ex_smem, s>>>(gdev, ph0);
+        mark(2);
         h->launches += 3;
         ENG_CUDA(cudaGetLastError());
         int batch = 2;
@@ -934,6 +984,7 @@ extern "C" int hica_p2_order_groups(hica_handle h, int32_t ngroups, const int32_
             for (int r = 0; r < batch; r++) {
                 for (int i = 0; i < win_max; i++) window_search(Phase{PH_SCAN, i, scan}, scan, Bscan);
                 k_g_round_end<<<G, 32, 0, s>>>(gdev);
+                mark(13);
                 HICA_LAUNCHED(h);
             }
             batch = 1;
@@ -967,6 +1018,19 @@ extern "C" int hica_p2_order_groups(hica_handle h, int32_t ngroups, const int32_
             out_stats[4 * gi + 3] = hst[gi].error;
         }
         if (hst[gi].error && err_group < 0) err_group = gi;
+    }
+    if (prof && !marks.empty()) {
+        double acc[14] = {0};
+        int cnt[14] = {0};
+        for (size_t i = 1; i < marks.size(); i++) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, marks[i - 1].second, marks[i].second);
+            acc[marks[i].first] += ms;
+            cnt[marks[i].first]++;
+        }
+        for (auto &mk : marks) cudaEventDestroy(mk.second);
+        for (int i = 1; i < 14; i++)
+            if (cnt[i]) fprintf(stderr, "[hica p2] %-18s n=%4d  %8.3f ms  avg %7.1f us\n", knames[i], cnt[i], acc[i], 1e3 * acc[i] / cnt[i]);
     }
     h->dbg[4] = since(t_h3);  // result read-back
     auto t_h4 = clk::now();
