@@ -213,6 +213,7 @@ __global__ void __launch_bounds__(EX_THREADS, 1) k_g_anchor(const GroupDev *gs, 
 //   tab_out[((s*2+o) << m) | before]                : scaffold s (orientation o) against all bins outside the
 //                                                      window, `before` = window scaffolds placed before s
 //   tab_win[((((s*m+s2)*2+o)*2+o2) << m) | between] : s placed before s2 with the scaffolds `between` in between
+constexpr int TAB_MPC = 4;  // table entries (sets before s) per CTA of the outside part
 __global__ void __launch_bounds__(128) k_g_tables(const GroupDev *gs, Phase ph, Tables tb)
 {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -220,50 +221,58 @@ __global__ void __launch_bounds__(128) k_g_tables(const GroupDev *gs, Phase ph, 
     const PhaseParams pp = phase_params(g, ph);
     if (!pp.active || g.st->skip) return;
     const int m = pp.m, ws = pp.ws, nslots = pp.nslots, n = pp.n;
-    const int nvo = tb.n_valid_out[m], nvw = tb.n_valid_win[m];
+    const int nmask = 1 << (m - 1);                                  // sets of the other m-1 window scaffolds
+    const int nchunk = (nmask + TAB_MPC - 1) / TAB_MPC;
+    const int nvo = 2 * m * nchunk;
     const int bx = blockIdx.x;
-    if (bx >= nvo + (nvw + 3) / 4) return;
+    if (bx >= nvo + m * m) return;
     __shared__ int wlen[8], woff[8];
-    __shared__ int p0_s, wtot_s;
-    __shared__ double red[4];
+    __shared__ double red[4][TAB_MPC];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) {
-        int p0 = 0;
-        for (int s = 0; s < ws; s++) { int sg = g.layout[s] >> 1; p0 += g.seg_ptr[sg + 1] - g.seg_ptr[sg]; }
-        int wt = 0;
-        for (int j = 0; j < m; j++) {
-            int sg = g.layout[ws + j] >> 1;
-            wlen[j] = g.seg_ptr[sg + 1] - g.seg_ptr[sg];
-            woff[j] = g.seg_ptr[sg];
-            wt += wlen[j];
-        }
-        p0_s = p0;
-        wtot_s = wt;
+    if (tid < m) {  // (a serial walk over the slots in front of the window cost every CTA a chain of global loads)
+        const int sg = g.layout[ws + tid] >> 1;
+        wlen[tid] = g.seg_ptr[sg + 1] - g.seg_ptr[sg];
+        woff[tid] = g.seg_ptr[sg];
     }
     __syncthreads();
     const int full = (1 << m) - 1;
     const int L = g.L;
     if (bx < nvo) {
-        // ---- one (scaffold, orientation, set-before) entry against all bins outside the window ----------
-        const int b = tb.valid_out[m][bx];
-        const int mask = b & full, o = (b >> m) & 1, s = b >> (m + 1);
+        // ---- scaffold s in orientation o against all bins outside the window, for TAB_MPC of the 2^(m-1) sets of
+        //      window scaffolds placed before it.  The sets only shift s by q bins, so every contact that is read
+        //      is weighted TAB_MPC ways: one entry per CTA was bound by L2 traffic (430 MB per launch at 100 kb).
+        const int so = bx / nchunk, chunk = bx - so * nchunk;
+        const int s = so >> 1, o = so & 1;
         double *wt_s = reinterpret_cast<double *>(smem);             // n weights
         int32_t *ord = reinterpret_cast<int32_t *>(wt_s + n);        // position -> bin of the current layout
         int32_t *spos = ord + n, *sent = spos + nslots + 1;
         for (int d = tid; d < n; d += blockDim.x) wt_s[d] = g.Wt[d];
         build_order_cta(SrcLayout{g.layout}, nslots, g.seg_ptr, g.seg_bins, ord, spos, sent, n);
-        int q = 0;
-        for (int j = 0; j < m; j++) if ((mask >> j) & 1) q += wlen[j];
-        const int len = wlen[s], p0 = p0_s, wtot = wtot_s;
+        int wtot = 0;
+        for (int j = 0; j < m; j++) wtot += wlen[j];
+        const int len = wlen[s], p0 = spos[ws];  // first position of the window
         const int n_outside = n - wtot;
         const int32_t *sbins = g.seg_bins + woff[s];
-        double acc = 0.;
+        int q[TAB_MPC], maskv[TAB_MPC];
+#pragma unroll
+        for (int i = 0; i < TAB_MPC; i++) {
+            const int u = min(chunk * TAB_MPC + i, nmask - 1);
+            const int mask = (u & ((1 << s) - 1)) | ((u >> s) << (s + 1));  // bit s stays clear
+            int qq = 0;
+            for (int j = 0; j < m; j++) if ((mask >> j) & 1) qq += wlen[j];
+            q[i] = qq;
+            maskv[i] = mask;
+        }
+        double acc[TAB_MPC];
+#pragma unroll
+        for (int i = 0; i < TAB_MPC; i++) acc[i] = 0.;
         for (int a0 = tid; a0 < n_outside; a0 += blockDim.x) {
-            const int apos = a0 < p0 ? a0 : a0 + wtot;
+            const bool before = a0 < p0;
+            const int apos = before ? a0 : a0 + wtot;
             const int abin = ord[apos];
             // the reference reads M[row of the earlier position][column of the later one]; both branches walk a
             // row of S / S^T so that neighbouring threads (neighbouring outside bins) touch neighbouring addresses
-            const double *base = (apos < p0 ? g.St : g.S) + abin;
+            const double *base = (before ? g.St : g.S) + abin;
             // 8 contacts in flight per thread: the loop is a chain of L2 round trips otherwise
             for (int t0 = 0; t0 < len; t0 += 8) {
                 double v[8];
@@ -272,50 +281,76 @@ __global__ void __launch_bounds__(128) k_g_tables(const GroupDev *gs, Phase ph, 
 #pragma unroll
                 for (int k = 0; k < 8; k++) {
                     const int t = min(t0 + k, len - 1);
-                    const int bpos = p0 + q + (o ? (len - 1 - t) : t);
-                    const int d = apos < bpos ? bpos - apos : apos - bpos;
-                    acc += v[k] * wt_s[d];
+                    const int off = o ? (len - 1 - t) : t;
+                    const int d0 = before ? (p0 + off - apos) : (apos - p0 - off);  // distance to position p0 + off
+#pragma unroll
+                    for (int i = 0; i < TAB_MPC; i++) acc[i] += v[k] * wt_s[before ? d0 + q[i] : d0 - q[i]];
                 }
             }
         }
-        for (int d = 16; d >= 1; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
-        if (lane == 0) red[warp] = acc;
+#pragma unroll
+        for (int i = 0; i < TAB_MPC; i++) {
+            double r = acc[i];
+            for (int d = 16; d >= 1; d >>= 1) r += __shfl_xor_sync(0xffffffffu, r, d);
+            if (lane == 0) red[warp][i] = r;
+        }
         __syncthreads();
-        if (tid == 0) g.tab_out[b] = (red[0] + red[1]) + (red[2] + red[3]);
+        if (tid < TAB_MPC && chunk * TAB_MPC + tid < nmask)
+            g.tab_out[(((s << 1) | o) << m) | maskv[tid]] = (red[0][tid] + red[1][tid]) + (red[2][tid] + red[3][tid]);
     } else {
-        // ---- four (scaffold pair, orientations, set-between) entries per block, one per warp ----------------
-        const int j = (bx - nvo) * 4 + warp;
-        if (j >= nvw) return;
-        const int bw = tb.valid_win[m][j];
-        int r = bw;
-        const int mask = r & full;
-        r >>= m;
-        const int o2 = r & 1, o = (r >> 1) & 1;
-        r >>= 2;
-        const int s2 = r % m, s = r / m;
-        int gap = 0;
-        for (int jj = 0; jj < m; jj++) if ((mask >> jj) & 1) gap += wlen[jj];
+        // ---- scaffold pair (s, s2) in orientations (o, o2), one warp each, for EVERY set of window scaffolds
+        //      between them (2^(m-2) entries, 8 at a time): the sets only change the gap
+        const int r = (bx - nvo) * 4 + warp;
+        if (r >= m * m * 4) return;
+        const int o2 = r & 1, o = (r >> 1) & 1, s2 = (r >> 2) % m, s = (r >> 2) / m;
+        if (s == s2) return;
+        const int lo_b = min(s, s2), hi_b = max(s, s2);
+        const int nm2 = 1 << (m - 2);
         const int len = wlen[s], len2 = wlen[s2];
         const int work = len * len2;
-        double acc = 0.;
-        for (int w0 = lane; w0 < work; w0 += 4 * 32) {  // 4 contacts in flight per lane
-            double v[4], wv[4];
+        const int32_t *b1 = g.seg_bins + woff[s], *b2 = g.seg_bins + woff[s2];
+        for (int u0 = 0; u0 < nm2; u0 += 8) {
+            int gap[8], maskv[8];
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const int w = w0 + 32 * k;
-                v[k] = 0.; wv[k] = 0.;
-                if (w < work) {
-                    const int t = w / len2, t2 = w - t * len2;
-                    const int off = o ? (len - 1 - t) : t, off2 = o2 ? (len2 - 1 - t2) : t2;
-                    v[k] = g.S[(int64_t)g.seg_bins[woff[s] + t] * L + g.seg_bins[woff[s2] + t2]];
-                    wv[k] = g.Wt[len - off + gap + off2];
+            for (int i = 0; i < 8; i++) {
+                const int u = min(u0 + i, nm2 - 1);
+                int mask = (u & ((1 << lo_b) - 1)) | ((u >> lo_b) << (lo_b + 1));        // bit lo_b clear
+                mask = (mask & ((1 << hi_b) - 1)) | ((mask >> hi_b) << (hi_b + 1));      // bit hi_b clear
+                int gg = 0;
+                for (int jj = 0; jj < m; jj++) if ((mask >> jj) & 1) gg += wlen[jj];
+                gap[i] = gg;
+                maskv[i] = mask;
+            }
+            double acc[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) acc[i] = 0.;
+            for (int w0 = lane; w0 < work; w0 += 4 * 32) {  // 4 contacts in flight per lane
+                double v[4];
+                int dd[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int w = w0 + 32 * k;
+                    v[k] = 0.; dd[k] = 0;
+                    if (w < work) {
+                        const int t = w / len2, t2 = w - t * len2;
+                        const int off = o ? (len - 1 - t) : t, off2 = o2 ? (len2 - 1 - t2) : t2;
+                        v[k] = g.S[(int64_t)b1[t] * L + b2[t2]];
+                        dd[k] = len - off + off2;
+                    }
                 }
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+#pragma unroll
+                    for (int i = 0; i < 8; i++) acc[i] += v[k] * g.Wt[dd[k] + gap[i]];
             }
 #pragma unroll
-            for (int k = 0; k < 4; k++) acc += v[k] * wv[k];
+            for (int i = 0; i < 8; i++) {
+                double rr = acc[i];
+                for (int d = 16; d >= 1; d >>= 1) rr += __shfl_xor_sync(0xffffffffu, rr, d);
+                if (lane == 0 && u0 + i < nm2)
+                    g.tab_win[(((((s * m + s2) * 2 + o) * 2 + o2)) << m) | maskv[i]] = rr;
+            }
         }
-        for (int d = 16; d >= 1; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
-        if (lane == 0) g.tab_win[bw] = acc;
     }
 }
 
@@ -923,7 +958,7 @@ extern "C" int hica_p2_order_groups(hica_handle h, int32_t ngroups, const int32_
     };
     mark(0);
     auto window_search = [&](Phase ph, int m, long long B) {
-        const unsigned nb_tab = (unsigned)(tb.n_valid_out[m] + (tb.n_valid_win[m] + 3) / 4);
+        const unsigned nb_tab = (unsigned)(2 * m * (((1 << (m - 1)) + TAB_MPC - 1) / TAB_MPC) + m * m);
         const unsigned nb_c = (unsigned)((B + 255) / 256);
         k_g_tables<<<dim3(nb_tab, G), 128, tab_smem, s>>>(gdev, ph, tb);
         mark(3);
