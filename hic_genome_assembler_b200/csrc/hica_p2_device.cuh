@@ -159,8 +159,18 @@ __device__ double pairwise_f(const F &f, int off, int n)
         double r[8];
 #pragma unroll
         for (int j = 0; j < 8; j++) r[j] = f(off + j);
-        int i;
-        for (i = 8; i < n - (n % 8); i += 8) {
+        int i = 8;
+        const int n8 = n - (n % 8);
+        for (; i + 16 <= n8; i += 16) {  // 16 gathers in flight, added in numpy's order
+            double v[16];
+#pragma unroll
+            for (int j = 0; j < 16; j++) v[j] = f(off + i + j);
+#pragma unroll
+            for (int j = 0; j < 8; j++) r[j] = __dadd_rn(r[j], v[j]);
+#pragma unroll
+            for (int j = 0; j < 8; j++) r[j] = __dadd_rn(r[j], v[8 + j]);
+        }
+        for (; i < n8; i += 8) {
 #pragma unroll
             for (int j = 0; j < 8; j++) r[j] = __dadd_rn(r[j], f(off + i + j));
         }

@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(128) k_g_total(const GroupDev *gs, Phase ph, i
     const PhaseParams pp = phase_params(g, ph);
     if (!pp.active) return;
     const int n = pp.n;
-    SmemPlan sp = carve(smem, 0, n, pp.nslots);
+    SmemPlan sp = carve(smem, n, n, pp.nslots);
     build_order_cta(SrcLayout{g.layout}, pp.nslots, g.seg_ptr, g.seg_bins, sp.o, sp.spos, sp.sent, n);
     const int k = blockIdx.x * blockDim.x + threadIdx.x + 1;
     if (k < n) {
@@ -167,9 +167,12 @@ __global__ void __launch_bounds__(128) k_g_total(const GroupDev *gs, Phase ph, i
     if (!last) return;
     __shared__ double t_s;
     __shared__ double chunk_s[128];
+    __threadfence();
+    for (int kk = 1 + threadIdx.x; kk < n; kk += blockDim.x) sp.tr[kk] = ld_cg_f64(g.tr + kk);  // staged: one round trip
+    __syncthreads();
     if (threadIdx.x == 0) {
         double t = 0.;
-        for (int kk = 1; kk < n; kk++) t = __dadd_rn(t, ld_cg_f64(g.tr + kk));
+        for (int kk = 1; kk < n; kk++) t = __dadd_rn(t, sp.tr[kk]);  // the builtin sum() of the reference: in k order
         g.st->total = t;
         g.st->done_blocks = 0;
         g.st->skip = (t == 0.0) ? 1 : 0;
@@ -937,7 +940,7 @@ extern "C" int hica_p2_order_groups(hica_handle h, int32_t ngroups, const int32_
     ENG_CUDA(cudaFuncSetAttribute(k_g_insert_scores, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex_smem));
     ENG_CUDA(cudaFuncSetAttribute(k_g_ins_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tot_smem));
     ENG_CUDA(cudaFuncSetAttribute(k_g_ins_rel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tot_smem));
-    ENG_CUDA(cudaFuncSetAttribute(k_g_total, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tot_smem));
+    ENG_CUDA(cudaFuncSetAttribute(k_g_total, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex_smem));
     const size_t tab_smem = sizeof(double) * Lmax + sizeof(int32_t) * (Lmax + 2 * (nseg_max + 1) + 2);
     ENG_CUDA(cudaFuncSetAttribute(k_g_tables, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tab_smem));
     const unsigned G = (unsigned)ngroups;
@@ -977,7 +980,7 @@ extern "C" int hica_p2_order_groups(hica_handle h, int32_t ngroups, const int32_
     // ---- brute force over the k largest scaffolds (:573-576)
     {
         Phase ph = {PH_BRUTE, 0, 0};
-        k_g_total<<<dim3(tot_blocks, G), 128, tot_smem, s>>>(gdev, ph, 1);
+        k_g_total<<<dim3(tot_blocks, G), 128, ex_smem, s>>>(gdev, ph, 1);
         mark(1);
         k_g_anchor<<<dim3(1, G), EX_THREADS, ex_smem, s>>>(gdev, ph);
         mark(2);
@@ -988,7 +991,7 @@ extern "C" int hica_p2_order_groups(hica_handle h, int32_t ngroups, const int32_
     for (int step = 0; step < ins_steps; step++) {
         Phase ph = {PH_INSERT, step, 0};
         const unsigned nb_c = 2 * (unsigned)(nseg_max + 1);
-        k_g_total<<<dim3(tot_blocks, G), 128, tot_smem, s>>>(gdev, ph, 1);
+        k_g_total<<<dim3(tot_blocks, G), 128, ex_smem, s>>>(gdev, ph, 1);
         mark(1);
         k_g_ins_rows<<<dim3((unsigned)((Lmax + INS_ROWS - 1) / INS_ROWS), G), 256, tot_smem, s>>>(gdev, ph);
         mark(8);
@@ -1008,7 +1011,7 @@ extern "C" int hica_p2_order_groups(hica_handle h, int32_t ngroups, const int32_
         Phase ph0 = {PH_SCAN, 0, scan};
         k_g_reset_for_scan<<<G, 32, 0, s>>>(gdev);
         mark(13);
-        k_g_total<<<dim3(tot_blocks, G), 128, tot_smem, s>>>(gdev, ph0, 1);
+        k_g_total<<<dim3(tot_blocks, G), 128, ex_smem, s>>>(gdev, ph0, 1);
         mark(1);
         k_g_anchor<<<dim3(1, G), EX_THREADS, ex_smem, s>>>(gdev, ph0);
         mark(2);
