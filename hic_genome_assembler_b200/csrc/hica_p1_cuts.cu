@@ -52,14 +52,31 @@ __device__ __forceinline__ bool hyp_valid(long long M, long long n, long long N)
     return M > 0 && n >= 0 && N >= 0 && n <= M && N <= M;  // scipy hypergeom._argcheck
 }
 
-// largest k in [klo, kmax] with logpmf(k) >= LOG_TINY, assuming logpmf is
-// non-increasing on [klo, kmax]; returns klo-1 if none.
+// A starting point for the tail sum: a k in [klo, kmax] beyond which the pmf is below e^LOG_TINY (logpmf is
+// non-increasing on [klo, kmax]); returns klo-1 if even pmf(klo) is.  The point is bracketed from the standard
+// deviation of the law (13 sd covers 80 nats of a Gaussian tail; further steps of 2 sd until the pmf is small
+// enough) instead of bisecting [klo, kmax]: 3-4 evaluations of the log-pmf instead of ~14.  Starting a few
+// terms further out than necessary only adds terms ~1e-35 and below; a start so far out that exp() of the
+// log-pmf could underflow is bisected back.
 __device__ long long hyp_tail_start(const HypParams &p, long long klo)
 {
     if (hyp_logpmf(p, p.kmax) >= LOG_TINY) return p.kmax;
     if (hyp_logpmf(p, klo) < LOG_TINY) return klo - 1;
-    long long a = klo, b = p.kmax;  // invariant: lp(a) >= tiny, lp(b) < tiny
-    while (b - a > 1) {
+    const double M = (double)p.M, n = (double)p.n, N = (double)p.N;
+    const double var = n * (N / M) * (1.0 - N / M) * ((M - n) / fmax(M - 1.0, 1.0));
+    const double sd = sqrt(fmax(var, 0.0));
+    long long step = (long long)ceil(13.0 * sd) + 4;
+    long long a = klo, b;  // invariant: lp(a) >= tiny
+    double lpb;
+    for (;;) {
+        b = min(p.kmax, a + step);
+        lpb = hyp_logpmf(p, b);
+        if (lpb < LOG_TINY) break;  // (b == kmax is below the threshold, checked above)
+        a = b;
+        step = (long long)ceil(2.0 * sd) + 2;  // heavier than Gaussian: creep outwards
+    }
+    if (lpb >= -600.0) return b;
+    while (b - a > 1) {  // far beyond the threshold: back to the largest k with lp(k) >= tiny
         long long mid = a + (b - a) / 2;
         if (hyp_logpmf(p, mid) >= LOG_TINY) a = mid; else b = mid;
     }
@@ -414,9 +431,18 @@ int find_breakpoints(hica_ctx *h, int64_t start, int64_t min_size, int64_t world
     *first_cut = -1;
     *n_hits = 0;
     for (;;) {
+        // The sliding-window pass that follows the significances is launched together with them (its result is
+        // simply dropped when the significances have to be re-evaluated with a smaller M): one round trip
+        // to the host per break search instead of two.
+        const bool slide = (ws == min_size && ws < Lw);  // sliding window compared against min_size (:487-488)
         for (;;) {
             if ((rc = reset_misc(h))) return rc;
             if ((rc = run_sig_mode0(h, Lw, M, psig))) return rc;
+            if (slide) {
+                k_break_hits<<<(unsigned)((Lw + 255) / 256), 256, 0, h->stream>>>(h->sig_d, Lw, (int)ws, h->misc_d);
+                HICA_LAUNCHED(h);
+                HICA_CUDA(cudaGetLastError());
+            }
             if ((rc = fetch_misc(h, 4))) return rc;
             *amb += h->misc_h[3];
             loop_count++;
@@ -424,18 +450,10 @@ int find_breakpoints(hica_ctx *h, int64_t start, int64_t min_size, int64_t world
             else break_sig = 1;
             if (break_sig == 1 || loop_count >= 5) break;
         }
-        // sliding window with window size ws, compared against min_size (:487-488)
-        if (ws == min_size && ws < Lw) {
-            if ((rc = reset_misc(h))) return rc;
-            k_break_hits<<<(unsigned)((Lw + 255) / 256), 256, 0, h->stream>>>(h->sig_d, Lw, (int)ws, h->misc_d);
-            HICA_LAUNCHED(h);
-            HICA_CUDA(cudaGetLastError());
-            if ((rc = fetch_misc(h, 4))) return rc;
-            if (h->misc_h[2] > 0) {
-                *first_cut = (int64_t)h->misc_h[1] + min_size;
-                *n_hits = h->misc_h[2];
-                return HICA_OK;
-            }
+        if (slide && h->misc_h[2] > 0) {
+            *first_cut = (int64_t)h->misc_h[1] + min_size;
+            *n_hits = h->misc_h[2];
+            return HICA_OK;
         }
         // a window narrower than min_size can never reach a difference of min_size,
         // but the reference still re-evaluates the significances (which may shrink M).
