@@ -192,6 +192,75 @@ __global__ void k_sig_mode0(const int32_t *__restrict__ x, int64_t Lw, long long
     if (s) atomicAdd(&misc[0], 1);
 }
 
+// mode 0 split in two so that the critical counts (x* depends on (M, c) only, ~30 us of serial arithmetic per
+// thread) can be computed WHILE the window counts are taken: crit[2c] = x*(M, c, c), crit[2c+1] = 0 / 1 (ambiguous)
+// / 2 (invalid parameters: NaN p-value, which counts as significant here, :466-469)
+__device__ __forceinline__ void crit_mode0_one(int64_t c, long long M, double psig, int32_t *__restrict__ crit)
+{
+    if (!hyp_valid(M, c, c)) { crit[2 * c] = 0; crit[2 * c + 1] = 2; return; }
+    bool amb = false;
+    const long long xc = hyp_critical(M, c, c, psig, &amb);
+    crit[2 * c] = xc > INT_MAX ? INT_MAX : (xc < INT_MIN ? INT_MIN : (int)xc);
+    crit[2 * c + 1] = amb ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(128) k_crit_mode0(int64_t Lw, long long M, double psig, int32_t *__restrict__ crit)
+{
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= 1 && c < Lw) crit_mode0_one(c, M, psig, crit);
+}
+
+// the first ncrit blocks compute critical counts (they are the long ones, so they start first), the others count
+template <typename RankT>
+__global__ void __launch_bounds__(128) k_window_counts_crit(const RankT *__restrict__ R, int64_t n, int64_t start,
+                                                            int32_t *__restrict__ x, int ncrit, long long M, double psig,
+                                                            int32_t *__restrict__ crit)
+{
+    if ((int)blockIdx.x < ncrit) {
+        const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        if (c >= 1 && c < n - start) crit_mode0_one(c, M, psig, crit);
+        return;
+    }
+    // row i = start + c
+    const int64_t c = (int64_t)blockIdx.x - ncrit + 1, i = start + c;
+    const RankT *row = R + i * n;
+    int cnt = 0;
+    for (int64_t k = threadIdx.x; k < c; k += blockDim.x) {
+        int64_t v = row[k];
+        cnt += (v >= start && v <= i);
+    }
+    __shared__ int part[4];
+    for (int d = 16; d >= 1; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        x[c] = part[0] + part[1] + part[2] + part[3];
+        if (c == 1) x[0] = 0;
+    }
+}
+
+__global__ void k_sig_cmp0(const int32_t *__restrict__ x, const int32_t *__restrict__ crit, int64_t Lw, long long M,
+                           double psig, uint8_t *__restrict__ sig, int32_t *__restrict__ misc)
+{
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= Lw) return;
+    int s = 0;
+    if (c > 0) {
+        const int f = crit[2 * c + 1];
+        const long long xv = x[c], kmin = max(0ll, 2 * (long long)c - M), kmax = c;
+        if (f == 2) s = 1;
+        else if (xv <= kmin) s = 1.0 < psig;
+        else if (xv > kmax) s = 0.0 < psig;
+        else {
+            const long long xc = crit[2 * c];
+            s = xv >= xc;
+            if (f == 1 && (xv == xc || xv == xc - 1)) atomicAdd(&misc[3], 1);
+        }
+    }
+    sig[c] = (uint8_t)s;
+    if (s) atomicAdd(&misc[0], 1);
+}
+
 // mode 1: all rows share (M, local, local): one critical value.
 __global__ void k_crit_single(long long M, long long n, long long N, double psig, int32_t *__restrict__ misc)
 {
@@ -269,10 +338,23 @@ __global__ void k_filter_intervals(const uint8_t *__restrict__ sig, int64_t star
 template <typename RankT>
 __global__ void __launch_bounds__(128) k_fb_counts(const RankT *__restrict__ R, int64_t n, int64_t start,
                                                    const int64_t *__restrict__ bounds, int64_t rows,
-                                                   int32_t *__restrict__ x)
+                                                   int32_t *__restrict__ x, long long M, double psig,
+                                                   int32_t *__restrict__ crit)
 {
     const int j = blockIdx.y;
     const int64_t cut = bounds[j], local = cut - start;
+    if ((int64_t)blockIdx.x == rows) {
+        // one extra block per cut: its critical count (a ~30 us serial computation that overlaps the counting
+        // instead of sitting between two kernels)
+        if (threadIdx.x == 0) {
+            bool amb = false;
+            long long xc = LLONG_MAX;  // invalid parameters: NaN p-value, `pval < psig` is False
+            if (hyp_valid(M, local, local)) xc = hyp_critical(M, local, local, psig, &amb);
+            crit[2 * j] = xc > INT_MAX ? INT_MAX : (xc < INT_MIN ? INT_MIN : (int)xc);
+            crit[2 * j + 1] = amb ? 1 : 0;
+        }
+        return;
+    }
     const RankT *row = R + (start + blockIdx.x) * n;
     int cnt = 0;
     for (int64_t k = threadIdx.x; k < local; k += blockDim.x) {
@@ -284,19 +366,6 @@ __global__ void __launch_bounds__(128) k_fb_counts(const RankT *__restrict__ R, 
     if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = cnt;
     __syncthreads();
     if (threadIdx.x == 0) x[(int64_t)j * rows + blockIdx.x] = part[0] + part[1] + part[2] + part[3];
-}
-
-__global__ void k_fb_crit(int64_t start, const int64_t *__restrict__ bounds, int nb, long long M, double psig,
-                          int32_t *__restrict__ crit)
-{
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= nb) return;
-    const long long local = bounds[j] - start;
-    bool amb = false;
-    long long xc = LLONG_MAX;  // invalid parameters: NaN p-value, `pval < psig` is False
-    if (hyp_valid(M, local, local)) xc = hyp_critical(M, local, local, psig, &amb);
-    crit[2 * j] = xc > INT_MAX ? INT_MAX : (xc < INT_MIN ? INT_MIN : (int)xc);
-    crit[2 * j + 1] = amb ? 1 : 0;
 }
 
 __global__ void k_fb_sig(const int32_t *__restrict__ x, int64_t rows, const int64_t *__restrict__ bounds, int nb,
@@ -426,8 +495,22 @@ int find_breakpoints(hica_ctx *h, int64_t start, int64_t min_size, int64_t world
     int64_t M = world;
     int64_t ws = min_size;
     int break_sig = 0, loop_count = 0;
-    int rc = run_window_counts(h, start);
-    if (rc) return rc;
+    int32_t *crit = reinterpret_cast<int32_t *>(h->q_d + (n + 16));  // 2 Lw ints; the filter uses the front of q_d
+    const unsigned nsig = (unsigned)((Lw + 127) / 128);
+    int rc;
+    bool have_crit = false;  // critical counts for the current M are in crit[]
+    if (Lw <= 1) {
+        if ((rc = run_window_counts(h, start))) return rc;
+    } else {
+        rc = with_rank(h, [&](auto *R) {
+            k_window_counts_crit<<<(unsigned)(Lw - 1) + nsig, 128, 0, h->stream>>>(R, n, start, h->x_d, (int)nsig, M, psig, crit);
+            HICA_LAUNCHED(h);
+            HICA_CUDA(cudaGetLastError());
+            return (int)HICA_OK;
+        });
+        if (rc) return rc;
+        have_crit = true;
+    }
     *first_cut = -1;
     *n_hits = 0;
     for (;;) {
@@ -437,7 +520,14 @@ int find_breakpoints(hica_ctx *h, int64_t start, int64_t min_size, int64_t world
         const bool slide = (ws == min_size && ws < Lw);  // sliding window compared against min_size (:487-488)
         for (;;) {
             if ((rc = reset_misc(h))) return rc;
-            if ((rc = run_sig_mode0(h, Lw, M, psig))) return rc;
+            if (!have_crit) {  // M has changed (or a window narrower than min_size re-evaluates): new critical counts
+                k_crit_mode0<<<nsig, 128, 0, h->stream>>>(Lw, M, psig, crit);
+                HICA_LAUNCHED(h);
+            }
+            k_sig_cmp0<<<nsig, 128, 0, h->stream>>>(h->x_d, crit, Lw, M, psig, h->sig_d, h->misc_d);
+            HICA_LAUNCHED(h);
+            HICA_CUDA(cudaGetLastError());
+            have_crit = true;
             if (slide) {
                 k_break_hits<<<(unsigned)((Lw + 255) / 256), 256, 0, h->stream>>>(h->sig_d, Lw, (int)ws, h->misc_d);
                 HICA_LAUNCHED(h);
@@ -446,7 +536,7 @@ int find_breakpoints(hica_ctx *h, int64_t start, int64_t min_size, int64_t world
             if ((rc = fetch_misc(h, 4))) return rc;
             *amb += h->misc_h[3];
             loop_count++;
-            if (((double)h->misc_h[0] / (double)Lw) >= .9) M = (int64_t)(M - start);
+            if (((double)h->misc_h[0] / (double)Lw) >= .9) { M = (int64_t)(M - start); have_crit = false; }
             else break_sig = 1;
             if (break_sig == 1 || loop_count >= 5) break;
         }
@@ -585,17 +675,17 @@ extern "C" int hica_p1_filter(hica_handle h, const int64_t *cuts_in, int64_t n_i
                 int rc;
                 if ((rc = reset_misc(h))) return rc;
                 rc = with_rank(h, [&](auto *R) {
-                    k_fb_counts<<<dim3((unsigned)rows, (unsigned)ne), 128, 0, h->stream>>>(R, n, start, eval, rows, fx);
+                    k_fb_counts<<<dim3((unsigned)rows + 1, (unsigned)ne), 128, 0, h->stream>>>(R, n, start, eval, rows, fx,
+                                                                                               M, psig, fcrit);
                     HICA_LAUNCHED(h);
                     return (int)HICA_OK;
                 });
                 if (rc) return rc;
-                k_fb_crit<<<1, 64, 0, h->stream>>>(start, eval, ne, M, psig, fcrit);
                 k_fb_sig<<<(unsigned)((rows * ne + 255) / 256), 256, 0, h->stream>>>(fx, rows, eval, ne, start, M, psig,
                                                                                   fcrit, fsig, h->misc_d);
                 k_fb_intervals<<<dim3((unsigned)nb, (unsigned)ne), 32, 0, h->stream>>>(fsig, rows, start, h->q_d, nb, eval,
                                                                                     M, psig, fflags, h->misc_d);
-                h->launches += 3;
+                h->launches += 2;
                 HICA_CUDA(cudaGetLastError());
                 HICA_CUDA(cudaMemcpyAsync(all_flags.data(), fflags, sizeof(int32_t) * ne * nb, cudaMemcpyDeviceToHost,
                                           h->stream));
