@@ -339,10 +339,26 @@ template <typename RankT>
 __global__ void __launch_bounds__(128) k_fb_counts(const RankT *__restrict__ R, int64_t n, int64_t start,
                                                    const int64_t *__restrict__ bounds, int64_t rows,
                                                    int32_t *__restrict__ x, long long M, double psig,
-                                                   int32_t *__restrict__ crit)
+                                                   int32_t *__restrict__ crit, const int64_t *__restrict__ all_bounds,
+                                                   int nb_all, int32_t *__restrict__ crit2)
 {
     const int j = blockIdx.y;
     const int64_t cut = bounds[j], local = cut - start;
+    if ((int64_t)blockIdx.x > rows) {
+        // ... and the critical counts of the second test (:648-666), one per interval of the list: they depend
+        // on (M, local, interval length) only.  crit2[2 (j nb + i)] = x*, [+1] = 0 / 1 ambiguous / 2 invalid
+        const int i = ((int)blockIdx.x - (int)rows - 1) * blockDim.x + threadIdx.x;
+        if (i >= nb_all) return;
+        const int64_t hi = all_bounds[i];
+        const int64_t lo = (i == 0) ? start : max(start, all_bounds[i - 1]);
+        int32_t *dst = crit2 + 2 * ((int64_t)j * nb_all + i);
+        if (hi <= lo || !hyp_valid(M, local, hi - lo)) { dst[0] = 0; dst[1] = 2; return; }
+        bool amb = false;
+        const long long xc = hyp_critical(M, local, hi - lo, psig, &amb);
+        dst[0] = xc > INT_MAX ? INT_MAX : (xc < INT_MIN ? INT_MIN : (int)xc);
+        dst[1] = amb ? 1 : 0;
+        return;
+    }
     if ((int64_t)blockIdx.x == rows) {
         // one extra block per cut: its critical count (a ~30 us serial computation that overlaps the counting
         // instead of sitting between two kernels)
@@ -392,7 +408,8 @@ __global__ void k_fb_sig(const int32_t *__restrict__ x, int64_t rows, const int6
 
 __global__ void k_fb_intervals(const uint8_t *__restrict__ sig, int64_t rows, int64_t start,
                                const int64_t *__restrict__ bounds, int nb, const int64_t *__restrict__ eval_cuts,
-                               long long M, double psig, int32_t *__restrict__ flags, int32_t *__restrict__ misc)
+                               long long M, double psig, int32_t *__restrict__ flags, int32_t *__restrict__ misc,
+                               const int32_t *__restrict__ crit2)
 {
     const int i = blockIdx.x, j = blockIdx.y;  // interval i of the whole list, evaluated for cut eval_cuts[j]
     const int64_t hi = bounds[i];
@@ -405,10 +422,16 @@ __global__ void k_fb_intervals(const uint8_t *__restrict__ sig, int64_t rows, in
         const uint8_t *sj = sig + (int64_t)j * rows;
         for (int64_t r = lo - start + threadIdx.x; r < r1; r += 32) cnt += sj[r];
         for (int d = 16; d >= 1; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
-        if (threadIdx.x == 0) {
-            int r = hyp_less(cnt, M, local, hi - lo, psig, 0);
-            flag = r & 1;
-            if (r & 2) atomicAdd(&misc[3], 1);
+        if (threadIdx.x == 0) {  // hyp_less(cnt, M, local, hi - lo, psig, NaN -> 0) with the precomputed critical count
+            const int32_t *cr = crit2 + 2 * ((int64_t)j * nb + i);
+            const long long N = hi - lo, kmin = max(0ll, N + local - M), kmax = min(local, N);
+            if (cr[1] == 2) flag = 0;
+            else if (cnt <= kmin) flag = 1.0 < psig;
+            else if (cnt > kmax) flag = 0.0 < psig;
+            else {
+                flag = cnt >= cr[0];
+                if (cr[1] == 1 && (cnt == cr[0] || cnt == (long long)cr[0] - 1)) atomicAdd(&misc[3], 1);
+            }
         }
     }
     if (threadIdx.x == 0) flags[(int64_t)j * nb + i] = flag;
@@ -658,7 +681,7 @@ extern "C" int hica_p1_filter(hica_handle h, const int64_t *cuts_in, int64_t n_i
             int chunk_lo = 0, chunk_hi = 0;  // cuts [chunk_lo, chunk_hi) of the list have flags in all_flags
             auto eval_chunk = [&](int i0) -> int {
                 const int ne = std::min(CHUNK, nb - i0);
-                const int64_t need = (int64_t)ne * rows * 5 + (int64_t)ne * nb * 4 + (int64_t)ne * 8 + 1024;
+                const int64_t need = (int64_t)ne * rows * 5 + (int64_t)ne * nb * 12 + (int64_t)ne * 8 + 1024;
                 if (h->cut_buf_cap < need) {
                     if (h->cut_buf) cudaFree(h->cut_buf);
                     h->cut_buf = nullptr;
@@ -670,13 +693,14 @@ extern "C" int hica_p1_filter(hica_handle h, const int64_t *cuts_in, int64_t n_i
                 int32_t *fx = (int32_t *)base;
                 int32_t *fflags = (int32_t *)(base + (int64_t)ne * rows * 4);
                 int32_t *fcrit = fflags + (int64_t)ne * nb;
-                uint8_t *fsig = (uint8_t *)(fcrit + 2 * ne);
+                int32_t *fcrit2 = fcrit + 2 * ne;
+                uint8_t *fsig = (uint8_t *)(fcrit2 + 2 * (int64_t)ne * nb);
                 const int64_t *eval = h->q_d + i0;
                 int rc;
                 if ((rc = reset_misc(h))) return rc;
                 rc = with_rank(h, [&](auto *R) {
-                    k_fb_counts<<<dim3((unsigned)rows + 1, (unsigned)ne), 128, 0, h->stream>>>(R, n, start, eval, rows, fx,
-                                                                                               M, psig, fcrit);
+                    k_fb_counts<<<dim3((unsigned)rows + 1 + (unsigned)((nb + 127) / 128), (unsigned)ne), 128, 0, h->stream>>>(
+                        R, n, start, eval, rows, fx, M, psig, fcrit, h->q_d, nb, fcrit2);
                     HICA_LAUNCHED(h);
                     return (int)HICA_OK;
                 });
@@ -684,7 +708,7 @@ extern "C" int hica_p1_filter(hica_handle h, const int64_t *cuts_in, int64_t n_i
                 k_fb_sig<<<(unsigned)((rows * ne + 255) / 256), 256, 0, h->stream>>>(fx, rows, eval, ne, start, M, psig,
                                                                                   fcrit, fsig, h->misc_d);
                 k_fb_intervals<<<dim3((unsigned)nb, (unsigned)ne), 32, 0, h->stream>>>(fsig, rows, start, h->q_d, nb, eval,
-                                                                                    M, psig, fflags, h->misc_d);
+                                                                                    M, psig, fflags, h->misc_d, fcrit2);
                 h->launches += 2;
                 HICA_CUDA(cudaGetLastError());
                 HICA_CUDA(cudaMemcpyAsync(all_flags.data(), fflags, sizeof(int32_t) * ne * nb, cudaMemcpyDeviceToHost,
