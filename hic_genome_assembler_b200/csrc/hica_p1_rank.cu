@@ -106,6 +106,19 @@ static int rank_rows(hica_ctx *h, int q, int64_t P)
 template <int EPT, int RT>
 static int launch_radix(hica_ctx *h, rankradix::RadixArgs &a)
 {
+    // first the sort on the high 32 bits of the key + fix-up, then the full 64-bit sort for the rows it gave up on
+    // (HICA_RANK_RADIX64=1: the 64-bit kernel for every row)
+    const char *v64 = getenv("HICA_RANK_RADIX64");
+    const bool only64 = v64 && atoi(v64) == 1;
+    if (!only64) {
+        const size_t smem32 = rankradix::smem_bytes32(EPT, RT);
+        HICA_CUDA(cudaFuncSetAttribute(rankradix::k_rank_radix32<EPT, RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem32));
+        HICA_CUDA(cudaMemsetAsync(h->x_d, 0, sizeof(int32_t) * h->n, h->stream));
+        a.redo = h->x_d;
+        rankradix::k_rank_radix32<EPT, RT><<<(unsigned)h->n, RT, smem32, h->stream>>>(a);
+        HICA_LAUNCHED(h);
+        a.only = h->x_d;
+    }
     const size_t smem = rankradix::smem_bytes(EPT, RT);
     HICA_CUDA(cudaFuncSetAttribute(rankradix::k_rank_radix<EPT, RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     rankradix::k_rank_radix<EPT, RT><<<(unsigned)h->n, RT, smem, h->stream>>>(a);
@@ -118,15 +131,13 @@ static int rank_rows_radix(hica_ctx *h)
 {
     rankradix::RadixArgs a = {};
     a.A = h->A; a.n = h->n; a.s_pair = h->s_pair; a.s_seq = h->s_seq; a.order = h->order; a.pos = h->pos;
-    a.kind = h->A_kind; a.R = h->R; a.row0 = 0;
+    a.kind = h->A_kind; a.R = h->R; a.row0 = 0; a.only = nullptr; a.redo = nullptr;
     const int64_t n = h->n;
     // measured at N = 16k on B200: 1024 threads x 16 elements 16.7 ms, 512 x 32 17.4 ms (bitonic network: 29 ms)
-    const char *v = getenv("HICA_RANK_RADIX_THREADS");
-    const bool wide = !(v && atoi(v) == 512);
     if (n <= 512 * 4) return launch_radix<4, 512>(h, a);
     if (n <= 512 * 8) return launch_radix<8, 512>(h, a);
-    if (n <= 512 * 16) return wide ? launch_radix<8, 1024>(h, a) : launch_radix<16, 512>(h, a);
-    return wide ? launch_radix<16, 1024>(h, a) : launch_radix<32, 512>(h, a);
+    if (n <= 512 * 16) return launch_radix<8, 1024>(h, a);
+    return launch_radix<16, 1024>(h, a);
 }
 
 extern "C" int hica_p1_rank(hica_handle h)

@@ -26,6 +26,8 @@ struct RadixArgs {
     int kind;
     void *R;
     int64_t row0;
+    const int32_t *only;  // not NULL: rank only the rows with only[row] != 0
+    int32_t *redo;        // k_rank_radix32: rows it could not finish (set to 1)
 };
 
 __device__ __forceinline__ unsigned long long okey(double v)
@@ -49,6 +51,7 @@ __global__ void __launch_bounds__(RT, 1) k_rank_radix(RadixArgs a)
     const int t = threadIdx.x, lane = t & 31, w = t >> 5;
     const int64_t row = a.row0 + blockIdx.x;
     const int64_t n = a.n;
+    if (a.only && !a.only[row]) return;
 
     // ---- load, transform, place at the reordered column index -------------------------------------
     const int64_t arow = a.order[row];
@@ -154,6 +157,162 @@ inline size_t smem_bytes(int ept, int rt)
 {
     const size_t P = (size_t)rt * ept, RW = rt / 32;
     return P * 8 + sizeof(uint32_t) * (RW * RADIX + 2 * RW) + 8 * 2 * RW + P * 2;
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// k_rank_radix32: the same sort on the HIGH 32 bits of the key only (4 passes instead of 8, 6 instead of 10 bytes
+// moved per element and pass, no register spills), followed by a fix-up: elements whose high words are equal form
+// a run (a few dozen pairs per row on real data, or long runs of identical values such as zeros); within a run the
+// order is decided by the low word, ties by position - the stable sort has left every run in position order, so a
+// run whose low words are all equal is already final, and short runs are finished by an insertion sort of their
+// head thread.  A long run with differing low words (not seen outside adversarial inputs) marks the row in
+// a.redo and the 64-bit kernel re-ranks it.
+constexpr int MAX_RUN = 32;
+
+template <int EPT, int RT>
+__global__ void __launch_bounds__(RT, 1) k_rank_radix32(RadixArgs a)
+{
+    constexpr int RW = RT / 32;
+    constexpr int P = RT * EPT;
+    extern __shared__ __align__(16) unsigned char smem[];
+    uint32_t *hi = reinterpret_cast<uint32_t *>(smem);       // P, moves with the sort
+    uint32_t *lo = hi + P;                                    // P, indexed by position (never moves)
+    uint32_t *cnt = lo + P;                                   // RW x RADIX
+    uint32_t *wtot = cnt + RW * RADIX;                        // 2 * RW scratch
+    uint32_t *red = wtot + 2 * RW;                            // 2 * RW
+    uint16_t *pay = reinterpret_cast<uint16_t *>(red + 2 * RW);  // P
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const int64_t row = a.row0 + blockIdx.x;
+    const int64_t n = a.n;
+
+    const int64_t arow = a.order[row];
+    const double spv = a.kind ? 1.0 : a.s_pair[arow];
+    const double rsv = a.kind == 2 ? 1.0 : a.s_seq[arow];
+    const double *src = a.A + arow * n;
+    uint32_t kor = 0u, kand = ~0u;
+    for (int64_t b = t; b < n; b += RT) {
+        const double d = a.kind ? src[b] : dist_transform(src[b], spv);
+        const unsigned long long key = okey(a.kind == 2 ? d : sim_transform(d, rsv));
+        const int p = a.pos[b];
+        const uint32_t kh = (uint32_t)(key >> 32);
+        hi[p] = kh;
+        lo[p] = (uint32_t)key;
+        pay[p] = (uint16_t)p;
+        kor |= kh;
+        kand &= kh;
+    }
+    for (int d = 16; d >= 1; d >>= 1) {
+        kor |= __shfl_xor_sync(0xffffffffu, kor, d);
+        kand &= __shfl_xor_sync(0xffffffffu, kand, d);
+    }
+    if (lane == 0) { red[w] = kor; red[RW + w] = kand; }
+    __syncthreads();
+    kor = 0u; kand = ~0u;
+    for (int i = 0; i < RW; i++) { kor |= red[i]; kand &= red[RW + i]; }
+    for (int i = (int)n + t; i < P; i += RT) { hi[i] = kor; pay[i] = (uint16_t)i; }  // pads: behind everything
+    const uint32_t varying = kor ^ kand;
+    __syncthreads();
+
+    uint32_t k[EPT];
+    uint32_t pr[EPT / 2];   // payloads, two per register
+    uint32_t rk[EPT / 2];   // warp-local ranks, two per register
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const int wbase = w * (32 * EPT);
+
+    for (int pass = 0; pass < 4; pass++) {
+        const int shift = 8 * pass;
+        if (((varying >> shift) & 0xffu) == 0u) continue;  // all keys agree on this byte
+        for (int i = t; i < RW * RADIX; i += RT) cnt[i] = 0u;
+#pragma unroll
+        for (int e = 0; e < EPT; e++) k[e] = hi[wbase + e * 32 + lane];
+#pragma unroll
+        for (int e = 0; e < EPT; e += 2)
+            pr[e >> 1] = (uint32_t)pay[wbase + e * 32 + lane] | ((uint32_t)pay[wbase + (e + 1) * 32 + lane] << 16);
+        __syncthreads();
+        uint32_t *mycnt = cnt + w * RADIX;
+#pragma unroll
+        for (int e = 0; e < EPT; e++) {
+            const unsigned dg = (k[e] >> shift) & 0xffu;
+            const unsigned peers = __match_any_sync(0xffffffffu, dg);
+            const unsigned before = peers & lt_mask;
+            unsigned old = 0;
+            if (before == 0u) {  // the lowest lane with this digit owns the counter update
+                old = mycnt[dg];
+                mycnt[dg] = old + __popc(peers);
+            }
+            old = __shfl_sync(0xffffffffu, old, __ffs(peers) - 1);
+            const uint32_t r = old + __popc(before);
+            if (e & 1) rk[e >> 1] |= r << 16; else rk[e >> 1] = r;
+            __syncwarp();
+        }
+        __syncthreads();
+        {
+            constexpr int TPD = RT / RADIX, WPT = RW / TPD;  // threads per digit, warps per thread
+            const int dgt = t / TPD, w0 = (t % TPD) * WPT;
+            uint32_t local[WPT];
+            uint32_t sum = 0;
+#pragma unroll
+            for (int i = 0; i < WPT; i++) { local[i] = cnt[(w0 + i) * RADIX + dgt]; sum += local[i]; }
+            uint32_t incl = sum;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += v;
+            }
+            if (lane == 31) wtot[w] = incl;
+            __syncthreads();
+            uint32_t base = 0;
+            for (int i = 0; i < w; i++) base += wtot[i];
+            uint32_t run = base + incl - sum;
+#pragma unroll
+            for (int i = 0; i < WPT; i++) { cnt[(w0 + i) * RADIX + dgt] = run; run += local[i]; }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int e = 0; e < EPT; e++) {
+            const unsigned dg = (k[e] >> shift) & 0xffu;
+            const uint32_t r = (e & 1) ? (rk[e >> 1] >> 16) : (rk[e >> 1] & 0xffffu);
+            const uint32_t dst = mycnt[dg] + r;
+            hi[dst] = k[e];
+            pay[dst] = (uint16_t)((e & 1) ? (pr[e >> 1] >> 16) : (pr[e >> 1] & 0xffffu));
+        }
+        __syncthreads();
+    }
+    // ---- fix-up inside runs of equal high words (the n real elements sit in front of the pads) ---------------
+    bool redo = false;
+    for (int i = t; i < (int)n; i += RT) {
+        const uint32_t h0 = hi[i];
+        if (i > 0 && hi[i - 1] == h0) continue;  // not a run head
+        int len = 1;
+        while (i + len < (int)n && hi[i + len] == h0) len++;
+        if (len == 1) continue;
+        if (len > MAX_RUN) {  // identical values (zeros) are already final; anything else goes to the 64-bit kernel
+            const uint32_t l0 = lo[pay[i]];
+            for (int j = 1; j < len; j++) if (lo[pay[i + j]] != l0) { redo = true; break; }
+            continue;
+        }
+        for (int j = 1; j < len; j++) {  // insertion sort by (low word, position); equal low words keep their order
+            const uint16_t pj = pay[i + j];
+            const uint32_t lj = lo[pj];
+            int q = j - 1;
+            while (q >= 0 && lo[pay[i + q]] > lj) { pay[i + q + 1] = pay[i + q]; q--; }
+            pay[i + q + 1] = pj;
+        }
+    }
+    if (__syncthreads_or(redo)) {
+        if (t == 0) a.redo[row] = 1;
+        return;
+    }
+    // ---- descending order = the ascending result read backwards ---------------------------------------------
+    uint16_t *out = reinterpret_cast<uint16_t *>(a.R) + row * n;
+    for (int64_t j = t; j < n; j += RT) out[j] = pay[n - 1 - j];
+}
+
+inline size_t smem_bytes32(int ept, int rt)
+{
+    const size_t P = (size_t)rt * ept, RW = rt / 32;
+    return P * 8 + sizeof(uint32_t) * (RW * RADIX + 4 * RW) + P * 2;
 }
 
 }  // namespace rankradix
