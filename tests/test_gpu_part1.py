@@ -159,6 +159,7 @@ def test_hypergeom_decisions_match_scipy(hica):
 def test_rank_multi_chunk_paths(hica, n, q, monkeypatch):
     """Rows longer than one sort chunk: chunk sort -> global strides -> chunk merge (forced with small chunks)."""
     monkeypatch.setenv("HICA_RANK_Q", str(q))
+    monkeypatch.setenv("HICA_RANK_ALGO", "bitonic")  # rows <= 16384 take the radix kernels otherwise
     rng = np.random.RandomState(n + q)
     S = rng.rand(n, n)
     hica.p1_upload_similarity(S)
@@ -169,8 +170,60 @@ def test_rank_multi_chunk_paths(hica, n, q, monkeypatch):
 
 def test_rank_with_heavy_ties_multi_chunk(hica, monkeypatch):
     monkeypatch.setenv("HICA_RANK_Q", "9")
+    monkeypatch.setenv("HICA_RANK_ALGO", "bitonic")
     rng = np.random.RandomState(1)
     S = np.round(rng.rand(900, 900), 1)
+    hica.p1_upload_similarity(S)
+    hica.p1_rank()
+    assert np.array_equal(hica.p1_get_rank(), O.rank_matrix_stable(S))
+
+
+def _same_high_word(n, rng, spread):
+    """values whose doubles share the high 32 bits and differ in the low word (spread distinct low words)"""
+    base = np.float64(1.25).view(np.uint64)
+    lowbits = rng.randint(0, spread, size=(n, n)).astype(np.uint64)
+    return (base + lowbits).view(np.float64)
+
+
+@pytest.mark.parametrize("n", [300, 700, 2100, 5000])
+def test_rank_radix_default_and_64bit_kernels_agree(hica, n, monkeypatch):
+    rng = np.random.RandomState(n)
+    S = rng.rand(n, n)
+    hica.p1_upload_similarity(S)
+    hica.p1_rank()
+    R = hica.p1_get_rank()
+    assert np.array_equal(R, O.rank_matrix_stable(S))
+    monkeypatch.setenv("HICA_RANK_RADIX64", "1")
+    hica.p1_upload_similarity(S)
+    hica.p1_rank()
+    assert np.array_equal(hica.p1_get_rank(), R)
+
+
+def test_rank_radix_fixup_of_equal_high_words(hica):
+    """The default kernel sorts on the high word of the key: short runs of equal high words are finished by the
+    insertion-sort fix-up, long runs of identical values are final as they are, and a long run with differing low
+    words sends the row to the 64-bit kernel - all three must give the stable-reversed order."""
+    rng = np.random.RandomState(5)
+    n = 600
+    # (a) a few distinct high words, many elements each, low words all different: rows are re-done in 64 bits
+    S = _same_high_word(n, rng, 1 << 30)
+    hica.p1_upload_similarity(S)
+    hica.p1_rank()
+    assert np.array_equal(hica.p1_get_rank(), O.rank_matrix_stable(S))
+    # (b) mostly tie-free values with pairs / triples that collide in the high word: the fix-up path
+    S = rng.rand(n, n)
+    cols = rng.randint(0, n, size=(n, 40))
+    for i in range(n):
+        for a, b in zip(cols[i, 0::2], cols[i, 1::2]):
+            hi = S[i, a].view(np.uint64) & np.uint64(0xffffffff00000000)
+            S[i, b] = (hi | np.uint64(rng.randint(0, 1 << 31))).view(np.float64)
+    hica.p1_upload_similarity(S)
+    hica.p1_rank()
+    assert np.array_equal(hica.p1_get_rank(), O.rank_matrix_stable(S))
+    # (c) long runs of identical values (zeros) next to distinct ones, and low words that repeat inside a run
+    S = rng.rand(n, n)
+    S[rng.rand(n, n) < 0.6] = 0.0
+    S[:, 5:25] = _same_high_word(n, rng, 3)[:, 5:25]
     hica.p1_upload_similarity(S)
     hica.p1_rank()
     assert np.array_equal(hica.p1_get_rank(), O.rank_matrix_stable(S))
