@@ -20,7 +20,7 @@ T_NAMES = ("upload", "distance", "linkage", "leaforder", "rank", "breakpoints", 
 ABI_SYMBOLS = (
     "hica_version", "hica_create", "hica_destroy", "hica_last_error", "hica_launch_count", "hica_get_timers",
     "hica_linkage_stats", "hica_debug_stats",
-    "hica_p1_upload", "hica_p1_upload_device", "hica_p1_set_row_sums", "hica_p1_distance", "hica_p1_get_distance",
+    "hica_p1_upload", "hica_p1_upload_symmetric", "hica_p1_upload_device", "hica_p1_set_row_sums", "hica_p1_distance", "hica_p1_get_distance",
     "hica_p1_get_pairwise_row_sums", "hica_p1_get_row_sums", "hica_p1_upload_distance", "hica_p1_linkage",
     "hica_p1_set_order", "hica_p1_get_reordered", "hica_p1_rank", "hica_p1_upload_similarity", "hica_p1_get_rank", "hica_p1_set_rank",
     "hica_p1_window_sig", "hica_p1_breakpoints", "hica_p1_filter", "hica_hypergeom_less",
@@ -56,6 +56,7 @@ def load_library():
     L.hica_get_timers.argtypes = [vp, vp]
     L.hica_p1_upload.argtypes = [vp, vp, i64]
     L.hica_p1_upload_device.argtypes = [vp, vp, i64]
+    L.hica_p1_upload_symmetric.argtypes = [vp, vp, i64]
     L.hica_p1_set_row_sums.argtypes = [vp, vp]
     L.hica_p1_distance.argtypes = [vp]
     L.hica_p1_get_distance.argtypes = [vp, vp]
@@ -159,6 +160,14 @@ class Handle:
             raise ValueError("square matrix expected")
         self.n = A.shape[0]
         self._check(self._L.hica_p1_upload(self._h, _ptr(A), self.n))
+
+    def p1_upload_symmetric(self, A: np.ndarray):
+        """Upload a symmetric matrix: only its upper triangle crosses PCIe (the lower one is never read)."""
+        A = _c(A, np.float64)
+        if A.ndim != 2 or A.shape[0] != A.shape[1]:
+            raise ValueError("square matrix expected")
+        self.n = A.shape[0]
+        self._check(self._L.hica_p1_upload_symmetric(self._h, _ptr(A), self.n))
 
     def p1_upload_device(self, dev_ptr: int, n: int):
         self.n = int(n)

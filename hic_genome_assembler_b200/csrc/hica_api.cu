@@ -2,6 +2,8 @@
 #include <stdarg.h>
 #include <stdio.h>
 
+#include <algorithm>
+
 #include "hica_common.cuh"
 
 static thread_local std::string g_create_error;
@@ -161,6 +163,49 @@ extern "C" int hica_p1_upload(hica_handle h, const double *A_host, int64_t n)
     if (rc) return rc;
     hica_timer t(h, HICA_T_UPLOAD);
     HICA_CUDA(cudaMemcpyAsync(h->A, A_host, sizeof(double) * n * n, cudaMemcpyHostToDevice, h->stream));
+    t.stop();
+    HICA_CUDA(cudaStreamSynchronize(h->stream));
+    return HICA_OK;
+}
+
+namespace {
+// A[i][j] = A[j][i] for i > j, 32 x 32 tiles through shared memory (tiles on or below the diagonal only)
+__global__ void __launch_bounds__(256) k_mirror_lower(double *__restrict__ A, int64_t n)
+{
+    __shared__ double tile[32][33];
+    const int64_t bi = blockIdx.y, bj = blockIdx.x;  // destination tile (rows bi, columns bj), bj <= bi
+    if (bj > bi) return;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int r = ty; r < 32; r += 8) {  // source tile: rows of block bj, columns of block bi
+        const int64_t sr = bj * 32 + r, sc = bi * 32 + tx;
+        tile[r][tx] = (sr < n && sc < n) ? A[sr * n + sc] : 0.;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const int64_t dr = bi * 32 + r, dc = bj * 32 + tx;
+        if (dr < n && dc < n && dr > dc) A[dr * n + dc] = tile[tx][r];
+    }
+}
+}  // namespace
+
+extern "C" int hica_p1_upload_symmetric(hica_handle h, const double *A_host, int64_t n)
+{
+    HICA_CHECK_HANDLE(h);
+    if (!A_host) return hica_set_error(h, HICA_ERR_ARG, "A_host is NULL");
+    int rc = p1_alloc(h, n);
+    if (rc) return rc;
+    hica_timer t(h, HICA_T_UPLOAD);
+    // row blocks of BS rows: the columns from the block's first row onwards (a 2-D copy each)
+    const int64_t BS = 512;
+    for (int64_t r0 = 0; r0 < n; r0 += BS) {
+        const int64_t rows = std::min(BS, n - r0);
+        HICA_CUDA(cudaMemcpy2DAsync(h->A + r0 * n + r0, sizeof(double) * n, A_host + r0 * n + r0, sizeof(double) * n,
+                                    sizeof(double) * (n - r0), rows, cudaMemcpyHostToDevice, h->stream));
+    }
+    const unsigned nb = (unsigned)((n + 31) / 32);
+    k_mirror_lower<<<dim3(nb, nb), 256, 0, h->stream>>>(h->A, n);
+    HICA_LAUNCHED(h);
+    HICA_CUDA(cudaGetLastError());
     t.stop();
     HICA_CUDA(cudaStreamSynchronize(h->stream));
     return HICA_OK;

@@ -65,6 +65,12 @@ int hica_debug_stats(hica_handle h, double *out16);
  * :1116-1118) to the device.  A_host may be pageable or pinned. */
 int hica_p1_upload(hica_handle h, const double *A_host, int64_t n);
 
+/* Same for a SYMMETRIC matrix (the contact map the reference builds is: it writes adjMat[i][j] and adjMat[j][i]
+ * together, scaffoldToChromosomes.py:1069-1082): only the upper triangle (row blocks right of the diagonal,
+ * ~53 % of the bytes) crosses PCIe, the lower triangle is mirrored on the device.  Elements below the diagonal
+ * of A_host are never read. */
+int hica_p1_upload_symmetric(hica_handle h, const double *A_host, int64_t n);
+
 /* Same, but the matrix is already in device memory (row-major, ld = n). The
  * library copies it; the caller keeps ownership of A_dev. */
 int hica_p1_upload_device(hica_handle h, const double *A_dev, int64_t n);

@@ -227,3 +227,20 @@ def test_rank_radix_fixup_of_equal_high_words(hica):
     hica.p1_upload_similarity(S)
     hica.p1_rank()
     assert np.array_equal(hica.p1_get_rank(), O.rank_matrix_stable(S))
+
+
+@pytest.mark.parametrize("n", [5, 33, 200, 1100])
+def test_symmetric_upload_reads_only_the_upper_triangle(hica, n):
+    A = _rand_sym(n, 11 + n)
+    hica.p1_upload(A)
+    hica.p1_set_row_sums(None)
+    hica.p1_distance()
+    D_full = hica.p1_get_distance()
+    rs_full = hica.p1_get_row_sums()
+    B = A.copy()
+    B[np.tril_indices(n, -1)] = -12345.0  # garbage below the diagonal must never be used
+    hica.p1_upload_symmetric(B)
+    hica.p1_set_row_sums(None)
+    hica.p1_distance()
+    assert np.array_equal(hica.p1_get_distance(), D_full)
+    assert np.array_equal(hica.p1_get_row_sums(), rs_full)
