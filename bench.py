@@ -232,6 +232,37 @@ def cpu_baseline(wl, args, quick=False):
             "host_cpu_count": os.cpu_count()}
 
 
+def score_kernel_probe(h, wl, last):
+    """The exact ordering-score kernel on its own (the device-resident search only re-scores a short list with it):
+    one scan window of the largest chromosome group, every candidate scored exactly (hica_p2_score_window),
+    3 timed calls after one warm-up.  Algorithmic bytes = candidates x L(L-1)/2 contacts x 8 B; the 5 MB chromosome
+    matrix is L2-resident, so the figure is an L2 rate quoted against the HBM peak."""
+    from hic_genome_assembler_b200 import part1, part2
+    groups = part1.chromosome_groups_compact(last["cuts"], last["leaves"], wl["bin_ids"], wl["scaffold_code"],
+                                             wl["scaffold_names"], wl["scaffold_sizes"])
+    groups = [g for g in groups if len(g) >= 5]
+    if not groups:
+        return None
+    g = max(groups, key=lambda g: sum(len(ids) for _, ids in g))
+    pool = sorted(g, key=lambda t: len(t[1]), reverse=True)
+    rows = np.concatenate([wl["row_of_bin_id"][ids] for _, ids in pool])
+    ptr = np.cumsum([0] + [len(ids) for _, ids in pool])
+    L = int(ptr[-1])
+    h.p2_use_p1_matrix()
+    h.p2_select(rows.astype(np.int32))
+    h.p2_set_segments(ptr.astype(np.int32), np.arange(L, dtype=np.int32))
+    base = [sg << 1 for sg in range(len(pool))]
+    total = h.p2_total(base)
+    orders, orients = part2.order_table(5), part2.orient_table(5)
+    ms = []
+    for it in range(4):
+        h.p2_score_window(base, 0, 5, orders, orients, total, 0.0)
+        if it:
+            ms.append(h.timers()["p2_score"])
+    ncand = orders.shape[0] * orients.shape[0]
+    return {"ms": float(np.median(ms)), "alg_bytes": 8.0 * ncand * (L * (L - 1) // 2), "candidates": int(ncand), "bins": L}
+
+
 # ----------------------------------------------------------------------------- main
 def main():
     args = parse_args()
@@ -331,6 +362,10 @@ def main():
         "linkage(K2)": {"ms": tm["linkage"], "alg_bytes": link_bytes},
         "rank(K5)": {"ms": tm["rank"], "alg_bytes": 12.0 * n * n},
     }
+    if not args.part1_only:
+        probe = score_kernel_probe(h, wl, last)
+        if probe:
+            kernels["score(K8: exact ordering score, one candidate per CTA)"] = probe
     for k in kernels.values():
         k["GBps"] = k["alg_bytes"] / (k["ms"] / 1e3) / 1e9 if k["ms"] > 0 else 0.0
         k["frac_of_hbm_peak"] = k["GBps"] / peak

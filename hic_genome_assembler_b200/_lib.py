@@ -151,7 +151,7 @@ class Handle:
         self._check(self._L.hica_linkage_stats(self._h, _ptr(out)))
         return {"searches": int(out[0]), "search_cycles": int(out[1]), "merge_cycles": int(out[2]),
                 "load_cycles": int(out[3]), "reduce_cycles": int(out[4]), "exchange_cycles": int(out[5]),
-                "cached_searches": int(out[6])}
+                "cached_searches": int(out[6]), "cache_slow_paths": int(out[7])}
 
     # -- Part 1 -----------------------------------------------------------
     def p1_upload(self, A: np.ndarray):

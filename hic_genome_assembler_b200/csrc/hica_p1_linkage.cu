@@ -432,9 +432,11 @@ extern "C" int hica_p1_linkage(hica_handle h, double *Z_host, int32_t *leaves_ho
         const bool dbg = getenv("HICA_NN_DEBUG") != nullptr;
         unsigned flags = 0;
         if (const char *e = getenv("HICA_NN_FLAGS")) flags = (unsigned)atoi(e);
+        const bool chain_global = getenv("HICA_NN_CHAIN_GLOBAL") != nullptr;  // tests: force the large-N variant
         for (int cs = cs_max; cs >= 1 && launched != HICA_OK; cs >>= 1) {
-            launched = dbg ? launch_nn_chain3<true, true>(h, cs, nn0_val, nn0_ent, flags)
-                           : launch_nn_chain3<true, false>(h, cs, nn0_val, nn0_ent, flags);
+            launched = chain_global ? -1
+                       : dbg        ? launch_nn_chain3<true, true>(h, cs, nn0_val, nn0_ent, flags)
+                                    : launch_nn_chain3<true, false>(h, cs, nn0_val, nn0_ent, flags);
             if (launched < 0)
                 launched = dbg ? launch_nn_chain3<false, true>(h, cs, nn0_val, nn0_ent, flags)
                                : launch_nn_chain3<false, false>(h, cs, nn0_val, nn0_ent, flags);

@@ -244,3 +244,58 @@ def test_symmetric_upload_reads_only_the_upper_triangle(hica, n):
     hica.p1_distance()
     assert np.array_equal(hica.p1_get_distance(), D_full)
     assert np.array_equal(hica.p1_get_row_sums(), rs_full)
+
+
+@pytest.mark.parametrize("env", [{"HICA_NN_CHAIN_GLOBAL": "1"}, {"HICA_NN_KERNEL": "2"}, {"HICA_NN_KERNEL": "1"},
+                                 {"HICA_NN_CLUSTER": "8"}, {"HICA_NN_CLUSTER": "2"}, {"HICA_NN_CLUSTER": "1"},
+                                 {"HICA_NN_THREADS": "128"}, {"HICA_NN_DEBUG": "1"}])
+@pytest.mark.parametrize("n,tie", [(3, False), (70, True), (333, True), (1200, False)])
+def test_linkage_kernel_variants_bitwise(hica, n, tie, env, monkeypatch):
+    """Every linkage kernel the library can fall back to - chain in global memory (large N), the kernels without
+    the nearest-neighbour cache (N > 32,767), smaller clusters (when 16 CTAs cannot be co-scheduled), fewer
+    threads, the instrumented build - gives scipy's Z and leaf order bit for bit."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    A = _rand_sym(n, 300 + n, tie)
+    D = O.convert_distance(A)
+    Z_ref, leaves_ref = O.average_cluster_leaves(D)
+    hica.p1_upload(A)
+    hica.p1_distance()
+    Z, leaves = hica.p1_linkage()
+    assert np.array_equal(Z, Z_ref)
+    assert list(leaves) == list(leaves_ref)
+
+
+def test_linkage_exact_ties_take_the_cache_slow_path(hica):
+    """Rows whose recorded nearest neighbour (bin 0) stays untouched while two other bins at exactly the same
+    distance merge: the merged cluster ties with the recorded minimum, which is the queued-update / cluster-barrier
+    path of the nearest-neighbour cache.  Plus block-constant distances (ties everywhere)."""
+    n = 60
+    rng = np.random.RandomState(3)
+    D = 2.0 + rng.rand(n, n)
+    D = (D + D.T) / 2
+    p, q, C = 10, 11, list(range(20, 32))
+    D[p, q] = D[q, p] = 0.1
+    D[0, p] = D[p, 0] = 0.5
+    D[0, q] = D[q, 0] = 0.6
+    for c in C:
+        for t in (0, p, q):
+            D[c, t] = D[t, c] = 0.7
+    np.fill_diagonal(D, 0.0)
+    Z_ref, leaves_ref = O.average_cluster_leaves(D)
+    hica.p1_upload_distance(D)
+    Z, leaves = hica.p1_linkage()
+    assert np.array_equal(Z, Z_ref) and list(leaves) == list(leaves_ref)
+    st = hica.linkage_stats()
+    assert st["cache_slow_paths"] > 0 and st["cached_searches"] > 0
+
+    n, b = 240, 12
+    D = np.full((n, n), 2.0)
+    for s0 in range(0, n, b):
+        D[s0:s0 + b, s0:s0 + b] = 1.0
+        D[s0:s0 + b // 2, s0:s0 + b // 2] = 0.5
+    np.fill_diagonal(D, 0.0)
+    Z_ref, leaves_ref = O.average_cluster_leaves(D)
+    hica.p1_upload_distance(D)
+    Z, leaves = hica.p1_linkage()
+    assert np.array_equal(Z, Z_ref) and list(leaves) == list(leaves_ref)
