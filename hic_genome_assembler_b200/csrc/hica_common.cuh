@@ -159,35 +159,6 @@ __device__ __forceinline__ void st_stream_f64x2(double *p, double2 v)
     asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y));
 }
 
-// numpy pairwise summation, one thread, arbitrary stride (DOUBLE_pairwise_sum).
-// Used where a whole sum is owned by one thread (diagonal traces); the row-sum
-// kernel uses a cooperative version of the same tree.
-__device__ inline double pairwise_sum_thread(const double *a, int64_t n, int64_t stride)
-{
-    if (n < 8) {
-        double res = 0.;
-        for (int64_t i = 0; i < n; i++) res = __dadd_rn(res, a[i * stride]);
-        return res;
-    }
-    if (n <= 128) {
-        double r[8];
-#pragma unroll
-        for (int j = 0; j < 8; j++) r[j] = a[j * stride];
-        int64_t i;
-        for (i = 8; i < n - (n % 8); i += 8) {
-#pragma unroll
-            for (int j = 0; j < 8; j++) r[j] = __dadd_rn(r[j], a[(i + j) * stride]);
-        }
-        double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
-                               __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
-        for (; i < n; i++) res = __dadd_rn(res, a[i * stride]);
-        return res;
-    }
-    int64_t n2 = n / 2;
-    n2 -= n2 % 8;
-    return __dadd_rn(pairwise_sum_thread(a, n2, stride), pairwise_sum_thread(a + n2 * stride, n - n2, stride));
-}
-
 // (1 - a/s) + 1, the distance transform of convertMatrix (:147); no contraction.
 __device__ __forceinline__ double dist_transform(double a, double s)
 {

@@ -146,42 +146,77 @@ __device__ __forceinline__ double exact_cost_cta(const double *__restrict__ S, c
     return exact_cost_finish(tr, n, total);
 }
 
-// numpy.trace over a gathered diagonal = numpy pairwise summation of f(0..n)
+// numpy.trace over a gathered diagonal = numpy pairwise summation of f(0..n).
+// pairwise_leaf: a block of at most 128 terms (8 interleaved accumulators, then the tail one by one).
 template <class F>
-__device__ double pairwise_f(const F &f, int off, int n)
+__device__ __forceinline__ double pairwise_leaf(const F &f, int off, int n)
 {
     if (n < 8) {
         double res = 0.;
         for (int i = 0; i < n; i++) res = __dadd_rn(res, f(off + i));
         return res;
     }
-    if (n <= 128) {
-        double r[8];
+    double r[8];
 #pragma unroll
-        for (int j = 0; j < 8; j++) r[j] = f(off + j);
-        int i = 8;
-        const int n8 = n - (n % 8);
-        for (; i + 16 <= n8; i += 16) {  // 16 gathers in flight, added in numpy's order
-            double v[16];
+    for (int j = 0; j < 8; j++) r[j] = f(off + j);
+    int i = 8;
+    const int n8 = n - (n % 8);
+    for (; i + 16 <= n8; i += 16) {  // 16 gathers in flight, added in numpy's order
+        double v[16];
 #pragma unroll
-            for (int j = 0; j < 16; j++) v[j] = f(off + i + j);
+        for (int j = 0; j < 16; j++) v[j] = f(off + i + j);
 #pragma unroll
-            for (int j = 0; j < 8; j++) r[j] = __dadd_rn(r[j], v[j]);
+        for (int j = 0; j < 8; j++) r[j] = __dadd_rn(r[j], v[j]);
 #pragma unroll
-            for (int j = 0; j < 8; j++) r[j] = __dadd_rn(r[j], v[8 + j]);
-        }
-        for (; i < n8; i += 8) {
-#pragma unroll
-            for (int j = 0; j < 8; j++) r[j] = __dadd_rn(r[j], f(off + i + j));
-        }
-        double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
-                               __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
-        for (; i < n; i++) res = __dadd_rn(res, f(off + i));
-        return res;
+        for (int j = 0; j < 8; j++) r[j] = __dadd_rn(r[j], v[8 + j]);
     }
-    int n2 = n / 2;
-    n2 -= n2 % 8;
-    return __dadd_rn(pairwise_f(f, off, n2), pairwise_f(f, off + n2, n - n2));
+    for (; i < n8; i += 8) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) r[j] = __dadd_rn(r[j], f(off + i + j));
+    }
+    double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                           __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+    for (; i < n; i++) res = __dadd_rn(res, f(off + i));
+    return res;
+}
+
+// The tree above the leaves (split at n/2 rounded down to a multiple of 8) is walked with an explicit stack: a
+// recursive version needs a call frame per level, and the default 1 KB device stack overflowed at 1,600 bins.
+template <class F>
+__device__ double pairwise_f(const F &f, int off, int n)
+{
+    constexpr int DEPTH = 28;  // > log2(2^31 / 128)
+    int s_off[DEPTH], s_n[DEPTH];
+    double s_left[DEPTH];
+    unsigned char s_state[DEPTH];
+    int sp = 0;
+    s_off[0] = off; s_n[0] = n; s_state[0] = 0;
+    double ret = 0.;
+    for (;;) {
+        const int o = s_off[sp], m = s_n[sp];
+        if (m <= 128) {
+            ret = pairwise_leaf(f, o, m);
+        } else {
+            int m2 = m / 2;
+            m2 -= m2 % 8;
+            if (s_state[sp] == 0) {         // descend into the left half
+                s_state[sp] = 1;
+                sp++;
+                s_off[sp] = o; s_n[sp] = m2; s_state[sp] = 0;
+                continue;
+            }
+            if (s_state[sp] == 1) {         // left half done: keep it, descend into the right half
+                s_left[sp] = ret;
+                s_state[sp] = 2;
+                sp++;
+                s_off[sp] = o + m2; s_n[sp] = m - m2; s_state[sp] = 0;
+                continue;
+            }
+            ret = __dadd_rn(s_left[sp], ret);
+        }
+        if (sp == 0) return ret;
+        sp--;
+    }
 }
 
 // order-preserving map double -> uint64 (for atomicMax on scores)

@@ -952,7 +952,12 @@ extern "C" int hica_p2_order_groups(hica_handle h, int32_t ngroups, const int32_
                                    "k_g_exact_near", "k_g_pick_window", "k_g_ins_rows", "k_g_ins_rel", "k_g_ins_select",
                                    "k_g_insert_scores", "k_g_pick_insert", "other"};
     std::vector<std::pair<int, cudaEvent_t>> marks;
+    const bool check = getenv("HICA_P2_CHECK") != nullptr;  // synchronise after every launch and name the one that failed
     auto mark = [&](int id) {
+        if (check) {
+            cudaError_t ce = cudaStreamSynchronize(s);
+            if (ce != cudaSuccess) fprintf(stderr, "[hica p2] %s failed: %s\n", knames[id], cudaGetErrorString(ce));
+        }
         if (!prof) return;
         cudaEvent_t e;
         cudaEventCreate(&e);
