@@ -67,7 +67,7 @@ struct GroupDev {
     int L, nseg, k, scanning;
     const int32_t *seg_ptr, *seg_bins, *cum;  // cum[j] = bins of the first j scaffolds in pool order
     int32_t *layout;
-    double *Wt, *tab_out, *tab_win, *rel, *near_score, *tr;
+    double *Wt, *tab_out, *tab_win, *rel, *near_score, *tr, *ins_d;  // ins_d: D[a] of the insertion step, L entries
     int32_t *near_id;
     GroupState *st;
 };
@@ -528,7 +528,7 @@ __device__ __forceinline__ InsertCand insert_cand(int c, int ne)
     return r;
 }
 
-// D[a] for every placed position (INS_ROWS per CTA, one warp per row at a time) -> tab_out[a].
+// D[a] for every placed position (INS_ROWS per CTA, one warp per row at a time) -> ins_d[a].
 constexpr int INS_ROWS = 16;
 __global__ void __launch_bounds__(256) k_g_ins_rows(const GroupDev *gs, Phase ph)
 {
@@ -561,7 +561,7 @@ __global__ void __launch_bounds__(256) k_g_ins_rows(const GroupDev *gs, Phase ph
 #pragma unroll 4
         for (int b = lane; b < start; b += 32) acc -= Trow[o[b]] * (Wt[a - b + Ls] - Wt[a - b]);
         for (int d = 16; d >= 1; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
-        if (lane == 0) g.tab_out[a] = acc;
+        if (lane == 0) g.ins_d[a] = acc;
     }
 }
 
@@ -585,7 +585,7 @@ __global__ void __launch_bounds__(128) k_g_ins_rel(const GroupDev *gs, Phase ph)
     const double *Wt = g.Wt;
     const int L = g.L;
     double acc = 0.;
-    for (int a = threadIdx.x; a < p; a += blockDim.x) acc += g.tab_out[a];
+    for (int a = threadIdx.x; a < p; a += blockDim.x) acc += g.ins_d[a];
     for (int a = threadIdx.x; a < P; a += blockDim.x) {
         const int oa = o[a];
         if (a < p) {
@@ -804,7 +804,7 @@ extern "C" int hica_p2_order_groups(hica_handle h, int32_t ngroups, const int32_
         g.Bmax = std::max<long long>(std::max<long long>(Bb, Bscan), 2ll * (g.nseg + 1));
         const int mmax = std::max(g.k, (int)scan);
         arena_bytes += 2 * padded<double>((size_t)g.L * g.L) + 3 * padded<int32_t>(g.nseg + 1) + padded<int32_t>(g.L) +
-                       2 * padded<double>(g.L + 1) + padded<double>((size_t)(mmax * 2) << mmax) +
+                       3 * padded<double>(g.L + 1) + padded<double>((size_t)(mmax * 2) << mmax) +
                        padded<double>((size_t)(mmax * mmax * 4) << mmax) + 2 * padded<double>(g.Bmax) +
                        padded<int32_t>(g.Bmax) + padded<GroupState>(1);
         Lmax = std::max(Lmax, g.L);
@@ -903,6 +903,7 @@ extern "C" int hica_p2_order_groups(hica_handle h, int32_t ngroups, const int32_
         d.L = g.L; d.nseg = g.nseg; d.k = g.k; d.scanning = g.nseg > n_scaffolds ? 1 : 0;
         d.Wt = ar.take<double>(g.L + 1);
         d.tr = ar.take<double>(g.L + 1);
+        d.ins_d = ar.take<double>(g.L + 1);
         const int mmax = std::max(g.k, (int)scan);
         d.tab_out = ar.take<double>((size_t)(mmax * 2) << mmax);
         d.tab_win = ar.take<double>((size_t)(mmax * mmax * 4) << mmax);

@@ -169,3 +169,31 @@ def test_block_diagonal_map_with_exact_ties(hica):
     assert np.array_equal(res["Z"], ref["Z"]) and list(res["leaves"]) == list(ref["leaves"])
     assert np.array_equal(hica.p1_get_rank(), ref["R"])
     assert res["initial_cuts"] == ref["initial_cuts"] and res["cuts"] == ref["cuts"]
+
+
+@pytest.mark.parametrize("n,nc,spc,seed", [(1700, 1, 40, 3), (3300, 2, 30, 5)])
+def test_device_engine_matches_exhaustive_scoring_at_long_chromosomes(hica, n, nc, spc, seed):
+    """Chromosomes of 1,600+ bins (the 50 kb configuration): the device-resident two-phase search against the
+    per-call path that scores EVERY candidate bit-exactly (the oracle takes minutes at this size).  Deep pairwise
+    trees, long diagonals and multi-pass kernels are only reached here."""
+    g = make_genome(n, n_chrom=nc, seed=seed, scaffolds_per_chrom=spc)
+    A = g.A.numpy()
+    names = [g.scaffold_names[s] for s in g.scaffold_of_bin]
+    groups = [[(i + 1, names[i]) for i in range(n) if g.true_chrom_of_bin[i] == ch] for ch in range(nc)]
+    index_of = {i + 1: i for i in range(n)}
+    hica.p2_upload(A)
+    got, cost, rounds, stats = part2.order_groups_device(hica, index_of, groups, 6, 5)
+    assert stats[:, 2].sum() == 0 and stats[:, 3].sum() == 0
+    for gi, grp in enumerate(groups):
+        want, wcost, wrounds = part2.order_chromosome(hica, index_of, grp, 6, 5)
+        assert got[gi] == want, gi
+        assert cost[gi] == wcost, gi
+        assert int(rounds[gi]) == wrounds, gi
+    # the total of the full layout against numpy's own pairwise sums (diagonal by diagonal, as the reference does)
+    grp = groups[0]
+    idx = np.array([index_of[b] for b, _ in grp])
+    M = A[np.ix_(idx, idx)]
+    want_total = sum(np.trace(M, k) for k in range(1, len(idx)))
+    hica.p2_select(idx.astype(np.int32))
+    hica.p2_set_segments(np.array([0, len(idx)], dtype=np.int32), np.arange(len(idx), dtype=np.int32))
+    assert hica.p2_total([0]) == want_total
