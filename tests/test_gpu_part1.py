@@ -248,7 +248,8 @@ def test_symmetric_upload_reads_only_the_upper_triangle(hica, n):
 
 @pytest.mark.parametrize("env", [{"HICA_NN_CHAIN_GLOBAL": "1"}, {"HICA_NN_KERNEL": "2"}, {"HICA_NN_KERNEL": "1"},
                                  {"HICA_NN_CLUSTER": "8"}, {"HICA_NN_CLUSTER": "2"}, {"HICA_NN_CLUSTER": "1"},
-                                 {"HICA_NN_THREADS": "128"}, {"HICA_NN_DEBUG": "1"}])
+                                 {"HICA_NN_THREADS": "128"}, {"HICA_NN_DEBUG": "1"},
+                                 {"HICA_NN_CLUSTER": "1", "HICA_NN_THREADS": "128"}])  # several passes over the slice
 @pytest.mark.parametrize("n,tie", [(3, False), (70, True), (333, True), (1200, False)])
 def test_linkage_kernel_variants_bitwise(hica, n, tie, env, monkeypatch):
     """Every linkage kernel the library can fall back to - chain in global memory (large N), the kernels without
