@@ -114,6 +114,7 @@ extern "C" int hica_destroy(hica_handle h)
     cudaFree(h->S);
     cudaFree(h->St);
     cudaFree(h->p2_arena);
+    cudaFree(h->rank_buf);
     cudaFree(h->cut_buf);
     cudaFree(h->seg_ptr);
     cudaFree(h->seg_bins);

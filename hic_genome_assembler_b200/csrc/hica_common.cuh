@@ -22,6 +22,8 @@ struct hica_ctx {
     void *p2_arena = nullptr;  // scratch arena of hica_p2_order_groups (grow-only)
     int64_t p2_arena_cap = 0;
     int64_t R_cap = 0;         // bytes allocated behind R
+    void *rank_buf = nullptr;  // key / payload scratch of the multi-chunk rank sort (grow-only)
+    int64_t rank_buf_cap = 0;
     void *cut_buf = nullptr;   // scratch of the batched noise filter (grow-only)
     int64_t cut_buf_cap = 0;
 
