@@ -75,8 +75,6 @@ struct GroupDev {
 struct Tables {  // enumeration tables per window width m (device pointers)
     const uint8_t *ord[9], *ori[9];
     int n_ord[9], n_ori[9];
-    const int32_t *valid_out[9], *valid_win[9];  // indices of the table entries that exist (set excludes s / s2)
-    int n_valid_out[9], n_valid_win[9];
 };
 
 enum { PH_BRUTE = 0, PH_INSERT = 1, PH_SCAN = 2 };
@@ -860,33 +858,6 @@ extern "C" int hica_p2_order_groups(hica_handle h, int32_t ngroups, const int32_
         ENG_CUDA(cudaMemcpyAsync(po, ord_scan, (size_t)n_ord_scan * scan, cudaMemcpyHostToDevice, s));
         ENG_CUDA(cudaMemcpyAsync(pr, ori_scan, (size_t)n_ori_scan * scan, cudaMemcpyHostToDevice, s));
         tb.ord[scan] = po; tb.ori[scan] = pr; tb.n_ord[scan] = n_ord_scan; tb.n_ori[scan] = n_ori_scan;
-    }
-    // ---- lists of the table entries that exist, per window width in use
-    {
-        std::vector<int> widths;
-        for (auto &g : gs) widths.push_back(g.k);
-        widths.push_back(scan);
-        std::sort(widths.begin(), widths.end());
-        widths.erase(std::unique(widths.begin(), widths.end()), widths.end());
-        for (int m : widths) {
-            std::vector<int32_t> vo, vw;
-            const int full = (1 << m) - 1;
-            for (int b = 0; b < ((m * 2) << m); b++) {
-                const int mask = b & full, sidx = b >> (m + 1);
-                if (!((mask >> sidx) & 1)) vo.push_back(b);
-            }
-            for (int b = 0; b < ((m * m * 4) << m); b++) {
-                const int mask = b & full, r = b >> (m + 2), s2 = r % m, s1 = r / m;
-                if (s1 < m && s1 != s2 && !((mask >> s1) & 1) && !((mask >> s2) & 1)) vw.push_back(b);
-            }
-            int32_t *dvo = ar.take<int32_t>(std::max<size_t>(1, vo.size()));
-            int32_t *dvw = ar.take<int32_t>(std::max<size_t>(1, vw.size()));
-            if (!vo.empty()) ENG_CUDA(cudaMemcpyAsync(dvo, vo.data(), sizeof(int32_t) * vo.size(), cudaMemcpyHostToDevice, s));
-            if (!vw.empty()) ENG_CUDA(cudaMemcpyAsync(dvw, vw.data(), sizeof(int32_t) * vw.size(), cudaMemcpyHostToDevice, s));
-            ENG_CUDA(cudaStreamSynchronize(s));  // vo / vw are about to go out of scope
-            tb.valid_out[m] = dvo; tb.valid_win[m] = dvw;
-            tb.n_valid_out[m] = (int)vo.size(); tb.n_valid_win[m] = (int)vw.size();
-        }
     }
     // ---- group descriptors
     std::vector<GroupDev> hdev(ngroups);
