@@ -55,10 +55,17 @@ __device__ __forceinline__ bool exact_cost_cluster(const double *__restrict__ S,
 }
 constexpr double NEAR_TOL = 1e-10;
 
-struct GroupState {
-    double total, best_cost, E_layout, rel0;
+struct WinState {  // per evaluated window: best closed-form score, that of the current arrangement, near list size
     unsigned long long amax_key;
-    int near_count, improved, converged, rounds, error, inexact, skip, done_blocks;
+    double rel0;
+    int near_count, pad;
+};
+
+struct GroupState {
+    double total, best_cost, E_layout;
+    WinState w0;  // the window of the phases that evaluate one window at a time (brute force, insertion)
+    int improved, converged, rounds, error, inexact, skip, done_blocks, n_improved;
+    int ws_next, pad;  // batched scan: first window of the current round that has not been validated yet
     long long n_exact;
 };
 
@@ -70,6 +77,7 @@ struct GroupDev {
     double *Wt, *tab_out, *tab_win, *rel, *near_score, *tr, *ins_d;  // ins_d: D[a] of the insertion step, L entries
     int32_t *near_id;
     GroupState *st;
+    WinState *win;  // batched scan: one per window slot
 };
 
 struct Tables {  // enumeration tables per window width m (device pointers)
@@ -78,11 +86,11 @@ struct Tables {  // enumeration tables per window width m (device pointers)
 };
 
 enum { PH_BRUTE = 0, PH_INSERT = 1, PH_SCAN = 2 };
-struct Phase { int kind, step, m_scan; };
+struct Phase { int kind, step, m_scan, zb; };  // zb > 0: batched scan, windows ws_next .. ws_next + zb - 1 at once
 
 struct PhaseParams { int active, nslots, n, ws, m; };
 
-__device__ __forceinline__ PhaseParams phase_params(const GroupDev &g, const Phase &ph)
+__device__ __forceinline__ PhaseParams phase_params(const GroupDev &g, const Phase &ph, int z = 0)
 {
     PhaseParams p;
     if (ph.kind == PH_BRUTE) {
@@ -94,10 +102,29 @@ __device__ __forceinline__ PhaseParams phase_params(const GroupDev &g, const Pha
         p.nslots = mbase + 1; p.n = g.cum[min(p.nslots, g.nseg)]; p.ws = 0; p.m = mbase;
         p.active = ph.step < steps;
     } else {
-        p.nslots = g.nseg; p.n = g.L; p.ws = ph.step; p.m = ph.m_scan;
-        p.active = g.scanning && ph.step + ph.m_scan <= g.nseg && !g.st->converged;
+        p.nslots = g.nseg; p.n = g.L; p.m = ph.m_scan;
+        p.ws = ph.zb ? g.st->ws_next + z : ph.step;
+        p.active = g.scanning && p.ws + ph.m_scan <= g.nseg && !g.st->converged;
     }
     return p;
+}
+
+// buffers and state of window slot z (slot 0 = the group's own buffers in the one-window phases)
+struct WinView {
+    double *tab_out, *tab_win, *rel, *near_score;
+    int32_t *near_id;
+    WinState *ws;
+};
+__device__ __forceinline__ WinView win_view(const GroupDev &g, const Phase &ph, int m, long long B, int z)
+{
+    WinView v;
+    v.tab_out = g.tab_out + (size_t)z * ((size_t)(m * 2) << m);
+    v.tab_win = g.tab_win + (size_t)z * ((size_t)(m * m * 4) << m);
+    v.rel = g.rel + (size_t)z * B;
+    v.near_score = g.near_score + (size_t)z * B;
+    v.near_id = g.near_id + (size_t)z * B;
+    v.ws = ph.zb ? g.win + z : &g.st->w0;
+    return v;
 }
 
 // ---------------------------------------------------------------------------
@@ -219,13 +246,15 @@ __global__ void __launch_bounds__(128) k_g_tables(const GroupDev *gs, Phase ph, 
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const GroupDev &g = gs[blockIdx.y];
-    const PhaseParams pp = phase_params(g, ph);
+    const int z = blockIdx.z;
+    const PhaseParams pp = phase_params(g, ph, z);
     if (!pp.active || g.st->skip) return;
     const int m = pp.m, ws = pp.ws, nslots = pp.nslots, n = pp.n;
     const int nmask = 1 << (m - 1);                                  // sets of the other m-1 window scaffolds
     const int nchunk = (nmask + TAB_MPC - 1) / TAB_MPC;
     const int nvo = 2 * m * nchunk;
     const int bx = blockIdx.x;
+    const WinView wv = win_view(g, ph, m, (long long)tb.n_ord[m] * tb.n_ori[m], z);
     if (bx >= nvo + m * m) return;
     __shared__ int wlen[8], woff[8];
     __shared__ double red[4][TAB_MPC];
@@ -297,7 +326,7 @@ __global__ void __launch_bounds__(128) k_g_tables(const GroupDev *gs, Phase ph, 
         }
         __syncthreads();
         if (tid < TAB_MPC && chunk * TAB_MPC + tid < nmask)
-            g.tab_out[(((s << 1) | o) << m) | maskv[tid]] = (red[0][tid] + red[1][tid]) + (red[2][tid] + red[3][tid]);
+            wv.tab_out[(((s << 1) | o) << m) | maskv[tid]] = (red[0][tid] + red[1][tid]) + (red[2][tid] + red[3][tid]);
     } else {
         // ---- scaffold pair (s, s2) in orientations (o, o2), one warp each, for EVERY set of window scaffolds
         //      between them (2^(m-2) entries, 8 at a time): the sets only change the gap
@@ -349,13 +378,13 @@ __global__ void __launch_bounds__(128) k_g_tables(const GroupDev *gs, Phase ph, 
                 double rr = acc[i];
                 for (int d = 16; d >= 1; d >>= 1) rr += __shfl_xor_sync(0xffffffffu, rr, d);
                 if (lane == 0 && u0 + i < nm2)
-                    g.tab_win[(((((s * m + s2) * 2 + o) * 2 + o2)) << m) | maskv[i]] = rr;
+                    wv.tab_win[(((((s * m + s2) * 2 + o) * 2 + o2)) << m) | maskv[i]] = rr;
             }
         }
     }
 }
 
-__device__ __forceinline__ double rel_of(const GroupDev &g, int m, const uint8_t *ord, const uint8_t *ori)
+__device__ __forceinline__ double rel_of(const WinView &g, int m, const uint8_t *ord, const uint8_t *ori)
 {
     int masks[8];
     int mask = 0;
@@ -381,25 +410,27 @@ __device__ __forceinline__ double rel_of(const GroupDev &g, int m, const uint8_t
 __global__ void __launch_bounds__(256) k_g_approx(const GroupDev *gs, Phase ph, Tables tb)
 {
     const GroupDev &g = gs[blockIdx.y];
-    const PhaseParams pp = phase_params(g, ph);
+    const int z = blockIdx.z;
+    const PhaseParams pp = phase_params(g, ph, z);
     if (!pp.active || g.st->skip) return;
     const int m = pp.m, n_ori = tb.n_ori[m];
     const long long B = (long long)tb.n_ord[m] * n_ori;
+    const WinView wv = win_view(g, ph, m, B, z);
     const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if ((long long)blockIdx.x * blockDim.x >= B) return;
     double rel = -INFINITY;
     if (c < B) {
         const int oi = (int)(c / n_ori), ri = (int)(c % n_ori);
-        rel = rel_of(g, m, tb.ord[m] + (size_t)oi * m, tb.ori[m] + (size_t)ri * m);
-        g.rel[c] = rel;
+        rel = rel_of(wv, m, tb.ord[m] + (size_t)oi * m, tb.ori[m] + (size_t)ri * m);
+        wv.rel[c] = rel;
     }
     double mx = rel;
     for (int d = 16; d >= 1; d >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, d));
-    if ((threadIdx.x & 31) == 0 && mx > -INFINITY) atomicMax(&g.st->amax_key, f64_order_key(mx));
+    if ((threadIdx.x & 31) == 0 && mx > -INFINITY) atomicMax(&wv.ws->amax_key, f64_order_key(mx));
     if (c == 0) {  // the current arrangement: identity order, current orientations
         uint8_t ido[8], idr[8];
         for (int j = 0; j < m; j++) { ido[j] = (uint8_t)j; idr[j] = (uint8_t)(g.layout[pp.ws + j] & 1); }
-        g.st->rel0 = rel_of(g, m, ido, idr);
+        wv.ws->rel0 = rel_of(wv, m, ido, idr);
     }
 }
 
@@ -407,20 +438,22 @@ __global__ void __launch_bounds__(256) k_g_approx(const GroupDev *gs, Phase ph, 
 __global__ void __launch_bounds__(256) k_g_select(const GroupDev *gs, Phase ph, Tables tb)
 {
     const GroupDev &g = gs[blockIdx.y];
-    const PhaseParams pp = phase_params(g, ph);
+    const int z = blockIdx.z;
+    const PhaseParams pp = phase_params(g, ph, z);
     GroupState *st = g.st;
     if (!pp.active || st->skip) return;
     const long long B = (long long)tb.n_ord[pp.m] * tb.n_ori[pp.m];
+    const WinView wv = win_view(g, ph, pp.m, B, z);
     const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= B) return;
-    const double amax = st->E_layout + (f64_from_order_key(st->amax_key) - st->rel0);
+    const double amax = st->E_layout + (f64_from_order_key(wv.ws->amax_key) - wv.ws->rel0);
     const double carried = ph.kind == PH_SCAN ? st->best_cost : 0.0;
     const double scale = fmax(fabs(amax), fmax(fabs(carried), fabs(st->E_layout)));
     const double thr = fmax(amax, carried) - NEAR_TOL * scale;
-    const double a = st->E_layout + (g.rel[c] - st->rel0);
+    const double a = st->E_layout + (wv.rel[c] - wv.ws->rel0);
     if (st->inexact || !(a < thr)) {
-        const int slot = atomicAdd(&st->near_count, 1);
-        g.near_id[slot] = (int)c;
+        const int slot = atomicAdd(&wv.ws->near_count, 1);
+        wv.near_id[slot] = (int)c;
     }
 }
 
@@ -430,21 +463,23 @@ k_g_exact_near(const GroupDev *gs, Phase ph, Tables tb)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const GroupDev &g = gs[blockIdx.y];
-    const PhaseParams pp = phase_params(g, ph);
+    const int z = blockIdx.z;
+    const PhaseParams pp = phase_params(g, ph, z);
     if (!pp.active || g.st->skip) return;
-    const int cnt = g.st->near_count;
+    const WinView wv = win_view(g, ph, pp.m, (long long)tb.n_ord[pp.m] * tb.n_ori[pp.m], z);
+    const int cnt = wv.ws->near_count;
     const int slot = blockIdx.x / EX_SPLIT, nslots_grid = gridDim.x / EX_SPLIT;  // one cluster per slot
     if (slot >= cnt) return;
     const int m = pp.m, n_ori = tb.n_ori[m];
     SmemPlan sp = carve(smem, pp.n, pp.n, pp.nslots);
     const double total = g.st->total;
     for (int i = slot; i < cnt; i += nslots_grid) {
-        const int c = g.near_id[i];
+        const int c = wv.near_id[i];
         const int oi = c / n_ori, ri = c % n_ori;
         SrcWindow src{g.layout, pp.ws, m, tb.ord[m] + (size_t)oi * m, tb.ori[m] + (size_t)ri * m};
         build_order_cta(src, pp.nslots, g.seg_ptr, g.seg_bins, sp.o, sp.spos, sp.sent, pp.n);
         double cost = 0.;
-        if (exact_cost_cluster(g.S, g.L, sp.o, pp.n, total, sp.tr, cost) && threadIdx.x == 0) g.near_score[i] = cost;
+        if (exact_cost_cluster(g.S, g.L, sp.o, pp.n, total, sp.tr, cost) && threadIdx.x == 0) wv.near_score[i] = cost;
     }
 }
 
@@ -465,7 +500,7 @@ __global__ void __launch_bounds__(256) k_g_pick_window(const GroupDev *gs, Phase
         }
         return;
     }
-    const int cnt = st->near_count;
+    const int cnt = st->w0.near_count;
     double bv = -INFINITY;
     int bi = INT_MAX;
     for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
@@ -494,11 +529,12 @@ __global__ void __launch_bounds__(256) k_g_pick_window(const GroupDev *gs, Phase
             st->best_cost = bv;
             st->E_layout = bv;
             st->improved = 1;
+            if (ph.kind == PH_SCAN) st->n_improved += 1;
         } else if (ph.kind == PH_BRUTE) {
             st->error = 1;  // the reference would fail on bestOrder == "NA"
         }
-        st->near_count = 0;
-        st->amax_key = 0ull;
+        st->w0.near_count = 0;
+        st->w0.amax_key = 0ull;
     }
 }
 
@@ -607,8 +643,8 @@ __global__ void __launch_bounds__(128) k_g_ins_rel(const GroupDev *gs, Phase ph)
         double rel = 0.;
         for (int w = 0; w < (int)blockDim.x / 32; w++) rel += red[w];
         g.rel[c] = rel;
-        atomicMax(&g.st->amax_key, f64_order_key(rel));
-        if (c == 0) g.st->rel0 = rel;
+        atomicMax(&g.st->w0.amax_key, f64_order_key(rel));
+        if (c == 0) g.st->w0.rel0 = rel;
     }
 }
 
@@ -626,10 +662,10 @@ __global__ void __launch_bounds__(128) k_g_ins_select(const GroupDev *gs, Phase 
     // is taken relative to that bound, which needs no absolute anchor.  Whether the best score beats the
     // initial bestCost of 0. (:338) is decided on the exact scores in k_g_pick_insert.
     const double hn = g.Wt[1] * st->total;  // w(1) = H_{n-1} / total
-    const double thr = f64_from_order_key(st->amax_key) - NEAR_TOL * hn;
+    const double thr = f64_from_order_key(st->w0.amax_key) - NEAR_TOL * hn;
     for (int c = threadIdx.x; c < B; c += blockDim.x) {
         const bool near = all || !(g.rel[c] < thr);
-        if (near) g.near_id[atomicAdd(&st->near_count, 1)] = c;
+        if (near) g.near_id[atomicAdd(&st->w0.near_count, 1)] = c;
     }
 }
 
@@ -642,7 +678,7 @@ k_g_insert_scores(const GroupDev *gs, Phase ph)
     const PhaseParams pp = phase_params(g, ph);
     if (!pp.active) return;
     const int m = pp.m, n = pp.n;
-    const int cnt = g.st->near_count;
+    const int cnt = g.st->w0.near_count;
     const int slot = blockIdx.x / EX_SPLIT, nslots_grid = gridDim.x / EX_SPLIT;  // one cluster per slot
     if (slot >= cnt) return;
     SmemPlan sp = carve(smem, n, n, m + 1);
@@ -668,7 +704,7 @@ __global__ void __launch_bounds__(32) k_g_pick_insert(const GroupDev *gs, Phase 
     const PhaseParams pp = phase_params(g, ph);
     if (!pp.active) return;
     GroupState *st = g.st;
-    const int m = pp.m, cnt = st->near_count;
+    const int m = pp.m, cnt = st->w0.near_count;
     double best = 0.0;  // bestCost starts at 0. (:338); strict '>' keeps the first maximum
     int bi = INT_MAX;
     for (int i = threadIdx.x; i < cnt; i += 32) {
@@ -693,19 +729,8 @@ __global__ void __launch_bounds__(32) k_g_pick_insert(const GroupDev *gs, Phase 
     g.layout[pos] = ((ne >> 1) << 1) | ori;
     st->best_cost = best;
     st->n_exact += cnt;
-    st->near_count = 0;
-    st->amax_key = 0ull;
-}
-
-__global__ void k_g_round_end(const GroupDev *gs)
-{
-    const GroupDev &g = gs[blockIdx.x];
-    if (threadIdx.x != 0 || !g.scanning) return;
-    GroupState *st = g.st;
-    if (st->converged) return;
-    st->rounds += 1;
-    if (!st->improved) st->converged = 1;
-    st->improved = 0;
+    st->w0.near_count = 0;
+    st->w0.amax_key = 0ull;
 }
 
 __global__ void k_g_reset_for_scan(const GroupDev *gs)
@@ -715,8 +740,88 @@ __global__ void k_g_reset_for_scan(const GroupDev *gs)
     g.st->improved = 0;
     g.st->converged = g.scanning ? 0 : 1;
     g.st->rounds = 0;
-    g.st->near_count = 0;
-    g.st->amax_key = 0ull;
+    g.st->w0.near_count = 0;
+    g.st->w0.amax_key = 0ull;
+    g.st->ws_next = 0;
+}
+
+// Batched scan (scanOrdering, :495-549).  The windows of a round are evaluated one after the other by the
+// reference, each on the layout the previous ones left behind - but a window that does not improve the carried
+// cost leaves nothing behind, so all windows from ws_next onwards are scored at once on the current layout and
+// this kernel walks them in order: the first one whose best exact score beats the carried cost is applied (it
+// was evaluated on exactly the layout the sequential loop would have given it), the ones after it are
+// discarded and re-evaluated by the next batch.  A round without improvements is one batch instead of
+// nseg - scan + 1 dependent steps.  One CTA per group.
+__global__ void __launch_bounds__(256) k_gb_pick(const GroupDev *gs, Phase ph, Tables tb)
+{
+    const GroupDev &g = gs[blockIdx.y];
+    GroupState *st = g.st;
+    if (!g.scanning || st->converged) return;
+    const int m = ph.m_scan, n_ori = tb.n_ori[m];
+    const long long B = (long long)tb.n_ord[m] * n_ori;
+    const int nwin = g.nseg - m + 1, ws0 = st->ws_next;
+    const int zn = min(ph.zb, nwin - ws0);
+    __shared__ double sv[8];
+    __shared__ int si[8];
+    __shared__ int hit_s;
+    const double carried = st->best_cost;
+    int hit = -1;
+    long long n_exact = 0;
+    for (int z = 0; z < zn && hit < 0; z++) {
+        const WinView wv = win_view(g, ph, m, B, z);
+        const int cnt = wv.ws->near_count;
+        double bv = -INFINITY;
+        int bi = INT_MAX;
+        for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+            const double sc = wv.near_score[i];
+            const int c = wv.near_id[i];
+            if (sc > bv || (sc == bv && c < bi)) { bv = sc; bi = c; }
+        }
+        for (int d = 16; d >= 1; d >>= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, bv, d);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, d);
+            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        }
+        if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = bv; si[threadIdx.x >> 5] = bi; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int w = 1; w < (int)blockDim.x / 32; w++)
+                if (sv[w] > bv || (sv[w] == bv && si[w] < bi)) { bv = sv[w]; bi = si[w]; }
+            hit_s = -1;
+            if (!st->skip && bv > carried) {  // accept rule of the reference: strictly better than the carried cost
+                const int ws = ws0 + z;
+                const int oi = bi / n_ori, ri = bi % n_ori;
+                int segs[8];
+                for (int j = 0; j < m; j++) segs[j] = g.layout[ws + j] >> 1;
+                for (int j = 0; j < m; j++)
+                    g.layout[ws + j] = (segs[tb.ord[m][(size_t)oi * m + j]] << 1) | (int)tb.ori[m][(size_t)ri * m + j];
+                st->best_cost = bv;
+                st->E_layout = bv;
+                st->improved = 1;
+                st->n_improved += 1;
+                hit_s = z;
+            }
+        }
+        __syncthreads();
+        hit = hit_s;
+        n_exact += cnt;
+        __syncthreads();
+    }
+    for (int z = threadIdx.x; z < ph.zb; z += blockDim.x) {  // every slot starts the next batch clean
+        g.win[z].near_count = 0;
+        g.win[z].amax_key = 0ull;
+    }
+    if (threadIdx.x == 0) {
+        st->n_exact += n_exact;
+        int next = (hit >= 0) ? ws0 + hit + 1 : ws0 + zn;
+        if (next >= nwin) {  // end of a round (:545-549): another one only if something changed
+            st->rounds += 1;
+            if (!st->improved) st->converged = 1;
+            st->improved = 0;
+            next = 0;
+        }
+        st->ws_next = next;
+    }
 }
 
 __global__ void k_g_gather(const double *__restrict__ G, int64_t gn, const int32_t *__restrict__ rows_all,
@@ -802,15 +907,27 @@ extern "C" int hica_p2_order_groups(hica_handle h, int32_t ngroups, const int32_
         g.Bmax = std::max<long long>(std::max<long long>(Bb, Bscan), 2ll * (g.nseg + 1));
         const int mmax = std::max(g.k, (int)scan);
         arena_bytes += 2 * padded<double>((size_t)g.L * g.L) + 3 * padded<int32_t>(g.nseg + 1) + padded<int32_t>(g.L) +
-                       3 * padded<double>(g.L + 1) + padded<double>((size_t)(mmax * 2) << mmax) +
-                       padded<double>((size_t)(mmax * mmax * 4) << mmax) + 2 * padded<double>(g.Bmax) +
-                       padded<int32_t>(g.Bmax) + padded<GroupState>(1);
+                       3 * padded<double>(g.L + 1) + padded<GroupState>(1);
         Lmax = std::max(Lmax, g.L);
         nseg_max = std::max(nseg_max, g.nseg);
         kmax = std::max(kmax, g.k);
         ins_steps = std::max(ins_steps, std::max(1, g.nseg - g.k));
         Bbrute_max = std::max(Bbrute_max, Bb);
         if (g.nseg > n_scaffolds) { any_scan = true; win_max = std::max(win_max, g.nseg - scan + 1); }
+    }
+    // batched scan: how many windows are evaluated at once (all of a round if their tables and candidate
+    // arrays fit in ~1 GB over all groups)
+    const size_t slot_bytes = sizeof(double) * (((size_t)(scan * 2) << scan) + ((size_t)(scan * scan * 4) << scan) + 2 * (size_t)Bscan) +
+                              sizeof(int32_t) * (size_t)Bscan + sizeof(WinState) + 64;
+    int zb = 1;
+    if (any_scan) zb = (int)std::max<size_t>(1, std::min<size_t>((size_t)win_max, ((size_t)1 << 30) / ((size_t)ngroups * slot_bytes)));
+    for (int gi = 0; gi < ngroups; gi++) {
+        const HostGroup &g = gs[gi];
+        const int mmax = std::max(g.k, (int)scan);
+        const size_t nb_cand = std::max<size_t>((size_t)g.Bmax, (size_t)zb * (size_t)Bscan);
+        arena_bytes += padded<double>(std::max((size_t)(mmax * 2) << mmax, (size_t)zb * ((size_t)(scan * 2) << scan))) +
+                       padded<double>(std::max((size_t)(mmax * mmax * 4) << mmax, (size_t)zb * ((size_t)(scan * scan * 4) << scan))) +
+                       2 * padded<double>(nb_cand) + padded<int32_t>(nb_cand) + padded<WinState>(zb);
     }
     const int64_t total_bins = seg_ptr[grp_ptr[ngroups]];
     for (int64_t b = 0; b < total_bins; b++)
@@ -876,12 +993,14 @@ extern "C" int hica_p2_order_groups(hica_handle h, int32_t ngroups, const int32_
         d.tr = ar.take<double>(g.L + 1);
         d.ins_d = ar.take<double>(g.L + 1);
         const int mmax = std::max(g.k, (int)scan);
-        d.tab_out = ar.take<double>((size_t)(mmax * 2) << mmax);
-        d.tab_win = ar.take<double>((size_t)(mmax * mmax * 4) << mmax);
-        d.rel = ar.take<double>(g.Bmax);
-        d.near_score = ar.take<double>(g.Bmax);
-        d.near_id = ar.take<int32_t>(g.Bmax);
+        d.tab_out = ar.take<double>(std::max((size_t)(mmax * 2) << mmax, (size_t)zb * ((size_t)(scan * 2) << scan)));
+        d.tab_win = ar.take<double>(std::max((size_t)(mmax * mmax * 4) << mmax, (size_t)zb * ((size_t)(scan * scan * 4) << scan)));
+        const size_t nb_cand = std::max<size_t>((size_t)g.Bmax, (size_t)zb * (size_t)Bscan);
+        d.rel = ar.take<double>(nb_cand);
+        d.near_score = ar.take<double>(nb_cand);
+        d.near_id = ar.take<int32_t>(nb_cand);
         d.st = ar.take<GroupState>(1);
+        d.win = ar.take<WinState>(std::max(1, zb));
         st_ptr[gi] = d.st;
         lay_ptr[gi] = lay;
         std::vector<int32_t> hp(g.nseg + 1), hb(g.L), hl(g.nseg + 1, 0);
@@ -891,6 +1010,7 @@ extern "C" int hica_p2_order_groups(hica_handle h, int32_t ngroups, const int32_
         for (int b = 0; b < g.L; b++) hb[b] = b;
         for (int sg = 0; sg < g.nseg; sg++) hl[sg] = sg << 1;
         ENG_CUDA(cudaMemsetAsync(d.st, 0, sizeof(GroupState), s));
+        ENG_CUDA(cudaMemsetAsync(d.win, 0, sizeof(WinState) * std::max(1, zb), s));
         ENG_CUDA(cudaMemcpyAsync(sp, hp.data(), sizeof(int32_t) * (g.nseg + 1), cudaMemcpyHostToDevice, s));
         ENG_CUDA(cudaMemcpyAsync(cum, hp.data(), sizeof(int32_t) * (g.nseg + 1), cudaMemcpyHostToDevice, s));
         ENG_CUDA(cudaMemcpyAsync(sb, hb.data(), sizeof(int32_t) * g.L, cudaMemcpyHostToDevice, s));
@@ -994,15 +1114,26 @@ extern "C" int hica_p2_order_groups(hica_handle h, int32_t ngroups, const int32_
         mark(2);
         h->launches += 3;
         ENG_CUDA(cudaGetLastError());
-        int batch = 2;
-        for (int pass = 0; pass < 10000; pass++) {
-            for (int r = 0; r < batch; r++) {
-                for (int i = 0; i < win_max; i++) window_search(Phase{PH_SCAN, i, scan}, scan, Bscan);
-                k_g_round_end<<<G, 32, 0, s>>>(gdev);
-                mark(13);
-                HICA_LAUNCHED(h);
+        // batches of zb windows (see k_gb_pick); a few batches between two looks at the converged flags
+        const Phase phb = {PH_SCAN, 0, scan, zb};
+        const unsigned nb_tab = (unsigned)(2 * scan * (((1 << (scan - 1)) + TAB_MPC - 1) / TAB_MPC) + scan * scan);
+        const unsigned nb_c = (unsigned)((Bscan + 255) / 256);
+        int reps = 3;
+        for (int pass = 0; pass < 100000; pass++) {
+            for (int r = 0; r < reps; r++) {
+                k_g_tables<<<dim3(nb_tab, G, (unsigned)zb), 128, tab_smem, s>>>(gdev, phb, tb);
+                mark(3);
+                k_g_approx<<<dim3(nb_c, G, (unsigned)zb), 256, 0, s>>>(gdev, phb, tb);
+                mark(4);
+                k_g_select<<<dim3(nb_c, G, (unsigned)zb), 256, 0, s>>>(gdev, phb, tb);
+                mark(5);
+                k_g_exact_near<<<dim3((unsigned)std::min<long long>(Bscan, 8) * EX_SPLIT, G, (unsigned)zb), EX_THREADS, ex_smem, s>>>(gdev, phb, tb);
+                mark(6);
+                k_gb_pick<<<dim3(1, G), 256, 0, s>>>(gdev, phb, tb);
+                mark(7);
+                h->launches += 5;
             }
-            batch = 1;
+            reps = 1;
             bool all_done = true;
             for (int gi = 0; gi < ngroups; gi++)
                 ENG_CUDA(cudaMemcpyAsync(&hst[gi], st_ptr[gi], sizeof(GroupState), cudaMemcpyDeviceToHost, s));
@@ -1027,7 +1158,7 @@ extern "C" int hica_p2_order_groups(hica_handle h, int32_t ngroups, const int32_
         if (out_cost) out_cost[gi] = hst[gi].best_cost;
         if (out_rounds) out_rounds[gi] = gs[gi].nseg > n_scaffolds ? hst[gi].rounds : 0;
         if (out_stats) {
-            out_stats[4 * gi + 0] = 0;
+            out_stats[4 * gi + 0] = hst[gi].n_improved;  // scan windows that changed the layout
             out_stats[4 * gi + 1] = hst[gi].n_exact;
             out_stats[4 * gi + 2] = hst[gi].inexact;
             out_stats[4 * gi + 3] = hst[gi].error;
