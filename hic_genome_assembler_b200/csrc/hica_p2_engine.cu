@@ -476,6 +476,16 @@ k_g_exact_near(const GroupDev *gs, Phase ph, Tables tb)
     for (int i = slot; i < cnt; i += nslots_grid) {
         const int c = wv.near_id[i];
         const int oi = c / n_ori, ri = c % n_ori;
+        {   // the current arrangement itself (usually the best candidate of a window that does not improve): its
+            // exact score is the cost of the current layout, which the group carries (E_layout)
+            const uint8_t *od = tb.ord[m] + (size_t)oi * m, *orr = tb.ori[m] + (size_t)ri * m;
+            bool ident = true;
+            for (int j = 0; j < m; j++) ident = ident && od[j] == j && orr[j] == (uint8_t)(g.layout[pp.ws + j] & 1);
+            if (ident) {
+                if (blockIdx.x % EX_SPLIT == 0 && threadIdx.x == 0) wv.near_score[i] = g.st->E_layout;
+                continue;
+            }
+        }
         SrcWindow src{g.layout, pp.ws, m, tb.ord[m] + (size_t)oi * m, tb.ori[m] + (size_t)ri * m};
         build_order_cta(src, pp.nslots, g.seg_ptr, g.seg_bins, sp.o, sp.spos, sp.sent, pp.n);
         double cost = 0.;
