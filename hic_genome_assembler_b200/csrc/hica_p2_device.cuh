@@ -183,7 +183,7 @@ __device__ __forceinline__ double pairwise_leaf(const F &f, int off, int n)
 // The tree above the leaves (split at n/2 rounded down to a multiple of 8) is walked with an explicit stack: a
 // recursive version needs a call frame per level, and the default 1 KB device stack overflowed at 1,600 bins.
 template <class F>
-__device__ double pairwise_f(const F &f, int off, int n)
+__device__ double pairwise_generic(const F &f, int off, int n)
 {
     constexpr int DEPTH = 28;  // > log2(2^31 / 128)
     int s_off[DEPTH], s_n[DEPTH];
@@ -217,6 +217,31 @@ __device__ double pairwise_f(const F &f, int off, int n)
         if (sp == 0) return ret;
         sp--;
     }
+}
+
+// Up to PW_INLINE_DEPTH levels of the tree are expanded at compile time (no stack at all).  The right half of a
+// split can be up to 7 terms longer than the left one, so sums of up to 114 * 2^PW_INLINE_DEPTH = 1,824 terms are
+// guaranteed to reach their leaves within that depth - every diagonal of a 1,800-bin chromosome; anything longer
+// takes the generic walk above with its stack in local memory, which is ~1.8x slower.
+constexpr int PW_INLINE_DEPTH = 4;
+template <int D, class F>
+__device__ __forceinline__ double pairwise_inline(const F &f, int off, int n)
+{
+    if (n <= 128) return pairwise_leaf(f, off, n);
+    if constexpr (D == 0) {
+        return pairwise_generic(f, off, n);
+    } else {
+        int n2 = n / 2;
+        n2 -= n2 % 8;
+        return __dadd_rn(pairwise_inline<D - 1>(f, off, n2), pairwise_inline<D - 1>(f, off + n2, n - n2));
+    }
+}
+
+template <class F>
+__device__ double pairwise_f(const F &f, int off, int n)
+{
+    if (n <= (114 << PW_INLINE_DEPTH)) return pairwise_inline<PW_INLINE_DEPTH>(f, off, n);
+    return pairwise_generic(f, off, n);
 }
 
 // order-preserving map double -> uint64 (for atomicMax on scores)
