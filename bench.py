@@ -47,6 +47,7 @@ def parse_args():
     ap.add_argument("--impl", default="hica", choices=["hica", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--part1-only", action="store_true")
+    ap.add_argument("--replicate-part1", action="store_true", help="N > 1: every rank runs the whole of Part1 (no row-block sharding)")
     ap.add_argument("--p2-host-loop", action="store_true", help="Part2 through per-call host loops (exact scoring of every candidate)")
     return ap.parse_args()
 
@@ -125,17 +126,27 @@ def gpu_step(h, wl, args, source, rank, world, dist):
     from hic_genome_assembler_b200 import part1, part2
     n = args.bins
     t0 = time.perf_counter()
+    from hic_genome_assembler_b200 import dist as hdist
+    import torch
+    dev = torch.device("cuda", h.device)
     if source[0] == "device":
         h.p1_upload_device(source[1], n)
+        up = None
     else:
         # the contact map is symmetric by construction (the reference writes [i][j] and [j][i] together):
-        # only its upper triangle crosses PCIe, the library mirrors it on the device
-        h.p1_upload_symmetric(source[1])
-    res = part1.run_part1_resident(h, min_size=5, min_frac=0.0, psig=.05)
+        # only its upper triangle crosses PCIe, the library mirrors it on the device.  With several GPUs every
+        # rank uploads its own row block and the matrix is assembled over NVLink (dist.upload_sharded).
+        up = hdist.upload_sharded(h, source[1], dev, symmetric=True)
+    if world > 1 and not args.replicate_part1:
+        res = hdist.run_part1_resident_sharded(h, dev, min_size=5, min_frac=0.0, psig=.05)
+    else:
+        res = part1.run_part1_resident(h, min_size=5, min_frac=0.0, psig=.05)
+    res["upload"] = up
     t1 = time.perf_counter()
     tm1 = h.timers()
     out = {"leaves": res["leaves"], "cuts": res["cuts"], "initial_cuts": res["initial_cuts"],
-           "ambiguous": res["ambiguous"], "t_part1": t1 - t0, "timers_p1": tm1, "linkage_stats": h.linkage_stats()}
+           "ambiguous": res["ambiguous"], "t_part1": t1 - t0, "timers_p1": tm1, "linkage_stats": h.linkage_stats(),
+           "upload": res.get("upload"), "stage_ms_sharded": res.get("stage_ms")}
     p2_pairs, p2_cands, p2_calls, kernel_ms_p2 = 0, 0, 0, 0.0
     orderings = {}
     if not args.part1_only:
@@ -148,7 +159,6 @@ def gpu_step(h, wl, args, source, rank, world, dist):
             index_of = wl["row_of_bin_id"]
         h.p2_use_p1_matrix()
         part2.STATS.update(candidates=0, bin_pairs=0, calls=0, exact=0)
-        from hic_genome_assembler_b200 import dist as hdist
         nbins = [len(g) if args.p2_host_loop else sum(len(ids) for _, ids in g) for g in groups]
         mine = hdist.shard_groups(nbins, world, rank)
         if args.p2_host_loop:
@@ -325,6 +335,10 @@ def main():
     sampler.start()
     res_dev, secs_dev, launches = timed(("device", A_dev.data_ptr()), args.steps)
     clocks = sampler.stop()
+    # the host-source path has its own first-use costs (NCCL communicators of the row-block gather, pinned
+    # staging): warm it up as well, untimed
+    for _ in range(2):
+        gpu_step(h, wl, args, ("host", wl["A_host"]), rank, world, dist)
     res_e2e, secs_e2e, _ = timed(("host", wl["A_host"]), args.steps)
 
     # ---- aggregate work over ranks
@@ -377,10 +391,14 @@ def main():
         "config": {"workload": workload_name(args), "bins": n, "chromosomes": args.chroms,
                    "part2": "skipped" if args.part1_only else "nScaffolds=6 scanScaffolds=5",
                    "l2": "inputs (%.2f GB matrix) larger than L2; no explicit flush" % (8.0 * n * n / 1e9),
-                   "sharding": "Part1 replicated per rank, Part2 chromosomes round-robin over ranks" if world > 1 else "1 GPU"},
+                   "sharding": ("Part1 replicated per rank" if args.replicate_part1 else
+                                "row-block sharded upload + NVLink all-gather of the matrix, linkage on rank 0 + leaf-order "
+                                "broadcast, rank matrix by row block + all-gather, cut searches replicated") +
+                               "; Part2 chromosome groups dealt to ranks largest first" if world > 1 else "1 GPU"},
         "seconds": {"part1": last["t_part1"], "part2": last["t_part2"], "total": last["t_total"],
                     "e2e_total": secs_e2e / args.steps, "e2e_part1": res_e2e[-1]["t_part1"],
-                    "e2e_part2": res_e2e[-1]["t_part2"], "e2e_upload_ms": res_e2e[-1]["timers_p1"]["upload"]},
+                    "e2e_part2": res_e2e[-1]["t_part2"], "e2e_upload_ms": res_e2e[-1]["timers_p1"]["upload"],
+                    "e2e_upload_rank0": res_e2e[-1].get("upload"), "sharded_stage_ms_rank0": last.get("stage_ms_sharded")},
         "stage_ms_part1": tm, "linkage_stats": last["linkage_stats"],
         "per_step_seconds": [[round(r["t_part1"], 4), round(r["t_part2"], 4)] for r in res_dev],
         "per_step_seconds_e2e": [[round(r["t_part1"], 4), round(r["t_part2"], 4)] for r in res_e2e],
@@ -391,7 +409,7 @@ def main():
         "e2e": {"value": e2e_value, "unit": "bin-pairs/s",
                 # hica_p1_upload_symmetric: row blocks of 512 rows, columns from the block's first row onwards
                 "h2d_bytes_per_step": int(sum(8 * min(512, n - r0) * (n - r0) for r0 in range(0, n, 512))),
-                "h2d_note": "symmetric upload: upper triangle only (%.2f GB of the %.2f GB matrix)" % (
+                "h2d_note": "all ranks together; symmetric upload: upper triangle only (%.2f GB of the %.2f GB matrix)" % (
                     sum(8 * min(512, n - r0) * (n - r0) for r0 in range(0, n, 512)) / 1e9, 8.0 * n * n / 1e9),
                 "d2h_bytes_per_step": int(32 * (n - 1) + 4 * n + 8 * len(last["cuts"]) + 24 * max(1, p2_calls))},
         "gpu_launches": int(launches),

@@ -20,6 +20,7 @@ T_NAMES = ("upload", "distance", "linkage", "leaforder", "rank", "breakpoints", 
 ABI_SYMBOLS = (
     "hica_version", "hica_create", "hica_destroy", "hica_last_error", "hica_launch_count", "hica_get_timers",
     "hica_linkage_stats", "hica_debug_stats",
+    "hica_p1_alloc", "hica_p1_upload_rows", "hica_p1_mirror_lower", "hica_p1_device_buffer", "hica_p1_rank_rows", "hica_p1_rank_commit",
     "hica_p1_upload", "hica_p1_upload_symmetric", "hica_p1_upload_device", "hica_p1_set_row_sums", "hica_p1_distance", "hica_p1_get_distance",
     "hica_p1_get_pairwise_row_sums", "hica_p1_get_row_sums", "hica_p1_upload_distance", "hica_p1_linkage",
     "hica_p1_set_order", "hica_p1_get_reordered", "hica_p1_rank", "hica_p1_upload_similarity", "hica_p1_get_rank", "hica_p1_set_rank",
@@ -57,6 +58,12 @@ def load_library():
     L.hica_p1_upload.argtypes = [vp, vp, i64]
     L.hica_p1_upload_device.argtypes = [vp, vp, i64]
     L.hica_p1_upload_symmetric.argtypes = [vp, vp, i64]
+    L.hica_p1_alloc.argtypes = [vp, i64]
+    L.hica_p1_upload_rows.argtypes = [vp, vp, i64, i64, C.c_int]
+    L.hica_p1_mirror_lower.argtypes = [vp]
+    L.hica_p1_device_buffer.argtypes = [vp, C.c_int, vp, vp, vp]
+    L.hica_p1_rank_rows.argtypes = [vp, i64, i64]
+    L.hica_p1_rank_commit.argtypes = [vp]
     L.hica_p1_set_row_sums.argtypes = [vp, vp]
     L.hica_p1_distance.argtypes = [vp]
     L.hica_p1_get_distance.argtypes = [vp, vp]
@@ -168,6 +175,34 @@ class Handle:
             raise ValueError("square matrix expected")
         self.n = A.shape[0]
         self._check(self._L.hica_p1_upload_symmetric(self._h, _ptr(A), self.n))
+
+    # row-block sharding: see hica.h and dist.run_part1_sharded
+    def p1_alloc(self, n: int):
+        self.n = int(n)
+        self._check(self._L.hica_p1_alloc(self._h, self.n))
+
+    def p1_upload_rows(self, rows: np.ndarray, r0: int, r1: int, symmetric: bool = False):
+        """rows = rows [r0, r1) of the n x n matrix (a C-contiguous (r1-r0) x n view of the host matrix)."""
+        rows = _c(rows, np.float64)
+        if rows.shape != (r1 - r0, self.n):
+            raise ValueError("row block of shape %s expected, got %s" % ((r1 - r0, self.n), rows.shape))
+        self._check(self._L.hica_p1_upload_rows(self._h, _ptr(rows) if r1 > r0 else None, int(r0), int(r1),
+                                                1 if symmetric else 0))
+
+    def p1_mirror_lower(self):
+        self._check(self._L.hica_p1_mirror_lower(self._h))
+
+    def p1_device_buffer(self, which: int) -> Tuple[int, int, int]:
+        """(device pointer, bytes, element bytes) of the matrix (which = 0) or the rank matrix (which = 1)."""
+        ptr, nbytes, eb = C.c_void_p(0), C.c_int64(0), C.c_int32(0)
+        self._check(self._L.hica_p1_device_buffer(self._h, int(which), C.byref(ptr), C.byref(nbytes), C.byref(eb)))
+        return int(ptr.value or 0), int(nbytes.value), int(eb.value)
+
+    def p1_rank_rows(self, r0: int, r1: int):
+        self._check(self._L.hica_p1_rank_rows(self._h, int(r0), int(r1)))
+
+    def p1_rank_commit(self):
+        self._check(self._L.hica_p1_rank_commit(self._h))
 
     def p1_upload_device(self, dev_ptr: int, n: int):
         self.n = int(n)

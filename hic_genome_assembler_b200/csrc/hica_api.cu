@@ -98,7 +98,7 @@ static void free_p1(hica_ctx *h)
     cudaFree(h->q_d); h->q_d = nullptr;
     cudaFree(h->plan_d); h->plan_d = nullptr; h->plan_n = 0;
     h->have_s_pair = h->have_s_seq = h->have_W = h->have_order = false;
-    h->rank_bytes = 0;
+    h->rank_bytes = h->rank_rows_bytes = 0;
     h->n = h->ld = 0;
     h->A_kind = 0;
 }
@@ -151,7 +151,7 @@ static int p1_alloc(hica_ctx *h, int64_t n)
         if ((rc = hica_realloc(h, &h->q_d, 4 * (n + 16)))) return rc;
     }
     h->have_s_pair = h->have_s_seq = h->have_W = h->have_order = false;
-    h->rank_bytes = 0;
+    h->rank_bytes = h->rank_rows_bytes = 0;
     h->A_kind = 0;
     return HICA_OK;
 }
@@ -210,6 +210,73 @@ extern "C" int hica_p1_upload_symmetric(hica_handle h, const double *A_host, int
     t.stop();
     HICA_CUDA(cudaStreamSynchronize(h->stream));
     return HICA_OK;
+}
+
+// ---- row-block sharded upload (the matrix is sharded by row block over the GPUs of a box) ------------
+extern "C" int hica_p1_alloc(hica_handle h, int64_t n)
+{
+    HICA_CHECK_HANDLE(h);
+    int rc = p1_alloc(h, n);
+    if (rc) return rc;
+    h->timers[HICA_T_UPLOAD] = 0.;
+    return HICA_OK;
+}
+
+extern "C" int hica_p1_upload_rows(hica_handle h, const double *rows_host, int64_t r0, int64_t r1, int symmetric)
+{
+    HICA_CHECK_HANDLE(h);
+    if (!h->A) return hica_set_error(h, HICA_ERR_STATE, "call hica_p1_alloc first");
+    const int64_t n = h->n;
+    if (r0 < 0 || r1 > n || r0 > r1) return hica_set_error(h, HICA_ERR_ARG, "bad row block [%lld, %lld)", (long long)r0, (long long)r1);
+    if (r1 > r0 && !rows_host) return hica_set_error(h, HICA_ERR_ARG, "rows_host is NULL");
+    hica_timer t(h, HICA_T_UPLOAD);
+    if (!symmetric) {
+        if (r1 > r0)
+            HICA_CUDA(cudaMemcpyAsync(h->A + r0 * n, rows_host, sizeof(double) * (r1 - r0) * n, cudaMemcpyHostToDevice, h->stream));
+    } else {
+        // sub-blocks of BS rows: the columns from the sub-block's first row onwards (see hica_p1_upload_symmetric)
+        const int64_t BS = 512;
+        for (int64_t b0 = r0; b0 < r1; b0 += BS) {
+            const int64_t rows = std::min(BS, r1 - b0);
+            HICA_CUDA(cudaMemcpy2DAsync(h->A + b0 * n + b0, sizeof(double) * n, rows_host + (b0 - r0) * n + b0,
+                                        sizeof(double) * n, sizeof(double) * (n - b0), rows, cudaMemcpyHostToDevice,
+                                        h->stream));
+        }
+    }
+    t.stop();
+    HICA_CUDA(cudaStreamSynchronize(h->stream));
+    return HICA_OK;
+}
+
+extern "C" int hica_p1_mirror_lower(hica_handle h)
+{
+    HICA_CHECK_HANDLE(h);
+    if (!h->A) return hica_set_error(h, HICA_ERR_STATE, "no matrix");
+    const unsigned nb = (unsigned)((h->n + 31) / 32);
+    k_mirror_lower<<<dim3(nb, nb), 256, 0, h->stream>>>(h->A, h->n);
+    HICA_LAUNCHED(h);
+    HICA_CUDA(cudaGetLastError());
+    HICA_CUDA(cudaStreamSynchronize(h->stream));
+    return HICA_OK;
+}
+
+extern "C" int hica_p1_device_buffer(hica_handle h, int which, void **ptr, int64_t *bytes, int32_t *elem_bytes)
+{
+    HICA_CHECK_HANDLE(h);
+    if (!ptr || !bytes || !elem_bytes) return hica_set_error(h, HICA_ERR_ARG, "NULL output");
+    const int64_t n = h->n;
+    switch (which) {
+    case 0:
+        if (!h->A) return hica_set_error(h, HICA_ERR_STATE, "no matrix (hica_p1_alloc / hica_p1_upload)");
+        *ptr = h->A; *elem_bytes = 8; *bytes = 8 * n * n;
+        return HICA_OK;
+    case 1:
+        if (!h->R || !h->rank_rows_bytes) return hica_set_error(h, HICA_ERR_STATE, "no rank matrix (hica_p1_rank / hica_p1_rank_rows)");
+        *ptr = h->R; *elem_bytes = h->rank_rows_bytes; *bytes = (int64_t)h->rank_rows_bytes * n * n;
+        return HICA_OK;
+    default:
+        return hica_set_error(h, HICA_ERR_ARG, "which must be 0 (matrix) or 1 (rank matrix)");
+    }
 }
 
 extern "C" int hica_p1_upload_device(hica_handle h, const double *A_dev, int64_t n)

@@ -42,6 +42,7 @@ struct hica_ctx {
     bool have_order = false;
     void *R = nullptr;           // rank matrix n x n, uint16 (n <= 65535) or int32
     int rank_bytes = 0;          // 2 or 4, 0 = none
+    int rank_rows_bytes = 0;     // element size of R once allocated (rows may still be missing: hica_p1_rank_rows)
     // linkage scratch
     double *Zraw = nullptr;      // (n-1) x 4 raw merges (device)
     int32_t *size_d = nullptr;   // cluster sizes

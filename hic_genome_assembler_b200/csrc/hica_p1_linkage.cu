@@ -377,7 +377,7 @@ int hica_set_order_internal(hica_ctx *h, const int32_t *order_host)
     HICA_CUDA(cudaGetLastError());
     HICA_CUDA(cudaStreamSynchronize(h->stream));
     h->have_order = true;
-    h->rank_bytes = 0;  // any rank matrix refers to the previous order
+    h->rank_bytes = h->rank_rows_bytes = 0;  // any rank matrix refers to the previous order
     return HICA_OK;
 }
 

@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(256) k_reordered(const double *__restrict__ A,
 }  // namespace
 
 template <typename PayT, int MAXT>
-static int rank_rows(hica_ctx *h, int q, int64_t P)
+static int rank_rows(hica_ctx *h, int q, int64_t P, int64_t lo, int64_t hi)
 {
     using namespace ranksort;
     const int64_t n = h->n;
@@ -62,9 +62,9 @@ static int rank_rows(hica_ctx *h, int q, int64_t P)
     a.kind = h->A_kind; a.q = q; a.P = P; a.R = h->R;
     if (nchunks == 1) {
         a.mode = 0; a.write_final = 1;
-        for (int64_t r0 = 0; r0 < n; r0 += 65535) {
+        for (int64_t r0 = lo; r0 < hi; r0 += 65535) {
             a.row0 = r0;
-            k_rank_chunk<PayT, MAXT><<<dim3(1, (unsigned)std::min<int64_t>(65535, n - r0)), threads, smem, h->stream>>>(a);
+            k_rank_chunk<PayT, MAXT><<<dim3(1, (unsigned)std::min<int64_t>(65535, hi - r0)), threads, smem, h->stream>>>(a);
             HICA_LAUNCHED(h);
         }
         HICA_CUDA(cudaGetLastError());
@@ -72,7 +72,7 @@ static int rank_rows(hica_ctx *h, int q, int64_t P)
     }
     // multi-chunk rows: chunk sort -> global strides -> chunk merge, in row batches that bound the scratch
     const int64_t per_row = P * (int64_t)(8 + sizeof(PayT));
-    int64_t rows_b = std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(n, 65535), (6ll << 30) / per_row));
+    int64_t rows_b = std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(hi - lo, 65535), (6ll << 30) / per_row));
     // the scratch stays in the handle and only grows: cudaMalloc / cudaFree of several GB per call cost up to
     // hundreds of ms (measured 164 vs 724 ms for the same sort at 32,000 bins)
     const int64_t need = rows_b * P * (int64_t)(8 + sizeof(PayT));
@@ -87,8 +87,8 @@ static int rank_rows(hica_ctx *h, int q, int64_t P)
     unsigned long long *sk = reinterpret_cast<unsigned long long *>(h->rank_buf);
     PayT *sp = reinterpret_cast<PayT *>(sk + rows_b * P);
     a.sk = sk; a.sp = sp;
-    for (int64_t r0 = 0; r0 < n; r0 += rows_b) {
-        const int64_t rows = std::min(rows_b, n - r0);
+    for (int64_t r0 = lo; r0 < hi; r0 += rows_b) {
+        const int64_t rows = std::min(rows_b, hi - r0);
         a.row0 = r0; a.mode = 0; a.write_final = 0;
         k_rank_chunk<PayT, MAXT><<<dim3((unsigned)nchunks, (unsigned)rows), threads, smem, h->stream>>>(a);
         HICA_LAUNCHED(h);
@@ -110,8 +110,10 @@ static int rank_rows(hica_ctx *h, int q, int64_t P)
 }
 
 template <int EPT, int RT>
-static int launch_radix(hica_ctx *h, rankradix::RadixArgs &a)
+static int launch_radix(hica_ctx *h, rankradix::RadixArgs &a, int64_t lo, int64_t hi)
 {
+    a.row0 = lo;
+    const unsigned rows = (unsigned)(hi - lo);
     // first the sort on the high 32 bits of the key + fix-up, then the full 64-bit sort for the rows it gave up on
     // (HICA_RANK_RADIX64=1: the 64-bit kernel for every row)
     const char *v64 = getenv("HICA_RANK_RADIX64");
@@ -121,39 +123,40 @@ static int launch_radix(hica_ctx *h, rankradix::RadixArgs &a)
         HICA_CUDA(cudaFuncSetAttribute(rankradix::k_rank_radix32<EPT, RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem32));
         HICA_CUDA(cudaMemsetAsync(h->x_d, 0, sizeof(int32_t) * h->n, h->stream));
         a.redo = h->x_d;
-        rankradix::k_rank_radix32<EPT, RT><<<(unsigned)h->n, RT, smem32, h->stream>>>(a);
+        rankradix::k_rank_radix32<EPT, RT><<<rows, RT, smem32, h->stream>>>(a);
         HICA_LAUNCHED(h);
         a.only = h->x_d;
     }
     const size_t smem = rankradix::smem_bytes(EPT, RT);
     HICA_CUDA(cudaFuncSetAttribute(rankradix::k_rank_radix<EPT, RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    rankradix::k_rank_radix<EPT, RT><<<(unsigned)h->n, RT, smem, h->stream>>>(a);
+    rankradix::k_rank_radix<EPT, RT><<<rows, RT, smem, h->stream>>>(a);
     HICA_LAUNCHED(h);
     HICA_CUDA(cudaGetLastError());
     return HICA_OK;
 }
 
-static int rank_rows_radix(hica_ctx *h)
+static int rank_rows_radix(hica_ctx *h, int64_t lo, int64_t hi)
 {
     rankradix::RadixArgs a = {};
     a.A = h->A; a.n = h->n; a.s_pair = h->s_pair; a.s_seq = h->s_seq; a.order = h->order; a.pos = h->pos;
     a.kind = h->A_kind; a.R = h->R; a.row0 = 0; a.only = nullptr; a.redo = nullptr;
     const int64_t n = h->n;
     // measured at N = 16k on B200: 1024 threads x 16 elements 16.7 ms, 512 x 32 17.4 ms (bitonic network: 29 ms)
-    if (n <= 512 * 4) return launch_radix<4, 512>(h, a);
-    if (n <= 512 * 8) return launch_radix<8, 512>(h, a);
-    if (n <= 512 * 16) return launch_radix<8, 1024>(h, a);
-    return launch_radix<16, 1024>(h, a);
+    if (n <= 512 * 4) return launch_radix<4, 512>(h, a, lo, hi);
+    if (n <= 512 * 8) return launch_radix<8, 512>(h, a, lo, hi);
+    if (n <= 512 * 16) return launch_radix<8, 1024>(h, a, lo, hi);
+    return launch_radix<16, 1024>(h, a, lo, hi);
 }
 
-extern "C" int hica_p1_rank(hica_handle h)
+// rank rows [lo, hi) of the reordered similarity matrix into R (allocated on first use)
+static int rank_range(hica_ctx *h, int64_t lo, int64_t hi)
 {
-    HICA_CHECK_HANDLE(h);
     if (!h->A) return hica_set_error(h, HICA_ERR_STATE, "no matrix uploaded");
     if (!h->have_order) return hica_set_error(h, HICA_ERR_STATE, "no order set (hica_p1_linkage / hica_p1_set_order)");
     if (h->A_kind != 2 && !h->have_s_seq) return hica_set_error(h, HICA_ERR_STATE, "row sums not set (hica_p1_set_row_sums)");
     if (h->A_kind == 0 && !h->have_s_pair) return hica_set_error(h, HICA_ERR_STATE, "call hica_p1_distance first");
     const int64_t n = h->n;
+    if (lo < 0 || hi > n || lo > hi) return hica_set_error(h, HICA_ERR_ARG, "bad row block [%lld, %lld)", (long long)lo, (long long)hi);
     int64_t P = 512;
     int lg = 9;
     while (P < n) { P <<= 1; lg++; }
@@ -168,21 +171,50 @@ extern "C" int hica_p1_rank(hica_handle h)
         h->R_cap = n * n * bytes;
     }
     h->rank_bytes = 0;
+    h->rank_rows_bytes = bytes;
     hica_timer t(h, HICA_T_RANK);
-    int rc;
+    int rc = HICA_OK;
     const char *algo = getenv("HICA_RANK_ALGO");
-    if (n <= 16384 && !(algo && algo[0] == 'b')) {
+    if (hi == lo) {
+        // an empty block (more ranks than rows): nothing to sort
+    } else if (n <= 16384 && !(algo && algo[0] == 'b')) {
         // rows that fit one CTA's shared memory: stable LSD radix sort (hica_p1_rankradix.cuh)
-        rc = rank_rows_radix(h);
+        rc = rank_rows_radix(h, lo, hi);
     } else {
         // longer rows (or HICA_RANK_ALGO=bitonic): chunked bitonic network with global merge steps
-        if (q == 14) rc = bytes == 2 ? rank_rows<uint16_t, 1024>(h, q, P) : rank_rows<uint32_t, 1024>(h, q, P);
-        else rc = bytes == 2 ? rank_rows<uint16_t, 512>(h, q, P) : rank_rows<uint32_t, 512>(h, q, P);
+        if (q == 14) rc = bytes == 2 ? rank_rows<uint16_t, 1024>(h, q, P, lo, hi) : rank_rows<uint32_t, 1024>(h, q, P, lo, hi);
+        else rc = bytes == 2 ? rank_rows<uint16_t, 512>(h, q, P, lo, hi) : rank_rows<uint32_t, 512>(h, q, P, lo, hi);
     }
     if (rc) return rc;
     t.stop();
     HICA_CUDA(cudaStreamSynchronize(h->stream));
-    h->rank_bytes = bytes;
+    return HICA_OK;
+}
+
+extern "C" int hica_p1_rank(hica_handle h)
+{
+    HICA_CHECK_HANDLE(h);
+    int rc = rank_range(h, 0, h->n);
+    if (rc) return rc;
+    h->rank_bytes = h->rank_rows_bytes;
+    return HICA_OK;
+}
+
+// Row-block sharded rank: this GPU ranks rows [r0, r1) of the reordered matrix only; the other row
+// blocks of R arrive through the caller's collective on hica_p1_device_buffer(h, 1, ...), after which
+// hica_p1_rank_commit declares R complete.
+extern "C" int hica_p1_rank_rows(hica_handle h, int64_t r0, int64_t r1)
+{
+    HICA_CHECK_HANDLE(h);
+    return rank_range(h, r0, r1);
+}
+
+extern "C" int hica_p1_rank_commit(hica_handle h)
+{
+    HICA_CHECK_HANDLE(h);
+    if (!h->R || !h->rank_rows_bytes) return hica_set_error(h, HICA_ERR_STATE, "no rank rows (hica_p1_rank_rows)");
+    if (!h->have_order) return hica_set_error(h, HICA_ERR_STATE, "the order changed since the rows were ranked");
+    h->rank_bytes = h->rank_rows_bytes;
     return HICA_OK;
 }
 
@@ -246,7 +278,7 @@ extern "C" int hica_p1_set_rank(hica_handle h, const int64_t *R_host, int64_t n)
         HICA_CUDA(cudaMemcpyAsync(h->R, tmp.data(), total * 4, cudaMemcpyHostToDevice, h->stream));
         HICA_CUDA(cudaStreamSynchronize(h->stream));
     }
-    h->rank_bytes = bytes;
+    h->rank_bytes = h->rank_rows_bytes = bytes;
     return HICA_OK;
 }
 

@@ -7,16 +7,174 @@ What shards
   * A single very large window search (bruteForceBestScore with nScaffolds = 8: 5.16 M candidates) can be
     split by candidate range; the winner is the first strict maximum over all ranks, i.e. an arg-max
     all-reduce on (score, -candidate index) (``reduce_first_max``).
-  * Part1's linkage is one sequential chain and runs on one GPU; at <= 50 kb the whole of Part1 is a fraction
-    of a second, so every rank runs it redundantly (deterministic, bit-identical) instead of exchanging the
-    working matrix.  Row-block sharding of the distance/rank/count kernels for the 10 kb configuration is not
-    built yet.
+  * Part1 (``run_part1_sharded``) - the contact matrix is cut into contiguous row blocks: every rank uploads
+    its own block over its own PCIe link, the full matrix is assembled on every GPU with an in-place
+    all-gather over NVLink (the one data-path collective of "assembling the distance matrix"), the sequential
+    linkage chain runs on ONE GPU (rank 0) and the leaf order is broadcast (N int32), the similarity rank
+    matrix is computed by row block and all-gathered, and the cut searches (launch-latency bound, 10 ms) run
+    replicated on every rank - deterministic, so every rank ends with the same cut indices without a
+    collective per break search.
 """
 from __future__ import annotations
 
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
+
+
+def row_blocks(n: int, world: int, balance_upper_triangle: bool = False, align: int = 1) -> List[Tuple[int, int]]:
+    """Contiguous row blocks [r0, r1) of an n-row matrix, one per rank (possibly empty for world > n).
+    ``balance_upper_triangle``: the blocks hold equal shares of the UPPER TRIANGLE (what a symmetric upload
+    sends over PCIe: row i contributes n - i entries) instead of equal row counts; boundaries are rounded to a
+    multiple of ``align`` rows."""
+    bounds = [0]
+    for k in range(1, world):
+        if balance_upper_triangle:
+            # rows [0, b) hold b*n - b(b-1)/2 ~ n^2/2 * (1 - (1 - b/n)^2) entries of the upper triangle
+            b = n * (1.0 - (1.0 - k / world) ** 0.5)
+        else:
+            b = n * k / world
+        b = int(round(b / align)) * align
+        bounds.append(min(n, max(bounds[-1], b)))
+    bounds.append(n)
+    return [(bounds[k], bounds[k + 1]) for k in range(world)]
+
+
+class _DevBuf:
+    """A device buffer of libhica as a zero-copy torch tensor (``__cuda_array_interface__``)."""
+
+    def __init__(self, ptr: int, shape, typestr: str):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+def device_tensor(h, which: int, device):
+    """The handle's matrix (which = 0, fp64 n x n) or rank matrix (which = 1) as a torch tensor that aliases
+    the library's device memory - the buffer the collectives of ``run_part1_sharded`` run on."""
+    import torch
+    ptr, nbytes, eb = h.p1_device_buffer(which)
+    n = h.n
+    if which == 0:
+        shape, typestr, dtype = (n, n), "<f8", torch.float64
+    else:
+        # uint16 / int32 ranks as raw bytes: the collective only moves them (NCCL has no 16-bit integer type)
+        shape, typestr, dtype = (n, n * eb), "|u1", torch.uint8
+    t = torch.as_tensor(_DevBuf(ptr, shape, typestr), device=device)
+    assert t.dtype == dtype and t.data_ptr() == ptr
+    return t
+
+
+def gather_row_blocks(full, blocks: Sequence[Tuple[int, int]], group=None):
+    """In-place all-gather of the row blocks of ``full`` (a 2-D tensor whose rows ``blocks[r]`` are valid on
+    rank r): afterwards every rank holds every row.  Equal blocks go through one ``all_gather_into_tensor``
+    (NCCL in-place all-gather over NVLink); ragged blocks through one broadcast per rank.  Works on CPU tensors
+    with the gloo backend (tests)."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return full
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    assert len(blocks) == world
+    sizes = {r1 - r0 for r0, r1 in blocks}
+    r0, r1 = blocks[rank]
+    if len(sizes) == 1 and blocks[0][0] == 0 and blocks[-1][1] == full.shape[0] and full.is_cuda:
+        dist.all_gather_into_tensor(full, full[r0:r1], group=group)
+    else:
+        works = []
+        for src, (b0, b1) in enumerate(blocks):
+            if b1 > b0:
+                works.append(dist.broadcast(full[b0:b1], src=dist.get_global_rank(group, src) if group is not None else src,
+                                            group=group, async_op=True))
+        for w in works:
+            w.wait()
+    return full
+
+
+def _dist_state(group=None):
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return 1, 0
+    return dist.get_world_size(group), dist.get_rank(group)
+
+
+def upload_sharded(h, A_host: np.ndarray, device, symmetric: bool = True, group=None) -> dict:
+    """Row-block sharded upload: this rank copies only its row block of ``A_host`` (the full n x n matrix in
+    the pinned host memory of every rank) over its own PCIe link; the matrix is then assembled on every GPU by
+    an in-place gather over NVLink, and the lower triangle mirrored on the device for a symmetric upload (then
+    only the part right of the diagonal crossed PCIe, the blocks being balanced by upper-triangle area)."""
+    import time
+    import torch
+    world, rank = _dist_state(group)
+    if world == 1:
+        (h.p1_upload_symmetric if symmetric else h.p1_upload)(A_host)
+        return {"row_block": (0, A_host.shape[0])}
+    n = A_host.shape[0]
+    t0 = time.perf_counter()
+    blocks = row_blocks(n, world, balance_upper_triangle=symmetric, align=512 if symmetric and n >= 512 * world else 1)
+    r0, r1 = blocks[rank]
+    h.p1_alloc(n)
+    h.p1_upload_rows(A_host[r0:r1], r0, r1, symmetric)
+    t1 = time.perf_counter()
+    A = device_tensor(h, 0, device)
+    gather_row_blocks(A, blocks, group)
+    torch.cuda.current_stream(device).synchronize()
+    if symmetric:
+        h.p1_mirror_lower()
+    t2 = time.perf_counter()
+    return {"row_block": (r0, r1), "upload_rows_ms": (t1 - t0) * 1e3, "gather_matrix_ms": (t2 - t1) * 1e3,
+            "h2d_bytes": int(sum(8 * min(512, r1 - b0) * (n - b0) for b0 in range(r0, r1, 512))) if symmetric
+            else 8 * (r1 - r0) * n}
+
+
+def run_part1_resident_sharded(h, device, min_size: int = 5, min_frac: float = .05, psig: float = .05,
+                               linkage_rank: int = 0, group=None) -> dict:
+    """Part1 on a matrix that is resident on every GPU of the group (``upload_sharded`` / ``p1_upload_device``):
+    row sums + distance transform everywhere (1 ms; the rank step needs the row sums on every GPU), the
+    sequential linkage chain on ONE GPU with its leaf order broadcast (N int32), the similarity rank matrix by
+    row block of the reordered matrix + in-place all-gather, the cut searches replicated (deterministic).
+    Returns the dict of ``part1.run_part1_resident`` on every rank."""
+    import time
+    import torch
+    import torch.distributed as dist
+    from . import part1
+    world, rank = _dist_state(group)
+    if world == 1:
+        return part1.run_part1_resident(h, min_size, min_frac, psig)
+    n = h.n
+    t2 = time.perf_counter()
+    h.p1_set_row_sums(None)
+    h.p1_distance()
+    leaves_t = torch.empty(n, dtype=torch.int32, device=device)
+    leaves = None
+    if rank == linkage_rank:
+        _, leaves = h.p1_linkage(want_Z=False)
+        leaves_t.copy_(torch.from_numpy(np.ascontiguousarray(leaves, dtype=np.int32)))
+    src = dist.get_global_rank(group, linkage_rank) if group is not None else linkage_rank
+    dist.broadcast(leaves_t, src=src, group=group)
+    if rank != linkage_rank:
+        leaves = leaves_t.cpu().numpy()
+        h.p1_set_order(leaves)
+    t3 = time.perf_counter()
+    rb = row_blocks(n, world)
+    h.p1_rank_rows(*rb[rank])
+    R = device_tensor(h, 1, device)
+    gather_row_blocks(R, rb, group)
+    torch.cuda.current_stream(device).synchronize()
+    h.p1_rank_commit()
+    t4 = time.perf_counter()
+    init, amb0 = h.p1_breakpoints(min_size, min_frac)
+    cuts, amb1 = h.p1_filter(init, psig)
+    t5 = time.perf_counter()
+    return dict(Z=None, leaves=np.asarray(leaves), initial_cuts=init, cuts=cuts, ambiguous=amb0 + amb1,
+                stage_ms={"distance_linkage_bcast": (t3 - t2) * 1e3, "rank_rows_gather": (t4 - t3) * 1e3,
+                          "cuts": (t5 - t4) * 1e3})
+
+
+def run_part1_sharded(h, A_host: np.ndarray, device, min_size: int = 5, min_frac: float = .05, psig: float = .05,
+                      symmetric: bool = True, linkage_rank: int = 0, group=None) -> dict:
+    """Part1 over all ranks of the process group: ``upload_sharded`` + ``run_part1_resident_sharded``."""
+    up = upload_sharded(h, A_host, device, symmetric, group)
+    res = run_part1_resident_sharded(h, device, min_size, min_frac, psig, linkage_rank, group)
+    res["upload"] = up
+    return res
 
 
 def shard_groups(group_sizes: Sequence[int], world: int, rank: int) -> List[int]:

@@ -75,6 +75,28 @@ int hica_p1_upload_symmetric(hica_handle h, const double *A_host, int64_t n);
  * library copies it; the caller keeps ownership of A_dev. */
 int hica_p1_upload_device(hica_handle h, const double *A_dev, int64_t n);
 
+/* ---- row-block sharding over the GPUs of one box -------------
+ * One process and one handle per GPU.  The contact matrix that removeRows
+ * (scaffoldToChromosomes.py:1116-1118) leaves in host memory is cut into
+ * contiguous row blocks; every GPU uploads its own block (so the N PCIe links
+ * work in parallel), the caller assembles the full matrix on every GPU with a
+ * collective over NVLink on the buffer hica_p1_device_buffer(h, 0) returns
+ * (torch.distributed / NCCL all-gather or broadcasts, in place), and - for a
+ * symmetric upload - hica_p1_mirror_lower fills the lower triangle.
+ *   hica_p1_alloc        allocate the n x n matrix without filling it
+ *   hica_p1_upload_rows  rows [r0, r1): rows_host points at row r0 (ld = n);
+ *                        symmetric != 0: only columns >= the row's 512-row
+ *                        sub-block start cross PCIe (the matrix must be
+ *                        symmetric; finish with hica_p1_mirror_lower)
+ *   hica_p1_device_buffer  which = 0: the matrix (fp64, n*n); which = 1: the
+ *                        rank matrix (uint16 for n <= 65535, else int32, n*n).
+ *                        The pointer stays valid until the next upload/alloc of
+ *                        a different n (matrix) or a larger rank matrix. */
+int hica_p1_alloc(hica_handle h, int64_t n);
+int hica_p1_upload_rows(hica_handle h, const double *rows_host, int64_t r0, int64_t r1, int symmetric);
+int hica_p1_mirror_lower(hica_handle h);
+int hica_p1_device_buffer(hica_handle h, int which, void **ptr, int64_t *bytes, int32_t *elem_bytes);
+
 /* binList[i].rowSum (removeRows, :134: builtin left-to-right sum).  Pass the
  * host values the reference computed, or NULL to compute them on the device in
  * the same left-to-right order. */
@@ -114,6 +136,12 @@ int hica_p1_get_reordered(hica_handle h, int what, double *out_host);
 /* numpy.argsort(S, axis=1)[:, ::-1] :1132 on the device; ties resolve as a
  * stable ascending sort reversed (descending column index). */
 int hica_p1_rank(hica_handle h);
+/* Row-block sharded form of hica_p1_rank (:1132): rank rows
+ * [r0, r1) of the reordered matrix only.  The other row blocks of the rank
+ * matrix are written by the caller's collective on hica_p1_device_buffer(h, 1);
+ * hica_p1_rank_commit then declares the rank matrix complete. */
+int hica_p1_rank_rows(hica_handle h, int64_t r0, int64_t r1);
+int hica_p1_rank_commit(hica_handle h);
 /* Seam input for :1132 when the similarity matrix S was computed elsewhere: upload it as is (identity
  * order); hica_p1_rank then sorts its rows directly. */
 int hica_p1_upload_similarity(hica_handle h, const double *S_host, int64_t n);

@@ -21,6 +21,25 @@ def test_shard_groups_is_a_partition_and_balanced():
     assert hd.shard_groups(sizes, 2, 0) == hd.shard_groups(list(sizes), 2, 0)   # deterministic
 
 
+def test_row_blocks_cover_all_rows_and_balance():
+    for n in (1, 5, 320, 3200, 16000, 16001):
+        for world in (1, 2, 3, 4, 8):
+            for bal in (False, True):
+                for align in (1, 512):
+                    b = hd.row_blocks(n, world, balance_upper_triangle=bal, align=align)
+                    assert len(b) == world and b[0][0] == 0 and b[-1][1] == n
+                    assert all(b[k][1] == b[k + 1][0] for k in range(world - 1))
+                    assert all(r0 <= r1 for r0, r1 in b)
+    # equal rows
+    assert hd.row_blocks(16000, 8) == [(2000 * k, 2000 * (k + 1)) for k in range(8)]
+    # equal upper-triangle area: the PCIe bytes of a symmetric upload are balanced to within one aligned step
+    n, world = 16000, 4
+    b = hd.row_blocks(n, world, balance_upper_triangle=True, align=512)
+    area = [sum(n - i for i in range(r0, r1)) for r0, r1 in b]
+    assert max(area) - min(area) <= 512 * n
+    assert b[0][1] - b[0][0] < b[-1][1] - b[-1][0]       # the first block has the longest rows, so the fewest
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
@@ -50,6 +69,14 @@ def _worker(rank, world, port, out_dir):
         for per_rank, carried, want in cases:
             b, i = per_rank[rank]
             assert hd.reduce_first_max(b, i, carried) == want
+        # in-place gather of ragged and of equal row blocks (the collective of run_part1_sharded, CPU tensors)
+        for n_rows, blocks in ((7, [(0, 3), (3, 7)]), (6, [(0, 3), (3, 6)]), (4, [(0, 4), (4, 4)])):
+            want = torch.arange(n_rows * 5, dtype=torch.float64).reshape(n_rows, 5)
+            full = torch.full((n_rows, 5), -1.0, dtype=torch.float64)
+            r0, r1 = blocks[rank]
+            full[r0:r1] = want[r0:r1]
+            hd.gather_row_blocks(full, blocks)
+            assert torch.equal(full, want)
         with open(os.path.join(out_dir, "ok%d" % rank), "w") as f:
             f.write("ok")
     finally:

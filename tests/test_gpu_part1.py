@@ -300,3 +300,53 @@ def test_linkage_exact_ties_take_the_cache_slow_path(hica):
     hica.p1_upload_distance(D)
     Z, leaves = hica.p1_linkage()
     assert np.array_equal(Z, Z_ref) and list(leaves) == list(leaves_ref)
+
+
+@pytest.mark.parametrize("n,blocks,sym", [(5, [(0, 2), (2, 5)], True), (200, [(0, 0), (0, 77), (77, 200)], False),
+                                          (1100, [(0, 512), (512, 600), (600, 1100)], True),
+                                          (700, [(0, 350), (350, 700)], False)])
+def test_row_block_upload_and_rank_equal_the_whole_matrix_calls(hica, n, blocks, sym, monkeypatch):
+    """The row-block sharded entry points (hica_p1_alloc / upload_rows / mirror_lower, rank_rows / rank_commit)
+    used block after block on one GPU give exactly what hica_p1_upload + hica_p1_rank give."""
+    A = _rand_sym(n, 5 * n + 1)
+    rs = O.sequential_row_sums(A)
+    D = O.convert_distance(A)
+    _, leaves = O.average_cluster_leaves(D)
+    S = O.convert_similarity(O.reorder(D, leaves), rs[np.asarray(leaves)])
+    B = A.copy()
+    if sym:
+        B[np.tril_indices(n, -1)] = -777.0   # never read by a symmetric row-block upload
+    hica.p1_alloc(n)
+    for r0, r1 in blocks:
+        hica.p1_upload_rows(B[r0:r1], r0, r1, symmetric=sym)
+    if sym:
+        hica.p1_mirror_lower()
+    ptr, nbytes, eb = hica.p1_device_buffer(0)
+    assert ptr != 0 and nbytes == 8 * n * n and eb == 8
+    hica.p1_set_row_sums(None)
+    hica.p1_distance()
+    assert np.array_equal(hica.p1_get_distance(), D)
+    assert np.array_equal(hica.p1_get_row_sums(), rs)
+    hica.p1_set_order(leaves)
+    with pytest.raises(Exception):
+        hica.p1_rank_commit()                 # nothing ranked yet
+    for r0, r1 in blocks[::-1]:               # any order
+        hica.p1_rank_rows(r0, r1)
+    with pytest.raises(Exception):
+        hica.p1_get_rank()                    # not committed yet
+    hica.p1_rank_commit()
+    ptr, nbytes, eb = hica.p1_device_buffer(1)
+    assert ptr != 0 and eb == 2 and nbytes == 2 * n * n
+    assert np.array_equal(hica.p1_get_rank(), O.rank_matrix_stable(S))
+    if n >= 600:                              # the multi-chunk bitonic path takes row ranges as well
+        monkeypatch.setenv("HICA_RANK_ALGO", "bitonic")
+        monkeypatch.setenv("HICA_RANK_Q", "9")
+        hica.p1_set_order(leaves)
+        for r0, r1 in blocks:
+            hica.p1_rank_rows(r0, r1)
+        hica.p1_rank_commit()
+        assert np.array_equal(hica.p1_get_rank(), O.rank_matrix_stable(S))
+    with pytest.raises(Exception):
+        hica.p1_rank_rows(3, n + 1)
+    with pytest.raises(Exception):
+        hica.p1_upload_rows(B[0:1], 1, 0)
