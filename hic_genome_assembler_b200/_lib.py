@@ -27,6 +27,7 @@ ABI_SYMBOLS = (
     "hica_p1_window_sig", "hica_p1_breakpoints", "hica_p1_filter", "hica_hypergeom_less",
     "hica_p2_upload", "hica_p2_use_p1_matrix", "hica_p2_select", "hica_p2_set_segments", "hica_p2_total",
     "hica_p2_score_candidates", "hica_p2_score_window", "hica_p2_score_orders", "hica_p2_order_groups",
+    "hica_io_read_matrix", "hica_io_last_error",
 )
 
 _lib = None
@@ -90,8 +91,29 @@ def load_library():
     L.hica_p2_score_window.argtypes = [vp, vp, i32, i32, i32, vp, i32, vp, i32, i64, i64, dbl, dbl, vp, vp, vp]
     L.hica_p2_score_orders.argtypes = [vp, vp, i64, i32, dbl, dbl, vp, vp, vp]
     L.hica_p2_order_groups.argtypes = [vp, i32, vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, i32, vp, i32, vp, vp, vp, vp]
+    L.hica_io_read_matrix.argtypes = [C.c_char_p, vp, i64, i64, vp, C.c_int, vp, vp]
+    L.hica_io_last_error.argtypes = []
+    L.hica_io_last_error.restype = C.c_char_p
     _lib = L
     return L
+
+
+def io_read_matrix(path: str, index_of_id: np.ndarray, n: int, out: Optional[np.ndarray] = None, threads: int = 0):
+    """hica_io_read_matrix: HiC-Pro triplet text -> dense symmetric n x n fp64 (host side, no GPU needed).
+    ``index_of_id[bin id]`` = matrix row or -1; ``out`` may be a preallocated (pinned) n x n float64 array.
+    Returns (matrix, lines parsed, lines applied)."""
+    L = load_library()
+    idx = np.ascontiguousarray(index_of_id, dtype=np.int32)
+    if out is None:
+        out = np.empty((n, n), dtype=np.float64)
+    if out.shape != (n, n) or out.dtype != np.float64 or not out.flags.c_contiguous:
+        raise ValueError("out must be a C-contiguous float64 array of shape (%d, %d)" % (n, n))
+    lines, edges = C.c_int64(0), C.c_int64(0)
+    rc = L.hica_io_read_matrix(os.fsencode(path), _ptr(idx), len(idx) - 1, n, _ptr(out), int(threads),
+                               C.byref(lines), C.byref(edges))
+    if rc:
+        raise HicaError(L.hica_io_last_error().decode())
+    return out, int(lines.value), int(edges.value)
 
 
 def _ptr(a: Optional[np.ndarray]):

@@ -1,0 +1,215 @@
+// hica_io.cu - host-side loader of the HiC-Pro sparse matrix text.  No device code: the file is
+// compiled by nvcc only so that it lands in libhica.so next to the kernels that consume its output.
+//
+// Replaces buildAdjacencyMatrix (scaffoldToChromosomes.py:70-98): the reference reads "id1\tid2\tvalue" lines with
+// Python's int()/float() into a list of lists (minutes at 16k bins, 8 GB of Python floats).  Here the file is
+// mmap-ed, cut at line boundaries into one chunk per thread, parsed in parallel into (row, column, value)
+// triplets and scattered into the caller's dense fp64 matrix (which may be the pinned staging buffer the upload
+// reads from).  Semantics kept from the reference:
+//   * both [i][j] and [j][i] are written (:90-91); lines naming a bin that is not in the index are skipped (:86-89);
+//   * when a cell is written more than once the LAST line in file order wins: every destination row is owned by
+//     exactly one scatter thread, and that thread walks the chunks in file order;
+//   * "line.strip('\r').strip('\n').split('\t')" (:84): columns beyond the third are ignored, blanks around a
+//     number are accepted (int()/float() strip them), the value goes through a correctly rounded decimal ->
+//     binary64 conversion (std::from_chars / strtod), the same result as Python's float();
+//   * a malformed line makes the reference raise ValueError/IndexError; here the call fails with the line number.
+#include <fcntl.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <atomic>
+#include <charconv>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "hica_common.cuh"
+
+namespace {
+
+struct Triplet {
+    int32_t i, j;
+    double v;
+};
+
+struct ChunkResult {
+    std::vector<Triplet> t;
+    int64_t lines = 0, applied = 0;
+    int64_t bad_line = -1;  // 0-based line index inside the chunk
+    std::string why;
+};
+
+inline bool is_blank(char c) { return c == ' ' || c == '\r' || c == '\v' || c == '\f'; }
+
+// int(): optional blanks, optional sign, decimal digits (Python also accepts '_' separators; not produced by HiC-Pro)
+bool parse_int(const char *b, const char *e, int64_t *out)
+{
+    while (b < e && is_blank(*b)) b++;
+    while (e > b && is_blank(e[-1])) e--;
+    if (b == e) return false;
+    bool neg = false;
+    if (*b == '+' || *b == '-') { neg = *b == '-'; b++; }
+    if (b == e) return false;
+    int64_t v = 0;
+    for (; b < e; b++) {
+        if (*b < '0' || *b > '9') return false;
+        if (v > (INT64_MAX - 9) / 10) return false;
+        v = v * 10 + (*b - '0');
+    }
+    *out = neg ? -v : v;
+    return true;
+}
+
+// float(): blanks, sign, decimal / exponent forms, inf / nan
+bool parse_float(const char *b, const char *e, double *out)
+{
+    while (b < e && is_blank(*b)) b++;
+    while (e > b && is_blank(e[-1])) e--;
+    if (b == e) return false;
+    const char *p = b;
+    if (*p == '+') {  // from_chars does not accept a leading '+'
+        p++;
+        if (p == e || *p == '+' || *p == '-') return false;
+    }
+    auto r = std::from_chars(p, e, *out, std::chars_format::general);
+    if (r.ec == std::errc() && r.ptr == e) return true;
+    // out-of-range values (Python gives inf / 0.0) and spellings from_chars rejects: strtod on a copy
+    std::string s(b, e);
+    if (s.find_first_of("xXpP") != std::string::npos) return false;  // float() has no hex literals
+    char *end = nullptr;
+    double v = strtod(s.c_str(), &end);
+    if (end != s.c_str() + s.size()) return false;
+    *out = v;
+    return true;
+}
+
+void parse_chunk(const char *b, const char *e, const int32_t *index_of_id, int64_t max_id, ChunkResult *res)
+{
+    res->t.reserve((size_t)((e - b) / 16 + 16));
+    const char *p = b;
+    while (p < e) {
+        const char *nl = (const char *)memchr(p, '\n', (size_t)(e - p));
+        const char *le = nl ? nl : e;
+        // three tab-separated columns; anything after a third tab is ignored
+        const char *t1 = (const char *)memchr(p, '\t', (size_t)(le - p));
+        const char *t2 = t1 ? (const char *)memchr(t1 + 1, '\t', (size_t)(le - t1 - 1)) : nullptr;
+        if (!t1 || !t2) {
+            res->bad_line = res->lines;
+            res->why = "fewer than three tab-separated columns";
+            return;
+        }
+        const char *t3 = (const char *)memchr(t2 + 1, '\t', (size_t)(le - t2 - 1));
+        const char *ve = t3 ? t3 : le;
+        int64_t id1, id2;
+        double v;
+        if (!parse_int(p, t1, &id1) || !parse_int(t1 + 1, t2, &id2)) {
+            res->bad_line = res->lines;
+            res->why = "bin id is not an integer";
+            return;
+        }
+        if (!parse_float(t2 + 1, ve, &v)) {
+            res->bad_line = res->lines;
+            res->why = "value is not a number";
+            return;
+        }
+        res->lines++;
+        if (id1 >= 0 && id1 <= max_id && id2 >= 0 && id2 <= max_id) {
+            const int32_t i = index_of_id[id1], j = index_of_id[id2];
+            if (i >= 0 && j >= 0) {
+                res->t.push_back({i, j, v});
+                res->applied++;
+            }
+        }
+        p = nl ? nl + 1 : e;
+    }
+}
+
+std::string g_io_error;
+
+int io_fail(const char *fmt, const char *a, long long b, const char *c)
+{
+    char buf[1024];
+    snprintf(buf, sizeof(buf), fmt, a, b, c);
+    g_io_error = buf;
+    return HICA_ERR_ARG;
+}
+
+}  // namespace
+
+extern "C" const char *hica_io_last_error(void) { return g_io_error.c_str(); }
+
+extern "C" int hica_io_read_matrix(const char *path, const int32_t *index_of_id, int64_t max_id, int64_t n,
+                                   double *A_host, int threads, int64_t *n_lines, int64_t *n_edges)
+{
+    if (!path || !index_of_id || !A_host || n < 0 || max_id < 0) return io_fail("%s: bad argument%.0lld%s", "hica_io_read_matrix", 0, "");
+    int fd = open(path, O_RDONLY);
+    if (fd < 0) return io_fail("cannot open %s%.0lld%s", path, 0, "");
+    struct stat st;
+    if (fstat(fd, &st) != 0) { close(fd); return io_fail("cannot stat %s%.0lld%s", path, 0, ""); }
+    const int64_t size = (int64_t)st.st_size;
+    int T = threads > 0 ? threads : (int)std::thread::hardware_concurrency();
+    T = std::max(1, std::min(T, 256));
+    // zero fill in parallel (first touch by the thread that later owns the rows)
+    {
+        std::vector<std::thread> th;
+        for (int t = 0; t < T; t++)
+            th.emplace_back([=] {
+                const int64_t r0 = n * t / T, r1 = n * (t + 1) / T;
+                if (r1 > r0) memset(A_host + r0 * n, 0, sizeof(double) * (size_t)((r1 - r0) * n));
+            });
+        for (auto &x : th) x.join();
+    }
+    if (n_lines) *n_lines = 0;
+    if (n_edges) *n_edges = 0;
+    if (size == 0) { close(fd); return HICA_OK; }
+    const char *data = (const char *)mmap(nullptr, (size_t)size, PROT_READ, MAP_PRIVATE, fd, 0);
+    close(fd);
+    if (data == MAP_FAILED) return io_fail("cannot mmap %s%.0lld%s", path, 0, "");
+    madvise((void *)data, (size_t)size, MADV_SEQUENTIAL);
+    // chunk boundaries at line starts
+    const int C = (int)std::max<int64_t>(1, std::min<int64_t>(T, size / 4096 + 1));
+    std::vector<int64_t> cut(C + 1);
+    cut[0] = 0;
+    cut[C] = size;
+    for (int c = 1; c < C; c++) {
+        int64_t p = std::max(cut[c - 1], size * c / C);
+        const char *nl = p < size ? (const char *)memchr(data + p, '\n', (size_t)(size - p)) : nullptr;
+        cut[c] = nl ? (nl - data) + 1 : size;
+    }
+    std::vector<ChunkResult> res(C);
+    {
+        std::vector<std::thread> th;
+        for (int c = 0; c < C; c++)
+            th.emplace_back([&, c] { parse_chunk(data + cut[c], data + cut[c + 1], index_of_id, max_id, &res[c]); });
+        for (auto &x : th) x.join();
+    }
+    munmap((void *)data, (size_t)size);
+    int64_t lines = 0, edges = 0;
+    for (int c = 0; c < C; c++) {
+        if (res[c].bad_line >= 0) return io_fail("%s: line %lld: %s", path, (long long)(lines + res[c].bad_line + 1), res[c].why.c_str());
+        lines += res[c].lines;
+        edges += res[c].applied;
+    }
+    // scatter: thread t owns destination rows [n t / T, n (t+1) / T) and walks all chunks in file order
+    {
+        std::vector<std::thread> th;
+        for (int t = 0; t < T; t++)
+            th.emplace_back([&, t] {
+                const int64_t r0 = n * t / T, r1 = n * (t + 1) / T;
+                if (r1 <= r0) return;
+                for (int c = 0; c < C; c++)
+                    for (const Triplet &e : res[c].t) {
+                        if (e.i >= r0 && e.i < r1) A_host[(int64_t)e.i * n + e.j] = e.v;
+                        if (e.j >= r0 && e.j < r1) A_host[(int64_t)e.j * n + e.i] = e.v;
+                    }
+            });
+        for (auto &x : th) x.join();
+    }
+    if (n_lines) *n_lines = lines;
+    if (n_edges) *n_edges = edges;
+    return HICA_OK;
+}

@@ -67,6 +67,20 @@ def read_matrix(matrix_file: str, bins: Sequence[Bin]) -> np.ndarray:
     return A
 
 
+def read_matrix_native(matrix_file: str, bins: Sequence[Bin], out: np.ndarray = None, threads: int = 0) -> np.ndarray:
+    """buildAdjacencyMatrix (:70-98) through libhica's mmap + multi-threaded parser (hica_io_read_matrix): same
+    result as ``read_matrix`` bit for bit; ``out`` may be the pinned staging buffer of the upload."""
+    from ._lib import io_read_matrix
+    n = len(bins)
+    max_id = max((b.ID for b in bins), default=0)
+    index_of_id = np.full(max_id + 1, -1, dtype=np.int32)
+    for i, b in enumerate(bins):
+        if b.ID >= 0:
+            index_of_id[b.ID] = i   # a repeated id keeps the LAST index, as the dict comprehension of :78 does
+    A, _, _ = io_read_matrix(matrix_file, index_of_id, n, out, threads)
+    return A
+
+
 def remove_zero_rows(A: np.ndarray, bins: List[Bin]) -> Tuple[np.ndarray, List[Bin]]:
     """removeRows(zeroRows=True) (:100-136): drop rows/columns whose numpy sum is 0, then rowSum = builtin
     left-to-right sum of what remains."""
@@ -78,6 +92,44 @@ def remove_zero_rows(A: np.ndarray, bins: List[Bin]) -> Tuple[np.ndarray, List[B
     for b, v in zip(bins, rs):
         b.rowSum = float(v)
     return A, bins
+
+
+# ---- the reference's own names and signatures, for the launcher (function replacement in the loaded modules) ----
+
+def buildAdjacencyMatrix(matrixFile, binList, binID_dict=False):
+    """Seam for buildAdjacencyMatrix (scaffoldToChromosomes.py:70-98, orderGenome.py:65-93): same arguments
+    (``binID_dict`` is unused there as well), returns the dense matrix as an ndarray instead of a list of lists
+    (every consumer wraps it in numpy.asmatrix; the list-mutating removeRows is rebound together with it)."""
+    A = read_matrix_native(matrixFile, binList)
+    print("Adjacency matrix initiated")
+    print("Rows in adjacency matrix " + str(len(A)))
+    return A
+
+
+def removeRows(matrix, binList, zeroRows=True, biasVals=False):
+    """Seam for removeRows (:100-136) on an ndarray: rows whose numpy sum is 0 (zeroRows) or whose bias lies
+    outside ``biasVals`` are dropped from the matrix (rows and columns) and from ``binList`` IN PLACE (the
+    reference ``del``s list items), then every bin's rowSum = builtin left-to-right sum of its row."""
+    A = np.asarray(matrix, dtype=np.float64)
+    sums = np.asarray(np.sum(np.asmatrix(A), axis=-1)).ravel() if A.size else np.zeros(0)
+    drop = []
+    for i in range(len(binList)):
+        if zeroRows == True and sums[i] == 0:  # noqa: E712 - as the reference compares
+            drop.append(i)
+            continue
+        if biasVals != False:  # noqa: E712
+            if binList[i].bias > biasVals[1] or binList[i].bias < biasVals[0]:
+                drop.append(i)
+    print("Rows/columns to remove " + str(len(drop)))
+    if drop:
+        keep = np.setdiff1d(np.arange(A.shape[0]), np.asarray(drop))
+        A = np.ascontiguousarray(A[np.ix_(keep, keep)])
+        for i in reversed(drop):
+            del binList[i]
+    rs = np.add.accumulate(A, axis=1)[:, -1] if A.shape[0] and A.shape[1] else np.zeros(len(binList))
+    for b, v in zip(binList, rs):
+        b.rowSum = v        # numpy.float64, as ``sum(numpy.asarray(r))`` returns
+    return A, binList
 
 
 def write_dendrogram_order(labels: Sequence[str], leaves: Sequence[int], path: str) -> None:
@@ -181,7 +233,7 @@ def run_files(h: Handle, cfg: Dict[str, object]) -> Dict[str, object]:
         raise NotImplementedError("the Louvain tail (modularity > 0) is randomised and outside the hot path")
     # ---- Part1 (scaffoldToChromosomes.runPipeline :1104-1173)
     bins = read_loci(cfg["hicProBedFile"], cfg["hicProBiasFile"])
-    A = read_matrix(cfg["hicProMatrixFile"], bins)
+    A = read_matrix_native(cfg["hicProMatrixFile"], bins)
     A, bins = remove_zero_rows(A, bins)
     res = part1.run_part1(h, A, min_size=min_size, min_frac=modularity, psig=psig,
                           row_sums=np.array([b.rowSum for b in bins]))
@@ -200,7 +252,7 @@ def run_files(h: Handle, cfg: Dict[str, object]) -> Dict[str, object]:
     # ---- Part2 (orderGenome.runPipeline :679-712): the matrix restricted to the assigned bins
     keep = {bid for grp in groups for bid, _ in grp}
     bins2 = read_loci(cfg["hicProBedFile"], cfg["hicProBiasFile"], keep_ids=keep)
-    G = read_matrix(cfg["hicProMatrixFile"], bins2)
+    G = read_matrix_native(cfg["hicProMatrixFile"], bins2)
     h.p2_upload(G)
     index_of = {b.ID: i for i, b in enumerate(bins2)}
     orderings, cost, rounds, _ = part2.order_groups_device(h, index_of, groups, int(cfg.get("nScaffolds", 6)),

@@ -86,7 +86,7 @@ class _DescendingRank:
         return out.astype(dtype) if dtype is not None else out
 
 
-def install(reference_dir: str, device: int = 0, no_plots: bool = False):
+def install(reference_dir: str, device: int = 0, no_plots: bool = False, native_loaders: bool = True):
     """Import the reference modules from ``reference_dir`` and rebind their hot-path functions.
     Returns (handle, part1 module, part2 module)."""
     reference_dir = os.path.abspath(reference_dir)
@@ -110,6 +110,16 @@ def install(reference_dir: str, device: int = 0, no_plots: bool = False):
     part1.filter_noisy_breakpoints = s1.filter_noisy_breakpoints
     part1.numpy = _NumpyShim(part1.numpy, s1)
 
+    if native_loaders:
+        # the HiC-Pro text -> dense matrix step through libhica's mmap parser (same names, same
+        # arguments; removeRows goes with it because the reference's version deletes list items)
+        from . import io as hio
+        for mod in (part1, part2):
+            if hasattr(mod, "buildAdjacencyMatrix"):
+                mod.buildAdjacencyMatrix = hio.buildAdjacencyMatrix
+            if hasattr(mod, "removeRows"):
+                mod.removeRows = hio.removeRows
+
     s2 = Part2Seams(h)
     part2.costFunction_numba = s2.costFunction_numba
     part2.bruteForceBestScore = s2.bruteForceBestScore
@@ -123,8 +133,10 @@ def main(argv=None):
     ap.add_argument("--reference-dir", required=True)
     ap.add_argument("--device", type=int, default=0)
     ap.add_argument("--no-plots", action="store_true")
+    ap.add_argument("--reference-loaders", action="store_true",
+                    help="keep the reference's own buildAdjacencyMatrix/removeRows (interpreted text parsing)")
     ns, rest = ap.parse_known_args(argv)
-    h, _, _ = install(ns.reference_dir, ns.device, ns.no_plots)
+    h, _, _ = install(ns.reference_dir, ns.device, ns.no_plots, native_loaders=not ns.reference_loaders)
     script = os.path.join(os.path.abspath(ns.reference_dir), "run_hicAssembler.py")
     old_argv = sys.argv
     sys.argv = [script] + rest

@@ -242,6 +242,25 @@ int hica_p2_order_groups(hica_handle h, int32_t ngroups, const int32_t *grp_ptr,
 int hica_p2_score_orders(hica_handle h, const int32_t *orders, int64_t B, int32_t L, double total,
                          double carried, double *best, int64_t *best_idx, double *scores_or_null);
 
+/* ---- loaders either side of the hot path ------------------ */
+
+/* buildAdjacencyMatrix (scaffoldToChromosomes.py:70-98): the sparse HiC-Pro
+ * matrix text ("id1<TAB>id2<TAB>value" per line) -> the dense symmetric n x n
+ * fp64 matrix, in host memory (no GPU involved; the file is mmap-ed and parsed
+ * by `threads` threads, 0 = all cores).
+ *   index_of_id  max_id+1 entries: matrix row of HiC-Pro bin id, or -1 when the
+ *                bin was dropped by initiateLoci (:35-68) - such lines are
+ *                skipped as in :86-89
+ *   A_host       n*n doubles owned by the caller (e.g. the pinned buffer
+ *                hica_p1_upload* reads from); zero-filled, then [i][j] and
+ *                [j][i] are set for every line, the last line winning (:90-91)
+ *   n_lines / n_edges  lines parsed / lines applied ("Edges added", :97)
+ * A malformed line fails the call (the reference raises); the message, with
+ * the 1-based line number, is returned by hica_io_last_error(). */
+int hica_io_read_matrix(const char *path, const int32_t *index_of_id, int64_t max_id, int64_t n,
+                        double *A_host, int threads, int64_t *n_lines, int64_t *n_edges);
+const char *hica_io_last_error(void);
+
 #ifdef __cplusplus
 }
 #endif

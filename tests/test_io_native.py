@@ -1,0 +1,155 @@
+"""CPU: the mmap + multi-threaded HiC-Pro matrix loader of libhica (hica_io_read_matrix) against the
+Python restatement of buildAdjacencyMatrix (io.read_matrix) and, in the build container, the reference itself."""
+import contextlib
+import io as _io
+import os
+
+import numpy as np
+import pytest
+
+from hic_genome_assembler_b200 import io as hio
+from hic_genome_assembler_b200._lib import HicaError, io_read_matrix
+from hic_genome_assembler_b200.synth import make_genome
+
+import ref_harness
+
+
+def _write_hicpro(path, A, ids, fmt="%.6f", crlf=False, extra_col=False, final_newline=True):
+    n = A.shape[0]
+    lines = []
+    for i in range(n):
+        for j in range(i, n):
+            if A[i, j] != 0:
+                lines.append("%d\t%d\t%s%s" % (ids[i], ids[j], fmt % A[i, j], "\t7" if extra_col else ""))
+    eol = "\r\n" if crlf else "\n"
+    with open(path, "w", newline="") as f:
+        f.write(eol.join(lines) + (eol if final_newline else ""))
+    return len(lines)
+
+
+def _bins(ids):
+    return [hio.Bin(int(b), "s", 0, 1, 1.0) for b in ids]
+
+
+@pytest.mark.parametrize("n,threads,kw", [(60, 1, {}), (300, 0, {}), (300, 5, dict(crlf=True)),
+                                          (120, 3, dict(extra_col=True, final_newline=False)),
+                                          (200, 64, dict(fmt="%.17g")), (150, 2, dict(fmt="%e"))])
+def test_native_loader_equals_the_python_restatement(tmp_path, n, threads, kw):
+    g = make_genome(n, n_chrom=4, seed=n, scaffolds_per_chrom=3)
+    A = g.A.numpy().copy()
+    A[np.random.RandomState(n).rand(n, n) < 0.3] = 0.0
+    A = np.triu(A) + np.triu(A, 1).T
+    ids = np.arange(1, n + 1) * 2 + 3                      # HiC-Pro ids need not be dense
+    path = str(tmp_path / "m.matrix")
+    n_lines = _write_hicpro(path, A, ids, **kw)
+    kept = [b for k, b in enumerate(_bins(ids)) if k % 7 != 3]   # initiateLoci dropped some bins ('nan' bias)
+    want = hio.read_matrix(path, kept)
+    got = hio.read_matrix_native(path, kept, threads=threads)
+    assert got.dtype == np.float64 and np.array_equal(got, want)
+    assert np.array_equal(got, got.T)
+    # counts: every line parsed, only lines between kept bins applied
+    idx = np.full(ids.max() + 1, -1, dtype=np.int32)
+    for i, b in enumerate(kept):
+        idx[b.ID] = i
+    out = np.full((len(kept), len(kept)), np.nan)          # a caller-owned buffer is zero-filled first
+    M, lines, edges = io_read_matrix(path, idx, len(kept), out=out, threads=threads)
+    assert M is out and lines == n_lines and np.array_equal(out, want)
+    keep = np.array([k % 7 != 3 for k in range(n)])
+    assert edges == int(np.count_nonzero(np.triu(A)[np.ix_(keep, keep)]))
+
+
+def test_last_line_wins_for_repeated_cells_in_any_thread_split(tmp_path):
+    rng = np.random.RandomState(4)
+    n = 40
+    lines = []
+    for _ in range(20000):                                  # many rewrites of few cells, both (i, j) and (j, i)
+        i, j = rng.randint(1, n + 1, size=2)
+        lines.append("%d\t%d\t%.6f" % (i, j, rng.rand()))
+    path = str(tmp_path / "dup.matrix")
+    open(path, "w").write("\n".join(lines) + "\n")
+    bins = _bins(range(1, n + 1))
+    want = hio.read_matrix(path, bins)
+    for threads in (1, 2, 7, 32):
+        assert np.array_equal(hio.read_matrix_native(path, bins, threads=threads), want)
+
+
+def test_number_spellings_follow_python(tmp_path):
+    vals = ["0.1", "+2.5", "-3", "1e-3", "1E+2", " 7.25 ", "inf", "-inf", "1e999", "1e-999", ".5", "5.",
+            "123456789.123456789", "4.9406564584124654e-324", "0.30000000000000004", "179769313486231570000e289"]
+    path = str(tmp_path / "v.matrix")
+    open(path, "w").write("".join("%d\t%d\t%s\n" % (k + 1, k + 1, v) for k, v in enumerate(vals)))
+    bins = _bins(range(1, len(vals) + 1))
+    got = hio.read_matrix_native(path, bins, threads=3)
+    want = np.array([float(v) for v in vals])
+    assert np.array_equal(np.diag(got), want)
+    open(path, "w").write("1\t1\tnan\n")
+    assert np.isnan(hio.read_matrix_native(path, bins[:1])[0, 0])
+
+
+@pytest.mark.parametrize("text,why", [("1\t2\n", "three"), ("1\tx\t0.5\n", "integer"), ("1\t2\tabc\n", "number"),
+                                      ("1\t2\t0.5\n\n3\t3\t1\n", "three"), ("1\t2\t0x10\n", "number")])
+def test_malformed_lines_fail_loudly_like_the_reference(tmp_path, text, why):
+    path = str(tmp_path / "bad.matrix")
+    open(path, "w").write("1\t1\t1.0\n" * 5 + text)
+    with pytest.raises(HicaError, match=why) as ei:
+        hio.read_matrix_native(path, _bins([1, 2, 3]))
+    assert "line 6" in str(ei.value) or "line 7" in str(ei.value)
+    with pytest.raises(Exception):                          # the Python restatement (= the reference's parse) raises too
+        hio.read_matrix(path, _bins([1, 2, 3]))
+
+
+def test_empty_and_missing_files(tmp_path):
+    path = str(tmp_path / "empty.matrix")
+    open(path, "w").close()
+    assert np.array_equal(hio.read_matrix_native(path, _bins([1, 2])), np.zeros((2, 2)))
+    with pytest.raises(HicaError, match="cannot open"):
+        hio.read_matrix_native(str(tmp_path / "nope.matrix"), _bins([1, 2]))
+
+
+@pytest.mark.reference
+def test_native_loader_equals_the_reference_buildAdjacencyMatrix(tmp_path):
+    if not ref_harness.reference_available():
+        pytest.skip("reference tree not mounted")
+    p1, _ = ref_harness.load_reference()
+    n = 180
+    g = make_genome(n, n_chrom=3, seed=9, scaffolds_per_chrom=4)
+    A = g.A.numpy()
+    ids = np.arange(1, n + 1)
+    path = str(tmp_path / "m.matrix")
+    _write_hicpro(path, A, ids)
+    ref_bins = [p1.Bin(int(b), "s", 0, 1, 1.0, 0.) for b in ids if b % 11 != 0]
+    with contextlib.redirect_stdout(_io.StringIO()):
+        want = np.array(p1.buildAdjacencyMatrix(path, ref_bins))
+    got = hio.read_matrix_native(path, [hio.Bin(b.ID, "s", 0, 1, 1.0) for b in ref_bins])
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.reference
+@pytest.mark.parametrize("bias_vals", [False, (0.5, 1.5)])
+def test_loader_seams_equal_the_reference_functions(tmp_path, bias_vals):
+    """buildAdjacencyMatrix + removeRows under the reference's own names: same matrix, same surviving bins, same
+    rowSum values (bitwise) as the reference's list-of-lists versions, including zero rows and the bias filter."""
+    if not ref_harness.reference_available():
+        pytest.skip("reference tree not mounted")
+    p1, _ = ref_harness.load_reference()
+    n = 90
+    g = make_genome(n, n_chrom=3, seed=2, scaffolds_per_chrom=3)
+    A = g.A.numpy().copy()
+    for z in (0, 17, 18, n - 1):                           # bins without contacts: rows that sum to zero
+        A[z, :] = 0.0
+        A[:, z] = 0.0
+    ids = np.arange(1, n + 1)
+    path = str(tmp_path / "m.matrix")
+    _write_hicpro(path, A, ids)
+    bias = 1.0 + 0.8 * np.sin(np.arange(n))
+    mk = lambda: [p1.Bin(int(b), "s%d" % (b % 5), 0, 1, float(bias[b - 1]), 0.) for b in ids]
+    with contextlib.redirect_stdout(_io.StringIO()):
+        bl_ref = mk()
+        m_ref = p1.buildAdjacencyMatrix(path, bl_ref)
+        m_ref, bl_ref = p1.removeRows(m_ref, bl_ref, zeroRows=True, biasVals=bias_vals)
+        bl = mk()
+        m = hio.buildAdjacencyMatrix(path, bl)
+        m, bl2 = hio.removeRows(m, bl, zeroRows=True, biasVals=bias_vals)
+    assert bl2 is bl and [b.ID for b in bl] == [b.ID for b in bl_ref] and len(bl) < n
+    assert np.array_equal(np.asarray(m), np.asarray(m_ref))
+    assert [float(b.rowSum) for b in bl] == [float(b.rowSum) for b in bl_ref]
