@@ -374,7 +374,10 @@ def main():
     kernels = {
         "distance(K1)": {"ms": tm["distance"], "alg_bytes": 16.0 * n * n},
         "linkage(K2)": {"ms": tm["linkage"], "alg_bytes": link_bytes},
-        "rank(K5)": {"ms": tm["rank"], "alg_bytes": 12.0 * n * n},
+        # the value sort runs on a second stream next to the linkage chain (rank_presort), the part after the
+        # leaf order is known (rank) is a column relabel: the kernel's own rate uses the sum of both
+        "rank(K5)": {"ms": tm["rank"] + tm.get("rank_presort", 0.0), "alg_bytes": 12.0 * n * n,
+                     "overlapped_with_linkage_ms": tm.get("rank_presort", 0.0), "after_linkage_ms": tm["rank"]},
     }
     if not args.part1_only:
         probe = score_kernel_probe(h, wl, last)

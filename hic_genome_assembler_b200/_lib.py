@@ -14,13 +14,13 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libhica.so")
 
-T_NAMES = ("upload", "distance", "linkage", "leaforder", "rank", "breakpoints", "filter", "p2_score")
+T_NAMES = ("upload", "distance", "linkage", "leaforder", "rank", "breakpoints", "filter", "p2_score", "rank_presort")
 
 # every symbol include/hica.h declares (checked by tests/test_abi.py)
 ABI_SYMBOLS = (
     "hica_version", "hica_create", "hica_destroy", "hica_last_error", "hica_launch_count", "hica_get_timers",
     "hica_linkage_stats", "hica_debug_stats",
-    "hica_p1_alloc", "hica_p1_upload_rows", "hica_p1_mirror_lower", "hica_p1_device_buffer", "hica_p1_rank_rows", "hica_p1_rank_commit",
+    "hica_p1_alloc", "hica_p1_upload_rows", "hica_p1_mirror_lower", "hica_p1_device_buffer", "hica_p1_rank_rows", "hica_p1_rank_commit", "hica_p1_rank_presort",
     "hica_p1_upload", "hica_p1_upload_symmetric", "hica_p1_upload_device", "hica_p1_set_row_sums", "hica_p1_distance", "hica_p1_get_distance",
     "hica_p1_get_pairwise_row_sums", "hica_p1_get_row_sums", "hica_p1_upload_distance", "hica_p1_linkage",
     "hica_p1_set_order", "hica_p1_get_reordered", "hica_p1_rank", "hica_p1_upload_similarity", "hica_p1_get_rank", "hica_p1_set_rank",
@@ -65,6 +65,7 @@ def load_library():
     L.hica_p1_device_buffer.argtypes = [vp, C.c_int, vp, vp, vp]
     L.hica_p1_rank_rows.argtypes = [vp, i64, i64]
     L.hica_p1_rank_commit.argtypes = [vp]
+    L.hica_p1_rank_presort.argtypes = [vp]
     L.hica_p1_set_row_sums.argtypes = [vp, vp]
     L.hica_p1_distance.argtypes = [vp]
     L.hica_p1_get_distance.argtypes = [vp, vp]
@@ -222,6 +223,10 @@ class Handle:
 
     def p1_rank_rows(self, r0: int, r1: int):
         self._check(self._L.hica_p1_rank_rows(self._h, int(r0), int(r1)))
+
+    def p1_rank_presort(self):
+        """Start the value sort of the rank step asynchronously (see hica.h); returns at once."""
+        self._check(self._L.hica_p1_rank_presort(self._h))
 
     def p1_rank_commit(self):
         self._check(self._L.hica_p1_rank_commit(self._h))

@@ -68,7 +68,12 @@ extern "C" int hica_create(int device, hica_handle *out)
     hica_ctx *h = new hica_ctx();
     h->device = device;
     h->sm_count = prop.multiProcessorCount;
-    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);  // lo = least, hi = greatest priority
+    if (cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&h->stream2, cudaStreamNonBlocking, prio_lo) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreate(&h->ev_pre0) != cudaSuccess || cudaEventCreate(&h->ev_pre1) != cudaSuccess ||
         cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess) {
         delete h;
         return hica_set_error(nullptr, HICA_ERR_CUDA, "stream/event creation failed");
@@ -107,6 +112,7 @@ extern "C" int hica_destroy(hica_handle h)
 {
     if (!h) return HICA_OK;
     cudaSetDevice(h->device);
+    hica_presort_cancel(h);
     cudaStreamSynchronize(h->stream);
     if (h->g_is_A) h->G = nullptr;
     free_p1(h);
@@ -125,6 +131,11 @@ extern "C" int hica_destroy(hica_handle h)
     cudaFreeHost(h->misc_h);
     cudaFree(h->red_d);
     cudaFreeHost(h->red_h);
+    cudaFree(h->pre_buf);
+    cudaEventDestroy(h->ev_fork);
+    cudaEventDestroy(h->ev_pre0);
+    cudaEventDestroy(h->ev_pre1);
+    cudaStreamDestroy(h->stream2);
     cudaEventDestroy(h->ev0);
     cudaEventDestroy(h->ev1);
     cudaStreamDestroy(h->stream);
@@ -135,6 +146,7 @@ extern "C" int hica_destroy(hica_handle h)
 static int p1_alloc(hica_ctx *h, int64_t n)
 {
     if (n < 2) return hica_set_error(h, HICA_ERR_ARG, "n must be >= 2 (got %lld)", (long long)n);
+    hica_presort_cancel(h);
     if (h->g_is_A) { h->G = nullptr; h->g_is_A = false; h->gn = 0; }
     if (h->n != n) {
         free_p1(h);

@@ -12,7 +12,9 @@
 
 struct hica_ctx {
     int device = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;      // highest priority
+    cudaStream_t stream2 = nullptr;     // lowest priority: the rank pre-sort next to the linkage chain
+    cudaEvent_t ev_fork = nullptr, ev_pre0 = nullptr, ev_pre1 = nullptr;
     std::string err;
     int64_t launches = 0;
     double timers[HICA_T_COUNT] = {0};
@@ -43,6 +45,10 @@ struct hica_ctx {
     void *R = nullptr;           // rank matrix n x n, uint16 (n <= 65535) or int32
     int rank_bytes = 0;          // 2 or 4, 0 = none
     int rank_rows_bytes = 0;     // element size of R once allocated (rows may still be missing: hica_p1_rank_rows)
+    // rank pre-sort (hica_p1_rank_presort): rows sorted in matrix order while the linkage runs
+    void *pre_buf = nullptr;     // Rpre (n*n uint16) | tie masks (n * tie_words uint32) | anytie (n) | redo (n) | iota (n)
+    int64_t pre_cap = 0;
+    bool presort_pending = false, presort_valid = false;
     // linkage scratch
     double *Zraw = nullptr;      // (n-1) x 4 raw merges (device)
     int32_t *size_d = nullptr;   // cluster sizes
@@ -126,6 +132,13 @@ static inline int hica_realloc(hica_ctx *h, T **p, int64_t count)
                               (long long)(sizeof(T) * (size_t)count), cudaGetErrorString(e));
     }
     return HICA_OK;
+}
+
+// The pre-sort reads A, s_pair and s_seq on stream2: anything that changes them waits for it and drops its result.
+static inline void hica_presort_cancel(hica_ctx *h)
+{
+    if (h->presort_pending) cudaStreamSynchronize(h->stream2);
+    h->presort_pending = h->presort_valid = false;
 }
 
 // ---- device helpers ----------------------------------------------------------

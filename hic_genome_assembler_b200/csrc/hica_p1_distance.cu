@@ -248,6 +248,7 @@ extern "C" int hica_p1_set_row_sums(hica_handle h, const double *rs)
 {
     HICA_CHECK_HANDLE(h);
     if (!h->A) return hica_set_error(h, HICA_ERR_STATE, "no matrix uploaded");
+    hica_presort_cancel(h);
     if (rs) {
         HICA_CUDA(cudaMemcpyAsync(h->s_seq, rs, sizeof(double) * h->n, cudaMemcpyHostToDevice, h->stream));
     } else {
@@ -268,6 +269,7 @@ extern "C" int hica_p1_distance(hica_handle h)
     if (!h->A) return hica_set_error(h, HICA_ERR_STATE, "no matrix uploaded");
     if (h->A_kind != 0) return hica_set_error(h, HICA_ERR_STATE, "handle holds a distance/similarity matrix, not ICE contacts");
     const int64_t n = h->n;
+    hica_presort_cancel(h);
     int rc = ensure_plan(h, n);
     if (rc) return rc;
     if (!h->W && (rc = hica_realloc(h, &h->W, n * h->ld))) return rc;

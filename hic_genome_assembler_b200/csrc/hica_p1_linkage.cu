@@ -368,6 +368,8 @@ int launch_nn_chain3(hica_ctx *h, int cluster_size, const double *nn0_val, const
 
 }  // namespace
 
+int hica_presort_start(hica_ctx *h);  // hica_p1_rank.cu
+
 int hica_set_order_internal(hica_ctx *h, const int32_t *order_host)
 {
     const int64_t n = h->n;
@@ -420,6 +422,7 @@ extern "C" int hica_p1_linkage(hica_handle h, double *Z_host, int32_t *leaves_ho
     k_fill_i32<<<(unsigned)((NN_MAX_CLUSTER * n + 255) / 256), 256, 0, h->stream>>>(h->size_d, NN_MAX_CLUSTER * n, 1);
     HICA_LAUNCHED(h);
     HICA_CUDA(cudaMemsetAsync(h->misc_d + 64, 0, 144 * sizeof(long long), h->stream));
+    HICA_CUDA(cudaEventRecord(h->ev_fork, h->stream));  // the rank pre-sort may start from here on (stream2)
     int launched = -1;
     int cs_max = NN_MAX_CLUSTER;
     if (const char *e = getenv("HICA_NN_CLUSTER")) cs_max = std::max(1, std::min(NN_MAX_CLUSTER, atoi(e)));
@@ -455,6 +458,9 @@ extern "C" int hica_p1_linkage(hica_handle h, double *Z_host, int32_t *leaves_ho
     }
     if (launched != HICA_OK) return hica_set_error(h, HICA_ERR_CUDA, "no cluster configuration could be launched");
     HICA_CUDA(cudaGetLastError());
+    // The chain keeps one cluster (16 SMs) busy for its whole duration: sort the rows of the similarity matrix on
+    // the other SMs meanwhile, in matrix order (low-priority stream; hica_p1_rank then only relabels the columns)
+    if ((rc = hica_presort_start(h))) return rc;
     t.stop();
     h->have_W = false;  // W has been consumed
 

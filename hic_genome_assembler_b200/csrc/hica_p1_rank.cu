@@ -23,6 +23,7 @@
 #include "hica_common.cuh"
 #include "hica_p1_ranksort.cuh"
 #include "hica_p1_rankradix.cuh"
+#include "hica_p1_rankremap.cuh"
 
 namespace {
 
@@ -110,7 +111,7 @@ static int rank_rows(hica_ctx *h, int q, int64_t P, int64_t lo, int64_t hi)
 }
 
 template <int EPT, int RT>
-static int launch_radix(hica_ctx *h, rankradix::RadixArgs &a, int64_t lo, int64_t hi)
+static int launch_radix(hica_ctx *h, rankradix::RadixArgs &a, int64_t lo, int64_t hi, cudaStream_t stream, int32_t *redo)
 {
     a.row0 = lo;
     const unsigned rows = (unsigned)(hi - lo);
@@ -121,18 +122,28 @@ static int launch_radix(hica_ctx *h, rankradix::RadixArgs &a, int64_t lo, int64_
     if (!only64) {
         const size_t smem32 = rankradix::smem_bytes32(EPT, RT);
         HICA_CUDA(cudaFuncSetAttribute(rankradix::k_rank_radix32<EPT, RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem32));
-        HICA_CUDA(cudaMemsetAsync(h->x_d, 0, sizeof(int32_t) * h->n, h->stream));
-        a.redo = h->x_d;
-        rankradix::k_rank_radix32<EPT, RT><<<rows, RT, smem32, h->stream>>>(a);
+        HICA_CUDA(cudaMemsetAsync(redo, 0, sizeof(int32_t) * h->n, stream));
+        a.redo = redo;
+        rankradix::k_rank_radix32<EPT, RT><<<rows, RT, smem32, stream>>>(a);
         HICA_LAUNCHED(h);
-        a.only = h->x_d;
+        a.only = redo;
     }
     const size_t smem = rankradix::smem_bytes(EPT, RT);
     HICA_CUDA(cudaFuncSetAttribute(rankradix::k_rank_radix<EPT, RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    rankradix::k_rank_radix<EPT, RT><<<rows, RT, smem, h->stream>>>(a);
+    rankradix::k_rank_radix<EPT, RT><<<rows, RT, smem, stream>>>(a);
     HICA_LAUNCHED(h);
     HICA_CUDA(cudaGetLastError());
     return HICA_OK;
+}
+
+static int rank_rows_radix(hica_ctx *h, rankradix::RadixArgs &a, int64_t lo, int64_t hi, cudaStream_t stream, int32_t *redo)
+{
+    const int64_t n = h->n;
+    // measured at N = 16k on B200: 1024 threads x 16 elements 16.7 ms, 512 x 32 17.4 ms (bitonic network: 29 ms)
+    if (n <= 512 * 4) return launch_radix<4, 512>(h, a, lo, hi, stream, redo);
+    if (n <= 512 * 8) return launch_radix<8, 512>(h, a, lo, hi, stream, redo);
+    if (n <= 512 * 16) return launch_radix<8, 1024>(h, a, lo, hi, stream, redo);
+    return launch_radix<16, 1024>(h, a, lo, hi, stream, redo);
 }
 
 static int rank_rows_radix(hica_ctx *h, int64_t lo, int64_t hi)
@@ -140,12 +151,111 @@ static int rank_rows_radix(hica_ctx *h, int64_t lo, int64_t hi)
     rankradix::RadixArgs a = {};
     a.A = h->A; a.n = h->n; a.s_pair = h->s_pair; a.s_seq = h->s_seq; a.order = h->order; a.pos = h->pos;
     a.kind = h->A_kind; a.R = h->R; a.row0 = 0; a.only = nullptr; a.redo = nullptr;
+    return rank_rows_radix(h, a, lo, hi, h->stream, h->x_d);
+}
+
+// ---- pre-sort in matrix order, overlapped with the linkage (see hica_p1_rankremap.cuh) ------------------------
+namespace {
+struct PreBuf {
+    uint16_t *Rpre;
+    uint32_t *tie;
+    int32_t *anytie, *redo, *iota;
+    int tie_words;
+};
+PreBuf pre_layout(hica_ctx *h)
+{
     const int64_t n = h->n;
-    // measured at N = 16k on B200: 1024 threads x 16 elements 16.7 ms, 512 x 32 17.4 ms (bitonic network: 29 ms)
-    if (n <= 512 * 4) return launch_radix<4, 512>(h, a, lo, hi);
-    if (n <= 512 * 8) return launch_radix<8, 512>(h, a, lo, hi);
-    if (n <= 512 * 16) return launch_radix<8, 1024>(h, a, lo, hi);
-    return launch_radix<16, 1024>(h, a, lo, hi);
+    PreBuf b;
+    b.tie_words = (int)((n + 31) / 32);
+    char *p = reinterpret_cast<char *>(h->pre_buf);
+    b.Rpre = reinterpret_cast<uint16_t *>(p);
+    p += ((size_t)n * n * 2 + 255) / 256 * 256;
+    b.tie = reinterpret_cast<uint32_t *>(p);
+    p += ((size_t)n * b.tie_words * 4 + 255) / 256 * 256;
+    b.anytie = reinterpret_cast<int32_t *>(p);
+    b.redo = b.anytie + n;
+    b.iota = b.redo + n;
+    return b;
+}
+__global__ void k_iota(int32_t *p, int64_t n)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) p[i] = (int32_t)i;
+}
+}  // namespace
+
+bool hica_presort_possible(hica_ctx *h)
+{
+    if (const char *e = getenv("HICA_RANK_OVERLAP")) if (atoi(e) == 0) return false;
+    if (const char *e = getenv("HICA_RANK_ALGO")) if (e[0] == 'b') return false;
+    if (getenv("HICA_RANK_RADIX64")) return false;  // a test switch of the one-step path
+    return h->A && h->A_kind == 0 && h->have_s_pair && h->have_s_seq && h->n >= 2 && h->n <= rankremap::MAX_N;
+}
+
+// Enqueue the pre-sort on stream2 behind ev_fork (recorded by the caller on the main stream).  No host sync.
+int hica_presort_start(hica_ctx *h)
+{
+    if (h->presort_pending || h->presort_valid) return HICA_OK;
+    if (!hica_presort_possible(h)) return HICA_OK;
+    const int64_t n = h->n;
+    const int64_t tw = (n + 31) / 32;
+    const int64_t need = (n * n * 2 + 255) / 256 * 256 + (n * tw * 4 + 255) / 256 * 256 + 3 * n * 4 + 256;
+    if (h->pre_cap < need) {
+        if (h->pre_buf) cudaFree(h->pre_buf);
+        h->pre_buf = nullptr;
+        h->pre_cap = 0;
+        if (cudaMalloc(&h->pre_buf, (size_t)need) != cudaSuccess) {
+            cudaGetLastError();
+            return HICA_OK;  // no room for the overlap: hica_p1_rank sorts in one step
+        }
+        h->pre_cap = need;
+    }
+    const PreBuf b = pre_layout(h);
+    HICA_CUDA(cudaStreamWaitEvent(h->stream2, h->ev_fork, 0));
+    HICA_CUDA(cudaEventRecord(h->ev_pre0, h->stream2));
+    k_iota<<<(unsigned)((n + 255) / 256), 256, 0, h->stream2>>>(b.iota, n);
+    HICA_LAUNCHED(h);
+    rankradix::RadixArgs a = {};
+    a.A = h->A; a.n = n; a.s_pair = h->s_pair; a.s_seq = h->s_seq; a.order = b.iota; a.pos = b.iota;
+    a.kind = 0; a.R = b.Rpre; a.only = nullptr; a.redo = nullptr;
+    a.tie = b.tie; a.anytie = b.anytie; a.tie_words = b.tie_words;
+    int rc = rank_rows_radix(h, a, 0, n, h->stream2, b.redo);
+    if (rc) return rc;
+    HICA_CUDA(cudaEventRecord(h->ev_pre1, h->stream2));
+    h->presort_pending = true;
+    return HICA_OK;
+}
+
+extern "C" int hica_p1_rank_presort(hica_handle h)
+{
+    HICA_CHECK_HANDLE(h);
+    if (!h->A) return hica_set_error(h, HICA_ERR_STATE, "no matrix uploaded");
+    if (h->A_kind == 0 && (!h->have_s_pair || !h->have_s_seq))
+        return hica_set_error(h, HICA_ERR_STATE, "call hica_p1_set_row_sums and hica_p1_distance first");
+    HICA_CUDA(cudaEventRecord(h->ev_fork, h->stream));
+    return hica_presort_start(h);
+}
+
+// finish a pre-sorted rank: relabel columns, order exact ties; rows [lo, hi) of the reordered matrix
+static int rank_rows_remap(hica_ctx *h, int64_t lo, int64_t hi)
+{
+    const PreBuf b = pre_layout(h);
+    if (h->presort_pending) {
+        HICA_CUDA(cudaEventSynchronize(h->ev_pre1));
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, h->ev_pre0, h->ev_pre1);
+        h->timers[HICA_T_RANK_PRESORT] = ms;
+        h->presort_pending = false;
+        h->presort_valid = true;
+    }
+    for (int64_t r0 = lo; r0 < hi; r0 += 65535 * 32) {
+        const unsigned rows = (unsigned)std::min<int64_t>(65535 * 32, hi - r0);
+        rankremap::k_rank_remap<<<rows, rankremap::RT, 0, h->stream>>>(b.Rpre, b.tie, b.anytie, b.tie_words, h->order, h->pos,
+                                                                      h->n, r0, reinterpret_cast<uint16_t *>(h->R));
+        HICA_LAUNCHED(h);
+    }
+    HICA_CUDA(cudaGetLastError());
+    return HICA_OK;
 }
 
 // rank rows [lo, hi) of the reordered similarity matrix into R (allocated on first use)
@@ -175,8 +285,13 @@ static int rank_range(hica_ctx *h, int64_t lo, int64_t hi)
     hica_timer t(h, HICA_T_RANK);
     int rc = HICA_OK;
     const char *algo = getenv("HICA_RANK_ALGO");
+    const bool presorted = (h->presort_pending || h->presort_valid) && hica_presort_possible(h);
+    if (!presorted) h->timers[HICA_T_RANK_PRESORT] = 0.;
     if (hi == lo) {
         // an empty block (more ranks than rows): nothing to sort
+    } else if (presorted) {
+        // the rows were sorted in matrix order while the linkage ran: relabel + tie order only
+        rc = rank_rows_remap(h, lo, hi);
     } else if (n <= 16384 && !(algo && algo[0] == 'b')) {
         // rows that fit one CTA's shared memory: stable LSD radix sort (hica_p1_rankradix.cuh)
         rc = rank_rows_radix(h, lo, hi);

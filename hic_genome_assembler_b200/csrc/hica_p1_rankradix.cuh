@@ -28,7 +28,31 @@ struct RadixArgs {
     int64_t row0;
     const int32_t *only;  // not NULL: rank only the rows with only[row] != 0
     int32_t *redo;        // k_rank_radix32: rows it could not finish (set to 1)
+    // pre-sort mode (hica_p1_rank_presort): bit j of tie[row * tie_words + j / 32] = "entry j of the output row has
+    // the same key as entry j - 1"; anytie[row] = 1 when any bit is set.  NULL otherwise.
+    uint32_t *tie;
+    int32_t *anytie;
+    int tie_words;
 };
+
+// tie mask of a finished row; eq(i) = "ascending elements i and i + 1 have equal keys".  All threads of the CTA call it.
+template <int RT, typename Eq>
+__device__ __forceinline__ void emit_ties(const RadixArgs &a, int64_t row, int64_t n, Eq eq)
+{
+    const int t = threadIdx.x, lane = t & 31;
+    uint32_t *tw = a.tie + row * a.tie_words;
+    bool any = false;
+    for (int64_t j0 = t - lane; j0 < n; j0 += RT) {  // warp-uniform bounds
+        const int64_t j = j0 + lane;
+        bool tie = false;
+        if (j >= 1 && j < n) tie = eq((int)(n - 1 - j));
+        const unsigned m = __ballot_sync(0xffffffffu, tie);
+        if (lane == 0) tw[j0 >> 5] = m;
+        any |= (m != 0u);
+    }
+    const int r = __syncthreads_or(any);
+    if (t == 0) a.anytie[row] = r ? 1 : 0;
+}
 
 __device__ __forceinline__ unsigned long long okey(double v)
 {
@@ -151,6 +175,7 @@ __global__ void __launch_bounds__(RT, 1) k_rank_radix(RadixArgs a)
     // ---- descending order = the ascending result read backwards (pads sit behind the n real elements) ----
     uint16_t *out = reinterpret_cast<uint16_t *>(a.R) + row * n;
     for (int64_t j = t; j < n; j += RT) out[j] = pay[n - 1 - j];
+    if (a.tie) emit_ties<RT>(a, row, n, [&](int i) { return keys[i] == keys[i + 1]; });
 }
 
 inline size_t smem_bytes(int ept, int rt)
@@ -307,6 +332,10 @@ __global__ void __launch_bounds__(RT, 1) k_rank_radix32(RadixArgs a)
     // ---- descending order = the ascending result read backwards ---------------------------------------------
     uint16_t *out = reinterpret_cast<uint16_t *>(a.R) + row * n;
     for (int64_t j = t; j < n; j += RT) out[j] = pay[n - 1 - j];
+    if (a.tie) {
+        __syncthreads();  // the fix-up moved payloads
+        emit_ties<RT>(a, row, n, [&](int i) { return hi[i] == hi[i + 1] && lo[pay[i]] == lo[pay[i + 1]]; });
+    }
 }
 
 inline size_t smem_bytes32(int ept, int rt)

@@ -17,6 +17,7 @@ What shards
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -144,6 +145,12 @@ def run_part1_resident_sharded(h, device, min_size: int = 5, min_frac: float = .
     h.p1_distance()
     leaves_t = torch.empty(n, dtype=torch.int32, device=device)
     leaves = None
+    # n <= 16384: every GPU sorts all rows by value in matrix order while the linkage chain runs (the linkage GPU
+    # on its 132 free SMs - hica_p1_linkage starts that itself - the others while they wait for the broadcast);
+    # the rank step is then a local column relabel and needs no gather
+    presort = n <= 16384 and os.environ.get("HICA_RANK_OVERLAP", "1") != "0"
+    if presort and rank != linkage_rank:
+        h.p1_rank_presort()
     if rank == linkage_rank:
         _, leaves = h.p1_linkage(want_Z=False)
         leaves_t.copy_(torch.from_numpy(np.ascontiguousarray(leaves, dtype=np.int32)))
@@ -153,12 +160,15 @@ def run_part1_resident_sharded(h, device, min_size: int = 5, min_frac: float = .
         leaves = leaves_t.cpu().numpy()
         h.p1_set_order(leaves)
     t3 = time.perf_counter()
-    rb = row_blocks(n, world)
-    h.p1_rank_rows(*rb[rank])
-    R = device_tensor(h, 1, device)
-    gather_row_blocks(R, rb, group)
-    torch.cuda.current_stream(device).synchronize()
-    h.p1_rank_commit()
+    if presort:
+        h.p1_rank()
+    else:
+        rb = row_blocks(n, world)
+        h.p1_rank_rows(*rb[rank])
+        R = device_tensor(h, 1, device)
+        gather_row_blocks(R, rb, group)
+        torch.cuda.current_stream(device).synchronize()
+        h.p1_rank_commit()
     t4 = time.perf_counter()
     init, amb0 = h.p1_breakpoints(min_size, min_frac)
     cuts, amb1 = h.p1_filter(init, psig)

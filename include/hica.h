@@ -48,7 +48,7 @@ int64_t hica_launch_count(hica_handle h);
  * call of each stage (index = HICA_T_*), measured on the handle's stream. */
 enum {
     HICA_T_UPLOAD = 0, HICA_T_DISTANCE, HICA_T_LINKAGE, HICA_T_LEAFORDER, HICA_T_RANK,
-    HICA_T_BREAKPOINTS, HICA_T_FILTER, HICA_T_P2_SCORE, HICA_T_COUNT
+    HICA_T_BREAKPOINTS, HICA_T_FILTER, HICA_T_P2_SCORE, HICA_T_RANK_PRESORT, HICA_T_COUNT
 };
 int hica_get_timers(hica_handle h, double *ms /* HICA_T_COUNT */);
 /* counters of the last hica_p1_linkage: nearest-neighbour searches, SM cycles spent in searches, in merges,
@@ -136,6 +136,18 @@ int hica_p1_get_reordered(hica_handle h, int what, double *out_host);
 /* numpy.argsort(S, axis=1)[:, ::-1] :1132 on the device; ties resolve as a
  * stable ascending sort reversed (descending column index). */
 int hica_p1_rank(hica_handle h);
+/* Start the value sort of :1132 BEFORE the leaf order is known (the values of a
+ * row do not depend on the order, only their column labels do): every row is
+ * sorted in matrix order on a second, low-priority stream and the call returns
+ * at once.  hica_p1_linkage starts it by itself next to the linkage chain
+ * (which keeps 16 of the 148 SMs busy for its whole duration); call it
+ * explicitly on GPUs that wait for another GPU's linkage.  A later hica_p1_rank
+ * / hica_p1_rank_rows then only relabels the columns and orders exact ties
+ * (HICA_T_RANK = that part, HICA_T_RANK_PRESORT = the overlapped sort).
+ * Needs the ICE matrix, hica_p1_set_row_sums and hica_p1_distance; n <= 16384
+ * (longer rows keep the one-step sort).  HICA_RANK_OVERLAP=0 disables it. */
+int hica_p1_rank_presort(hica_handle h);
+
 /* Row-block sharded form of hica_p1_rank (:1132): rank rows
  * [r0, r1) of the reordered matrix only.  The other row blocks of the rank
  * matrix are written by the caller's collective on hica_p1_device_buffer(h, 1);

@@ -74,7 +74,7 @@ def _worker_p1(rank, world, port, out_dir):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     try:
         out = {}
-        for n, nc, sym in ((1200, 6, True), (1201, 5, False), (2100, 7, True)):
+        for n, nc, sym in ((1200, 6, True), (1201, 5, False), (2100, 7, True)):  # all below 16,384 bins: pre-sorted rank
             g = make_genome(n, n_chrom=nc, seed=5, scaffolds_per_chrom=8)
             A = np.ascontiguousarray(g.A.numpy())
             h = Handle(rank)

@@ -350,3 +350,80 @@ def test_row_block_upload_and_rank_equal_the_whole_matrix_calls(hica, n, blocks,
         hica.p1_rank_rows(3, n + 1)
     with pytest.raises(Exception):
         hica.p1_upload_rows(B[0:1], 1, 0)
+
+
+def _planted_ties(n, seed, zero_frac=0.3):
+    """A positive matrix whose rows hold runs of exactly tied values of many lengths (2 ... n/3) next to zeros."""
+    rng = np.random.RandomState(seed)
+    A = rng.rand(n, n) + 0.05
+    sizes = [s for s in (2, 3, 7, 31, 32, 33, 34, 40, 63, 64, 65, 100, n // 3) if s <= n // 2]
+    for i in range(n):
+        perm = rng.permutation(n)
+        at = 0
+        for s in sizes:
+            if at + s > n:
+                break
+            A[i, perm[at:at + s]] = np.float64(rng.randint(1, 50)) / 8.0 + 0.015625 * (s % 5)
+            at += s
+    A[rng.rand(n, n) < zero_frac] = 0.0
+    np.fill_diagonal(A, 1.0)
+    return A
+
+
+@pytest.mark.parametrize("n,zero_frac", [(2, 0.0), (16, 0.3), (33, 0.0), (700, 0.3), (1500, 0.6), (2049, 0.05)])
+def test_presorted_rank_equals_the_one_step_rank(hica, n, zero_frac, monkeypatch):
+    """hica_p1_rank_presort (value sort in matrix order, started before the order is known) + hica_p1_rank (column
+    relabel + order inside runs of exact ties) = the one-step kernels = the oracle, on tie-heavy rows."""
+    A = _planted_ties(n, 17 * n + 1, zero_frac)
+    rs = O.sequential_row_sums(A)
+    D = O.convert_distance(A)
+    order = np.random.RandomState(n).permutation(n)
+    S = O.convert_similarity(O.reorder(D, order), rs[order])
+    want = O.rank_matrix_stable(S)
+    hica.p1_upload(A)
+    hica.p1_set_row_sums(rs)
+    hica.p1_distance()
+    hica.p1_rank_presort()
+    hica.p1_set_order(order)
+    hica.p1_rank()
+    t = hica.timers()
+    assert t["rank_presort"] > 0.0                      # the overlapped sort really ran
+    assert np.array_equal(hica.p1_get_rank(), want)
+    # the pre-sort stays valid for another order of the same matrix ...
+    order2 = order[::-1].copy()
+    hica.p1_set_order(order2)
+    hica.p1_rank_rows(0, n // 2)
+    hica.p1_rank_rows(n // 2, n)
+    hica.p1_rank_commit()
+    S2 = O.convert_similarity(O.reorder(D, order2), rs[order2])
+    assert np.array_equal(hica.p1_get_rank(), O.rank_matrix_stable(S2))
+    # ... and is dropped when the row sums change
+    hica.p1_set_row_sums(rs * 2.0)
+    hica.p1_set_order(order)
+    hica.p1_rank()
+    S3 = O.convert_similarity(O.reorder(D, order), (rs * 2.0)[order])
+    assert np.array_equal(hica.p1_get_rank(), O.rank_matrix_stable(S3))
+    # the one-step path, explicitly
+    monkeypatch.setenv("HICA_RANK_OVERLAP", "0")
+    hica.p1_set_row_sums(rs)
+    hica.p1_distance()
+    hica.p1_rank_presort()                              # a no-op now
+    hica.p1_set_order(order)
+    hica.p1_rank()
+    assert np.array_equal(hica.p1_get_rank(), want)
+
+
+@pytest.mark.parametrize("n,nc", [(640, 8), (1600, 10)])
+def test_linkage_starts_the_presort_and_part1_is_unchanged(hica, n, nc, monkeypatch):
+    from hic_genome_assembler_b200 import part1
+    g = make_genome(n, n_chrom=nc, seed=n, scaffolds_per_chrom=6)
+    A = g.A.numpy()
+    hica.p1_upload(A)
+    res = part1.run_part1_resident(hica, min_size=5, min_frac=0.0)
+    assert hica.timers()["rank_presort"] > 0.0
+    R = hica.p1_get_rank()
+    monkeypatch.setenv("HICA_RANK_OVERLAP", "0")
+    hica.p1_upload(A)
+    ref = part1.run_part1_resident(hica, min_size=5, min_frac=0.0)
+    assert list(res["leaves"]) == list(ref["leaves"]) and res["cuts"] == ref["cuts"]
+    assert np.array_equal(R, hica.p1_get_rank())
