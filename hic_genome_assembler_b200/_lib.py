@@ -27,7 +27,7 @@ ABI_SYMBOLS = (
     "hica_p1_window_sig", "hica_p1_breakpoints", "hica_p1_filter", "hica_hypergeom_less",
     "hica_p2_upload", "hica_p2_use_p1_matrix", "hica_p2_select", "hica_p2_set_segments", "hica_p2_total",
     "hica_p2_score_candidates", "hica_p2_score_window", "hica_p2_score_orders", "hica_p2_order_groups",
-    "hica_io_read_matrix", "hica_io_last_error",
+    "hica_io_read_matrix", "hica_io_last_error", "hica_io_log_transform",
 )
 
 _lib = None
@@ -93,6 +93,7 @@ def load_library():
     L.hica_p2_score_orders.argtypes = [vp, vp, i64, i32, dbl, dbl, vp, vp, vp]
     L.hica_p2_order_groups.argtypes = [vp, i32, vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, i32, vp, i32, vp, vp, vp, vp]
     L.hica_io_read_matrix.argtypes = [C.c_char_p, vp, i64, i64, vp, C.c_int, vp, vp]
+    L.hica_io_log_transform.argtypes = [vp, vp, i64, dbl, dbl, C.c_int, C.c_int]
     L.hica_io_last_error.argtypes = []
     L.hica_io_last_error.restype = C.c_char_p
     _lib = L
@@ -412,3 +413,15 @@ class Handle:
         self._check(self._L.hica_p2_score_orders(self._h, _ptr(orders), B, n, total, carried, C.byref(best),
                                                  C.byref(bi), _ptr(sc)))
         return best.value, bi.value, sc
+
+
+def io_log_transform(M: np.ndarray, base: float = 10.0, reverse: bool = False, threads: int = 0,
+                     offset: float = 1.0) -> np.ndarray:
+    """hica_io_log_transform on a float64 array (host side): a new array of the same shape."""
+    L = load_library()
+    a = np.ascontiguousarray(M, dtype=np.float64)
+    out = np.empty_like(a)
+    rc = L.hica_io_log_transform(_ptr(a), _ptr(out), a.size, float(base), float(offset), 1 if reverse else 0, int(threads))
+    if rc:
+        raise ValueError(L.hica_io_last_error().decode())
+    return out

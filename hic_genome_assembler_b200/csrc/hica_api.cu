@@ -73,6 +73,7 @@ extern "C" int hica_create(int device, hica_handle *out)
     if (cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
         cudaStreamCreateWithPriority(&h->stream2, cudaStreamNonBlocking, prio_lo) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreate(&h->ev_pre0) != cudaSuccess || cudaEventCreate(&h->ev_pre1) != cudaSuccess ||
         cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess) {
         delete h;
@@ -133,6 +134,7 @@ extern "C" int hica_destroy(hica_handle h)
     cudaFreeHost(h->red_h);
     cudaFree(h->pre_buf);
     cudaEventDestroy(h->ev_fork);
+    cudaEventDestroy(h->ev_join);
     cudaEventDestroy(h->ev_pre0);
     cudaEventDestroy(h->ev_pre1);
     cudaStreamDestroy(h->stream2);

@@ -14,7 +14,7 @@ struct hica_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;      // highest priority
     cudaStream_t stream2 = nullptr;     // lowest priority: the rank pre-sort next to the linkage chain
-    cudaEvent_t ev_fork = nullptr, ev_pre0 = nullptr, ev_pre1 = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_pre0 = nullptr, ev_pre1 = nullptr;
     std::string err;
     int64_t launches = 0;
     double timers[HICA_T_COUNT] = {0};

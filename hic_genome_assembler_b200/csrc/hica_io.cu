@@ -20,6 +20,8 @@
 #include <sys/stat.h>
 #include <unistd.h>
 
+#include <math.h>
+
 #include <algorithm>
 #include <atomic>
 #include <charconv>
@@ -211,5 +213,44 @@ extern "C" int hica_io_read_matrix(const char *path, const int32_t *index_of_id,
     }
     if (n_lines) *n_lines = lines;
     if (n_edges) *n_edges = edges;
+    return HICA_OK;
+}
+
+// logTransformMatrix (scaffoldToChromosomes.py:165-183, orderGenome.py:160-178): an interpreted double loop over
+// all N^2 entries in the reference (minutes at 16k bins, and an 8 GB list of lists) that sits on the critical path
+// of the unchanged entry point although it only feeds the plots.  Same arithmetic, same libm:
+//   forward  v != 0 -> math.log(float(v) + off, base) = log(v + off) / log(base)    (CPython: m_log(x) / m_log(base))
+//   reverse  v != 0 -> (float(base) ** v) - off       = pow(base, v) - off
+// with off = 1. in scaffoldToChromosomes.py and off = 0. (no offset at all) in orderGenome.py.
+// A forward argument v + off <= 0 makes math.log raise ValueError in the reference: the call fails.
+extern "C" int hica_io_log_transform(const double *in, double *out, int64_t count, double base, double offset,
+                                     int reverse, int threads)
+{
+    if (!in || !out || count < 0) return io_fail("%s: bad argument%.0lld%s", "hica_io_log_transform", 0, "");
+    int T = threads > 0 ? threads : (int)std::thread::hardware_concurrency();
+    T = std::max(1, std::min<int>(T, (int)std::min<int64_t>(256, count / 65536 + 1)));
+    const double lb = log(base);
+    std::atomic<int64_t> bad(-1);
+    std::vector<std::thread> th;
+    for (int t = 0; t < T; t++)
+        th.emplace_back([&, t] {
+            const int64_t i0 = count * t / T, i1 = count * (t + 1) / T;
+            for (int64_t i = i0; i < i1; i++) {
+                const double v = in[i];
+                double r = 0.0;
+                if (v != 0.) {
+                    if (!reverse) {
+                        const double x = v + offset;
+                        if (!(x > 0.) && !(x != x)) { bad.store(i); r = 0.0; }
+                        else r = log(x) / lb;
+                    } else {
+                        r = pow(base, v) - offset;
+                    }
+                }
+                out[i] = r;
+            }
+        });
+    for (auto &x : th) x.join();
+    if (bad.load() >= 0) return io_fail("%s: math domain error at entry %lld%s", "logTransformMatrix", (long long)bad.load(), "");
     return HICA_OK;
 }

@@ -78,6 +78,7 @@ struct GroupDev {
     int32_t *near_id;
     GroupState *st;
     WinState *win;  // batched scan: one per window slot
+    const double *Hp;  // Hp[j] = sum_{i=1..j} 1/i (shared by all groups): unnormalised weights of the insertion step
 };
 
 struct Tables {  // enumeration tables per window width m (device pointers)
@@ -584,7 +585,7 @@ __global__ void __launch_bounds__(256) k_g_ins_rows(const GroupDev *gs, Phase ph
     if (n < 2) return;
     const int ne = g.layout[m];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const double *Wt = g.Wt;
+    const double *Hp = g.Hp;
     const int seg = ne >> 1;
     const int Ls = g.seg_ptr[seg + 1] - g.seg_ptr[seg], P = n - Ls;
     if (m < 1 || (int)(blockIdx.x * INS_ROWS) >= P) return;
@@ -601,9 +602,11 @@ __global__ void __launch_bounds__(256) k_g_ins_rows(const GroupDev *gs, Phase ph
         const double *Srow = g.S + (int64_t)o[a] * g.L, *Trow = g.St + (int64_t)o[a] * g.L;
         double acc = 0.;
 #pragma unroll 4
-        for (int b = end + lane; b < P; b += 32) acc += Srow[o[b]] * (Wt[b - a + Ls] - Wt[b - a]);
+        // total * (w(d + Ls) - w(d)) = Hp[d - 1] - Hp[d + Ls - 1]  (the scores of this step stay unnormalised, so
+        // that they do not have to wait for the total, which is computed next to them on the other stream)
+        for (int b = end + lane; b < P; b += 32) acc += Srow[o[b]] * (Hp[b - a - 1] - Hp[b - a + Ls - 1]);
 #pragma unroll 4
-        for (int b = lane; b < start; b += 32) acc -= Trow[o[b]] * (Wt[a - b + Ls] - Wt[a - b]);
+        for (int b = lane; b < start; b += 32) acc -= Trow[o[b]] * (Hp[a - b - 1] - Hp[a - b + Ls - 1]);
         for (int d = 16; d >= 1; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
         if (lane == 0) g.ins_d[a] = acc;
     }
@@ -626,7 +629,8 @@ __global__ void __launch_bounds__(128) k_g_ins_rel(const GroupDev *gs, Phase ph)
     const InsertCand cd = insert_cand(c, ne);
     const int p = (m >= 1) ? sp.spos[cd.i] : 0;
     const int32_t *o = sp.o;
-    const double *Wt = g.Wt;
+    const double *Hp = g.Hp;
+    const double hn = Hp[n - 1];  // total * w(d) = Hp[n - 1] - Hp[d - 1]
     const int L = g.L;
     double acc = 0.;
     for (int a = threadIdx.x; a < p; a += blockDim.x) acc += g.ins_d[a];
@@ -636,13 +640,13 @@ __global__ void __launch_bounds__(128) k_g_ins_rel(const GroupDev *gs, Phase ph)
             const double *Srow = g.S + (int64_t)oa * L;
             for (int t = 0; t < Ls; t++) {
                 const int nb = g.seg_bins[b0 + (cd.ori ? (Ls - 1 - t) : t)];
-                acc += Srow[nb] * Wt[p + t - a];
+                acc += Srow[nb] * (hn - Hp[p + t - a - 1]);
             }
         } else {
             const double *Trow = g.St + (int64_t)oa * L;  // St[oa][nb] = S[nb][oa]
             for (int t = 0; t < Ls; t++) {
                 const int nb = g.seg_bins[b0 + (cd.ori ? (Ls - 1 - t) : t)];
-                acc += Trow[nb] * Wt[a + Ls - p - t];
+                acc += Trow[nb] * (hn - Hp[a + Ls - p - t - 1]);
             }
         }
     }
@@ -666,12 +670,12 @@ __global__ void __launch_bounds__(128) k_g_ins_select(const GroupDev *gs, Phase 
     if (!pp.active) return;
     GroupState *st = g.st;
     const int B = 2 * (pp.m + 1);
-    const bool all = st->inexact || pp.n < 2;
+    const bool all = st->inexact || pp.n < 2 || st->total == 0.0;
     // The closed form differs from the exact score by a few n ulp of the score itself, and no score exceeds
     // H_{n-1} = sum_{k<n} 1/k (the traces add up to total, and w(k) <= w(1) = H_{n-1} / total): the tolerance
     // is taken relative to that bound, which needs no absolute anchor.  Whether the best score beats the
     // initial bestCost of 0. (:338) is decided on the exact scores in k_g_pick_insert.
-    const double hn = g.Wt[1] * st->total;  // w(1) = H_{n-1} / total
+    const double hn = g.Hp[pp.n - 1] * fabs(st->total);  // the closed-form scores of this step are total x cost
     const double thr = f64_from_order_key(st->w0.amax_key) - NEAR_TOL * hn;
     for (int c = threadIdx.x; c < B; c += blockDim.x) {
         const bool near = all || !(g.rel[c] < thr);
@@ -986,6 +990,14 @@ extern "C" int hica_p2_order_groups(hica_handle h, int32_t ngroups, const int32_
         ENG_CUDA(cudaMemcpyAsync(pr, ori_scan, (size_t)n_ori_scan * scan, cudaMemcpyHostToDevice, s));
         tb.ord[scan] = po; tb.ori[scan] = pr; tb.n_ord[scan] = n_ord_scan; tb.n_ori[scan] = n_ori_scan;
     }
+    // ---- harmonic prefix sums Hp[j] = sum_{i=1..j} 1/i, shared by all groups (insertion step, closed form)
+    double *Hp_d = ar.take<double>((size_t)Lmax + 2);
+    {
+        std::vector<double> hp((size_t)Lmax + 2, 0.);
+        for (int j = 1; j <= Lmax + 1; j++) hp[j] = hp[j - 1] + 1.0 / (double)j;
+        ENG_CUDA(cudaMemcpyAsync(Hp_d, hp.data(), sizeof(double) * hp.size(), cudaMemcpyHostToDevice, s));
+        ENG_CUDA(cudaStreamSynchronize(s));  // hp goes out of scope
+    }
     // ---- group descriptors
     std::vector<GroupDev> hdev(ngroups);
     std::vector<GroupState *> st_ptr(ngroups);
@@ -1000,6 +1012,7 @@ extern "C" int hica_p2_order_groups(hica_handle h, int32_t ngroups, const int32_
         d.seg_ptr = sp; d.seg_bins = sb; d.cum = cum; d.layout = lay;
         d.L = g.L; d.nseg = g.nseg; d.k = g.k; d.scanning = g.nseg > n_scaffolds ? 1 : 0;
         d.Wt = ar.take<double>(g.L + 1);
+        d.Hp = Hp_d;
         d.tr = ar.take<double>(g.L + 1);
         d.ins_d = ar.take<double>(g.L + 1);
         const int mmax = std::max(g.k, (int)scan);
@@ -1098,12 +1111,23 @@ extern "C" int hica_p2_order_groups(hica_handle h, int32_t ngroups, const int32_
     for (int step = 0; step < ins_steps; step++) {
         Phase ph = {PH_INSERT, step, 0};
         const unsigned nb_c = 2 * (unsigned)(nseg_max + 1);
-        k_g_total<<<dim3(tot_blocks, G), 128, ex_smem, s>>>(gdev, ph, 1);
+        // the closed-form scores of the step are kept unnormalised (total x cost), so they do not depend on the
+        // total: both run side by side, the total on the main stream, the scores on the second one
+        cudaStream_t s2 = prof ? s : h->stream2;
+        if (!prof) {
+            ENG_CUDA(cudaEventRecord(h->ev_fork, s));
+            ENG_CUDA(cudaStreamWaitEvent(s2, h->ev_fork, 0));
+        }
+        k_g_total<<<dim3(tot_blocks, G), 128, ex_smem, s>>>(gdev, ph, 0);
         mark(1);
-        k_g_ins_rows<<<dim3((unsigned)((Lmax + INS_ROWS - 1) / INS_ROWS), G), 256, tot_smem, s>>>(gdev, ph);
+        k_g_ins_rows<<<dim3((unsigned)((Lmax + INS_ROWS - 1) / INS_ROWS), G), 256, tot_smem, s2>>>(gdev, ph);
         mark(8);
-        k_g_ins_rel<<<dim3(nb_c, G), 128, tot_smem, s>>>(gdev, ph);
+        k_g_ins_rel<<<dim3(nb_c, G), 128, tot_smem, s2>>>(gdev, ph);
         mark(9);
+        if (!prof) {
+            ENG_CUDA(cudaEventRecord(h->ev_join, s2));
+            ENG_CUDA(cudaStreamWaitEvent(s, h->ev_join, 0));
+        }
         k_g_ins_select<<<dim3(1, G), 128, 0, s>>>(gdev, ph);
         mark(10);
         k_g_insert_scores<<<dim3(std::min(nb_c, 8u) * EX_SPLIT, G), EX_THREADS, ex_smem, s>>>(gdev, ph);

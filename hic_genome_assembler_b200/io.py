@@ -132,6 +132,19 @@ def removeRows(matrix, binList, zeroRows=True, biasVals=False):
     return A, binList
 
 
+def logTransformMatrix(matrix, logBase=10, reverse=False, _offset=1.0):
+    """Seam for scaffoldToChromosomes.logTransformMatrix (:165-183: log(v + 1) / base**v - 1): same arguments, same
+    values bit for bit (libm log / pow on the host, all cores), returned as numpy.matrix like the original."""
+    from ._lib import io_log_transform
+    M = np.asarray(np.asmatrix(matrix), dtype=np.float64)
+    return np.asmatrix(io_log_transform(M, float(logBase), bool(reverse), offset=_offset))
+
+
+def logTransformMatrix_part2(matrix, logBase=10, reverse=False):
+    """Seam for orderGenome.logTransformMatrix (orderGenome.py:160-178), which has no +1 / -1 offset."""
+    return logTransformMatrix(matrix, logBase, reverse, _offset=0.0)
+
+
 def write_dendrogram_order(labels: Sequence[str], leaves: Sequence[int], path: str) -> None:
     with open(path, "w") as f:
         f.write("\n".join("%s\t%d" % (labels[l], l) for l in leaves))

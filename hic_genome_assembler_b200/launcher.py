@@ -119,6 +119,8 @@ def install(reference_dir: str, device: int = 0, no_plots: bool = False, native_
                 mod.buildAdjacencyMatrix = hio.buildAdjacencyMatrix
             if hasattr(mod, "removeRows"):
                 mod.removeRows = hio.removeRows
+            if hasattr(mod, "logTransformMatrix"):   # 8f-3: feeds the plots only, but sits on the critical path
+                mod.logTransformMatrix = hio.logTransformMatrix if mod is part1 else hio.logTransformMatrix_part2
 
     s2 = Part2Seams(h)
     part2.costFunction_numba = s2.costFunction_numba

@@ -273,6 +273,15 @@ int hica_io_read_matrix(const char *path, const int32_t *index_of_id, int64_t ma
                         double *A_host, int threads, int64_t *n_lines, int64_t *n_edges);
 const char *hica_io_last_error(void);
 
+/* logTransformMatrix (scaffoldToChromosomes.py:165-183 with offset = 1,
+ * orderGenome.py:160-178 with offset = 0): out[i] = 0 where in[i] == 0, else
+ * log(in[i] + offset) / log(base) (reverse = 0) or pow(base, in[i]) - offset
+ * (reverse != 0), with the host libm the reference's math.log / ** use;
+ * `count` entries, in == out allowed.  Fails ("math domain error") where the
+ * reference's math.log would raise. */
+int hica_io_log_transform(const double *in, double *out, int64_t count, double base, double offset,
+                          int reverse, int threads);
+
 #ifdef __cplusplus
 }
 #endif

@@ -153,3 +153,37 @@ def test_loader_seams_equal_the_reference_functions(tmp_path, bias_vals):
     assert bl2 is bl and [b.ID for b in bl] == [b.ID for b in bl_ref] and len(bl) < n
     assert np.array_equal(np.asarray(m), np.asarray(m_ref))
     assert [float(b.rowSum) for b in bl] == [float(b.rowSum) for b in bl_ref]
+
+
+def test_log_transform_matches_python_math(tmp_path):
+    import math
+    rng = np.random.RandomState(3)
+    M = rng.rand(70, 70) * 50
+    M[rng.rand(70, 70) < 0.3] = 0.0
+    M[0, :5] = [1e-300, 1e300, -0.5, 5e-324, 1.0]
+    fwd = hio.logTransformMatrix(M, logBase=10)
+    want = np.array([[math.log(float(v) + 1., 10) if v != 0. else 0.0 for v in row] for row in M])
+    assert isinstance(fwd, np.matrix) and np.array_equal(np.asarray(fwd), want)
+    back = hio.logTransformMatrix(fwd, logBase=10, reverse=True)
+    want_b = np.array([[(float(10) ** v) - 1. if v != 0. else 0.0 for v in row] for row in np.asarray(fwd)])
+    assert np.array_equal(np.asarray(back), want_b)
+    assert np.array_equal(np.asarray(hio.logTransformMatrix(M, logBase=2)),
+                          np.array([[math.log(float(v) + 1., 2) if v != 0. else 0.0 for v in row] for row in M]))
+    M[3, 3] = -1.0
+    with pytest.raises(ValueError, match="math domain error"):   # math.log(0.) raises in the reference
+        hio.logTransformMatrix(M)
+
+
+@pytest.mark.reference
+def test_log_transform_seam_equals_the_reference(tmp_path):
+    if not ref_harness.reference_available():
+        pytest.skip("reference tree not mounted")
+    p1, p2 = ref_harness.load_reference()
+    g = make_genome(150, n_chrom=3, seed=1, scaffolds_per_chrom=3)
+    A = g.A.numpy().copy()
+    A[A < np.median(A)] = 0.0
+    for mod, seam in ((p1, hio.logTransformMatrix), (p2, hio.logTransformMatrix_part2)):   # the two modules differ
+        f = np.asarray(mod.logTransformMatrix(A, logBase=10))
+        assert np.array_equal(np.asarray(seam(A, logBase=10)), f)
+        assert np.array_equal(np.asarray(seam(f, logBase=10, reverse=True)),
+                              np.asarray(mod.logTransformMatrix(f, logBase=10, reverse=True)))
