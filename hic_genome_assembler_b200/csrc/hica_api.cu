@@ -130,6 +130,8 @@ extern "C" int hica_destroy(hica_handle h)
     cudaFree(h->tr_d);
     cudaFree(h->misc_d);
     cudaFreeHost(h->misc_h);
+    cudaFree(h->ra_d);
+    cudaFreeHost(h->ra_h);
     cudaFree(h->red_d);
     cudaFreeHost(h->red_h);
     cudaFree(h->pre_buf);

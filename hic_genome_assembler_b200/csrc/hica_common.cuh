@@ -60,6 +60,7 @@ struct hica_ctx {
     int32_t *misc_d = nullptr;   // small result buffer (device)
     int32_t *misc_h = nullptr;   // pinned mirror
     int64_t *q_d = nullptr;      // query buffer for hypergeom batches
+    int32_t *ra_d = nullptr, *ra_h = nullptr;  // run-ahead state of the break-search loop (device / pinned)
     int64_t scratch_n = 0;
     // pairwise-sum plan (leaf table + combine tree) for rows of length plan_n
     int32_t *plan_d = nullptr;

@@ -239,10 +239,10 @@ __global__ void __launch_bounds__(128) k_window_counts_crit(const RankT *__restr
     }
 }
 
-__global__ void k_sig_cmp0(const int32_t *__restrict__ x, const int32_t *__restrict__ crit, int64_t Lw, long long M,
-                           double psig, uint8_t *__restrict__ sig, int32_t *__restrict__ misc)
+__device__ __forceinline__ void sig_cmp0_one(int64_t c, const int32_t *__restrict__ x, const int32_t *__restrict__ crit,
+                                             int64_t Lw, long long M, double psig, uint8_t *__restrict__ sig,
+                                             int32_t *__restrict__ misc)
 {
-    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= Lw) return;
     int s = 0;
     if (c > 0) {
@@ -259,6 +259,12 @@ __global__ void k_sig_cmp0(const int32_t *__restrict__ x, const int32_t *__restr
     }
     sig[c] = (uint8_t)s;
     if (s) atomicAdd(&misc[0], 1);
+}
+
+__global__ void k_sig_cmp0(const int32_t *__restrict__ x, const int32_t *__restrict__ crit, int64_t Lw, long long M,
+                           double psig, uint8_t *__restrict__ sig, int32_t *__restrict__ misc)
+{
+    sig_cmp0_one((int64_t)blockIdx.x * blockDim.x + threadIdx.x, x, crit, Lw, M, psig, sig, misc);
 }
 
 // mode 1: all rows share (M, local, local): one critical value.
@@ -294,9 +300,9 @@ __global__ void k_sig_mode1(const int32_t *__restrict__ x, int64_t rows, int64_t
 
 // break signal of get_sliding_window_distance_metrics with w == min_size:
 // b[t] == w  <=>  sig[t..t+w) all 1 and sig[t+w..t+2w) all 0 (full right half).
-__global__ void k_break_hits(const uint8_t *__restrict__ sig, int64_t Lw, int w, int32_t *__restrict__ misc)
+__device__ __forceinline__ void break_hit_one(int64_t t, const uint8_t *__restrict__ sig, int64_t Lw, int w,
+                                              int32_t *__restrict__ misc)
 {
-    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= Lw - w || t + 2 * (int64_t)w > Lw) return;
     int a = 0, b = 0;
     for (int k = 0; k < w; k++) { a += sig[t + k]; b += sig[t + w + k]; }
@@ -304,6 +310,11 @@ __global__ void k_break_hits(const uint8_t *__restrict__ sig, int64_t Lw, int w,
         atomicMin(&misc[1], (int)t);
         atomicAdd(&misc[2], 1);
     }
+}
+
+__global__ void k_break_hits(const uint8_t *__restrict__ sig, int64_t Lw, int w, int32_t *__restrict__ misc)
+{
+    break_hit_one((int64_t)blockIdx.x * blockDim.x + threadIdx.x, sig, Lw, w, misc);
 }
 
 // filter stage: for every interval [bounds[j-1] or start, bounds[j]) sum the row
@@ -575,6 +586,146 @@ int find_breakpoints(hica_ctx *h, int64_t start, int64_t min_size, int64_t world
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Run-ahead form of the break-search loop of pre_process_all_matrix_breakpoints (:513-551).  Every search starts
+// where the previous one found its first cut, so the searches are strictly sequential - but the common case (the
+// significances are evaluated once, the sliding window of width min_size finds a hit) needs no host decision at
+// all.  The start index lives in device memory, a one-thread kernel applies the reference's rules after each
+// search, and the host enqueues several searches back to back with ONE read-back per batch instead of one per
+// search.  Anything else (>= 90 % significant rows -> M shrinks, no hit -> narrower windows, tiny remainders) sets
+// need_host and the host-driven find_breakpoints() repeats that search from the same index.
+constexpr int RA_MAX_CUTS = 4096;
+constexpr int RA_BATCH = 8;
+struct RaState {
+    int32_t ind, done, need_host, count, amb, searches, pad0, pad1;
+    int32_t cuts[RA_MAX_CUTS];
+};
+
+__global__ void k_ra_reset(int32_t *__restrict__ misc, int iters)
+{
+    const int i = threadIdx.x;
+    if (i < iters * 8) misc[i] = ((i & 7) == 1) ? INT_MAX : 0;
+}
+
+template <typename RankT>
+__global__ void __launch_bounds__(128) k_ra_counts(const RankT *__restrict__ R, int64_t n, const RaState *__restrict__ st,
+                                                   int32_t *__restrict__ x, int ncrit, double psig, int32_t *__restrict__ crit)
+{
+    if (st->done | st->need_host) return;
+    const int64_t start = st->ind, Lw = n - start;
+    if (Lw <= 1) return;
+    if ((int)blockIdx.x < ncrit) {
+        const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        if (c >= 1 && c < Lw) crit_mode0_one(c, Lw, psig, crit);  // world size M = n - ind (:535)
+        return;
+    }
+    const int64_t c = (int64_t)blockIdx.x - ncrit + 1, i = start + c;
+    if (c >= Lw) return;
+    const RankT *row = R + i * n;
+    int cnt = 0;
+    for (int64_t k = threadIdx.x; k < c; k += blockDim.x) {
+        int64_t v = row[k];
+        cnt += (v >= start && v <= i);
+    }
+    __shared__ int part[4];
+    for (int d = 16; d >= 1; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        x[c] = part[0] + part[1] + part[2] + part[3];
+        if (c == 1) x[0] = 0;
+    }
+}
+
+__global__ void k_ra_sig(const int32_t *__restrict__ x, const int32_t *__restrict__ crit, int64_t n,
+                         const RaState *__restrict__ st, double psig, uint8_t *__restrict__ sig, int32_t *__restrict__ misc)
+{
+    if (st->done | st->need_host) return;
+    const int64_t Lw = n - st->ind;
+    if (Lw <= 1) return;
+    sig_cmp0_one((int64_t)blockIdx.x * blockDim.x + threadIdx.x, x, crit, Lw, Lw, psig, sig, misc);
+}
+
+__global__ void k_ra_hits(const uint8_t *__restrict__ sig, int64_t n, const RaState *__restrict__ st, int w,
+                          int32_t *__restrict__ misc)
+{
+    if (st->done | st->need_host) return;
+    const int64_t Lw = n - st->ind;
+    if (Lw <= 1 || w >= Lw) return;  // no sliding pass (:487: ws < Lw)
+    break_hit_one((int64_t)blockIdx.x * blockDim.x + threadIdx.x, sig, Lw, w, misc);
+}
+
+// One CTA.  Common case (thread 0): < 90 % significant rows and a hit at width min_size -> commit the cut.
+// Otherwise, when the remaining world is small (the end game inside the last chromosome, where M shrinks and the
+// windows narrow), the whole of find_matrix_pvalue_breakpoints' control flow (:437-511) runs here: up to five
+// re-evaluations with M <- M - start while >= 90 % of the rows are significant (loop_count persists), the sliding
+// pass after every evaluation at width min_size, one more evaluation per narrower width (they can shrink M and
+// count ambiguous decisions, never produce a cut).  Larger worlds that need this go back to the host.
+constexpr int RA_DECIDE_THREADS = 512;
+constexpr int RA_SLOW_MAX = 4096;
+__global__ void __launch_bounds__(RA_DECIDE_THREADS) k_ra_decide(RaState *st, const int32_t *__restrict__ misc, int64_t n,
+                                                                 int min_size, int64_t stop_ind, const int32_t *__restrict__ x,
+                                                                 int32_t *__restrict__ crit, uint8_t *__restrict__ sig, double psig)
+{
+    __shared__ int32_t sm[8];
+    const int t = threadIdx.x;
+    if (st->done | st->need_host) return;
+    const int64_t start = st->ind, Lw = n - start;
+    if (Lw <= 1 || min_size >= Lw) { if (t == 0) st->need_host = 1; return; }
+    int sum = misc[0], first = misc[1], hits = misc[2], amb1 = misc[3];
+    auto commit = [&](int amb_total) {  // thread 0: leftmost hit + min_size (:488, :540), then the stop rules (:541-549)
+        if (st->count >= RA_MAX_CUTS) { st->need_host = 2; return; }
+        st->amb += amb_total;
+        st->searches += 1;
+        const int64_t ind = start + (int64_t)first + min_size;
+        st->ind = (int32_t)ind;
+        st->cuts[st->count++] = (int32_t)ind;
+        if (ind >= stop_ind || (n - ind) <= min_size) st->done = 1;
+    };
+    if (((double)sum / (double)Lw) < .9 && hits > 0) {
+        if (t == 0) commit(amb1);
+        return;
+    }
+    if (Lw > RA_SLOW_MAX) { if (t == 0) st->need_host = 1; return; }
+    long long M = Lw;
+    int ws = min_size, break_sig = 0, loop_count = 0, amb = 0;
+    bool have_eval = true;  // the first evaluation came from k_ra_sig / k_ra_hits
+    for (;;) {
+        const bool slide = (ws == min_size && ws < Lw);
+        for (;;) {
+            if (!have_eval) {
+                __syncthreads();
+                if (t < 8) sm[t] = (t == 1) ? INT_MAX : 0;
+                __syncthreads();
+                for (int64_t c = t; c < Lw; c += RA_DECIDE_THREADS) {
+                    if (c >= 1) crit_mode0_one(c, M, psig, crit);
+                    sig_cmp0_one(c, x, crit, Lw, M, psig, sig, sm);
+                }
+                __syncthreads();
+                if (slide)
+                    for (int64_t tt = t; tt < Lw; tt += RA_DECIDE_THREADS) break_hit_one(tt, sig, Lw, ws, sm);
+                __syncthreads();
+                sum = sm[0]; first = sm[1]; hits = sm[2]; amb1 = sm[3];
+            }
+            have_eval = false;
+            amb += amb1;
+            loop_count++;
+            if (((double)sum / (double)Lw) >= .9) M = M - start;
+            else break_sig = 1;
+            if (break_sig == 1 || loop_count >= 5) break;
+        }
+        if (slide && hits > 0) {
+            if (t == 0) commit(amb);
+            return;
+        }
+        ws -= 1;
+        if (ws == 0) {  // no cut: pre_process_all_matrix_breakpoints stops here (:538-539)
+            if (t == 0) { st->amb += amb; st->searches += 1; st->done = 1; }
+            return;
+        }
+    }
+}
+
 }  // namespace
 
 extern "C" int hica_p1_window_sig(hica_handle h, int64_t start, int64_t cut, int64_t M, double psig, int mode,
@@ -622,15 +773,71 @@ extern "C" int hica_p1_breakpoints(hica_handle h, int64_t min_size, double min_f
     int64_t ind = 0, count = 0, amb = 0;
     *n_cuts = 0;
     if (min_frac == 1.0) { t.stop(); return HICA_OK; }
-    for (;;) {
-        int64_t first = -1, hits = 0;
-        int rc = find_breakpoints(h, ind, min_size, n - ind, .05, &first, &hits, &amb);
-        if (rc) return rc;
-        if (hits == 0) break;
-        ind += first;
-        if (count < capacity && cuts_host) cuts_host[count] = ind;
-        count++;
-        if (ind >= stop_ind || (n - ind) <= min_size) break;
+    const char *ra_env = getenv("HICA_CUTS_RUNAHEAD");
+    const bool run_ahead = !(ra_env && atoi(ra_env) == 0) && n <= 0x7fffffff && min_size <= 0x7fffffff;
+    if (!run_ahead) {
+        for (;;) {
+            int64_t first = -1, hits = 0;
+            int rc = find_breakpoints(h, ind, min_size, n - ind, .05, &first, &hits, &amb);
+            if (rc) return rc;
+            if (hits == 0) break;
+            ind += first;
+            if (count < capacity && cuts_host) cuts_host[count] = ind;
+            count++;
+            if (ind >= stop_ind || (n - ind) <= min_size) break;
+        }
+    } else {
+        // run-ahead: batches of RA_BATCH searches driven from device memory (see RaState above)
+        constexpr int RA_INTS = (int)(sizeof(RaState) / sizeof(int32_t));
+        if (!h->ra_d) {
+            HICA_CUDA(cudaMalloc((void **)&h->ra_d, sizeof(int32_t) * (RA_INTS + 8 * RA_BATCH)));
+            HICA_CUDA(cudaMallocHost((void **)&h->ra_h, sizeof(RaState)));
+        }
+        RaState *st_d = reinterpret_cast<RaState *>(h->ra_d), *st_h = reinterpret_cast<RaState *>(h->ra_h);
+        int32_t *misc_ra = h->ra_d + RA_INTS;
+        memset(st_h, 0, 8 * sizeof(int32_t));
+        HICA_CUDA(cudaMemcpyAsync(st_d, st_h, 8 * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+        int32_t *crit = reinterpret_cast<int32_t *>(h->q_d + (n + 16));
+        const unsigned ncrit = (unsigned)((n + 127) / 128);
+        bool finished = false;
+        while (!finished) {
+            k_ra_reset<<<1, 8 * RA_BATCH, 0, h->stream>>>(misc_ra, RA_BATCH);
+            HICA_LAUNCHED(h);
+            int rc = with_rank(h, [&](auto *R) {
+                for (int it = 0; it < RA_BATCH; it++) {
+                    int32_t *mi = misc_ra + 8 * it;
+                    k_ra_counts<<<(unsigned)(n - 1) + ncrit, 128, 0, h->stream>>>(R, n, st_d, h->x_d, (int)ncrit, .05, crit);
+                    k_ra_sig<<<ncrit, 128, 0, h->stream>>>(h->x_d, crit, n, st_d, .05, h->sig_d, mi);
+                    k_ra_hits<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->sig_d, n, st_d, (int)min_size, mi);
+                    k_ra_decide<<<1, RA_DECIDE_THREADS, 0, h->stream>>>(st_d, mi, n, (int)min_size, stop_ind, h->x_d, crit, h->sig_d, .05);
+                    h->launches += 4;
+                }
+                HICA_CUDA(cudaGetLastError());
+                return (int)HICA_OK;
+            });
+            if (rc) return rc;
+            HICA_CUDA(cudaMemcpyAsync(st_h, st_d, sizeof(RaState), cudaMemcpyDeviceToHost, h->stream));
+            HICA_CUDA(cudaStreamSynchronize(h->stream));
+            if (st_h->need_host == 2) return hica_set_error(h, HICA_ERR_ARG, "more than %d cut indices", RA_MAX_CUTS);
+            if (st_h->done) break;
+            if (st_h->need_host) {  // the uncommon cases: the host-driven search repeats this one from the same index
+                int64_t first = -1, hits = 0, amb1 = 0;
+                rc = find_breakpoints(h, st_h->ind, min_size, n - st_h->ind, .05, &first, &hits, &amb1);
+                if (rc) return rc;
+                st_h->amb += (int32_t)amb1;
+                st_h->need_host = 0;
+                if (hits == 0) { finished = true; break; }
+                if (st_h->count >= RA_MAX_CUTS) return hica_set_error(h, HICA_ERR_ARG, "more than %d cut indices", RA_MAX_CUTS);
+                st_h->ind += (int32_t)first;
+                st_h->cuts[st_h->count++] = st_h->ind;
+                if (st_h->ind >= stop_ind || (n - st_h->ind) <= min_size) { finished = true; break; }
+                HICA_CUDA(cudaMemcpyAsync(st_d, st_h, sizeof(RaState), cudaMemcpyHostToDevice, h->stream));
+            }
+        }
+        count = st_h->count;
+        amb = st_h->amb;
+        for (int64_t i = 0; i < count && i < capacity; i++)
+            if (cuts_host) cuts_host[i] = st_h->cuts[i];
     }
     *n_cuts = count;
     if (ambiguous) *ambiguous = amb;

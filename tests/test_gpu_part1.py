@@ -427,3 +427,24 @@ def test_linkage_starts_the_presort_and_part1_is_unchanged(hica, n, nc, monkeypa
     ref = part1.run_part1_resident(hica, min_size=5, min_frac=0.0)
     assert list(res["leaves"]) == list(ref["leaves"]) and res["cuts"] == ref["cuts"]
     assert np.array_equal(R, hica.p1_get_rank())
+
+
+@pytest.mark.parametrize("n,nc,seed,min_size,min_frac", [(400, 8, 7, 5, 0.0), (640, 8, 11, 5, 0.05), (900, 12, 3, 3, 0.0),
+                                                         (900, 12, 3, 7, 0.3), (300, 1, 5, 5, 0.0), (60, 3, 1, 5, 0.0),
+                                                         (1600, 20, 9, 5, 0.0), (200, 5, 2, 150, 0.0)])
+def test_run_ahead_break_search_equals_the_host_driven_loop(hica, n, nc, seed, min_size, min_frac, monkeypatch):
+    """hica_p1_breakpoints with the searches driven from device memory (batches, one read-back per batch) against
+    the loop that returns to the host after every search, and against the oracle."""
+    g = make_genome(n, n_chrom=nc, seed=seed, scaffolds_per_chrom=5)
+    A = g.A.numpy()
+    ref = O.part1_cut_indices(A, min_size=min_size, min_frac=min_frac, psig=.05)
+    hica.p1_upload(A)
+    hica.p1_set_row_sums(None)
+    hica.p1_distance()
+    hica.p1_linkage(want_Z=False)
+    hica.p1_rank()
+    fast, amb_fast = hica.p1_breakpoints(min_size, min_frac)
+    monkeypatch.setenv("HICA_CUTS_RUNAHEAD", "0")
+    slow, amb_slow = hica.p1_breakpoints(min_size, min_frac)
+    assert fast == slow == ref["initial_cuts"]
+    assert amb_fast == amb_slow
