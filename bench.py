@@ -396,7 +396,10 @@ def main():
                    "l2": "inputs (%.2f GB matrix) larger than L2; no explicit flush" % (8.0 * n * n / 1e9),
                    "sharding": ("Part1 replicated per rank" if args.replicate_part1 else
                                 "row-block sharded upload + NVLink all-gather of the matrix, linkage on rank 0 + leaf-order "
-                                "broadcast, rank matrix by row block + all-gather, cut searches replicated") +
+                                "broadcast, " + ("rank: value sort on every GPU while the chain runs, local column relabel"
+                                                 if n <= 16384 and os.environ.get("HICA_RANK_OVERLAP", "1") != "0"
+                                                 else "rank matrix by row block + all-gather") +
+                                ", cut searches replicated") +
                                "; Part2 chromosome groups dealt to ranks largest first" if world > 1 else "1 GPU"},
         "seconds": {"part1": last["t_part1"], "part2": last["t_part2"], "total": last["t_total"],
                     "e2e_total": secs_e2e / args.steps, "e2e_part1": res_e2e[-1]["t_part1"],
