@@ -28,6 +28,8 @@
 #include <math.h>
 #include <stdlib.h>
 
+#include <string.h>
+
 #include <algorithm>
 #include <numeric>
 
@@ -261,9 +263,44 @@ int64_t uf_find(std::vector<int64_t> &parent, int64_t x)
 void label_and_order(const std::vector<double> &raw, int64_t n, std::vector<double> &Z, std::vector<int32_t> &leaves)
 {
     const int64_t m = n - 1;
+    // argsort(heights, kind='mergesort') (_hierarchy_impl.py: linkage sorts the nn_chain output stably by height):
+    // a stable LSD radix sort on the order-preserving 64-bit image of the heights, 11 bits per pass, passes on
+    // which all keys agree skipped - 0.15 ms at 16k merges where std::stable_sort with an indirect compare took 1 ms.
+    // (-0.0 and +0.0 compare equal in the reference; both map to the key of +0.0.  NaN heights cannot occur:
+    // every height is an average of finite entries.)
     std::vector<int64_t> idx(m);
-    std::iota(idx.begin(), idx.end(), 0);
-    std::stable_sort(idx.begin(), idx.end(), [&](int64_t a, int64_t b) { return raw[4 * a + 2] < raw[4 * b + 2]; });
+    {
+        std::vector<uint64_t> key(m), key2(m);
+        std::vector<int64_t> idx2(m);
+        uint64_t kor = 0, kand = ~0ull;
+        for (int64_t i = 0; i < m; i++) {
+            double v = raw[4 * i + 2];
+            if (v == 0.0) v = 0.0;
+            uint64_t b;
+            memcpy(&b, &v, 8);
+            b = (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+            key[i] = b;
+            idx[i] = i;
+            kor |= b;
+            kand &= b;
+        }
+        const uint64_t varying = kor ^ kand;
+        std::vector<uint32_t> cnt(2048);
+        for (int shift = 0; shift < 64; shift += 11) {
+            if (((varying >> shift) & 2047ull) == 0) continue;
+            std::fill(cnt.begin(), cnt.end(), 0u);
+            for (int64_t i = 0; i < m; i++) cnt[(key[i] >> shift) & 2047ull]++;
+            uint32_t run = 0;
+            for (int d = 0; d < 2048; d++) { const uint32_t c = cnt[d]; cnt[d] = run; run += c; }
+            for (int64_t i = 0; i < m; i++) {
+                const uint32_t dst = cnt[(key[i] >> shift) & 2047ull]++;
+                key2[dst] = key[i];
+                idx2[dst] = idx[i];
+            }
+            key.swap(key2);
+            idx.swap(idx2);
+        }
+    }
     std::vector<int64_t> parent(2 * n - 1), sz(2 * n - 1, 0);
     std::iota(parent.begin(), parent.end(), 0);
     for (int64_t i = 0; i < n; i++) sz[i] = 1;

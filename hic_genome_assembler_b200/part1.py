@@ -92,27 +92,44 @@ def chromosome_groups_compact(cuts: Sequence[int], leaves: Sequence[int], bin_id
     gid = np.searchsorted(np.asarray(list(cuts), dtype=np.int64), np.arange(n), side="right")
     code_o = code[leaves]
     key = gid * S + code_o
-    uniq, first, counts = np.unique(key, return_index=True, return_counts=True)
+    n_keys = (len(cuts) + 1) * S
+    if n_keys <= (1 << 22):
+        # small key space: counting instead of np.unique's sort (1.2 ms at 16k bins)
+        counts_full = np.bincount(key, minlength=n_keys)
+        uniq = np.nonzero(counts_full)[0]
+        counts = counts_full[uniq]
+        first_full = np.empty(n_keys, dtype=np.int64)
+        first_full[key[::-1]] = np.arange(n - 1, -1, -1)   # repeated index: the last assignment (lowest row) wins
+        first = first_full[uniq]
+    else:
+        uniq, first, counts = np.unique(key, return_index=True, return_counts=True)
     total = np.bincount(code, minlength=S)
     by_scaf = np.lexsort((bin_ids, code))            # bins of every scaffold, ascending bin id
     start = np.concatenate([[0], np.cumsum(total)])
-    n_groups = len(cuts) + 1
-    order = np.lexsort((first, uniq // S))           # (group, first appearance)
+    grp_of, sc = uniq // S, uniq % S
+    # round((float(c) / float(total)) * 100., 2) >= percent_to_assign (:1060-1066), decided without a Python call
+    # per entry: rounding to two decimals moves x by at most 0.005, so only entries within 0.01 of the threshold
+    # need the reference's own round()
+    x = counts.astype(np.float64) / total[sc].astype(np.float64) * 100.
+    assigned = x >= percent_to_assign + 0.01
+    for k in np.nonzero((~assigned) & (x > percent_to_assign - 0.01))[0]:
+        assigned[k] = round(float(x[k]), 2) >= percent_to_assign
+    order = np.lexsort((first, grp_of))              # (group, first appearance)
+    order = order[assigned[order]]
+    sorted_bins = bin_ids[by_scaf]
+    size_arr = np.asarray(scaffold_size_bp, dtype=np.int64)
+    g_of, s_of = grp_of[order].tolist(), sc[order].tolist()
+    lo, hi = start[sc[order]].tolist(), start[sc[order] + 1].tolist()
+    bp_of = size_arr[sc[order]].tolist()
     final, sizes = [], []
-    pos = 0
-    for g in range(n_groups):
-        members, bp = [], 0
-        while pos < len(order) and uniq[order[pos]] // S == g:
-            s = int(uniq[order[pos]] % S)
-            c = int(counts[order[pos]])
-            pct = round((float(c) / float(total[s])) * 100., 2)
-            if pct >= percent_to_assign:
-                members.append((scaffold_names[s], bin_ids[by_scaf[start[s]:start[s + 1]]]))
-                bp += int(scaffold_size_bp[s])
-            pos += 1
-        if members:
-            final.append(members)
-            sizes.append(bp)
+    prev = -1
+    for g, s_, a_, b_, bp in zip(g_of, s_of, lo, hi, bp_of):
+        if g != prev:
+            final.append([])
+            sizes.append(0)
+            prev = g
+        final[-1].append((scaffold_names[s_], sorted_bins[a_:b_]))
+        sizes[-1] += bp
     ranked = sorted(zip(final, sizes), key=lambda p: p[1], reverse=True)
     return [g for g, _ in ranked]
 

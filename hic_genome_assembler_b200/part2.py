@@ -278,25 +278,32 @@ def order_groups_device(h: Handle, genome_index_of_bin: Dict[int, int],
         # initiateBinsAndScaffolds is a stable sort by bin count, descending
         pools = []
         for g in chrom_groups:
-            scafs = [Scaf.__new__(Scaf) for _ in g]
-            for s, (nm, ids) in zip(scafs, g):
-                s.name, s.bins, s.orientation, s.seg = nm, ids, "+", -1
-            pools.append(sorted(scafs, key=lambda s: len(s.bins), reverse=True))
+            lens = np.fromiter((len(ids) for _, ids in g), dtype=np.int64, count=len(g))
+            pools.append([g[i] for i in np.argsort(-lens, kind="stable").tolist()])
         lookup = genome_index_of_bin if isinstance(genome_index_of_bin, np.ndarray) else None
+        all_ids = [ids for pool in pools for _, ids in pool]
+        lens_all = np.fromiter((len(a) for a in all_ids), dtype=np.int64, count=len(all_ids))
+        seg_ptr = np.concatenate([[0], np.cumsum(lens_all)]).tolist()
+        grp_ptr = np.concatenate([[0], np.cumsum([len(p) for p in pools])]).tolist()
+        flat = np.concatenate(all_ids) if all_ids else np.zeros(0, dtype=np.int64)
+        if lookup is not None:
+            rows = lookup[flat]
+        else:
+            rows = np.fromiter((genome_index_of_bin[int(b)] for b in flat), dtype=np.int64, count=len(flat))
+        pool_names = [[nm for nm, _ in pool] for pool in pools]
+        pool_lens = [[len(ids) for _, ids in pool] for pool in pools]
     else:
         pools = [_pool(g) for g in chrom_groups]
-        lookup = None
-    grp_ptr, seg_ptr, rows, nrows = [0], [0], [], 0
-    for pool in pools:
-        for s in pool:
-            if lookup is not None:
-                rows.append(lookup[s.bins])
-            else:
+        grp_ptr, seg_ptr, rows, nrows = [0], [0], [], 0
+        for pool in pools:
+            for s in pool:
                 rows.append(np.fromiter((genome_index_of_bin[int(b)] for b in s.bins), dtype=np.int64, count=len(s.bins)))
-            nrows += len(s.bins)
-            seg_ptr.append(nrows)
-        grp_ptr.append(len(seg_ptr) - 1)
-    rows = np.concatenate(rows) if rows else np.zeros(0, dtype=np.int64)
+                nrows += len(s.bins)
+                seg_ptr.append(nrows)
+            grp_ptr.append(len(seg_ptr) - 1)
+        rows = np.concatenate(rows) if rows else np.zeros(0, dtype=np.int64)
+        pool_names = [[s.name for s in pool] for pool in pools]
+        pool_lens = [[len(s.bins) for s in pool] for pool in pools]
     ks = sorted({min(n_scaffolds, len(p)) for p in pools})
     brute = {k: (order_table(k), orient_table(k)) for k in ks}
     layout, cost, rounds, stats = h.p2_order_groups(grp_ptr, seg_ptr, rows, n_scaffolds, scan, brute,
@@ -304,9 +311,10 @@ def order_groups_device(h: Handle, genome_index_of_bin: Dict[int, int],
     out = []
     for gi, pool in enumerate(pools):
         ent = layout[grp_ptr[gi]:grp_ptr[gi + 1]]
-        out.append([(pool[e >> 1].name, "-" if (e & 1) else "+") for e in ent])
+        names = pool_names[gi]
+        out.append([(names[e >> 1], "-" if (e & 1) else "+") for e in ent.tolist()])
         # algorithmic work = what the reference evaluates: candidates x L(L-1)/2 bin pairs each
-        lens = [len(s.bins) for s in pool]
+        lens = pool_lens[gi]
         k = min(n_scaffolds, len(pool))
         pairs = lambda n: n * (n - 1) // 2  # noqa: E731
         nb = sum(lens[:k])
