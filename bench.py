@@ -78,13 +78,13 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index = index
-        self.samples = []
+        self.samples = []   # (arrival time, csv line)
         self.proc = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "25"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -93,9 +93,11 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.samples.append(line.strip())
+            self.samples.append((time.perf_counter(), line.strip()))
 
-    def stop(self):
+    def stop(self, windows=None):
+        """windows: [(t0, t1), ...] in time.perf_counter() seconds - only samples taken inside a timed region count
+        (the sampler is started before the warm-up so that nvidia-smi's start-up time does not eat the region)."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -104,7 +106,9 @@ class ClockSampler:
         except Exception:
             pass
         sm, mx, reasons = [], [], set()
-        for s in self.samples:
+        for ts, s in self.samples:
+            if windows and not any(a <= ts <= b for a, b in windows):
+                continue
             f = [x.strip() for x in s.split(",")]
             if len(f) < 6:
                 continue
@@ -117,7 +121,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "sampled": "inside the timed regions (value and e2e), every 25 ms"}
 
 
 # ----------------------------------------------------------------------------- one GPU step
@@ -327,19 +331,23 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return results, float(t.item()), h.launches - launches0
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     # warm-up (also JIT-free: everything is precompiled)
     for _ in range(max(args.warmup, 3)):
         gpu_step(h, wl, args, ("device", A_dev.data_ptr()), rank, world, dist)
 
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    w0 = time.perf_counter()
     res_dev, secs_dev, launches = timed(("device", A_dev.data_ptr()), args.steps)
-    clocks = sampler.stop()
+    windows = [(w0, time.perf_counter())]
     # the host-source path has its own first-use costs (NCCL communicators of the row-block gather, pinned
     # staging): warm it up as well, untimed
     for _ in range(2):
         gpu_step(h, wl, args, ("host", wl["A_host"]), rank, world, dist)
+    w0 = time.perf_counter()
     res_e2e, secs_e2e, _ = timed(("host", wl["A_host"]), args.steps)
+    windows.append((w0, time.perf_counter()))
+    clocks = sampler.stop(windows)
 
     # ---- aggregate work over ranks
     n = args.bins
@@ -422,7 +430,7 @@ def main():
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": "nn3::k_nn_chain3 (linkage: one 16-CTA cluster, latency-bound chain)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": NCU_DRAM_BYTES.get(n), "traffic_source": "profiles/r01_ncu_full_summary.txt (ncu --set full, "
+                     "traffic": NCU_DRAM_BYTES.get(n), "traffic_source": "profiles/r01_ncu_full_final2_summary.txt (ncu --set full, "
                      "dram__bytes_read.sum + dram__bytes_write.sum per launch)" if n in NCU_DRAM_BYTES else None,
                      "alg_bytes_per_launch": link_bytes, "peak_source": peak_src, "per_kernel": kernels},
     }
