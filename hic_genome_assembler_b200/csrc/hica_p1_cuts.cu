@@ -341,32 +341,6 @@ __global__ void k_break_hits(const uint8_t *__restrict__ sig, int64_t Lw, int w,
     break_hit_one((int64_t)blockIdx.x * blockDim.x + threadIdx.x, sig, Lw, w, misc);
 }
 
-// filter stage: for every interval [bounds[j-1] or start, bounds[j]) sum the row
-// significances and run the second hypergeometric test (:648-666).
-__global__ void k_filter_intervals(const uint8_t *__restrict__ sig, int64_t start, const int64_t *__restrict__ bounds,
-                                   int nb, long long M, long long local, double psig, int32_t *__restrict__ flags,
-                                   int32_t *__restrict__ misc)
-{
-    int j = blockIdx.x;  // one warp per interval
-    if (j >= nb) return;
-    // fc_prev (:643-655) is `start` for the first bound and the previous bound afterwards;
-    // an interval whose bound equals fc_prev is skipped.
-    const int64_t hi = bounds[j];
-    const int64_t lo = (j == 0) ? start : max(start, bounds[j - 1]);
-    int flag = 0;
-    if (hi > lo) {
-        int cnt = 0;
-        for (int64_t r = lo - start + threadIdx.x; r < hi - start; r += 32) cnt += sig[r];
-        for (int d = 16; d >= 1; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
-        if (threadIdx.x == 0) {
-            int r = hyp_less(cnt, M, local, hi - lo, psig, 0);
-            flag = r & 1;
-            if (r & 2) atomicAdd(&misc[3], 1);
-        }
-    }
-    if (threadIdx.x == 0) flags[j] = flag;
-}
-
 // ---- batched filter stage: every cut of the current list at once (the host loop of :607-700 stops at the
 // first cut with a significant later interval, but the evaluations of one (start, list) are independent, so
 // they run as one set of launches and one read-back instead of one round trip per cut) -------------------
@@ -880,8 +854,6 @@ extern "C" int hica_p1_filter(hica_handle h, const int64_t *cuts_in, int64_t n_i
     std::vector<int64_t> altered(cuts_in, cuts_in + n_in);
     std::set<int64_t> prev_filtered, filtered;
     int64_t amb = 0;
-    int32_t *flags_d = h->misc_d + 16;
-    int32_t *flags_h = h->misc_h + 16;
     for (;;) {
         int64_t start = 0;
         filtered.clear();

@@ -72,3 +72,40 @@ def test_compact_groups_equal_tuple_groups():
     got = part1.chromosome_groups_compact(cuts, leaves, bin_ids, code, names, sizes)
     flat = [[(int(b), nm) for nm, ids in g for b in ids] for g in got]
     assert flat == want
+
+
+def test_compact_groups_assignment_threshold_follows_python_round():
+    """A scaffold belongs to a group when round(100 c / total, 2) >= 51 (:1060-1066).  Shares that land within
+    rounding distance of the threshold (50.995 % ... 51.005 %) must be decided exactly as the reference's round()
+    does, shares far from it take the vectorised path; scaffolds split 50/50 belong to no group."""
+    cases = []   # (bins of the scaffold in group 0, total bins of the scaffold)
+    for tot in (200, 2000, 1999, 1567, 10000, 7919):
+        for c in {int(tot * .51) - 1, int(tot * .51), int(tot * .51) + 1, (tot * 50995) // 100000,
+                  (tot * 50995) // 100000 + 1, (tot * 51005) // 100000, tot // 2, tot}:
+            if 0 < c <= tot:
+                cases.append((c, tot))
+    names, code, sizes = [], [], []
+    in_first = []
+    for s, (c, tot) in enumerate(cases):
+        names.append("s%d" % s)
+        sizes.append(1000 + s)
+        code += [s] * tot
+        in_first += [True] * c + [False] * (tot - c)
+    code = np.array(code)
+    in_first = np.array(in_first)
+    n = len(code)
+    leaves = np.concatenate([np.nonzero(in_first)[0], np.nonzero(~in_first)[0]])
+    cuts = [int(in_first.sum())]
+    bin_ids = np.arange(1, n + 1)
+    want = part1.chromosome_groups(cuts, leaves, bin_ids, [names[c] for c in code], dict(zip(names, sizes)))
+    got = part1.chromosome_groups_compact(cuts, leaves, bin_ids, code, names, sizes)
+    flat = [[(int(b), nm) for nm, ids in g for b in ids] for g in got]
+    assert flat == want
+    # the reference's own expression, entry by entry (the first group is the one that holds a scaffold lying in it
+    # with all its bins)
+    full = {names[s] for s, (c, tot) in enumerate(cases) if c == tot}
+    g0 = [g for g in got if full & {nm for nm, _ in g}]
+    assert len(g0) == 1
+    first_group = {nm for nm, _ in g0[0]}
+    for s, (c, tot) in enumerate(cases):
+        assert (names[s] in first_group) == (round((float(c) / float(tot)) * 100., 2) >= 51.), (c, tot)
