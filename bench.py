@@ -405,7 +405,7 @@ def main():
                    "sharding": ("Part1 replicated per rank" if args.replicate_part1 else
                                 "row-block sharded upload + NVLink all-gather of the matrix, linkage on rank 0 + leaf-order "
                                 "broadcast, " + ("rank: value sort on every GPU while the chain runs, local column relabel"
-                                                 if n <= 16384 and os.environ.get("HICA_RANK_OVERLAP", "1") != "0"
+                                                 if n <= 65535 and os.environ.get("HICA_RANK_OVERLAP", "1") != "0"
                                                  else "rank matrix by row block + all-gather") +
                                 ", cut searches replicated") +
                                "; Part2 chromosome groups dealt to ranks largest first" if world > 1 else "1 GPU"},

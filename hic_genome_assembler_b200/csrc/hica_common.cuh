@@ -49,6 +49,7 @@ struct hica_ctx {
     void *pre_buf = nullptr;     // Rpre (n*n uint16) | tie masks (n * tie_words uint32) | anytie (n) | redo (n) | iota (n)
     int64_t pre_cap = 0;
     bool presort_pending = false, presort_valid = false;
+    int presort_chunk = 0;       // 0: rows pre-sorted by the radix kernels; > 0: chunk-wise by the bitonic network, entries per chunk
     // linkage scratch
     double *Zraw = nullptr;      // (n-1) x 4 raw merges (device)
     int32_t *size_d = nullptr;   // cluster sizes

@@ -48,8 +48,17 @@ __global__ void __launch_bounds__(256) k_reordered(const double *__restrict__ A,
 
 }  // namespace
 
+struct ChunkTarget {       // where a chunked sort reads its labels from and writes its result to
+    const int32_t *order, *pos;
+    void *R;
+    uint32_t *tie;         // pre-sort mode only
+    int tie_words;
+    cudaStream_t stream;
+    bool sync;             // wait for the stream before returning
+};
+
 template <typename PayT, int MAXT>
-static int rank_rows(hica_ctx *h, int q, int64_t P, int64_t lo, int64_t hi)
+static int rank_rows(hica_ctx *h, int q, int64_t P, int64_t lo, int64_t hi, const ChunkTarget &tg)
 {
     using namespace ranksort;
     const int64_t n = h->n;
@@ -59,13 +68,14 @@ static int rank_rows(hica_ctx *h, int q, int64_t P, int64_t lo, int64_t hi)
     const size_t smem = (size_t)(CP + (CP >> 4)) * (8 + sizeof(PayT));
     HICA_CUDA(cudaFuncSetAttribute(k_rank_chunk<PayT, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ChunkArgs a = {};
-    a.A = h->A; a.n = n; a.s_pair = h->s_pair; a.s_seq = h->s_seq; a.order = h->order; a.pos = h->pos;
-    a.kind = h->A_kind; a.q = q; a.P = P; a.R = h->R;
+    a.A = h->A; a.n = n; a.s_pair = h->s_pair; a.s_seq = h->s_seq; a.order = tg.order; a.pos = tg.pos;
+    a.kind = h->A_kind; a.q = q; a.P = P; a.R = tg.R; a.tie = tg.tie; a.tie_words = tg.tie_words;
+    cudaStream_t stream = tg.stream;
     if (nchunks == 1) {
         a.mode = 0; a.write_final = 1;
         for (int64_t r0 = lo; r0 < hi; r0 += 65535) {
             a.row0 = r0;
-            k_rank_chunk<PayT, MAXT><<<dim3(1, (unsigned)std::min<int64_t>(65535, hi - r0)), threads, smem, h->stream>>>(a);
+            k_rank_chunk<PayT, MAXT><<<dim3(1, (unsigned)std::min<int64_t>(65535, hi - r0)), threads, smem, stream>>>(a);
             HICA_LAUNCHED(h);
         }
         HICA_CUDA(cudaGetLastError());
@@ -91,21 +101,21 @@ static int rank_rows(hica_ctx *h, int q, int64_t P, int64_t lo, int64_t hi)
     for (int64_t r0 = lo; r0 < hi; r0 += rows_b) {
         const int64_t rows = std::min(rows_b, hi - r0);
         a.row0 = r0; a.mode = 0; a.write_final = 0;
-        k_rank_chunk<PayT, MAXT><<<dim3((unsigned)nchunks, (unsigned)rows), threads, smem, h->stream>>>(a);
+        k_rank_chunk<PayT, MAXT><<<dim3((unsigned)nchunks, (unsigned)rows), threads, smem, stream>>>(a);
         HICA_LAUNCHED(h);
         for (long long kp = 2ll * CP; kp <= P; kp <<= 1) {
             for (long long j = kp >> 1; j >= CP; j >>= 1) {
                 const int64_t work = (P >> 1) * rows;
-                k_rank_global_step<PayT><<<(unsigned)((work + 255) / 256), 256, 0, h->stream>>>(sk, sp, P, kp, j, rows);
+                k_rank_global_step<PayT><<<(unsigned)((work + 255) / 256), 256, 0, stream>>>(sk, sp, P, kp, j, rows);
                 HICA_LAUNCHED(h);
             }
             a.mode = 1; a.k_merge = kp; a.write_final = (kp == P) ? 1 : 0;
-            k_rank_chunk<PayT, MAXT><<<dim3((unsigned)nchunks, (unsigned)rows), threads, smem, h->stream>>>(a);
+            k_rank_chunk<PayT, MAXT><<<dim3((unsigned)nchunks, (unsigned)rows), threads, smem, stream>>>(a);
             HICA_LAUNCHED(h);
         }
     }
     cudaError_t e = cudaGetLastError();
-    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    if (e == cudaSuccess && tg.sync) e = cudaStreamSynchronize(stream);
     if (e != cudaSuccess) return hica_set_error(h, HICA_ERR_CUDA, "rank: %s", cudaGetErrorString(e));
     return HICA_OK;
 }
@@ -184,12 +194,28 @@ __global__ void k_iota(int32_t *p, int64_t n)
 }
 }  // namespace
 
+static int rank_rows_chunked(hica_ctx *h, int64_t lo, int64_t hi, const ChunkTarget &tg, int *q_out);
+
+// rows that fit one CTA's shared memory are pre-sorted by the radix kernels, longer ones (up to 65,535 entries:
+// 16-bit labels) chunk-wise by the bitonic network (HICA_RANK_ALGO=bitonic forces that path for short rows: tests)
+static bool presort_uses_chunks(hica_ctx *h)
+{
+    const char *algo = getenv("HICA_RANK_ALGO");
+    return h->n > rankremap::MAX_N || (algo && algo[0] == 'b');
+}
+
 bool hica_presort_possible(hica_ctx *h)
 {
     if (const char *e = getenv("HICA_RANK_OVERLAP")) if (atoi(e) == 0) return false;
-    if (const char *e = getenv("HICA_RANK_ALGO")) if (e[0] == 'b') return false;
     if (getenv("HICA_RANK_RADIX64")) return false;  // a test switch of the one-step path
-    return h->A && h->A_kind == 0 && h->have_s_pair && h->have_s_seq && h->n >= 2 && h->n <= rankremap::MAX_N;
+    if (!(h->A && h->A_kind == 0 && h->have_s_pair && h->have_s_seq && h->n >= 2 && h->n <= 65535)) return false;
+    if (h->presort_pending || h->presort_valid) return true;  // made under the settings of its own time
+    if (presort_uses_chunks(h)) {
+        const char *e = getenv("HICA_RANK_OVERLAP_CHUNKED");
+        if (e && atoi(e) == 0) return false;  // 32,000 bins: rank 156.7 -> 3.1 ms on the critical path, linkage 174 -> 190 ms
+        if (rankremap::remap_big_smem(h->n) > 200 * 1024) return false;
+    }
+    return true;
 }
 
 // Enqueue the pre-sort on stream2 behind ev_fork (recorded by the caller on the main stream).  No host sync.
@@ -215,11 +241,20 @@ int hica_presort_start(hica_ctx *h)
     HICA_CUDA(cudaEventRecord(h->ev_pre0, h->stream2));
     k_iota<<<(unsigned)((n + 255) / 256), 256, 0, h->stream2>>>(b.iota, n);
     HICA_LAUNCHED(h);
-    rankradix::RadixArgs a = {};
-    a.A = h->A; a.n = n; a.s_pair = h->s_pair; a.s_seq = h->s_seq; a.order = b.iota; a.pos = b.iota;
-    a.kind = 0; a.R = b.Rpre; a.only = nullptr; a.redo = nullptr;
-    a.tie = b.tie; a.anytie = b.anytie; a.tie_words = b.tie_words;
-    int rc = rank_rows_radix(h, a, 0, n, h->stream2, b.redo);
+    int rc;
+    if (presort_uses_chunks(h)) {
+        const ChunkTarget tg = {b.iota, b.iota, b.Rpre, b.tie, b.tie_words, h->stream2, false};
+        int q = 0;
+        rc = rank_rows_chunked(h, 0, n, tg, &q);
+        h->presort_chunk = 1 << q;
+    } else {
+        rankradix::RadixArgs a = {};
+        a.A = h->A; a.n = n; a.s_pair = h->s_pair; a.s_seq = h->s_seq; a.order = b.iota; a.pos = b.iota;
+        a.kind = 0; a.R = b.Rpre; a.only = nullptr; a.redo = nullptr;
+        a.tie = b.tie; a.anytie = b.anytie; a.tie_words = b.tie_words;
+        rc = rank_rows_radix(h, a, 0, n, h->stream2, b.redo);
+        h->presort_chunk = 0;
+    }
     if (rc) return rc;
     HICA_CUDA(cudaEventRecord(h->ev_pre1, h->stream2));
     h->presort_pending = true;
@@ -248,6 +283,16 @@ static int rank_rows_remap(hica_ctx *h, int64_t lo, int64_t hi)
         h->presort_pending = false;
         h->presort_valid = true;
     }
+    if (h->presort_chunk > 0) {
+        rankremap::RemapBigArgs ra = {b.Rpre, b.tie, b.tie_words, h->order, h->pos, h->n, lo, reinterpret_cast<uint16_t *>(h->R),
+                                      h->presort_chunk, h->A, h->s_pair, h->s_seq};
+        const size_t smem = rankremap::remap_big_smem(h->n);
+        HICA_CUDA(cudaFuncSetAttribute(rankremap::k_rank_remap_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        rankremap::k_rank_remap_big<<<(unsigned)(hi - lo), rankremap::RT, smem, h->stream>>>(ra);
+        HICA_LAUNCHED(h);
+        HICA_CUDA(cudaGetLastError());
+        return HICA_OK;
+    }
     for (int64_t r0 = lo; r0 < hi; r0 += 65535 * 32) {
         const unsigned rows = (unsigned)std::min<int64_t>(65535 * 32, hi - r0);
         rankremap::k_rank_remap<<<rows, rankremap::RT, 0, h->stream>>>(b.Rpre, b.tie, b.anytie, b.tie_words, h->order, h->pos,
@@ -256,6 +301,21 @@ static int rank_rows_remap(hica_ctx *h, int64_t lo, int64_t hi)
     }
     HICA_CUDA(cudaGetLastError());
     return HICA_OK;
+}
+
+static int rank_rows_chunked(hica_ctx *h, int64_t lo, int64_t hi, const ChunkTarget &tg, int *q_out)
+{
+    const int64_t n = h->n;
+    int64_t P = 512;
+    int lg = 9;
+    while (P < n) { P <<= 1; lg++; }
+    int qmax = 14;  // measured at N=16k on B200: q=14 (1024 thr, some spills) 29 ms, q=13 (512 thr, 2 chunks/row) 47 ms
+    if (const char *e = getenv("HICA_RANK_Q")) qmax = std::max(9, std::min(14, atoi(e)));
+    const int q = std::min(lg, qmax);
+    if (q_out) *q_out = q;
+    const int bytes = n <= 65535 ? 2 : 4;
+    if (q == 14) return bytes == 2 ? rank_rows<uint16_t, 1024>(h, q, P, lo, hi, tg) : rank_rows<uint32_t, 1024>(h, q, P, lo, hi, tg);
+    return bytes == 2 ? rank_rows<uint16_t, 512>(h, q, P, lo, hi, tg) : rank_rows<uint32_t, 512>(h, q, P, lo, hi, tg);
 }
 
 // rank rows [lo, hi) of the reordered similarity matrix into R (allocated on first use)
@@ -267,12 +327,6 @@ static int rank_range(hica_ctx *h, int64_t lo, int64_t hi)
     if (h->A_kind == 0 && !h->have_s_pair) return hica_set_error(h, HICA_ERR_STATE, "call hica_p1_distance first");
     const int64_t n = h->n;
     if (lo < 0 || hi > n || lo > hi) return hica_set_error(h, HICA_ERR_ARG, "bad row block [%lld, %lld)", (long long)lo, (long long)hi);
-    int64_t P = 512;
-    int lg = 9;
-    while (P < n) { P <<= 1; lg++; }
-    int qmax = 14;  // measured at N=16k on B200: q=14 (1024 thr, some spills) 29 ms, q=13 (512 thr, 2 chunks/row) 47 ms
-    if (const char *e = getenv("HICA_RANK_Q")) qmax = std::max(9, std::min(14, atoi(e)));
-    const int q = std::min(lg, qmax);
     const int bytes = n <= 65535 ? 2 : 4;
     if (h->R_cap < n * n * bytes) {  // grow-only: cudaMalloc/cudaFree of 0.5 GB per call costs tens of ms
         if (h->R) { cudaFree(h->R); h->R = nullptr; }
@@ -297,8 +351,8 @@ static int rank_range(hica_ctx *h, int64_t lo, int64_t hi)
         rc = rank_rows_radix(h, lo, hi);
     } else {
         // longer rows (or HICA_RANK_ALGO=bitonic): chunked bitonic network with global merge steps
-        if (q == 14) rc = bytes == 2 ? rank_rows<uint16_t, 1024>(h, q, P, lo, hi) : rank_rows<uint32_t, 1024>(h, q, P, lo, hi);
-        else rc = bytes == 2 ? rank_rows<uint16_t, 512>(h, q, P, lo, hi) : rank_rows<uint32_t, 512>(h, q, P, lo, hi);
+        const ChunkTarget tg = {h->order, h->pos, h->R, nullptr, 0, h->stream, true};
+        rc = rank_rows_chunked(h, lo, hi, tg, nullptr);
     }
     if (rc) return rc;
     t.stop();

@@ -120,4 +120,129 @@ __global__ void __launch_bounds__(RT) k_rank_remap(const uint16_t *__restrict__ 
     for (int64_t j = t; j < n; j += RT) out[j] = V[j];
 }
 
+// The same for rows of up to 65,535 entries that were pre-sorted chunk-wise by the bitonic network
+// (hica_p1_ranksort.cuh): row storage in dynamic shared memory, the any-tie flag is derived from the mask, and the
+// tie bit of the first entry of every chunk (which the chunk kernel cannot see) is decided here from the values.
+struct RemapBigArgs {
+    const uint16_t *Rpre;
+    const uint32_t *tie;
+    int tie_words;
+    const int32_t *order, *pos;
+    int64_t n, row0;
+    uint16_t *R;
+    int chunk;                  // entries per sorted chunk (power of two)
+    const double *A;            // the resident contact matrix and its row sums (key of one entry = the rank kernels')
+    const double *s_pair, *s_seq;
+};
+
+inline size_t remap_big_smem(int64_t n)
+{
+    const size_t tw = (size_t)((n + 31) / 32), max_long = (size_t)(n / (SHORT_RUN + 1) + 1);
+    return ((size_t)n * 2 + 15) / 16 * 16 + tw * 4 * 2 + max_long * 4 * 2 + 64;
+}
+
+__global__ void __launch_bounds__(RT) k_rank_remap_big(RemapBigArgs a)
+{
+    extern __shared__ __align__(16) unsigned char dsm[];
+    const int64_t n = a.n;
+    const int tie_words = a.tie_words;
+    const int max_long = (int)(n / (SHORT_RUN + 1) + 1);
+    uint16_t *V = reinterpret_cast<uint16_t *>(dsm);
+    uint32_t *T = reinterpret_cast<uint32_t *>(dsm + ((size_t)n * 2 + 15) / 16 * 16);
+    uint32_t *bitmap = T + tie_words;
+    int *run_start = reinterpret_cast<int *>(bitmap + tie_words);
+    int *run_len = run_start + max_long;
+    __shared__ int nlong, any_s;
+    __shared__ uint32_t wsum[RT / 32];
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const int64_t row = a.row0 + blockIdx.x;
+    const int64_t arow = a.order[row];
+    const uint16_t *src = a.Rpre + arow * n;
+    uint16_t *out = a.R + row * n;
+    if (t == 0) { nlong = 0; any_s = 0; }
+    for (int i = t; i < tie_words; i += RT) T[i] = a.tie[arow * tie_words + i];
+    __syncthreads();
+    // first entry of every chunk: tied to the last entry of the chunk before it?
+    {
+        const double sp = a.s_pair[arow], rs = a.s_seq[arow];
+        const double *Arow = a.A + arow * n;
+        for (int64_t b = (int64_t)a.chunk * (t + 1); b < n; b += (int64_t)a.chunk * RT) {
+            const double v0 = sim_transform(dist_transform(Arow[src[b - 1]], sp), rs);
+            const double v1 = sim_transform(dist_transform(Arow[src[b]], sp), rs);
+            if (rankradix::okey(v0) == rankradix::okey(v1)) atomicOr(&T[b >> 5], 1u << (b & 31));
+        }
+    }
+    __syncthreads();
+    {
+        uint32_t any = 0;
+        for (int i = t; i < tie_words; i += RT) any |= T[i];
+        if (any) any_s = 1;
+    }
+    for (int64_t j = t; j < n; j += RT) V[j] = (uint16_t)a.pos[src[j]];
+    __syncthreads();
+    if (any_s) {
+        auto bit = [&](int j) { return (T[j >> 5] >> (j & 31)) & 1u; };
+        for (int j = t; j + 1 < (int)n; j += RT) {
+            if (bit(j) || !bit(j + 1)) continue;
+            int q = j + 1;
+            while (q < (int)n) {
+                const uint32_t inv = ~T[q >> 5] >> (q & 31);
+                if (inv) { q += __ffs(inv) - 1; break; }
+                q = (q | 31) + 1;
+            }
+            if (q > (int)n) q = (int)n;
+            const int len = q - j;
+            if (len <= SHORT_RUN) {
+                for (int x = 1; x < len; x++) {
+                    const uint16_t v = V[j + x];
+                    int y = x - 1;
+                    while (y >= 0 && V[j + y] < v) { V[j + y + 1] = V[j + y]; y--; }
+                    V[j + y + 1] = v;
+                }
+            } else {
+                const int k = atomicAdd(&nlong, 1);
+                run_start[k] = j;
+                run_len[k] = len;
+            }
+        }
+        __syncthreads();
+        const int nl = nlong;
+        const int wpt = (tie_words + RT - 1) / RT;           // bitmap words per thread, contiguous
+        const int w_lo = min(tie_words, t * wpt), w_hi = min(tie_words, w_lo + wpt);
+        for (int r = 0; r < nl; r++) {
+            const int j0 = run_start[r], len = run_len[r];
+            for (int i = t; i < tie_words; i += RT) bitmap[i] = 0u;
+            __syncthreads();
+            for (int q = t; q < len; q += RT) {
+                const uint32_t v = V[j0 + q];
+                atomicOr(&bitmap[v >> 5], 1u << (v & 31));
+            }
+            __syncthreads();
+            uint32_t c = 0;
+            for (int i = w_lo; i < w_hi; i++) c += __popc(bitmap[i]);
+            uint32_t incl = c;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += v;
+            }
+            if (lane == 31) wsum[w] = incl;
+            __syncthreads();
+            uint32_t below = incl - c;
+            for (int i = 0; i < w; i++) below += wsum[i];
+            for (int i = w_lo; i < w_hi; i++) {
+                uint32_t word = bitmap[i];
+                while (word) {
+                    const int b = __ffs(word) - 1;
+                    word &= word - 1;
+                    V[j0 + len - 1 - (int)below] = (uint16_t)(i * 32 + b);
+                    below++;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int64_t j = t; j < n; j += RT) out[j] = V[j];
+}
+
 }  // namespace rankremap

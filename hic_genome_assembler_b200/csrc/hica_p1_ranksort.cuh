@@ -76,6 +76,11 @@ struct ChunkArgs {
     void *R;                 // final rank rows [n][n]
     int64_t row0;            // first (reordered) row of this batch
     int write_final;         // 1: write R, 0: write scratch
+    // pre-sort mode (hica_p1_rank_presort): bit j of tie[row * tie_words + j / 32] = "entry j of the output row has the
+    // same key as entry j - 1", for every j that is not the first entry of a chunk (those bits are left 0 and are
+    // decided by k_rank_remap_big, which sees both chunks).  NULL otherwise.
+    uint32_t *tie;
+    int tie_words;
 };
 
 __device__ __forceinline__ unsigned long long order_key(double v)
@@ -229,6 +234,15 @@ __global__ void __launch_bounds__(MAXT, 1) k_rank_chunk(ChunkArgs a)
         for (int i = t; i < CP; i += T) {
             const long long b = base + i;
             if (b < a.n) out[b] = spay[pad(i)];
+        }
+        if (a.tie) {  // CP and T are multiples of 32: every warp covers 32 consecutive, 32-aligned entries
+            uint32_t *tw = a.tie + row * a.tie_words;
+            for (int i = t; i < CP; i += T) {
+                const long long b = base + i;
+                const bool tie = i > 0 && b < a.n && skeys[pad(i)] == skeys[pad(i - 1)];
+                const unsigned m = __ballot_sync(0xffffffffu, tie);
+                if (lane == 0 && b < a.n) tw[b >> 5] = m;
+            }
         }
     } else {
         unsigned long long *gk = a.sk + (int64_t)rowb * a.P + base;

@@ -145,10 +145,12 @@ def run_part1_resident_sharded(h, device, min_size: int = 5, min_frac: float = .
     h.p1_distance()
     leaves_t = torch.empty(n, dtype=torch.int32, device=device)
     leaves = None
-    # n <= 16384: every GPU sorts all rows by value in matrix order while the linkage chain runs (the linkage GPU
+    # n <= 65535: every GPU sorts all rows by value in matrix order while the linkage chain runs (the linkage GPU
     # on its 132 free SMs - hica_p1_linkage starts that itself - the others while they wait for the broadcast);
-    # the rank step is then a local column relabel and needs no gather
-    presort = n <= 16384 and os.environ.get("HICA_RANK_OVERLAP", "1") != "0"
+    # the rank step is then a local column relabel and needs no gather.  (If the library declines the pre-sort,
+    # p1_rank simply sorts all rows in one step on every GPU: still correct, no gather either.)
+    presort = n <= 65535 and os.environ.get("HICA_RANK_OVERLAP", "1") != "0" and (
+        n <= 16384 or os.environ.get("HICA_RANK_OVERLAP_CHUNKED", "1") != "0")
     if presort and rank != linkage_rank:
         h.p1_rank_presort()
     if rank == linkage_rank:

@@ -144,8 +144,11 @@ int hica_p1_rank(hica_handle h);
  * explicitly on GPUs that wait for another GPU's linkage.  A later hica_p1_rank
  * / hica_p1_rank_rows then only relabels the columns and orders exact ties
  * (HICA_T_RANK = that part, HICA_T_RANK_PRESORT = the overlapped sort).
- * Needs the ICE matrix, hica_p1_set_row_sums and hica_p1_distance; n <= 16384
- * (longer rows keep the one-step sort).  HICA_RANK_OVERLAP=0 disables it. */
+ * Needs the ICE matrix, hica_p1_set_row_sums and hica_p1_distance; n <= 65535
+ * (16-bit column labels; rows of up to 16,384 entries are sorted by the radix
+ * kernels, longer ones chunk-wise by the bitonic network).
+ * HICA_RANK_OVERLAP=0 disables it, HICA_RANK_OVERLAP_CHUNKED=0 only for the
+ * chunk-wise path. */
 int hica_p1_rank_presort(hica_handle h);
 
 /* Row-block sharded form of hica_p1_rank (:1132): rank rows

@@ -448,3 +448,43 @@ def test_run_ahead_break_search_equals_the_host_driven_loop(hica, n, nc, seed, m
     slow, amb_slow = hica.p1_breakpoints(min_size, min_frac)
     assert fast == slow == ref["initial_cuts"]
     assert amb_fast == amb_slow
+
+
+@pytest.mark.parametrize("n,q,zero_frac", [(33, 9, 0.3), (700, 9, 0.3), (1500, 9, 0.6), (2049, 10, 0.05), (1500, 14, 0.3)])
+def test_presorted_rank_through_the_chunked_bitonic_sort(hica, n, q, zero_frac, monkeypatch):
+    """Rows longer than one CTA's shared memory are pre-sorted chunk-wise by the bitonic network (forced here at
+    small n with small chunks): tie masks come from the chunk kernel, the tie bit at every chunk boundary and the
+    order inside runs of equal keys from k_rank_remap_big.  Same result as the oracle's stable-reversed argsort."""
+    monkeypatch.setenv("HICA_RANK_ALGO", "bitonic")
+    monkeypatch.setenv("HICA_RANK_Q", str(q))
+    A = _planted_ties(n, 31 * n + 7, zero_frac)
+    rs = O.sequential_row_sums(A)
+    D = O.convert_distance(A)
+    hica.p1_upload(A)
+    hica.p1_set_row_sums(rs)
+    hica.p1_distance()
+    hica.p1_rank_presort()
+    for seed in (0, 1):
+        order = np.random.RandomState(n + seed).permutation(n)
+        hica.p1_set_order(order)
+        if seed == 0:
+            hica.p1_rank()
+            assert hica.timers()["rank_presort"] > 0.0
+        else:
+            hica.p1_rank_rows(n // 3, n)
+            hica.p1_rank_rows(0, n // 3)
+            hica.p1_rank_commit()
+        S = O.convert_similarity(O.reorder(D, order), rs[order])
+        assert np.array_equal(hica.p1_get_rank(), O.rank_matrix_stable(S))
+    # and through the linkage (which starts the pre-sort itself)
+    g = make_genome(max(n, 60), n_chrom=3, seed=n, scaffolds_per_chrom=4)
+    from hic_genome_assembler_b200 import part1
+    hica.p1_upload(g.A.numpy())
+    res = part1.run_part1_resident(hica, min_size=5, min_frac=0.0)
+    assert hica.timers()["rank_presort"] > 0.0
+    R = hica.p1_get_rank()
+    monkeypatch.setenv("HICA_RANK_OVERLAP", "0")
+    hica.p1_upload(g.A.numpy())
+    ref = part1.run_part1_resident(hica, min_size=5, min_frac=0.0)
+    assert list(res["leaves"]) == list(ref["leaves"]) and res["cuts"] == ref["cuts"]
+    assert np.array_equal(R, hica.p1_get_rank())
