@@ -187,3 +187,19 @@ def test_log_transform_seam_equals_the_reference(tmp_path):
         assert np.array_equal(np.asarray(seam(A, logBase=10)), f)
         assert np.array_equal(np.asarray(seam(f, logBase=10, reverse=True)),
                               np.asarray(mod.logTransformMatrix(f, logBase=10, reverse=True)))
+
+
+def test_native_loader_on_the_golden_hicpro_files():
+    """The committed HiC-Pro inputs of the golden pipeline run (bed + biases + iced matrix, written for the
+    unmodified reference by tests/golden/make_golden.py): loci, matrix, zero-row removal and row sums through the
+    native loader equal the Python restatement of the reference's loaders."""
+    d = os.path.join(os.path.dirname(__file__), "golden", "pipeline_320", "in")
+    bins = hio.read_loci(os.path.join(d, "synth_abs.bed"), os.path.join(d, "synth_iced.matrix.biases"))
+    want = hio.read_matrix(os.path.join(d, "synth_iced.matrix"), bins)
+    got = hio.read_matrix_native(os.path.join(d, "synth_iced.matrix"), bins, threads=4)
+    assert got.shape == (len(bins), len(bins)) and np.array_equal(got, want)
+    A1, b1 = hio.remove_zero_rows(want.copy(), list(bins))
+    with contextlib.redirect_stdout(_io.StringIO()):
+        A2, b2 = hio.removeRows(got.copy(), [hio.Bin(b.ID, b.chrom, b.start, b.stop, b.bias) for b in bins])
+    assert np.array_equal(A1, A2) and [b.ID for b in b1] == [b.ID for b in b2]
+    assert [float(b.rowSum) for b in b1] == [float(b.rowSum) for b in b2]
