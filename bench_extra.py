@@ -1,0 +1,182 @@
+"""bench.py's other BASELINE.json configurations (imported by bench.py, same JSON contract).
+
+candidates_config   configs[2]: "batched scoring of 10^5 candidate permutations/orientations per chromosome,
+                    sharded 1/2/4/8 GPUs" (orderGenome.py:432-473 / :513-541).  SURVEY 8d fixes the batch: the first
+                    10^5 candidates of the n = 7 enumeration (322,560 in all) on an L = 800 chromosome, every one
+                    scored EXACTLY by K8 (numba's summation order) on the full chromosome matrix; the candidate
+                    range is split over the ranks and the winner is the first strict maximum over all of them -
+                    an arg-max on (score, -index) (dist.reduce_first_max).
+config_10kb         configs[4]: 160,000 bins, fp32 matrix sharded by row block over the GPUs, linkage on one GPU.
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+
+# DRAM / L2 bytes of one k_score launch of this configuration (ncu --set full; profiles/r02_k_score_*.txt)
+NCU_K_SCORE = {}
+
+
+def _chromosome(seed, device):
+    """One chromosome of the 100 kb genome: 800 bins in 40 scaffolds (portable generator)."""
+    from hic_genome_assembler_b200.synth import make_genome_portable
+    g = make_genome_portable(800, n_chrom=1, seed=seed, scaffolds_per_chrom=40, device=device)
+    names = [g.scaffold_names[s] for s in g.scaffold_of_bin]
+    return g, [(i + 1, names[i]) for i in range(800)]
+
+
+def candidates_config(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    import bench as B
+    from hic_genome_assembler_b200 import dist as hdist, part2
+    from hic_genome_assembler_b200._lib import Handle
+    dev = torch.device("cuda", local_rank)
+    g, nodes = _chromosome(args.seed, dev)
+    A_pinned = torch.empty(g.A.shape, dtype=torch.float64, pin_memory=True)
+    A_pinned.copy_(g.A)
+    torch.cuda.synchronize()
+    A_host = A_pinned.numpy()
+    index_of = {i + 1: i for i in range(800)}
+    NC, WIN = 100000, 7
+    orders, orients = part2.order_table(WIN), part2.orient_table(WIN)
+    per = (NC + world - 1) // world
+    lo, hi = min(NC, rank * per), min(NC, (rank + 1) * per)
+    h = Handle(local_rank)
+    pool = part2._pool(nodes)
+    L = sum(len(s.bins) for s in pool)
+    pairs = L * (L - 1) // 2
+
+    def setup():
+        """Host matrix -> device, the chromosome registered as segments (what orderChromosome does once)."""
+        h.p2_upload(A_host)
+        chrom = part2.DeviceChromosome(h, index_of, pool)
+        total = chrom.total(pool)
+        return [s.entry() for s in pool], total
+
+    def score(base, total):
+        best, idx = 0.0, -1
+        if hi > lo:
+            best, idx, _ = h.p2_score_window(base, 0, WIN, orders, orients, total, 0.0, cand_lo=lo, cand_hi=hi)
+        return hdist.reduce_first_max(best, idx, 0.0, device=dev)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(steps, with_setup):
+        out, kms = [], []
+        base, total = setup()
+        barrier()
+        l0 = h.launches
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(steps):
+            if with_setup:
+                base, total = setup()
+            out.append(score(base, total))
+            kms.append(h.timers()["p2_score"])
+        e1.record()
+        barrier()
+        secs = max(time.perf_counter() - t0, e0.elapsed_time(e1) / 1e3)
+        t = torch.tensor([secs], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return out, float(t.item()), kms, h.launches - l0
+
+    sampler = B.ClockSampler(local_rank)
+    sampler.start()
+    timed(max(args.warmup, 3), True)
+    w0 = time.perf_counter()
+    res, secs, kms, launches = timed(args.steps, False)
+    windows = [(w0, time.perf_counter())]
+    w0 = time.perf_counter()
+    res2, secs2, _, _ = timed(args.steps, True)
+    windows.append((w0, time.perf_counter()))
+    clocks = sampler.stop(windows)
+    kt = torch.tensor([float(np.mean(kms))], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(kt, op=dist.ReduceOp.MAX)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+    # ---- parity: the sharded winner == the single-GPU winner over the whole range == the C oracle on a prefix
+    base, total = setup()
+    best1, idx1, _ = h.p2_score_window(base, 0, WIN, orders, orients, total, 0.0, cand_lo=0, cand_hi=NC)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import c_oracle as CO
+    import fast_oracle as FO
+    NP = 3000
+    scafs = [FO.FScaf(s.name, s.bins) for s in pool]
+    lut = np.concatenate([[-1], np.arange(800)])
+    M, local = FO._sub(A_host, lut, scafs)
+    cands = []
+    n_or = orients.shape[0]
+    for c in range(NP):
+        oi, ri = divmod(c, n_or)
+        win = [(scafs[int(orders[oi][j])], "-" if orients[ri][j] else "+") for j in range(WIN)]
+        cands.append(win + [(s, "+") for s in scafs[WIN:]])
+    t0 = time.perf_counter()
+    ob, oidx, osc = CO.score_batch(M, FO._rows(cands, local), CO.total_weight(M), 0.0, want_scores=True)
+    t_c = time.perf_counter() - t0
+    gb, gidx, gsc = h.p2_score_window(base, 0, WIN, orders, orients, total, 0.0, cand_lo=0, cand_hi=NP, want_scores=True)
+    parity = {"sharded_equals_single_gpu": bool(all(r == (best1, idx1) for r in res + res2)),
+              "first_%d_scores_bitwise_equal_c_oracle" % NP: bool(np.array_equal(gsc, osc) and (gb, gidx) == (ob, oidx)),
+              "winner": [best1, int(idx1)]}
+    # ---- CPU baseline: the reference's own inner loop (ix_ gather + numba score, orderGenome.py:463) on a sample
+    import hica_oracle as O
+    O.ordering_cost_numba(M[:16, :16], 1.0)
+    rows = FO._rows(cands[:1500], local)
+    t0 = time.perf_counter()
+    tw = O.total_weight(M)
+    for r in rows:
+        O.ordering_cost_numba(M[np.ix_(r, r)], tw)
+    t_cpu = time.perf_counter() - t0
+    peak, peak_src = B.hbm_peak()
+    k_ms = float(kt.item())
+    alg = 8.0 * per * pairs
+    achieved = alg / (k_ms / 1e3) / 1e9
+    line = {
+        "metric": "Part2 candidate scoring: bin-pairs/s over 10^5 exactly scored candidates (L=800)",
+        "value": NC * pairs / (secs / args.steps), "unit": "bin-pairs/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": secs / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "first 100,000 candidates of the n=7 order x orientation enumeration (322,560), each scored "
+                               "on the full 800-bin chromosome (40 scaffolds) - BASELINE configs[2]",
+                   "candidates": NC, "bins": L, "pairs_per_candidate": pairs, "seed": args.seed,
+                   "l2": "the 5.1 MB chromosome matrix is L2-resident by design (SURVEY 8d): rate quoted against HBM, dram/lts bytes alongside",
+                   "sharding": "candidate range split over %d rank(s) + arg-max all-gather on (score, -index)" % world},
+        "candidates_per_s": NC / (secs / args.steps),
+        "parity": parity,
+        "e2e": {"value": NC * pairs / (secs2 / args.steps), "unit": "bin-pairs/s", "ms_per_step": secs2 / args.steps * 1e3,
+                "h2d_bytes_per_step": int(A_host.nbytes + 4 * 800 * 2 + orders.size + orients.size + 4 * len(pool)),
+                "d2h_bytes_per_step": 24, "note": "chromosome matrix from pinned host memory + segment tables + scoring + result"},
+        "gpu_launches": int(launches), "clocks": clocks,
+        "roofline": {"bound": "hbm", "kernel": "k_score (K8: exact ordering score, one candidate per CTA)", "achieved": achieved,
+                     "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+                     "alg_bytes_per_launch": alg, "kernel_ms": k_ms,
+                     "traffic": NCU_K_SCORE.get("dram_bytes"), "lts_bytes": NCU_K_SCORE.get("lts_bytes"),
+                     "note": "frac > 1 is an L2 rate: every candidate re-reads the same 5.1 MB matrix"},
+        "cpu_baseline": {"value": len(rows) * pairs / t_cpu, "unit": "bin-pairs/s", "cores": 1, "kind": "port",
+                         "sample": "numpy.ix_ gather + numba costFunction (orderGenome.py:463) on the first %d candidates, %.1f s; "
+                                   "C restatement of the score alone: %d candidates in %.2f s" % (len(rows), t_cpu, NP, t_c)},
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0 if all(v is True for k, v in parity.items() if k != "winner") else 3
+
+
+def config_10kb(args, rank, world, local_rank):
+    from hic_genome_assembler_b200 import dist10kb
+    return dist10kb.bench(args, rank, world, local_rank)

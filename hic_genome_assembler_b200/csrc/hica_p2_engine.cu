@@ -15,10 +15,21 @@
 //   2. every candidate within a relative 1e-10 of the best closed-form score (or of the carried best cost)
 //      is re-scored with the bit-exact numba-order routine, and the reference's accept rule (first strict
 //      maximum above the carried cost) is applied to those exact scores.
-// The closed form differs from numba's summation order only by rounding (<= ~3n ulp, 3e-13 relative at
-// n = 800, for non-negative symmetric contacts), so the exact winner is always inside the re-scored set and
-// the result is bit-identical to scoring every candidate exactly.  Matrices with negative or asymmetric
-// entries (for which that bound does not hold) are detected at gather time and re-scored in full.
+// Why the exact winner is always inside the re-scored set (non-negative symmetric contacts; matrices with
+// negative or asymmetric entries are detected at gather time and re-scored in full).  With u = 2^-53, a
+// candidate's score is a sum of T = n(n-1)/2 non-negative terms M[a][b] * w(b-a).  The weights carry a relative
+// error of at most (n+2)u (a sum of <= n positive reciprocals, one subtraction-free suffix, one division), and
+// ANY summation order of T non-negative terms has a relative error of at most (T-1)u / (1 - (T-1)u) (Higham,
+// Accuracy and Stability of Numerical Algorithms, section 4.2) - so the closed form, whatever the shape of its
+// table reductions, is within (T + n + 2)u of the true value relative to the largest score in play.  The
+// numba-order routine sums the same terms along diagonals (<= 2n additions on any path), divides twice and
+// adds n quotients: within (3n + 2)u.  Anchoring on the exact cost of the current layout subtracts two such
+// quantities.  near_tol(n) = max(1e-10, 4 (T + 4n + 4) u) therefore bounds |closed form - exact| / scale with
+// a factor >= 2 to spare at every n: 1.4e-10 at n = 800, 5.7e-10 at 1,600, 1.4e-8 at 8,000 (the fixed 1e-10 of
+// round 1 was only argued for n <= ~1,000).  The insertion step's closed form has terms of both signs
+// (weight differences Hp[d-1] - Hp[d+Ls-1]); there the tolerance is taken relative to H_{n-1} |total|, which
+// bounds the sum of the ABSOLUTE terms, and the same any-order bound applies.  A wider tolerance costs exact
+// re-scores, never correctness.
 #include <cooperative_groups.h>
 #include <limits.h>
 #include <math.h>
@@ -53,7 +64,12 @@ __device__ __forceinline__ bool exact_cost_cluster(const double *__restrict__ S,
     cl.sync();  // CTA 0 is done with tr: the next candidate may overwrite it
     return part == 0;
 }
-constexpr double NEAR_TOL = 1e-10;
+__host__ __device__ inline double near_tol(int n)
+{
+    const double T = 0.5 * (double)n * (double)(n - 1) + 4.0 * (double)n + 4.0;
+    const double t = 4.0 * T * 1.1102230246251565e-16;
+    return t > 1e-10 ? t : 1e-10;
+}
 
 struct WinState {  // per evaluated window: best closed-form score, that of the current arrangement, near list size
     unsigned long long amax_key;
@@ -450,7 +466,7 @@ __global__ void __launch_bounds__(256) k_g_select(const GroupDev *gs, Phase ph, 
     const double amax = st->E_layout + (f64_from_order_key(wv.ws->amax_key) - wv.ws->rel0);
     const double carried = ph.kind == PH_SCAN ? st->best_cost : 0.0;
     const double scale = fmax(fabs(amax), fmax(fabs(carried), fabs(st->E_layout)));
-    const double thr = fmax(amax, carried) - NEAR_TOL * scale;
+    const double thr = fmax(amax, carried) - near_tol(g.L) * scale;
     const double a = st->E_layout + (wv.rel[c] - wv.ws->rel0);
     if (st->inexact || !(a < thr)) {
         const int slot = atomicAdd(&wv.ws->near_count, 1);
@@ -560,7 +576,7 @@ __global__ void __launch_bounds__(256) k_g_pick_window(const GroupDev *gs, Phase
 // F(p_i) = sum_{a < p_i} D[a] with  D[a] = sum_{b >= end(a)} g(a, b) - sum_{b < start(a)} g(b, a),  start/end = the
 // bounds of the scaffold that holds position a: a pair in different scaffolds counts +1 while only its left end
 // is left of p, which is exactly "straddles p".  So one pass over the placed matrix gives all m+1 values of F.
-// Candidates within NEAR_TOL (relative to an upper bound of any score) of the best closed-form score are
+// Candidates within near_tol(n) (relative to an upper bound of any score) of the best closed-form score are
 // re-scored bit-exactly and the reference's rule (first maximum, strictly above 0.) is applied to those.
 struct InsertCand { int i, ori; };
 __device__ __forceinline__ InsertCand insert_cand(int c, int ne)
@@ -676,7 +692,7 @@ __global__ void __launch_bounds__(128) k_g_ins_select(const GroupDev *gs, Phase 
     // is taken relative to that bound, which needs no absolute anchor.  Whether the best score beats the
     // initial bestCost of 0. (:338) is decided on the exact scores in k_g_pick_insert.
     const double hn = g.Hp[pp.n - 1] * fabs(st->total);  // the closed-form scores of this step are total x cost
-    const double thr = f64_from_order_key(st->w0.amax_key) - NEAR_TOL * hn;
+    const double thr = f64_from_order_key(st->w0.amax_key) - near_tol(pp.n) * hn;
     for (int c = threadIdx.x; c < B; c += blockDim.x) {
         const bool near = all || !(g.rel[c] < thr);
         if (near) g.near_id[atomicAdd(&st->w0.near_count, 1)] = c;

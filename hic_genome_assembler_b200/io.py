@@ -136,6 +136,13 @@ def logTransformMatrix(matrix, logBase=10, reverse=False, _offset=1.0):
     """Seam for scaffoldToChromosomes.logTransformMatrix (:165-183: log(v + 1) / base**v - 1): same arguments, same
     values bit for bit (libm log / pow on the host, all cores), returned as numpy.matrix like the original."""
     from ._lib import io_log_transform
+    from .lazy import LazyMatrix
+    if isinstance(matrix, LazyMatrix) and not matrix.materialised:
+        # device-backed input (runPipeline :1135, :1155 - the result feeds plots and the Louvain tail only): defer
+        src = matrix
+        return LazyMatrix(src.shape, lambda: io_log_transform(np.asarray(src.materialise(), dtype=np.float64),
+                                                              float(logBase), bool(reverse), offset=_offset),
+                          None, "log" if not reverse else "unlog")
     M = np.asarray(np.asmatrix(matrix), dtype=np.float64)
     return np.asmatrix(io_log_transform(M, float(logBase), bool(reverse), offset=_offset))
 

@@ -22,11 +22,35 @@ import sys
 import types
 
 from ._lib import Handle
+from .lazy import LazyMatrix, LazyRank
 from .part1 import Seams as Part1Seams
 from .part2 import _Seams as Part2Seams
 
 _OPTIONAL = ("hmmlearn", "hmmlearn.hmm", "community", "matplotlib", "matplotlib.pyplot", "matplotlib.colors",
              "matplotlib.patches", "xarray")
+
+
+class _StubModule(types.ModuleType):
+    """Stand-in for an optional package that is not installed: any attribute is a do-nothing callable that can
+    itself be called, indexed into or used as a namespace (``matplotlib.use('Agg')``, ``plt.cm.Reds`` ...)."""
+
+    def __getattr__(self, name):
+        if name.startswith("__") and name.endswith("__"):
+            raise AttributeError(name)
+        return _StubAttr(self.__name__ + "." + name)
+
+
+class _StubAttr:
+    def __init__(self, name):
+        self._name = name
+
+    def __call__(self, *a, **k):
+        return _StubAttr(self._name + "()")
+
+    def __getattr__(self, name):
+        if name.startswith("__") and name.endswith("__"):
+            raise AttributeError(name)
+        return _StubAttr(self._name + "." + name)
 
 
 def _stub_missing_optional_modules(verbose=True):
@@ -40,7 +64,7 @@ def _stub_missing_optional_modules(verbose=True):
         try:
             importlib.import_module(name)
         except Exception:
-            m = types.ModuleType(name)
+            m = _StubModule(name)
             sys.modules[name] = m
             if "." in name:
                 setattr(sys.modules[name.split(".")[0]], name.split(".")[1], m)
@@ -69,9 +93,22 @@ class _NumpyShim(types.ModuleType):
             return _DescendingRank(self.__dict__["_seams"].argsort_desc(a))
         return real.argsort(a, axis, *args, **kwargs)
 
+    # runPipeline wraps what the seams return in numpy.asmatrix (:1123) / numpy.asarray (:1132): device-backed
+    # objects pass through untouched, so that the next seam still recognises them
+    def asmatrix(self, data, dtype=None):
+        if isinstance(data, LazyMatrix) and dtype is None:
+            return data
+        return self.__dict__["_real"].asmatrix(data, dtype)
+
+    def asarray(self, a, dtype=None, *args, **kwargs):
+        if isinstance(a, (LazyMatrix, LazyRank)) and dtype is None and not args and not kwargs:
+            return a
+        return self.__dict__["_real"].asarray(a, dtype, *args, **kwargs)
+
 
 class _DescendingRank:
-    """Result of the shimmed argsort: the reference immediately takes ``[:, ::-1]`` of it."""
+    """Result of the shimmed argsort: the reference immediately takes ``[:, ::-1]`` of it, which gives back the
+    device-resident descending rank (a LazyRank); any other use sees the ascending int64 host array."""
 
     def __init__(self, R_desc):
         self._R = R_desc
@@ -79,14 +116,15 @@ class _DescendingRank:
     def __getitem__(self, key):
         if isinstance(key, tuple) and len(key) == 2 and key[0] == slice(None) and key[1] == slice(None, None, -1):
             return self._R
-        return self._R[:, ::-1][key]
+        return self._R.materialise()[:, ::-1][key]
 
     def __array__(self, dtype=None, copy=None):
-        out = self._R[:, ::-1]
+        out = self._R.materialise()[:, ::-1]
         return out.astype(dtype) if dtype is not None else out
 
 
-def install(reference_dir: str, device: int = 0, no_plots: bool = False, native_loaders: bool = True):
+def install(reference_dir: str, device: int = 0, no_plots: bool = False, native_loaders: bool = True,
+            per_call_part2: bool = False, handle=None):
     """Import the reference modules from ``reference_dir`` and rebind their hot-path functions.
     Returns (handle, part1 module, part2 module)."""
     reference_dir = os.path.abspath(reference_dir)
@@ -95,10 +133,14 @@ def install(reference_dir: str, device: int = 0, no_plots: bool = False, native_
     stubbed = _stub_missing_optional_modules()
     if reference_dir not in sys.path:
         sys.path.insert(0, reference_dir)
-    h = Handle(device)  # fails loudly without libhica.so / a GPU
+    # fails loudly without libhica.so / a GPU (``handle``: an already open Handle - tests inject theirs)
+    h = handle if handle is not None else Handle(device)
     plot = importlib.import_module("plotContactMaps")
     if no_plots or any(s.startswith("matplotlib") or s == "xarray" for s in stubbed):
-        plot.plotContactMap = lambda *a, **k: None
+        def _no_plot(*a, **k):
+            return None
+        _no_plot._hica_noop = True   # lets the seams skip work whose only consumer is a plot
+        plot.plotContactMap = _no_plot
     part1 = importlib.import_module("scaffoldToChromosomes")
     part2 = importlib.import_module("orderGenome")
 
@@ -122,7 +164,12 @@ def install(reference_dir: str, device: int = 0, no_plots: bool = False, native_
             if hasattr(mod, "logTransformMatrix"):   # 8f-3: feeds the plots only, but sits on the critical path
                 mod.logTransformMatrix = hio.logTransformMatrix if mod is part1 else hio.logTransformMatrix_part2
 
-    s2 = Part2Seams(h)
+    s2 = Part2Seams(h, part2)
+    if not per_call_part2:
+        # the fast lane: the whole of orderGenome (:591-628) is ONE device-resident call
+        part2.orderGenome = s2.orderGenome
+        part2.orderChromosome = s2.orderChromosome
+        part2.giveNewAdjMat = s2.giveNewAdjMat
     part2.costFunction_numba = s2.costFunction_numba
     part2.bruteForceBestScore = s2.bruteForceBestScore
     part2.checkAllScores = s2.checkAllScores
@@ -137,8 +184,11 @@ def main(argv=None):
     ap.add_argument("--no-plots", action="store_true")
     ap.add_argument("--reference-loaders", action="store_true",
                     help="keep the reference's own buildAdjacencyMatrix/removeRows (interpreted text parsing)")
+    ap.add_argument("--per-call-part2", action="store_true",
+                    help="keep the reference's orderGenome/orderChromosome loops and rebind only the inner search functions")
     ns, rest = ap.parse_known_args(argv)
-    h, _, _ = install(ns.reference_dir, ns.device, ns.no_plots, native_loaders=not ns.reference_loaders)
+    h, _, _ = install(ns.reference_dir, ns.device, ns.no_plots, native_loaders=not ns.reference_loaders,
+                      per_call_part2=ns.per_call_part2)
     script = os.path.join(os.path.abspath(ns.reference_dir), "run_hicAssembler.py")
     old_argv = sys.argv
     sys.argv = [script] + rest

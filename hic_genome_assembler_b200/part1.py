@@ -16,6 +16,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import numpy as np
 
 from ._lib import Handle
+from .lazy import LazyMatrix, LazyRank, host_array
 
 
 def run_part1(h: Handle, A: np.ndarray, min_size: int = 5, min_frac: float = .05, psig: float = .05,
@@ -139,29 +140,32 @@ def chromosome_groups_compact(cuts: Sequence[int], leaves: Sequence[int], bin_id
 # --------------------------------------------------------------------------- #
 
 
-class DeviceBackedMatrix(np.matrix):
-    """numpy.matrix that remembers which device state it mirrors."""
-
-    _hica_tag = None
-
-    def __array_finalize__(self, obj):
-        np.matrix.__array_finalize__(self, obj)
-        self._hica_tag = None  # views / copies are plain host data
-
-
-def _tag(M: np.ndarray, tag) -> DeviceBackedMatrix:
-    out = np.asmatrix(M).view(DeviceBackedMatrix)
-    out._hica_tag = tag
-    return out
+def _weak(obj):
+    """weakref to ``obj`` or None (lists cannot be weakly referenced): identity caches hold no bare addresses."""
+    import weakref
+    try:
+        return weakref.ref(obj)
+    except TypeError:
+        return None
 
 
 class Seams:
-    """Replacements for the module-level functions of scaffoldToChromosomes.py on the hot path."""
+    """Replacements for the module-level functions of scaffoldToChromosomes.py on the hot path (same names,
+    arguments and return conventions).  The N x N matrices they hand back are :class:`lazy.LazyMatrix` /
+    :class:`lazy.LazyRank` objects: the device keeps the state, and the host copy is built only if something
+    other than the next seam looks at it (runPipeline :1116-1157 never does, unless plotting is installed).
+    A seam that is handed a matrix it does not recognise as its own device state uploads it - any call
+    sequence works, the resident one is just the fast lane."""
 
     def __init__(self, h: Handle):
         self.h = h
         self._epoch = 0
+        self._live = []          # weak references to lazies that still need the current device state
+        self._order = None
+        self._rank_obj = None    # LazyRank of the resident rank matrix
+        self._rank_host = None   # weakref to a host rank matrix that is known to equal the resident one
 
+    # ---- bookkeeping
     def _fresh(self, kind):
         self._epoch += 1
         return (kind, self._epoch)
@@ -170,44 +174,87 @@ class Seams:
         tag = getattr(M, "_hica_tag", None)
         return tag is not None and tag == (kind, self._epoch)
 
+    def _lazy(self, n, thunk, tag, kind):
+        import weakref
+        m = LazyMatrix((n, n), thunk, tag, kind)
+        self._live = [w for w in self._live if w() is not None and not w().materialised]
+        self._live.append(weakref.ref(m))
+        return m
+
+    def _before_overwrite(self, kinds=None):
+        """Device state that live lazies still stand for is about to change (a new upload replaces the matrix:
+        all kinds; a new order: "Dperm" and "S"; new row sums: "S"): they are brought to the host first - they stay
+        valid, nothing is ever silently stale."""
+        keep = []
+        for w in self._live:
+            m = w()
+            if m is None or m.materialised:
+                continue
+            if m._hica_tag is not None and (kinds is None or m.kind in kinds):
+                m.materialise()
+            else:
+                keep.append(w)
+        self._live = keep
+        if kinds is None:
+            self._rank_obj = None
+            self._rank_host = None
+
+    @staticmethod
+    def _row_sums(binList):
+        return np.asarray([b.rowSum for b in binList], dtype=np.float64)
+
     # convertMatrix(adjacencyMatrix, binList, distance=True, similarity=False) :138-155
     def convertMatrix(self, adjacencyMatrix, binList, distance=True, similarity=False):
         t0 = time.time()
         h = self.h
         if distance == True:  # noqa: E712 - the reference compares with == True
-            A = np.ascontiguousarray(np.asarray(adjacencyMatrix, dtype=np.float64))
-            h.p1_upload(A)
-            h.p1_set_row_sums(np.asarray([b.rowSum for b in binList], dtype=np.float64))
-            h.p1_distance()
-            out = _tag(h.p1_get_distance(), self._fresh("D"))
+            rs = self._row_sums(binList)
+            if isinstance(adjacencyMatrix, LazyMatrix) and not adjacencyMatrix.materialised:
+                # a deferred input (the pipeline's closing convertMatrix(logTransformMatrix(.., reverse=True)),
+                # :1155, feeds only a plot): stay deferred, do the work if and when somebody looks
+                src = adjacencyMatrix
+                out = self._lazy(len(src), lambda: np.asarray(self._distance(host_array(src), rs).materialise()),
+                                 None, "D(deferred)")
+            else:
+                out = self._distance(host_array(adjacencyMatrix), rs)
         elif similarity == True:  # noqa: E712
-            rs = np.asarray([b.rowSum for b in binList], dtype=np.float64)
+            rs = self._row_sums(binList)
             if self._is_current(adjacencyMatrix, "Dperm"):
                 # reordered distance matrix of the resident ICE matrix: row sums follow the reordered binList
-                order = self._order
                 full = np.empty(h.n)
-                full[np.asarray(order)] = rs
+                full[np.asarray(self._order)] = rs
+                self._before_overwrite({"S"})
                 h.p1_set_row_sums(full)
-                out = _tag(h.p1_get_reordered(1), self._fresh("S"))
             else:
-                D = np.ascontiguousarray(np.asarray(adjacencyMatrix, dtype=np.float64))
+                D = host_array(adjacencyMatrix)
+                self._before_overwrite()
                 h.p1_upload_distance(D)
                 h.p1_set_row_sums(rs)
                 h.p1_set_order(np.arange(D.shape[0], dtype=np.int32))
                 self._order = list(range(D.shape[0]))
-                out = _tag(h.p1_get_reordered(1), self._fresh("S"))
+            out = self._lazy(h.n, lambda: h.p1_get_reordered(1), self._fresh("S"), "S")
         else:
             out = np.asmatrix(adjacencyMatrix)
         print("Time to convert matrix " + str(time.time() - t0))
         return out
+
+    def _distance(self, A, rs):
+        h = self.h
+        self._before_overwrite()
+        h.p1_upload(A)
+        h.p1_set_row_sums(rs)
+        h.p1_distance()
+        return self._lazy(h.n, lambda: h.p1_get_distance(), self._fresh("D"), "D")
 
     # averageClusterNodes(adjacencyMatrix, nodeLabels, noPlot=True) :187-208
     def averageClusterNodes(self, adjacencyMatrix, nodeLabels, noPlot=True):
         t0 = time.time()
         h = self.h
         if not self._is_current(adjacencyMatrix, "D"):
-            h.p1_upload_distance(np.ascontiguousarray(np.asarray(adjacencyMatrix, dtype=np.float64)))
-            self._fresh("Dhost")
+            D = host_array(adjacencyMatrix)
+            self._before_overwrite()
+            h.p1_upload_distance(D)
+            self._dhost = (self._fresh("Dhost"), _weak(adjacencyMatrix))
         Z, leaves = h.p1_linkage(want_Z=True)
         leaves = [int(v) for v in leaves]
         self._order = leaves
@@ -220,43 +267,61 @@ class Seams:
         h = self.h
         order = [int(v) for v in newOrder]
         tag = getattr(matrix, "_hica_tag", None)
-        if tag is not None and tag[1] == self._epoch and tag[0] in ("D", "Dhost"):
-            h.p1_set_order(np.asarray(order, dtype=np.int32))
-            self._order = order
-            out = _tag(h.p1_get_reordered(0), self._fresh("Dperm"))
-        else:
+        resident = tag is not None and tag == ("D", self._epoch)
+        dh = getattr(self, "_dhost", None)   # the host matrix averageClusterNodes uploaded, if it is this very object
+        if not resident and dh is not None and dh[0] == ("Dhost", self._epoch) and dh[1] is not None and dh[1]() is matrix:
+            resident = True
+        if not resident:
             # a matrix that is not the resident one: upload it as is and gather on the device
-            h.p1_upload_distance(np.ascontiguousarray(np.asarray(matrix, dtype=np.float64)))
+            D = host_array(matrix)
+            self._before_overwrite()
+            h.p1_upload_distance(D)
             self._fresh("Dhost")
-            h.p1_set_order(np.asarray(order, dtype=np.int32))
-            self._order = order
-            out = _tag(h.p1_get_reordered(0), self._fresh("Dperm"))
+        self._before_overwrite({"Dperm", "S"})
+        h.p1_set_order(np.asarray(order, dtype=np.int32))
+        self._order = order
+        out = self._lazy(h.n, lambda: h.p1_get_reordered(0), self._fresh("Dperm"), "Dperm")
         return out, [binList[i] for i in order]
 
     # numpy.argsort(adjMat, axis=1)[:, ::-1] :1132 (bound through the module's `numpy` name)
-    def argsort_desc(self, S) -> np.ndarray:
+    def argsort_desc(self, S) -> LazyRank:
         h = self.h
         if not self._is_current(S, "S"):
-            h.p1_upload_similarity(np.ascontiguousarray(np.asarray(S, dtype=np.float64)))
+            Sh = host_array(S)
+            self._before_overwrite()
+            h.p1_upload_similarity(Sh)
             self._fresh("Shost")
         h.p1_rank()
-        R = h.p1_get_rank()
-        self._rank_key = (R.__array_interface__["data"][0], R.shape)  # the device already holds this R
-        return R
+        self._rank_obj = LazyRank(h.n, h.p1_get_rank, ("R", self._epoch))
+        self._rank_host = None
+        return self._rank_obj
 
     def _ensure_rank(self, argsorted_mat):
-        R = np.asarray(argsorted_mat)
-        key = (R.__array_interface__["data"][0], R.shape)
-        if getattr(self, "_rank_key", None) != key:
-            self.h.p1_set_rank(np.ascontiguousarray(R, dtype=np.int64))
-            self._rank_key = key
+        if argsorted_mat is self._rank_obj and self._rank_obj is not None and self._rank_obj._hica_tag == ("R", self._epoch):
+            return                                     # the device already holds this rank matrix
+        if self._rank_host is not None and self._rank_host() is argsorted_mat:
+            return                                     # the very array object that was uploaded last (still alive)
+        if self._rank_obj is not None and self._rank_obj._host is not None and argsorted_mat is self._rank_obj._host \
+                and self._rank_obj._hica_tag == ("R", self._epoch):
+            return                                     # the host copy of the resident rank matrix
+        R = np.ascontiguousarray(np.asarray(argsorted_mat), dtype=np.int64)
+        self._rank_obj = None
+        self.h.p1_set_rank(R)
+        self._fresh("Rhost")
+        self._rank_host = _weak(argsorted_mat)
+
+    def _report(self, amb, tie):
+        if amb:
+            print("- WARNING - {} hypergeometric decisions fell within 1e-7 of the significance level".format(amb))
+        if tie:
+            print("- WARNING - {} significance decisions depend on the order numpy.argsort gives exactly tied "
+                  "values (implementation-defined, scaffoldToChromosomes.py:1132)".format(tie))
 
     # pre_process_all_matrix_breakpoints(argsorted_mat, min_size=5, min_frac=.05, psig=.05) :513-551
     def pre_process_all_matrix_breakpoints(self, argsorted_mat, min_size=5, min_frac=.05, psig=.05):
         self._ensure_rank(argsorted_mat)
         cuts, amb = self.h.p1_breakpoints(int(min_size), float(min_frac))
-        if amb:
-            print("- WARNING - {} hypergeometric decisions fell within 1e-7 of the significance level".format(amb))
+        self._report(amb, self.h.tie_sensitive() if hasattr(self.h, "tie_sensitive") else 0)
         print("- Breakpoints found {}".format(len(cuts)))
         return cuts
 
@@ -266,8 +331,7 @@ class Seams:
             return []
         self._ensure_rank(argsorted_mat)
         cuts, amb = self.h.p1_filter([int(v) for v in original_inds], float(psig))
-        if amb:
-            print("- WARNING - {} hypergeometric decisions fell within 1e-7 of the significance level".format(amb))
+        self._report(amb, self.h.tie_sensitive() if hasattr(self.h, "tie_sensitive") else 0)
         print("- Original cut indices {}".format(list(original_inds)))
         print("- Filtered cut indices {}".format(cuts))
         return cuts

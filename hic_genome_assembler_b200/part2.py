@@ -263,6 +263,38 @@ def _pool(nodes: Sequence[Tuple[int, str]]) -> List[Scaf]:
     return sorted(by_name.values(), key=lambda s: len(s.bins), reverse=True)
 
 
+def reference_work(lens: Sequence[int], n_scaffolds: int, scan: int, rounds: int) -> Tuple[int, int]:
+    """What the reference evaluates for one chromosome group whose scaffolds (pool order: bin count descending)
+    have ``lens`` bins and whose sliding-window search ran ``rounds`` rounds: (candidates, candidates x
+    L(L-1)/2 bin pairs each) over bruteForceBestScore (:432-473), the checkAllScores steps (:475-493, a
+    do-while) and scanOrdering (:495-549).  The device engine reaches the same decisions by filtering the
+    candidates in closed form and re-scoring a short list exactly, so this is REFERENCE-EQUIVALENT work, not
+    memory traffic of the GPU path; bench.py and its reference arm both count with this function."""
+    if n_scaffolds >= 9:
+        n_scaffolds = 8
+    scan = min(scan, n_scaffolds)
+    lens = list(lens)
+    k = min(n_scaffolds, len(lens))
+    pairs = lambda n: n * (n - 1) // 2  # noqa: E731
+    nb = sum(lens[:k])
+    cand = order_table(k).shape[0] * orient_table(k).shape[0] if nb >= 2 else 0
+    work = cand * pairs(nb)
+    placed, bins, first = k, nb, True
+    while first or placed < len(lens):
+        first = False
+        if placed < len(lens):
+            m, bins, placed = placed, bins + lens[placed], placed + 1
+        else:
+            m = placed - 1
+        cand += 2 * (m + 1)
+        work += 2 * (m + 1) * pairs(bins)
+    if len(lens) > n_scaffolds:
+        c = int(rounds) * (len(lens) - scan + 1) * order_table(scan).shape[0] * orient_table(scan).shape[0]
+        cand += c
+        work += c * pairs(sum(lens))
+    return cand, work
+
+
 def order_groups_device(h: Handle, genome_index_of_bin: Dict[int, int],
                         chrom_groups: Sequence[Sequence[Tuple[int, str]]], n_scaffolds: int = 6, scan: int = 5):
     """orderGenome (:591-628) for all groups in ONE device call (hica_p2_order_groups): every chromosome runs its
@@ -313,29 +345,12 @@ def order_groups_device(h: Handle, genome_index_of_bin: Dict[int, int],
         ent = layout[grp_ptr[gi]:grp_ptr[gi + 1]]
         names = pool_names[gi]
         out.append([(names[e >> 1], "-" if (e & 1) else "+") for e in ent.tolist()])
-        # algorithmic work = what the reference evaluates: candidates x L(L-1)/2 bin pairs each
-        lens = pool_lens[gi]
-        k = min(n_scaffolds, len(pool))
-        pairs = lambda n: n * (n - 1) // 2  # noqa: E731
-        nb = sum(lens[:k])
-        cand = order_table(k).shape[0] * orient_table(k).shape[0] if nb >= 2 else 0
-        work = cand * pairs(nb)
-        placed, bins, first = k, nb, True
-        while first or placed < len(pool):
-            first = False
-            if placed < len(pool):
-                m, bins, placed = placed, bins + lens[placed], placed + 1
-            else:
-                m = placed - 1
-            cand += 2 * (m + 1)
-            work += 2 * (m + 1) * pairs(bins)
-        if len(pool) > n_scaffolds:
-            c = int(rounds[gi]) * (len(pool) - scan + 1) * order_table(scan).shape[0] * orient_table(scan).shape[0]
-            cand += c
-            work += c * pairs(sum(lens))
+        cand, work = reference_work(pool_lens[gi], n_scaffolds, scan, int(rounds[gi]))
         STATS["candidates"] += cand
         STATS["bin_pairs"] += work
         STATS["exact"] = STATS.get("exact", 0) + int(stats[gi, 1])
+        Lg = sum(pool_lens[gi])
+        STATS["exact_pairs"] = STATS.get("exact_pairs", 0) + int(stats[gi, 1]) * (Lg * (Lg - 1) // 2)
     STATS["calls"] += 1
     return out, cost, rounds, stats
 
@@ -365,18 +380,119 @@ def order_genome(h: Handle, G: Optional[np.ndarray], bin_ids: Sequence[int],
 class _Seams:
     """Callable replacements for the module-level functions of orderGenome.py; the launcher binds them
     into the loaded reference module.  They operate on the reference's own Scaffold objects
-    (``name``, ``binList``, ``orientation``, ``flipOrientation()``)."""
+    (``name``, ``binList``, ``orientation``, ``flipOrientation()``).
 
-    def __init__(self, h: Handle):
+    Two levels are rebound.  ``orderGenome`` / ``orderChromosome`` (:591-628, :551-586) are the fast lane: the
+    genome matrix goes to the device once and every chromosome group runs its brute force, insertion steps and
+    window scans in ONE device-resident call (``order_groups_device`` - the engine bench.py measures).  The
+    inner functions (``bruteForceBestScore``, ``checkAllScores``, ``scanOrdering``, ``costFunction_numba``) stay
+    rebound as well for callers that drive them one by one (the notebook does)."""
+
+    def __init__(self, h: Handle, module=None):
         self.h = h
-        self._genome_key = None
+        self.mod = module          # the loaded reference module (Scaffold, initiateBinsAndScaffolds, plotModule)
+        self._genome = None        # (weakref to the host matrix object, shape) that is resident as the P2 matrix
+
+    # ---- residency of the genome matrix: identity of the host object, never a bare address
+    def _upload_genome(self, matrix):
+        import weakref
+        cur = self._genome
+        if cur is not None and cur[0]() is matrix:
+            return
+        M = np.ascontiguousarray(np.asarray(matrix, dtype=np.float64))
+        self.h.p2_upload(M)
+        try:
+            self._genome = (weakref.ref(matrix),)
+        except TypeError:          # a list of lists: uploaded, not remembered
+            self._genome = None
+
+    def _forget_genome(self):
+        self._genome = None
+
+    # orderGenome(matrix, chromList, binList, resolution, nScaffolds=6, scanScaffolds=5, plotChrom=True, ...) :591-628
+    def orderGenome(self, matrix, chromList, binList, resolution, nScaffolds=6, scanScaffolds=5, plotChrom=True,
+                    showPlot=True, savePlotDir=False, plotTitleSuffix=False):
+        import time
+        t0 = time.time()
+        mod = self.mod
+        self._upload_genome(matrix)
+        ids = np.fromiter((b.ID for b in binList), dtype=np.int64, count=len(binList))
+        lut = np.full(int(ids.max()) + 2 if len(ids) else 2, -1, dtype=np.int64)
+        lut[ids] = np.arange(len(ids))
+        groups = [[(int(b), nm) for b, nm in grp] for grp in chromList]
+        live = [i for i, g in enumerate(groups) if g]
+        orderings, costs, rounds, _ = order_groups_device(self.h, lut, [groups[i] for i in live], int(nScaffolds),
+                                                          int(scanScaffolds))
+        by_group = dict(zip(live, zip(orderings, costs, rounds)))
+        fullGenomeOrder = []
+        noop_plot = mod is None or getattr(mod.plotModule.plotContactMap, "_hica_noop", False)
+        for i, chromGroup in enumerate(chromList):
+            print("#####################" + "\n" + "#####################")
+            print("Working on Chr_" + str(i + 1) + "...")
+            scaffoldList, scaffoldDict = mod.initiateBinsAndScaffolds(chromGroup)
+            chromOrder = []
+            if i in by_group:
+                got, cost, rnd = by_group[i]
+                for name, o in got:
+                    sObj = scaffoldDict[name]
+                    if sObj.orientation != o:
+                        sObj.flipOrientation()
+                    chromOrder.append(sObj)
+                print("Best cost at the end of the final step = " + str(float(cost)) + " (" + str(int(rnd)) + " scan rounds)")
+            print("Final ordering...")
+            for sObj in chromOrder:
+                print(sObj.name, sObj.orientation)
+            fullGenomeOrder.append(chromOrder)
+            if plotChrom != True or noop_plot:  # noqa: E712
+                continue
+            chrName = "Chr_" + str(i + 1)
+            adjMat, orderDict = mod.giveNewAdjMat(np.asmatrix(matrix), chromOrder, binList)
+            mod.plotModule.plotContactMap(adjMat, resolution=resolution, tickCount=11, highlightChroms=False,
+                                          wInches=24, hInches=24, lP=1, hP=98, reverseColorMap='',
+                                          showPlot=showPlot, savePlot=savePlotDir + "/" + chrName + ".png",
+                                          title=chrName, titleSuffix=plotTitleSuffix)
+        print("RunTime for total genome with plotting and saving .pngs = " + str(time.time() - t0))
+        return fullGenomeOrder
+
+    # orderChromosome(chromGroup, matrix, binList, nScaffolds=6, scanScaffolds=5) :551-586
+    def orderChromosome(self, chromGroup, matrix, binList, nScaffolds=6, scanScaffolds=5):
+        self._upload_genome(matrix)
+        lut_ids = np.fromiter((b.ID for b in binList), dtype=np.int64, count=len(binList))
+        lut = np.full(int(lut_ids.max()) + 2, -1, dtype=np.int64)
+        lut[lut_ids] = np.arange(len(lut_ids))
+        got, cost, rounds, _ = order_groups_device(self.h, lut, [[(int(b), nm) for b, nm in chromGroup]],
+                                                   int(nScaffolds), int(scanScaffolds))
+        scaffoldList, scaffoldDict = self.mod.initiateBinsAndScaffolds(chromGroup)
+        out = []
+        for name, o in got[0]:
+            sObj = scaffoldDict[name]
+            if sObj.orientation != o:
+                sObj.flipOrientation()
+            out.append(sObj)
+        print("Best cost at the end of the final step = " + str(float(cost[0])))
+        print("Final ordering...")
+        for s in out:
+            print(s.name, s.orientation)
+        return out
+
+    # giveNewAdjMat(matrix, scaffList, binList) :297-308 - the N x N gather is deferred: after orderGenome it only
+    # feeds the whole-genome plot (:700-704)
+    def giveNewAdjMat(self, matrix, scaffList, binList):
+        from .lazy import LazyMatrix
+        nList = [n for sObj in scaffList for n in sObj.binList]
+        orderDict = {gID: i for i, gID in enumerate(nList)}
+        binIndices = {b.ID: i for i, b in enumerate(binList)}
+        indices = [binIndices[n] for n in nList]
+        src = matrix
+        return LazyMatrix((len(indices), len(indices)),
+                          lambda: np.asmatrix(np.asarray(src)[np.ix_(indices, indices)]), None, "giveNewAdjMat"), orderDict
 
     # costFunction_numba(matrix, total) :184-191
     def costFunction_numba(self, matrix, total):
         M = np.ascontiguousarray(np.asarray(matrix, dtype=np.float64))
         n = M.shape[0]
         self.h.p2_upload(M)
-        self._genome_key = None
+        self._forget_genome()
         self.h.p2_select(np.arange(n, dtype=np.int32))
         _, _, sc = self.h.p2_score_orders(np.arange(n, dtype=np.int32)[None, :], float(total), 0.0, want_scores=True)
         return float(sc[0])
@@ -393,7 +509,7 @@ class _Seams:
     def _resident_matrix(self, matrix, orderDict, sObjs) -> DeviceChromosome:
         M = np.ascontiguousarray(np.asarray(matrix, dtype=np.float64))
         self.h.p2_upload(M)
-        self._genome_key = None
+        self._forget_genome()
         scafs = [Scaf(s.name, self._plus_bins(s), s.orientation) for s in sObjs]
         # every row of `matrix` is addressed through orderDict (binID -> row)
         return DeviceChromosome(self.h, dict(orderDict), scafs), scafs
@@ -423,11 +539,7 @@ class _Seams:
 
     # scanOrdering(orderedScaffolds, scaffoldDict, orderDict, matrix, binList, bestCost, scanScaffolds=5) :495-549
     def scanOrdering(self, orderedScaffolds, scaffoldDict, orderDict, matrix, binList, bestCost, scanScaffolds=5):
-        M = np.asarray(matrix)
-        key = (M.__array_interface__["data"][0], M.shape)
-        if key != self._genome_key:
-            self.h.p2_upload(np.ascontiguousarray(M, dtype=np.float64))
-            self._genome_key = key
+        self._upload_genome(matrix)
         index_of = {b.ID: i for i, b in enumerate(binList)}
         scafs = [Scaf(s.name, self._plus_bins(s), s.orientation) for s in orderedScaffolds]
         chrom = DeviceChromosome(self.h, index_of, scafs)
