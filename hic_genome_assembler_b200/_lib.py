@@ -24,7 +24,7 @@ ABI_SYMBOLS = (
     "hica_p1_upload", "hica_p1_upload_symmetric", "hica_p1_upload_device", "hica_p1_set_row_sums", "hica_p1_distance", "hica_p1_get_distance",
     "hica_p1_get_pairwise_row_sums", "hica_p1_get_row_sums", "hica_p1_upload_distance", "hica_p1_linkage",
     "hica_p1_set_order", "hica_p1_get_reordered", "hica_p1_rank", "hica_p1_upload_similarity", "hica_p1_get_rank", "hica_p1_set_rank",
-    "hica_p1_window_sig", "hica_p1_breakpoints", "hica_p1_filter", "hica_hypergeom_less",
+    "hica_p1_window_sig", "hica_p1_breakpoints", "hica_p1_filter", "hica_p1_tie_report", "hica_hypergeom_less",
     "hica_p2_upload", "hica_p2_use_p1_matrix", "hica_p2_select", "hica_p2_set_segments", "hica_p2_total",
     "hica_p2_score_candidates", "hica_p2_score_window", "hica_p2_score_orders", "hica_p2_order_groups",
     "hica_io_read_matrix", "hica_io_last_error", "hica_io_log_transform",
@@ -82,6 +82,7 @@ def load_library():
     L.hica_p1_window_sig.argtypes = [vp, i64, i64, i64, dbl, C.c_int, vp, vp, vp]
     L.hica_p1_breakpoints.argtypes = [vp, i64, dbl, vp, i64, vp, vp]
     L.hica_p1_filter.argtypes = [vp, vp, i64, dbl, vp, vp, vp]
+    L.hica_p1_tie_report.argtypes = [vp, vp]
     L.hica_hypergeom_less.argtypes = [vp, vp, vp, vp, vp, i64, dbl, vp]
     L.hica_p2_upload.argtypes = [vp, vp, i64]
     L.hica_p2_use_p1_matrix.argtypes = [vp]
@@ -322,6 +323,17 @@ class Handle:
         self._check(self._L.hica_p1_filter(self._h, _ptr(cin), cin.size, float(psig), _ptr(cout), C.byref(n),
                                            C.byref(amb)))
         return [int(v) for v in cout[: n.value]], amb.value
+
+    def tie_report(self) -> dict:
+        """hica_p1_tie_report: significance decisions of the last breakpoint / filter searches that depend on the
+        order of exactly tied similarities (numpy.argsort's order is implementation-defined, :1132)."""
+        out = np.zeros(4, dtype=np.int64)
+        self._check(self._L.hica_p1_tie_report(self._h, _ptr(out)))
+        return {"available": bool(out[0]), "breakpoints": int(out[1]), "filter": int(out[2]), "rows_with_ties": int(out[3])}
+
+    def tie_sensitive(self) -> int:
+        r = self.tie_report()
+        return max(r["breakpoints"], 0) + max(r["filter"], 0) if r["available"] else 0
 
     def hypergeom_less(self, x, M, n, N, psig: float = .05) -> np.ndarray:
         x, M, n, N = (_c(np.broadcast_to(np.asarray(v), np.broadcast(x, M, n, N).shape).ravel(), np.int64)

@@ -135,6 +135,8 @@ extern "C" int hica_destroy(hica_handle h)
     cudaFree(h->red_d);
     cudaFreeHost(h->red_h);
     cudaFree(h->pre_buf);
+    cudaFree(h->tie_own);
+    cudaFree(h->xt_d);
     cudaEventDestroy(h->ev_fork);
     cudaEventDestroy(h->ev_join);
     cudaEventDestroy(h->ev_pre0);

@@ -50,6 +50,15 @@ struct hica_ctx {
     int64_t pre_cap = 0;
     bool presort_pending = false, presort_valid = false;
     int presort_chunk = 0;       // 0: rows pre-sorted by the radix kernels; > 0: chunk-wise by the bitonic network, entries per chunk
+    // exact-tie masks of the rank matrix (tie-order sensitivity report of the cut searches): bit k of a row is set
+    // when sorted entry k has exactly the same similarity as entry k - 1
+    int64_t rank_epoch = 0, tie_epoch = -1;  // tie_* describe the rank matrix of this epoch
+    int tie_src = 0;                 // 0: not available; 1: the pre-sort's masks (rows by MATRIX index, via order[]); 2: tie_own
+    uint32_t *tie_own = nullptr;     // masks computed from R and the resident matrix (rows by reordered index)
+    int64_t tie_own_cap = 0;
+    int2 *xt_d = nullptr;            // (x_lo, x_hi) next to the window counts in x_d
+    int64_t xt_cap = 0;
+    int64_t tie_breakpoints = -1, tie_filter = -1, tie_rows = -1;  // results of the last calls (-1: unknown)
     // linkage scratch
     double *Zraw = nullptr;      // (n-1) x 4 raw merges (device)
     int32_t *size_d = nullptr;   // cluster sizes

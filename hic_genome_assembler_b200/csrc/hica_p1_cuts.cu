@@ -170,6 +170,86 @@ __device__ __forceinline__ int count_in_window(const RankT *__restrict__ row, in
     return cnt;
 }
 
+
+// ---- tie-order sensitivity (SURVEY 7 hard part 3) ---------------------------------------------------------------
+// numpy.argsort (scaffoldToChromosomes.py:1132) gives exactly tied similarities an implementation-defined order;
+// this library uses "stable ascending, reversed".  A window count x = #{k < len : lo <= row[k] <= hi} depends on
+// that order only when the window boundary (between sorted positions len-1 and len) falls INSIDE a run of tied
+// values [g0, g1): any k_in = len - g0 of the run's g members may be the ones inside the boundary.  With m_in of
+// them in [lo, hi] the count can be anything in
+//     x_lo = x_fixed + max(0, k_in - (g - m_in))   ...   x_hi = x_fixed + min(k_in, m_in),
+// x_fixed = the count over positions < g0.  A decision that differs between x_lo and x_hi is reported.
+struct TieInfo {
+    const uint32_t *bits;  // n rows x words; bit k: entry k ties with entry k - 1.  nullptr: not available
+    const int32_t *map;    // mask row of reordered row i (nullptr: i itself)
+    int words;
+};
+
+template <typename RankT>
+__device__ __forceinline__ int2 tie_window_bounds(const TieInfo ti, int64_t row_index, const RankT *__restrict__ row,
+                                                  int64_t n, int64_t len, int64_t lo, int64_t hi, int x, int *sh /* >= 12 ints */)
+{
+    // every thread of the CTA calls; the result is valid in thread 0
+    bool tied = false;
+    const uint32_t *tr = nullptr;
+    if (ti.bits && len >= 1 && len < n) {
+        tr = ti.bits + (int64_t)(ti.map ? ti.map[row_index] : row_index) * ti.words;
+        tied = (tr[len >> 5] >> (len & 31)) & 1u;
+    }
+    if (!tied) return make_int2(x, x);
+    if (threadIdx.x < 32) {  // warp 0: run start g0 (last clear bit at or below len-1) and end g1 (first clear bit above len)
+        const int lane = threadIdx.x;
+        int g0 = 0, g1 = (int)n;
+        for (int wbase = (int)((len - 1) >> 5); wbase >= 0; wbase -= 32) {
+            const int w = wbase - lane;
+            uint32_t inv = 0u;
+            if (w >= 0) {
+                inv = ~tr[w];
+                if (w == (int)((len - 1) >> 5)) { const int b = (int)((len - 1) & 31); if (b < 31) inv &= (2u << b) - 1u; }
+            }
+            const uint32_t found = __ballot_sync(0xffffffffu, inv != 0u);
+            if (found) {
+                const int src = __ffs(found) - 1;  // lowest lane = highest word
+                const uint32_t iv = __shfl_sync(0xffffffffu, inv, src);
+                g0 = (wbase - src) * 32 + (31 - __clz(iv));
+                break;
+            }
+        }
+        for (int wbase = (int)((len + 1) >> 5); wbase < ti.words; wbase += 32) {
+            const int w = wbase + lane;
+            uint32_t inv = 0u;
+            if (w < ti.words) {
+                inv = ~tr[w];
+                if (w == (int)((len + 1) >> 5)) inv &= ~0u << ((len + 1) & 31);
+            }
+            const uint32_t found = __ballot_sync(0xffffffffu, inv != 0u);
+            if (found) {
+                const int src = __ffs(found) - 1;
+                const uint32_t iv = __shfl_sync(0xffffffffu, inv, src);
+                g1 = min((int)n, (wbase + src) * 32 + (__ffs(iv) - 1));
+                break;
+            }
+        }
+        if (lane == 0) { sh[8] = g0; sh[9] = g1; }
+    }
+    __syncthreads();
+    const int g0 = sh[8], g1 = sh[9];
+    int a = count_in_window(row + g0, len - g0, lo, hi), b = count_in_window(row + len, (int64_t)g1 - len, lo, hi);
+    for (int d = 16; d >= 1; d >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, d); b += __shfl_xor_sync(0xffffffffu, b, d); }
+    if ((threadIdx.x & 31) == 0) { sh[threadIdx.x >> 5] = a; sh[4 + (threadIdx.x >> 5)] = b; }
+    __syncthreads();
+    int2 r = make_int2(x, x);
+    if (threadIdx.x == 0) {
+        const int nw = (blockDim.x + 31) >> 5;
+        int as = 0, bs = 0;
+        for (int w = 0; w < nw; w++) { as += sh[w]; bs += sh[4 + w]; }
+        const int k_in = (int)(len - g0), g = g1 - g0, m_in = as + bs, x_fixed = x - as;
+        r.x = x_fixed + max(0, k_in - (g - m_in));
+        r.y = x_fixed + min(k_in, m_in);
+    }
+    return r;
+}
+
 // ---------------------------------------------------------------------------
 template <typename RankT>
 __global__ void __launch_bounds__(128) k_window_counts(const RankT *__restrict__ R, int64_t n, int64_t start,
@@ -242,7 +322,7 @@ __global__ void __launch_bounds__(128) k_crit_mode0(int64_t Lw, long long M, dou
 template <typename RankT>
 __global__ void __launch_bounds__(128) k_window_counts_crit(const RankT *__restrict__ R, int64_t n, int64_t start,
                                                             int32_t *__restrict__ x, int ncrit, long long M, double psig,
-                                                            int32_t *__restrict__ crit)
+                                                            int32_t *__restrict__ crit, TieInfo ti, int2 *__restrict__ xt)
 {
     if ((int)blockIdx.x < ncrit) {
         const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -253,32 +333,41 @@ __global__ void __launch_bounds__(128) k_window_counts_crit(const RankT *__restr
     const int64_t c = (int64_t)blockIdx.x - ncrit + 1, i = start + c;
     const RankT *row = R + i * n;
     int cnt = count_in_window(row, c, start, i);
-    __shared__ int part[4];
+    __shared__ int part[12];
     for (int d = 16; d >= 1; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
     if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = cnt;
     __syncthreads();
+    const int xv = part[0] + part[1] + part[2] + part[3];
+    __syncthreads();
+    const int2 b = tie_window_bounds(ti, i, row, n, c, start, i, xv, part);
     if (threadIdx.x == 0) {
-        x[c] = part[0] + part[1] + part[2] + part[3];
-        if (c == 1) x[0] = 0;
+        x[c] = xv;
+        xt[c] = b;
+        if (c == 1) { x[0] = 0; xt[0] = make_int2(0, 0); }
     }
 }
 
 __device__ __forceinline__ void sig_cmp0_one(int64_t c, const int32_t *__restrict__ x, const int32_t *__restrict__ crit,
                                              int64_t Lw, long long M, double psig, uint8_t *__restrict__ sig,
-                                             int32_t *__restrict__ misc)
+                                             int32_t *__restrict__ misc, const int2 *__restrict__ xt = nullptr)
 {
     if (c >= Lw) return;
     int s = 0;
     if (c > 0) {
         const int f = crit[2 * c + 1];
-        const long long xv = x[c], kmin = max(0ll, 2 * (long long)c - M), kmax = c;
-        if (f == 2) s = 1;
-        else if (xv <= kmin) s = 1.0 < psig;
-        else if (xv > kmax) s = 0.0 < psig;
-        else {
-            const long long xc = crit[2 * c];
-            s = xv >= xc;
-            if (f == 1 && (xv == xc || xv == xc - 1)) atomicAdd(&misc[3], 1);
+        const long long kmin = max(0ll, 2 * (long long)c - M), kmax = c, xc = crit[2 * c];
+        auto decide = [&](long long xv) -> int {
+            if (f == 2) return 1;
+            if (xv <= kmin) return 1.0 < psig;
+            if (xv > kmax) return 0.0 < psig;
+            return xv >= xc;
+        };
+        const long long xv = x[c];
+        s = decide(xv);
+        if (f == 1 && xv > kmin && xv <= kmax && (xv == xc || xv == xc - 1)) atomicAdd(&misc[3], 1);
+        if (xt) {  // would another order of exactly tied similarities change this decision?
+            const int2 b = xt[c];
+            if (b.x != b.y && decide(b.x) != decide(b.y)) atomicAdd(&misc[6], 1);
         }
     }
     sig[c] = (uint8_t)s;
@@ -286,9 +375,9 @@ __device__ __forceinline__ void sig_cmp0_one(int64_t c, const int32_t *__restric
 }
 
 __global__ void k_sig_cmp0(const int32_t *__restrict__ x, const int32_t *__restrict__ crit, int64_t Lw, long long M,
-                           double psig, uint8_t *__restrict__ sig, int32_t *__restrict__ misc)
+                           double psig, uint8_t *__restrict__ sig, int32_t *__restrict__ misc, const int2 *__restrict__ xt)
 {
-    sig_cmp0_one((int64_t)blockIdx.x * blockDim.x + threadIdx.x, x, crit, Lw, M, psig, sig, misc);
+    sig_cmp0_one((int64_t)blockIdx.x * blockDim.x + threadIdx.x, x, crit, Lw, M, psig, sig, misc, xt);
 }
 
 // mode 1: all rows share (M, local, local): one critical value.
@@ -349,7 +438,7 @@ __global__ void __launch_bounds__(128) k_fb_counts(const RankT *__restrict__ R, 
                                                    const int64_t *__restrict__ bounds, int64_t rows,
                                                    int32_t *__restrict__ x, long long M, double psig,
                                                    int32_t *__restrict__ crit, const int64_t *__restrict__ all_bounds,
-                                                   int nb_all, int32_t *__restrict__ crit2)
+                                                   int nb_all, int32_t *__restrict__ crit2, TieInfo ti, int2 *__restrict__ xt)
 {
     const int j = blockIdx.y;
     const int64_t cut = bounds[j], local = cut - start;
@@ -382,16 +471,19 @@ __global__ void __launch_bounds__(128) k_fb_counts(const RankT *__restrict__ R, 
     }
     const RankT *row = R + (start + blockIdx.x) * n;
     int cnt = count_in_window(row, local, start, cut);
-    __shared__ int part[4];
+    __shared__ int part[12];
     for (int d = 16; d >= 1; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
     if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = cnt;
     __syncthreads();
-    if (threadIdx.x == 0) x[(int64_t)j * rows + blockIdx.x] = part[0] + part[1] + part[2] + part[3];
+    const int xv = part[0] + part[1] + part[2] + part[3];
+    __syncthreads();
+    const int2 b = tie_window_bounds(ti, start + blockIdx.x, row, n, local, start, cut, xv, part);
+    if (threadIdx.x == 0) { x[(int64_t)j * rows + blockIdx.x] = xv; xt[(int64_t)j * rows + blockIdx.x] = b; }
 }
 
 __global__ void k_fb_sig(const int32_t *__restrict__ x, int64_t rows, const int64_t *__restrict__ bounds, int nb,
                          int64_t start, long long M, double psig, const int32_t *__restrict__ crit,
-                         uint8_t *__restrict__ sig, int32_t *__restrict__ misc)
+                         uint8_t *__restrict__ sig, int32_t *__restrict__ misc, const int2 *__restrict__ xt)
 {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= rows * nb) return;
@@ -400,13 +492,16 @@ __global__ void k_fb_sig(const int32_t *__restrict__ x, int64_t rows, const int6
     const bool valid = hyp_valid(M, local, local);
     int s = 0;
     if (valid) {
-        const long long kmin = max(0ll, 2 * local - M), kmax = local, xv = x[idx];
-        if (xv <= kmin) s = 1.0 < psig;
-        else if (xv > kmax) s = 0.0 < psig;
-        else {
-            s = xv >= crit[2 * j];
-            if (crit[2 * j + 1] && (xv == crit[2 * j] || xv == (long long)crit[2 * j] - 1)) atomicAdd(&misc[3], 1);
-        }
+        const long long kmin = max(0ll, 2 * local - M), kmax = local, xv = x[idx], xc = crit[2 * j];
+        auto decide = [&](long long v) -> int {
+            if (v <= kmin) return 1.0 < psig;
+            if (v > kmax) return 0.0 < psig;
+            return v >= xc;
+        };
+        s = decide(xv);
+        if (crit[2 * j + 1] && xv > kmin && xv <= kmax && (xv == xc || xv == xc - 1)) atomicAdd(&misc[3], 1);
+        const int2 b = xt[idx];
+        if (b.x != b.y && decide(b.x) != decide(b.y)) atomicAdd(&misc[8 + j], 1);  // per evaluated cut (j < CHUNK)
     }
     sig[idx] = (uint8_t)s;
 }
@@ -442,6 +537,29 @@ __global__ void k_fb_intervals(const uint8_t *__restrict__ sig, int64_t rows, in
     if (threadIdx.x == 0) flags[(int64_t)j * nb + i] = flag;
 }
 
+}  // namespace
+int hica_tie_ensure(hica_ctx *h);                                                               // hica_p1_rank.cu
+void hica_tie_info(hica_ctx *h, const uint32_t **bits, const int32_t **map, int *words);        // hica_p1_rank.cu
+namespace {
+
+TieInfo tie_info(hica_ctx *h)
+{
+    TieInfo ti;
+    hica_tie_info(h, &ti.bits, &ti.map, &ti.words);
+    return ti;
+}
+
+int ensure_xt(hica_ctx *h, int64_t count)
+{
+    if (h->xt_cap >= count) return HICA_OK;
+    if (h->xt_d) cudaFree(h->xt_d);
+    h->xt_d = nullptr;
+    h->xt_cap = 0;
+    HICA_CUDA(cudaMalloc((void **)&h->xt_d, sizeof(int2) * (size_t)count));
+    h->xt_cap = count;
+    return HICA_OK;
+}
+
 template <typename F>
 int with_rank(hica_ctx *h, F f)
 {
@@ -453,7 +571,8 @@ int with_rank(hica_ctx *h, F f)
 int reset_misc(hica_ctx *h)
 {
     h->misc_h[0] = 0; h->misc_h[1] = INT_MAX; h->misc_h[2] = 0; h->misc_h[3] = 0; h->misc_h[4] = 0; h->misc_h[5] = 0;
-    HICA_CUDA(cudaMemcpyAsync(h->misc_d, h->misc_h, 6 * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    for (int i = 6; i < 12; i++) h->misc_h[i] = 0;  // [6]: tie-order sensitive decisions; [8..11]: the same per cut of a filter chunk
+    HICA_CUDA(cudaMemcpyAsync(h->misc_d, h->misc_h, 12 * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
     return HICA_OK;
 }
 
@@ -517,7 +636,7 @@ int run_sig_mode1(hica_ctx *h, int64_t start, int64_t cut, int64_t M, double psi
 // find_matrix_pvalue_breakpoints (:413-511): returns the leftmost relative cut
 // offset (or -1) and the number of hits.
 int find_breakpoints(hica_ctx *h, int64_t start, int64_t min_size, int64_t world, double psig, int64_t *first_cut,
-                     int64_t *n_hits, int64_t *amb)
+                     int64_t *n_hits, int64_t *amb, int64_t *tie)
 {
     const int64_t n = h->n, Lw = n - start;
     int64_t M = world;
@@ -527,11 +646,14 @@ int find_breakpoints(hica_ctx *h, int64_t start, int64_t min_size, int64_t world
     const unsigned nsig = (unsigned)((Lw + 127) / 128);
     int rc;
     bool have_crit = false;  // critical counts for the current M are in crit[]
+    const TieInfo ti = tie_info(h);
+    if ((rc = ensure_xt(h, n + 16))) return rc;
+    const bool have_xt = Lw > 1;
     if (Lw <= 1) {
         if ((rc = run_window_counts(h, start))) return rc;
     } else {
         rc = with_rank(h, [&](auto *R) {
-            k_window_counts_crit<<<(unsigned)(Lw - 1) + nsig, 128, 0, h->stream>>>(R, n, start, h->x_d, (int)nsig, M, psig, crit);
+            k_window_counts_crit<<<(unsigned)(Lw - 1) + nsig, 128, 0, h->stream>>>(R, n, start, h->x_d, (int)nsig, M, psig, crit, ti, h->xt_d);
             HICA_LAUNCHED(h);
             HICA_CUDA(cudaGetLastError());
             return (int)HICA_OK;
@@ -552,7 +674,7 @@ int find_breakpoints(hica_ctx *h, int64_t start, int64_t min_size, int64_t world
                 k_crit_mode0<<<nsig, 128, 0, h->stream>>>(Lw, M, psig, crit);
                 HICA_LAUNCHED(h);
             }
-            k_sig_cmp0<<<nsig, 128, 0, h->stream>>>(h->x_d, crit, Lw, M, psig, h->sig_d, h->misc_d);
+            k_sig_cmp0<<<nsig, 128, 0, h->stream>>>(h->x_d, crit, Lw, M, psig, h->sig_d, h->misc_d, have_xt ? h->xt_d : nullptr);
             HICA_LAUNCHED(h);
             HICA_CUDA(cudaGetLastError());
             have_crit = true;
@@ -561,8 +683,9 @@ int find_breakpoints(hica_ctx *h, int64_t start, int64_t min_size, int64_t world
                 HICA_LAUNCHED(h);
                 HICA_CUDA(cudaGetLastError());
             }
-            if ((rc = fetch_misc(h, 4))) return rc;
+            if ((rc = fetch_misc(h, 8))) return rc;
             *amb += h->misc_h[3];
+            *tie += h->misc_h[6];
             loop_count++;
             if (((double)h->misc_h[0] / (double)Lw) >= .9) { M = (int64_t)(M - start); have_crit = false; }
             else break_sig = 1;
@@ -591,7 +714,7 @@ int find_breakpoints(hica_ctx *h, int64_t start, int64_t min_size, int64_t world
 constexpr int RA_MAX_CUTS = 4096;
 constexpr int RA_BATCH = 8;
 struct RaState {
-    int32_t ind, done, need_host, count, amb, searches, pad0, pad1;
+    int32_t ind, done, need_host, count, amb, searches, tie, pad1;  // tie: decisions that depend on the order of exact ties
     int32_t cuts[RA_MAX_CUTS];
 };
 
@@ -603,7 +726,8 @@ __global__ void k_ra_reset(int32_t *__restrict__ misc, int iters)
 
 template <typename RankT>
 __global__ void __launch_bounds__(128) k_ra_counts(const RankT *__restrict__ R, int64_t n, const RaState *__restrict__ st,
-                                                   int32_t *__restrict__ x, int ncrit, double psig, int32_t *__restrict__ crit)
+                                                   int32_t *__restrict__ x, int ncrit, double psig, int32_t *__restrict__ crit,
+                                                   TieInfo ti, int2 *__restrict__ xt)
 {
     if (st->done | st->need_host) return;
     const int64_t start = st->ind, Lw = n - start;
@@ -617,23 +741,28 @@ __global__ void __launch_bounds__(128) k_ra_counts(const RankT *__restrict__ R, 
     if (c >= Lw) return;
     const RankT *row = R + i * n;
     int cnt = count_in_window(row, c, start, i);
-    __shared__ int part[4];
+    __shared__ int part[12];
     for (int d = 16; d >= 1; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
     if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = cnt;
     __syncthreads();
+    const int xv = part[0] + part[1] + part[2] + part[3];
+    __syncthreads();
+    const int2 b = tie_window_bounds(ti, i, row, n, c, start, i, xv, part);
     if (threadIdx.x == 0) {
-        x[c] = part[0] + part[1] + part[2] + part[3];
-        if (c == 1) x[0] = 0;
+        x[c] = xv;
+        xt[c] = b;
+        if (c == 1) { x[0] = 0; xt[0] = make_int2(0, 0); }
     }
 }
 
 __global__ void k_ra_sig(const int32_t *__restrict__ x, const int32_t *__restrict__ crit, int64_t n,
-                         const RaState *__restrict__ st, double psig, uint8_t *__restrict__ sig, int32_t *__restrict__ misc)
+                         const RaState *__restrict__ st, double psig, uint8_t *__restrict__ sig, int32_t *__restrict__ misc,
+                         const int2 *__restrict__ xt)
 {
     if (st->done | st->need_host) return;
     const int64_t Lw = n - st->ind;
     if (Lw <= 1) return;
-    sig_cmp0_one((int64_t)blockIdx.x * blockDim.x + threadIdx.x, x, crit, Lw, Lw, psig, sig, misc);
+    sig_cmp0_one((int64_t)blockIdx.x * blockDim.x + threadIdx.x, x, crit, Lw, Lw, psig, sig, misc, xt);
 }
 
 __global__ void k_ra_hits(const uint8_t *__restrict__ sig, int64_t n, const RaState *__restrict__ st, int w,
@@ -655,17 +784,19 @@ constexpr int RA_DECIDE_THREADS = 512;
 constexpr int RA_SLOW_MAX = 4096;
 __global__ void __launch_bounds__(RA_DECIDE_THREADS) k_ra_decide(RaState *st, const int32_t *__restrict__ misc, int64_t n,
                                                                  int min_size, int64_t stop_ind, const int32_t *__restrict__ x,
-                                                                 int32_t *__restrict__ crit, uint8_t *__restrict__ sig, double psig)
+                                                                 int32_t *__restrict__ crit, uint8_t *__restrict__ sig, double psig,
+                                                                 const int2 *__restrict__ xt)
 {
     __shared__ int32_t sm[8];
     const int t = threadIdx.x;
     if (st->done | st->need_host) return;
     const int64_t start = st->ind, Lw = n - start;
     if (Lw <= 1 || min_size >= Lw) { if (t == 0) st->need_host = 1; return; }
-    int sum = misc[0], first = misc[1], hits = misc[2], amb1 = misc[3];
-    auto commit = [&](int amb_total) {  // thread 0: leftmost hit + min_size (:488, :540), then the stop rules (:541-549)
+    int sum = misc[0], first = misc[1], hits = misc[2], amb1 = misc[3], tie1 = misc[6];
+    auto commit = [&](int amb_total, int tie_total) {  // thread 0: leftmost hit + min_size (:488, :540), then the stop rules (:541-549)
         if (st->count >= RA_MAX_CUTS) { st->need_host = 2; return; }
         st->amb += amb_total;
+        st->tie += tie_total;
         st->searches += 1;
         const int64_t ind = start + (int64_t)first + min_size;
         st->ind = (int32_t)ind;
@@ -673,12 +804,12 @@ __global__ void __launch_bounds__(RA_DECIDE_THREADS) k_ra_decide(RaState *st, co
         if (ind >= stop_ind || (n - ind) <= min_size) st->done = 1;
     };
     if (((double)sum / (double)Lw) < .9 && hits > 0) {
-        if (t == 0) commit(amb1);
+        if (t == 0) commit(amb1, tie1);
         return;
     }
     if (Lw > RA_SLOW_MAX) { if (t == 0) st->need_host = 1; return; }
     long long M = Lw;
-    int ws = min_size, break_sig = 0, loop_count = 0, amb = 0;
+    int ws = min_size, break_sig = 0, loop_count = 0, amb = 0, tie = 0;
     bool have_eval = true;  // the first evaluation came from k_ra_sig / k_ra_hits
     for (;;) {
         const bool slide = (ws == min_size && ws < Lw);
@@ -689,28 +820,29 @@ __global__ void __launch_bounds__(RA_DECIDE_THREADS) k_ra_decide(RaState *st, co
                 __syncthreads();
                 for (int64_t c = t; c < Lw; c += RA_DECIDE_THREADS) {
                     if (c >= 1) crit_mode0_one(c, M, psig, crit);
-                    sig_cmp0_one(c, x, crit, Lw, M, psig, sig, sm);
+                    sig_cmp0_one(c, x, crit, Lw, M, psig, sig, sm, xt);
                 }
                 __syncthreads();
                 if (slide)
                     for (int64_t tt = t; tt < Lw; tt += RA_DECIDE_THREADS) break_hit_one(tt, sig, Lw, ws, sm);
                 __syncthreads();
-                sum = sm[0]; first = sm[1]; hits = sm[2]; amb1 = sm[3];
+                sum = sm[0]; first = sm[1]; hits = sm[2]; amb1 = sm[3]; tie1 = sm[6];
             }
             have_eval = false;
             amb += amb1;
+            tie += tie1;
             loop_count++;
             if (((double)sum / (double)Lw) >= .9) M = M - start;
             else break_sig = 1;
             if (break_sig == 1 || loop_count >= 5) break;
         }
         if (slide && hits > 0) {
-            if (t == 0) commit(amb);
+            if (t == 0) commit(amb, tie);
             return;
         }
         ws -= 1;
         if (ws == 0) {  // no cut: pre_process_all_matrix_breakpoints stops here (:538-539)
-            if (t == 0) { st->amb += amb; st->searches += 1; st->done = 1; }
+            if (t == 0) { st->amb += amb; st->tie += tie; st->searches += 1; st->done = 1; }
             return;
         }
     }
@@ -760,15 +892,22 @@ extern "C" int hica_p1_breakpoints(hica_handle h, int64_t min_size, double min_f
     hica_timer t(h, HICA_T_BREAKPOINTS);
     const int64_t n = h->n;
     const int64_t stop_ind = (int64_t)((double)n - ((double)n * min_frac));
-    int64_t ind = 0, count = 0, amb = 0;
+    int64_t ind = 0, count = 0, amb = 0, tie = 0;
     *n_cuts = 0;
+    h->tie_breakpoints = -1;
     if (min_frac == 1.0) { t.stop(); return HICA_OK; }
+    {
+        int rc0 = hica_tie_ensure(h);
+        if (rc0) return rc0;
+        if ((rc0 = ensure_xt(h, n + 16))) return rc0;
+    }
+    const TieInfo ti = tie_info(h);
     const char *ra_env = getenv("HICA_CUTS_RUNAHEAD");
     const bool run_ahead = !(ra_env && atoi(ra_env) == 0) && n <= 0x7fffffff && min_size <= 0x7fffffff;
     if (!run_ahead) {
         for (;;) {
             int64_t first = -1, hits = 0;
-            int rc = find_breakpoints(h, ind, min_size, n - ind, .05, &first, &hits, &amb);
+            int rc = find_breakpoints(h, ind, min_size, n - ind, .05, &first, &hits, &amb, &tie);
             if (rc) return rc;
             if (hits == 0) break;
             ind += first;
@@ -796,10 +935,10 @@ extern "C" int hica_p1_breakpoints(hica_handle h, int64_t min_size, double min_f
             int rc = with_rank(h, [&](auto *R) {
                 for (int it = 0; it < RA_BATCH; it++) {
                     int32_t *mi = misc_ra + 8 * it;
-                    k_ra_counts<<<(unsigned)(n - 1) + ncrit, 128, 0, h->stream>>>(R, n, st_d, h->x_d, (int)ncrit, .05, crit);
-                    k_ra_sig<<<ncrit, 128, 0, h->stream>>>(h->x_d, crit, n, st_d, .05, h->sig_d, mi);
+                    k_ra_counts<<<(unsigned)(n - 1) + ncrit, 128, 0, h->stream>>>(R, n, st_d, h->x_d, (int)ncrit, .05, crit, ti, h->xt_d);
+                    k_ra_sig<<<ncrit, 128, 0, h->stream>>>(h->x_d, crit, n, st_d, .05, h->sig_d, mi, h->xt_d);
                     k_ra_hits<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->sig_d, n, st_d, (int)min_size, mi);
-                    k_ra_decide<<<1, RA_DECIDE_THREADS, 0, h->stream>>>(st_d, mi, n, (int)min_size, stop_ind, h->x_d, crit, h->sig_d, .05);
+                    k_ra_decide<<<1, RA_DECIDE_THREADS, 0, h->stream>>>(st_d, mi, n, (int)min_size, stop_ind, h->x_d, crit, h->sig_d, .05, h->xt_d);
                     h->launches += 4;
                 }
                 HICA_CUDA(cudaGetLastError());
@@ -811,10 +950,11 @@ extern "C" int hica_p1_breakpoints(hica_handle h, int64_t min_size, double min_f
             if (st_h->need_host == 2) return hica_set_error(h, HICA_ERR_ARG, "more than %d cut indices", RA_MAX_CUTS);
             if (st_h->done) break;
             if (st_h->need_host) {  // the uncommon cases: the host-driven search repeats this one from the same index
-                int64_t first = -1, hits = 0, amb1 = 0;
-                rc = find_breakpoints(h, st_h->ind, min_size, n - st_h->ind, .05, &first, &hits, &amb1);
+                int64_t first = -1, hits = 0, amb1 = 0, tie1 = 0;
+                rc = find_breakpoints(h, st_h->ind, min_size, n - st_h->ind, .05, &first, &hits, &amb1, &tie1);
                 if (rc) return rc;
                 st_h->amb += (int32_t)amb1;
+                st_h->tie += (int32_t)tie1;
                 st_h->need_host = 0;
                 if (hits == 0) { finished = true; break; }
                 if (st_h->count >= RA_MAX_CUTS) return hica_set_error(h, HICA_ERR_ARG, "more than %d cut indices", RA_MAX_CUTS);
@@ -826,11 +966,15 @@ extern "C" int hica_p1_breakpoints(hica_handle h, int64_t min_size, double min_f
         }
         count = st_h->count;
         amb = st_h->amb;
+        tie = st_h->tie;
         for (int64_t i = 0; i < count && i < capacity; i++)
             if (cuts_host) cuts_host[i] = st_h->cuts[i];
     }
     *n_cuts = count;
-    if (ambiguous) *ambiguous = amb;
+    // decisions that could differ from the reference's: p-values within 1e-7 of the significance level, and counts
+    // that depend on the order numpy.argsort gives exactly tied similarities (hica_p1_tie_report has the breakdown)
+    if (ti.bits) h->tie_breakpoints = tie;
+    if (ambiguous) *ambiguous = amb + (ti.bits ? tie : 0);
     t.stop();
     if (count > capacity) return hica_set_error(h, HICA_ERR_ARG, "cuts capacity %lld too small for %lld cuts",
                                                 (long long)capacity, (long long)count);
@@ -853,7 +997,13 @@ extern "C" int hica_p1_filter(hica_handle h, const int64_t *cuts_in, int64_t n_i
     const int64_t max_rounds = 10 * n_in;
     std::vector<int64_t> altered(cuts_in, cuts_in + n_in);
     std::set<int64_t> prev_filtered, filtered;
-    int64_t amb = 0;
+    int64_t amb = 0, tie = 0;
+    h->tie_filter = -1;
+    {
+        int rc0 = hica_tie_ensure(h);
+        if (rc0) return rc0;
+    }
+    const TieInfo ti = tie_info(h);
     for (;;) {
         int64_t start = 0;
         filtered.clear();
@@ -874,9 +1024,10 @@ extern "C" int hica_p1_filter(hica_handle h, const int64_t *cuts_in, int64_t n_i
             constexpr int CHUNK = 4;
             std::vector<int32_t> all_flags((size_t)CHUNK * nb);
             int chunk_lo = 0, chunk_hi = 0;  // cuts [chunk_lo, chunk_hi) of the list have flags in all_flags
+            int64_t tie_chunk[CHUNK] = {0, 0, 0, 0};  // tie-sensitive row decisions per evaluated cut
             auto eval_chunk = [&](int i0) -> int {
                 const int ne = std::min(CHUNK, nb - i0);
-                const int64_t need = (int64_t)ne * rows * 5 + (int64_t)ne * nb * 12 + (int64_t)ne * 8 + 1024;
+                const int64_t need = (int64_t)ne * rows * 13 + (int64_t)ne * nb * 12 + (int64_t)ne * 8 + 1024 + 64;
                 if (h->cut_buf_cap < need) {
                     if (h->cut_buf) cudaFree(h->cut_buf);
                     h->cut_buf = nullptr;
@@ -890,26 +1041,28 @@ extern "C" int hica_p1_filter(hica_handle h, const int64_t *cuts_in, int64_t n_i
                 int32_t *fcrit = fflags + (int64_t)ne * nb;
                 int32_t *fcrit2 = fcrit + 2 * ne;
                 uint8_t *fsig = (uint8_t *)(fcrit2 + 2 * (int64_t)ne * nb);
+                int2 *fxt = (int2 *)(((uintptr_t)(fsig + (int64_t)ne * rows) + 15) & ~(uintptr_t)15);
                 const int64_t *eval = h->q_d + i0;
                 int rc;
                 if ((rc = reset_misc(h))) return rc;
                 rc = with_rank(h, [&](auto *R) {
                     k_fb_counts<<<dim3((unsigned)rows + 1 + (unsigned)((nb + 127) / 128), (unsigned)ne), 128, 0, h->stream>>>(
-                        R, n, start, eval, rows, fx, M, psig, fcrit, h->q_d, nb, fcrit2);
+                        R, n, start, eval, rows, fx, M, psig, fcrit, h->q_d, nb, fcrit2, ti, fxt);
                     HICA_LAUNCHED(h);
                     return (int)HICA_OK;
                 });
                 if (rc) return rc;
                 k_fb_sig<<<(unsigned)((rows * ne + 255) / 256), 256, 0, h->stream>>>(fx, rows, eval, ne, start, M, psig,
-                                                                                  fcrit, fsig, h->misc_d);
+                                                                                  fcrit, fsig, h->misc_d, fxt);
                 k_fb_intervals<<<dim3((unsigned)nb, (unsigned)ne), 32, 0, h->stream>>>(fsig, rows, start, h->q_d, nb, eval,
                                                                                     M, psig, fflags, h->misc_d, fcrit2);
                 h->launches += 2;
                 HICA_CUDA(cudaGetLastError());
                 HICA_CUDA(cudaMemcpyAsync(all_flags.data(), fflags, sizeof(int32_t) * ne * nb, cudaMemcpyDeviceToHost,
                                           h->stream));
-                if ((rc = fetch_misc(h, 6))) return rc;
+                if ((rc = fetch_misc(h, 12))) return rc;
                 amb += h->misc_h[3];
+                for (int q = 0; q < CHUNK; q++) tie_chunk[q] = h->misc_h[8 + q];
                 chunk_lo = i0;
                 chunk_hi = i0 + ne;
                 return HICA_OK;
@@ -921,6 +1074,7 @@ extern "C" int hica_p1_filter(hica_handle h, const int64_t *cuts_in, int64_t n_i
                     if (rc) return rc;
                 }
                 const int32_t *row_flags = all_flags.data() + (i - chunk_lo) * nb;
+                tie += tie_chunk[i - chunk_lo];  // only the evaluations the reference's loop reaches are counted
                 int right_most_ind = -1;
                 for (int j = 0; j < nb; j++) if (row_flags[j]) right_most_ind = j;
                 if (right_most_ind >= 0) {
@@ -944,8 +1098,23 @@ extern "C" int hica_p1_filter(hica_handle h, const int64_t *cuts_in, int64_t n_i
     int64_t k = 0;
     for (int64_t v : filtered) cuts_out[k++] = v;
     *n_out = k;
-    if (ambiguous) *ambiguous = amb;
+    if (ti.bits) h->tie_filter = tie;
+    if (ambiguous) *ambiguous = amb + (ti.bits ? tie : 0);
     t.stop();
+    return HICA_OK;
+}
+
+extern "C" int hica_p1_tie_report(hica_handle h, int64_t *out4)
+{
+    HICA_CHECK_HANDLE(h);
+    if (!out4) return hica_set_error(h, HICA_ERR_ARG, "out4 is NULL");
+    int rc = h->rank_bytes ? hica_tie_ensure(h) : HICA_OK;
+    if (rc) return rc;
+    const bool avail = h->rank_bytes && h->tie_epoch == h->rank_epoch && h->tie_src != 0;
+    out4[0] = avail ? 1 : 0;
+    out4[1] = avail ? h->tie_breakpoints : -1;
+    out4[2] = avail ? h->tie_filter : -1;
+    out4[3] = avail ? h->tie_rows : -1;
     return HICA_OK;
 }
 

@@ -357,7 +357,88 @@ static int rank_range(hica_ctx *h, int64_t lo, int64_t hi)
     if (rc) return rc;
     t.stop();
     HICA_CUDA(cudaStreamSynchronize(h->stream));
+    h->rank_epoch++;
+    if (presorted && lo == 0 && hi == n && hica_presort_possible(h)) {  // the pre-sort recorded the exact ties of every row
+        h->tie_src = 1;
+        h->tie_epoch = h->rank_epoch;
+    }
     return HICA_OK;
+}
+
+// ---- exact-tie masks for a rank matrix that did not come from the pre-sort -----------------------------------
+// bit k of reordered row i: S[i][R[i][k]] == S[i][R[i][k-1]] (same order key as the sort used)
+template <typename RankT>
+__global__ void __launch_bounds__(256) k_tie_mask(const double *__restrict__ A, int64_t n, const double *__restrict__ s_pair,
+                                                  const double *__restrict__ s_seq, const int32_t *__restrict__ order,
+                                                  int kind, const RankT *__restrict__ R, int tie_words,
+                                                  uint32_t *__restrict__ tie, int32_t *__restrict__ rows_with_ties)
+{
+    const int64_t i = blockIdx.x;
+    const int64_t a = order[i];
+    const double *Arow = A + a * n;
+    const double sp = kind == 0 ? s_pair[a] : 0., rs = kind != 2 ? s_seq[a] : 0.;
+    const RankT *row = R + i * n;
+    auto key = [&](int64_t k) {
+        const double v = Arow[order[row[k]]];
+        const double d = kind ? v : dist_transform(v, sp);
+        return ranksort::order_key(kind == 2 ? d : sim_transform(d, rs));
+    };
+    int any = 0;
+    const int64_t padded = (int64_t)tie_words * 32;
+    for (int64_t k = threadIdx.x; k < padded; k += blockDim.x) {
+        const bool eq = (k >= 1 && k < n) ? (key(k) == key(k - 1)) : false;
+        const uint32_t w = __ballot_sync(0xffffffffu, eq);
+        if ((threadIdx.x & 31) == 0) tie[i * tie_words + (k >> 5)] = w;
+        any |= (w != 0u);
+    }
+    if (__syncthreads_or(any) && threadIdx.x == 0) atomicAdd(rows_with_ties, 1);
+}
+
+// Make the tie masks of the CURRENT rank matrix available (or mark them unavailable: a rank matrix supplied from the
+// host without its values).  Called by the cut searches.
+int hica_tie_ensure(hica_ctx *h)
+{
+    if (h->tie_epoch == h->rank_epoch) return HICA_OK;
+    h->tie_epoch = h->rank_epoch;
+    h->tie_src = 0;
+    h->tie_rows = -1;
+    if (!h->A || !h->have_order || !h->rank_bytes) return HICA_OK;
+    if (h->A_kind != 2 && !h->have_s_seq) return HICA_OK;
+    if (h->A_kind == 0 && !h->have_s_pair) return HICA_OK;
+    if (const char *e = getenv("HICA_TIE_REPORT")) if (atoi(e) == 0) return HICA_OK;
+    const int64_t n = h->n;
+    const int tw = (int)((n + 31) / 32);
+    const int64_t need = n * tw;
+    if (h->tie_own_cap < need) {
+        if (h->tie_own) cudaFree(h->tie_own);
+        h->tie_own = nullptr;
+        h->tie_own_cap = 0;
+        HICA_CUDA(cudaMalloc((void **)&h->tie_own, sizeof(uint32_t) * (size_t)need));
+        h->tie_own_cap = need;
+    }
+    HICA_CUDA(cudaMemsetAsync(h->misc_d + 16, 0, sizeof(int32_t), h->stream));
+    if (h->rank_bytes == 2)
+        k_tie_mask<<<(unsigned)n, 256, 0, h->stream>>>(h->A, n, h->s_pair, h->s_seq, h->order, h->A_kind,
+                                                       (const uint16_t *)h->R, tw, h->tie_own, h->misc_d + 16);
+    else
+        k_tie_mask<<<(unsigned)n, 256, 0, h->stream>>>(h->A, n, h->s_pair, h->s_seq, h->order, h->A_kind,
+                                                       (const int32_t *)h->R, tw, h->tie_own, h->misc_d + 16);
+    HICA_LAUNCHED(h);
+    HICA_CUDA(cudaGetLastError());
+    HICA_CUDA(cudaMemcpyAsync(h->misc_h + 16, h->misc_d + 16, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    HICA_CUDA(cudaStreamSynchronize(h->stream));
+    h->tie_rows = h->misc_h[16];
+    h->tie_src = 2;
+    return HICA_OK;
+}
+
+// (bits, row map, words per row) for the cut kernels; bits == nullptr: no tie information
+void hica_tie_info(hica_ctx *h, const uint32_t **bits, const int32_t **map, int *words)
+{
+    *bits = nullptr; *map = nullptr; *words = (int)((h->n + 31) / 32);
+    if (h->tie_epoch != h->rank_epoch) return;
+    if (h->tie_src == 1) { *bits = pre_layout(h).tie; *map = h->order; }
+    else if (h->tie_src == 2) *bits = h->tie_own;
 }
 
 extern "C" int hica_p1_rank(hica_handle h)
@@ -384,6 +465,7 @@ extern "C" int hica_p1_rank_commit(hica_handle h)
     if (!h->R || !h->rank_rows_bytes) return hica_set_error(h, HICA_ERR_STATE, "no rank rows (hica_p1_rank_rows)");
     if (!h->have_order) return hica_set_error(h, HICA_ERR_STATE, "the order changed since the rows were ranked");
     h->rank_bytes = h->rank_rows_bytes;
+    h->rank_epoch++;   // rows of other GPUs have arrived: the tie masks are recomputed from R on first use
     return HICA_OK;
 }
 
@@ -448,6 +530,10 @@ extern "C" int hica_p1_set_rank(hica_handle h, const int64_t *R_host, int64_t n)
         HICA_CUDA(cudaStreamSynchronize(h->stream));
     }
     h->rank_bytes = h->rank_rows_bytes = bytes;
+    h->rank_epoch++;
+    h->tie_epoch = h->rank_epoch;   // a rank matrix without its values: no tie information
+    h->tie_src = 0;
+    h->tie_rows = -1;
     return HICA_OK;
 }
 

@@ -175,7 +175,9 @@ def run_part1_resident_sharded(h, device, min_size: int = 5, min_frac: float = .
     init, amb0 = h.p1_breakpoints(min_size, min_frac)
     cuts, amb1 = h.p1_filter(init, psig)
     t5 = time.perf_counter()
+    tie = h.tie_report()
     return dict(Z=None, leaves=np.asarray(leaves), initial_cuts=init, cuts=cuts, ambiguous=amb0 + amb1,
+                tie_sensitive=(tie["breakpoints"] + tie["filter"]) if tie["available"] else None,
                 stage_ms={"distance_linkage_bcast": (t3 - t2) * 1e3, "rank_rows_gather": (t4 - t3) * 1e3,
                           "cuts": (t5 - t4) * 1e3})
 

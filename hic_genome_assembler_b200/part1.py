@@ -36,7 +36,9 @@ def run_part1_resident(h: Handle, min_size: int = 5, min_frac: float = .05, psig
     h.p1_rank()
     init, amb0 = h.p1_breakpoints(min_size, min_frac)
     cuts, amb1 = h.p1_filter(init, psig)
-    return dict(Z=Z, leaves=leaves, initial_cuts=init, cuts=cuts, ambiguous=amb0 + amb1)
+    tie = h.tie_report()
+    return dict(Z=Z, leaves=leaves, initial_cuts=init, cuts=cuts, ambiguous=amb0 + amb1,
+                tie_sensitive=(tie["breakpoints"] + tie["filter"]) if tie["available"] else None)
 
 
 # --------------------------------------------------------------------------- #

@@ -179,13 +179,31 @@ int hica_p1_window_sig(hica_handle h, int64_t start, int64_t cut, int64_t M, dou
                        uint8_t *sig_host, int64_t *x_host, int64_t *ambiguous);
 
 /* pre_process_all_matrix_breakpoints :513-551 (first-stage psig is the literal
- * .05 as in the reference, :535). */
+ * .05 as in the reference, :535).  *ambiguous = the number of significance
+ * decisions that could come out differently in the reference: p-values within
+ * 1e-7 of the significance level, plus decisions that depend on the order
+ * numpy.argsort gives EXACTLY TIED similarities (:1132, implementation-defined;
+ * see hica_p1_tie_report). */
 int hica_p1_breakpoints(hica_handle h, int64_t min_size, double min_frac,
                         int64_t *cuts_host, int64_t capacity, int64_t *n_cuts, int64_t *ambiguous);
 
 /* filter_noisy_breakpoints :553-727. */
 int hica_p1_filter(hica_handle h, const int64_t *cuts_in, int64_t n_in, double psig,
                    int64_t *cuts_out, int64_t *n_out, int64_t *ambiguous);
+
+/* Tie-order sensitivity of the last hica_p1_breakpoints / hica_p1_filter calls.
+ * The rank matrix replaces numpy.argsort(S, axis=1)[:, ::-1] (:1132), whose order
+ * of exactly tied values is implementation-defined (this library: stable
+ * ascending, reversed).  A windowed count x = #{k < c : lo <= R[i][k] <= hi}
+ * (:455-459, :631) depends on that order only when position c falls inside a run
+ * of tied values; the cut kernels then bound the count over all orders of the
+ * run, x_lo <= x <= x_hi, and count the decisions that differ between the two.
+ *   out4[0]  1 when tie information exists for the current rank matrix (it does
+ *            not for a rank matrix supplied through hica_p1_set_rank)
+ *   out4[1]  tie-sensitive decisions in the last hica_p1_breakpoints (-1: n/a)
+ *   out4[2]  ... in the last hica_p1_filter
+ *   out4[3]  rows of the rank matrix that contain a tie (-1: not counted) */
+int hica_p1_tie_report(hica_handle h, int64_t *out4);
 
 /* P(X >= x) decisions `sf(x-1; M, n, N) < psig` for a batch of scalar queries
  * (hyper_geom :352-368); out[i] = 1/0, or 2 when inside the safety margin. */

@@ -466,6 +466,161 @@ def filter_noisy_breakpoints(R: np.ndarray, original_inds: Sequence[int],
     return sorted(filtered.keys())
 
 
+# ---- tie-order sensitivity of the window counts (hard part 3) ---------------------------------
+#
+# numpy.argsort(S, axis=1)[:, ::-1] (scaffoldToChromosomes.py:1132) orders exactly tied similarities arbitrarily.
+# A count x = #{k < c : lo <= R[i][k] <= hi} (:455-459, :631) depends on that order only when sorted position c
+# falls inside a run of tied values.  Over all orders of the run it ranges over [x_lo, x_hi]:
+
+
+def count_bounds(vals_sorted: np.ndarray, cols_sorted: np.ndarray, c: int, lo: int, hi: int) -> Tuple[int, int, int]:
+    """(x, x_lo, x_hi) for one row: ``vals_sorted`` = the row's similarities in rank order (descending),
+    ``cols_sorted`` = R[i] (the columns in that order), window = the first ``c`` entries, in range = [lo, hi]."""
+    n = len(vals_sorted)
+    inr = (cols_sorted >= lo) & (cols_sorted <= hi)
+    x = int(np.count_nonzero(inr[:c]))
+    if c <= 0 or c >= n or vals_sorted[c] != vals_sorted[c - 1]:
+        return x, x, x
+    v = vals_sorted[c]
+    g0 = c - 1
+    while g0 > 0 and vals_sorted[g0 - 1] == v:
+        g0 -= 1
+    g1 = c + 1
+    while g1 < n and vals_sorted[g1] == v:
+        g1 += 1
+    x_fixed = int(np.count_nonzero(inr[:g0]))
+    m_in = int(np.count_nonzero(inr[g0:g1]))
+    k_in, g = c - g0, g1 - g0
+    return x, x_fixed + max(0, k_in - (g - m_in)), x_fixed + min(k_in, m_in)
+
+
+def _sig0(x, M, psig=.05):
+    """mode-0 decision vector for counts x[1:], n = N = c (NaN counts as significant, :466-469)."""
+    sig = np.zeros(len(x), dtype=np.int64)
+    if len(x) > 1:
+        c = np.arange(1, len(x))
+        with np.errstate(all='ignore'):
+            p = hyper_geom(np.asarray(x[1:]), M, c, c)
+        sig[1:] = np.where(p >= psig, 0, 1)
+    return sig
+
+
+def tie_sensitive_breakpoints(S: np.ndarray, R: np.ndarray, min_size: int = 5, min_frac: float = .05) -> int:
+    """How many row decisions of pre_process_all_matrix_breakpoints (:513-551, through
+    find_matrix_pvalue_breakpoints :413-511) depend on the order of exactly tied similarities; every evaluation
+    of the significances counts (they are re-evaluated when M shrinks and for every narrower window)."""
+    N = len(R)
+    stop_ind = int(N - (N * min_frac))
+    ind, total = 0, 0
+    if min_frac == 1:
+        return 0
+    Ssorted = np.take_along_axis(np.asarray(S), np.asarray(R), 1)
+    while True:
+        start = ind
+        L = N - start
+        x = np.zeros(L, dtype=np.int64)
+        xlo, xhi = x.copy(), x.copy()
+        for i in range(start + 1, N):
+            c = i - start
+            x[c], xlo[c], xhi[c] = count_bounds(Ssorted[i], R[i], c, start, i)
+        M, ws, break_sig, loop_count, cuts = N - start, min_size, 0, 0, []
+        while True:
+            while True:
+                sig = _sig0(x, M)
+                total += int(np.count_nonzero(_sig0(xlo, M) != _sig0(xhi, M)))
+                loop_count += 1
+                if (int(sig.sum()) / len(sig)) >= .9:
+                    M = int(M - start)
+                else:
+                    break_sig = 1
+                if break_sig == 1 or loop_count >= 5:
+                    break
+            b = sliding_break_signal(sig, ws)
+            cuts = [] if b is None else [int(t) + min_size for t in np.nonzero(b == min_size)[0]]
+            if cuts:
+                break
+            ws -= 1
+            if ws == 0:
+                break
+        if not cuts:
+            break
+        ind += cuts[0]
+        if ind >= stop_ind or (N - ind) <= min_size:
+            break
+    return total
+
+
+def tie_sensitive_filter(S: np.ndarray, R: np.ndarray, original_inds: Sequence[int], psig: float = .05) -> int:
+    """The same for the row decisions of filter_noisy_breakpoints (:617-636), over the (start, cut) pairs its loop
+    evaluates (NaN p-values count as not significant there)."""
+    if len(original_inds) == 0:
+        return 0
+    N = len(R)
+    MD = int(N / 5)
+    Ssorted = np.take_along_axis(np.asarray(S), np.asarray(R), 1)
+    total = 0
+    max_rounds = 10 * len(original_inds)
+    altered = list(original_inds)
+    prev_filtered: Dict[int, str] = {}
+    while True:
+        start = 0
+        filtered: Dict[int, str] = {}
+        round_count = 0
+        while True:
+            if round_count >= max_rounds:
+                break
+            M = N - start
+            noise_found = 0
+            keep_from = 0
+            for i, c in enumerate(altered):
+                local = c - start
+                sig = filter_row_significance(R, start, c, psig)
+                hi = min(N, start + MD + 1)
+                lo_x = np.zeros(hi - start, dtype=np.int64)
+                hi_x = lo_x.copy()
+                for ii in range(start, hi):
+                    _, lo_x[ii - start], hi_x[ii - start] = count_bounds(Ssorted[ii], R[ii], local, start, c)
+                with np.errstate(all='ignore'):
+                    total += int(np.count_nonzero((hyper_geom(lo_x, M, local, local) < psig) !=
+                                                  (hyper_geom(hi_x, M, local, local) < psig)))
+                cs = np.concatenate([[0], np.cumsum(sig)])
+                right_most = None
+                right_most_ind = None
+                fc_prev = start
+                for ai_ind, ai in enumerate(altered):
+                    lo, hi_ = fc_prev, ai
+                    if ai == fc_prev:
+                        continue
+                    fc_prev = ai
+                    npts = max(0, hi_ - lo)
+                    if npts == 0:
+                        break
+                    xs = int(cs[hi_ - start] - cs[lo - start])
+                    with np.errstate(all='ignore'):
+                        noise_p = hyper_geom(xs, M, local, npts)
+                    if noise_p < psig:
+                        right_most = ai
+                        right_most_ind = ai_ind
+                if right_most is not None:
+                    start = right_most
+                    filtered[right_most] = ''
+                    noise_found = 1
+                    keep_from = right_most_ind
+                    break
+                filtered[c] = ''
+                keep_from = i
+            round_count += 1
+            if noise_found == 0:
+                break
+            altered = altered[keep_from:]
+        if prev_filtered != filtered:
+            altered = sorted(filtered)
+            prev_filtered = filtered
+        else:
+            break
+    return total
+
+
 def part1_cut_indices(A: np.ndarray, min_size: int = 5, min_frac: float = 0.0,
                       psig: float = .05, stable_rank: bool = False):
     """The Part1 hot path from the dense ICE matrix to (Z, leaves, initial cuts,
