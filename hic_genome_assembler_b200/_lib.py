@@ -27,6 +27,8 @@ ABI_SYMBOLS = (
     "hica_p1_window_sig", "hica_p1_breakpoints", "hica_p1_filter", "hica_p1_tie_report", "hica_hypergeom_less",
     "hica_p2_upload", "hica_p2_use_p1_matrix", "hica_p2_select", "hica_p2_set_segments", "hica_p2_total",
     "hica_p2_score_candidates", "hica_p2_score_window", "hica_p2_score_orders", "hica_p2_order_groups",
+    "hica_s32_alloc", "hica_s32_buffer", "hica_s32_row_sums", "hica_s32_build_w", "hica_s32_ipc_export", "hica_s32_ipc_open",
+    "hica_s32_ipc_close", "hica_s32_linkage",
     "hica_io_read_matrix", "hica_io_last_error", "hica_io_log_transform",
 )
 
@@ -93,6 +95,14 @@ def load_library():
     L.hica_p2_score_window.argtypes = [vp, vp, i32, i32, i32, vp, i32, vp, i32, i64, i64, dbl, dbl, vp, vp, vp]
     L.hica_p2_score_orders.argtypes = [vp, vp, i64, i32, dbl, dbl, vp, vp, vp]
     L.hica_p2_order_groups.argtypes = [vp, i32, vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, i32, vp, i32, vp, vp, vp, vp]
+    L.hica_s32_alloc.argtypes = [vp, i64, i64, i64, C.c_int]
+    L.hica_s32_buffer.argtypes = [vp, C.c_int, vp, vp]
+    L.hica_s32_row_sums.argtypes = [vp]
+    L.hica_s32_build_w.argtypes = [vp, vp, i64]
+    L.hica_s32_ipc_export.argtypes = [vp, C.c_int, vp]
+    L.hica_s32_ipc_open.argtypes = [vp, vp, vp]
+    L.hica_s32_ipc_close.argtypes = [vp, vp]
+    L.hica_s32_linkage.argtypes = [vp, vp, vp]
     L.hica_io_read_matrix.argtypes = [C.c_char_p, vp, i64, i64, vp, C.c_int, vp, vp]
     L.hica_io_log_transform.argtypes = [vp, vp, i64, dbl, dbl, C.c_int, C.c_int]
     L.hica_io_last_error.argtypes = []
@@ -341,6 +351,43 @@ class Handle:
         out = np.empty(x.size, dtype=np.uint8)
         self._check(self._L.hica_hypergeom_less(self._h, _ptr(x), _ptr(M), _ptr(n), _ptr(N), x.size, psig, _ptr(out)))
         return out
+
+    # -- 10 kb configuration: fp32 storage, row-block sharding (see hica.h) ----
+    def s32_alloc(self, n: int, r0: int, r1: int, with_linkage_matrix: bool):
+        self._check(self._L.hica_s32_alloc(self._h, int(n), int(r0), int(r1), 1 if with_linkage_matrix else 0))
+        self.s32 = (int(n), int(r0), int(r1), (int(n) + 15) // 16 * 16)
+
+    def s32_buffer(self, which: int) -> Tuple[int, int]:
+        ptr, nbytes = C.c_void_p(0), C.c_int64(0)
+        self._check(self._L.hica_s32_buffer(self._h, int(which), C.byref(ptr), C.byref(nbytes)))
+        return int(ptr.value or 0), int(nbytes.value)
+
+    def s32_row_sums(self):
+        self._check(self._L.hica_s32_row_sums(self._h))
+
+    def s32_build_w(self, dst_ptr: int = 0, ld: int = 0):
+        self._check(self._L.hica_s32_build_w(self._h, C.c_void_p(dst_ptr) if dst_ptr else None, int(ld)))
+
+    def s32_ipc_export(self, which: int) -> bytes:
+        buf = C.create_string_buffer(64)
+        self._check(self._L.hica_s32_ipc_export(self._h, int(which), buf))
+        return buf.raw
+
+    def s32_ipc_open(self, handle: bytes) -> int:
+        ptr = C.c_void_p(0)
+        buf = C.create_string_buffer(handle, 64)
+        self._check(self._L.hica_s32_ipc_open(self._h, buf, C.byref(ptr)))
+        return int(ptr.value or 0)
+
+    def s32_ipc_close(self, ptr: int):
+        self._check(self._L.hica_s32_ipc_close(self._h, C.c_void_p(ptr)))
+
+    def s32_linkage(self, want_Z: bool = True):
+        n = self.s32[0]
+        Z = np.empty((n - 1, 4)) if want_Z else None
+        leaves = np.empty(n, dtype=np.int32)
+        self._check(self._L.hica_s32_linkage(self._h, _ptr(Z), _ptr(leaves)))
+        return Z, leaves
 
     # -- Part 2 -----------------------------------------------------------
     def p2_upload(self, G: np.ndarray):

@@ -6,6 +6,8 @@
 
 #include "hica_common.cuh"
 
+void hica_s32_release(hica_ctx *h);  // hica_p1_shard32.cu
+
 static thread_local std::string g_create_error;
 
 int hica_set_error(hica_ctx *h, int code, const char *fmt, ...)
@@ -134,6 +136,7 @@ extern "C" int hica_destroy(hica_handle h)
     cudaFreeHost(h->ra_h);
     cudaFree(h->red_d);
     cudaFreeHost(h->red_h);
+    hica_s32_release(h);
     cudaFree(h->pre_buf);
     cudaFree(h->tie_own);
     cudaFree(h->xt_d);

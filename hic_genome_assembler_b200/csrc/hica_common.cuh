@@ -77,6 +77,13 @@ struct hica_ctx {
     int64_t plan_n = 0;
     int plan_m = 0, plan_levels = 0;
 
+    // ---- 10 kb configuration: fp32 storage, the matrix sharded by row block over the GPUs (hica_p1_shard32.cu) ----
+    int64_t s32_n = 0, s32_r0 = 0, s32_r1 = 0, s32_ld = 0;
+    float *A32 = nullptr;        // rows [r0, r1) of the ICE matrix, (r1 - r0) x n
+    double *s32_sum = nullptr;   // n row sums (own rows computed here, the others gathered by the caller)
+    float *W32 = nullptr;        // n x ld mirrored working matrix, on the linkage GPU only
+    std::vector<void *> ipc_open;  // peer mappings opened with hica_s32_ipc_open
+
     // ---- Part 2 state ---------------------------------------------------
     double *G = nullptr;   // genome matrix (owned unless g_is_A)
     int64_t gn = 0;

@@ -531,3 +531,87 @@ extern "C" int hica_p1_linkage(hica_handle h, double *Z_host, int32_t *leaves_ho
     t2.stop();
     return rc;
 }
+
+// ---- 10 kb configuration: the chain on the fp32 working matrix of hica_p1_shard32.cu -------------------------------
+namespace {
+
+template <bool CHAIN_SMEM>
+int launch_nn_chain2_f32(hica_ctx *h, int cluster_size, size_t smem_bytes, float *W, int n, int64_t ld, int32_t *size_d,
+                         int32_t *chain_d, double *Zraw)
+{
+    auto kern = nn2::k_nn_chain2<CHAIN_SMEM, float>;
+    HICA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+    if (cluster_size > 8) HICA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(cluster_size);
+    cfg.blockDim = dim3(512);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = h->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cluster_size;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int max_clusters = 0;
+    cudaError_t e = cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg);
+    if (e != cudaSuccess || max_clusters < 1) {
+        cudaGetLastError();
+        return -1;
+    }
+    HICA_CUDA(cudaLaunchKernelEx(&cfg, kern, W, n, ld, size_d, chain_d, Zraw, reinterpret_cast<long long *>(h->misc_d + 64)));
+    HICA_LAUNCHED(h);
+    return HICA_OK;
+}
+
+}  // namespace
+
+extern "C" int hica_s32_linkage(hica_handle h, double *Z_host, int32_t *leaves_host)
+{
+    HICA_CHECK_HANDLE(h);
+    if (!h->W32) return hica_set_error(h, HICA_ERR_STATE, "this GPU holds no working matrix (hica_s32_alloc with_linkage_matrix)");
+    const int64_t n = h->s32_n;
+    double *Zraw = nullptr;
+    int32_t *size_d = nullptr, *chain_d = nullptr;
+    int rc;
+    if ((rc = hica_realloc(h, &Zraw, 4 * (n - 1)))) return rc;
+    if ((rc = hica_realloc(h, &size_d, (int64_t)NN_MAX_CLUSTER * n))) { cudaFree(Zraw); return rc; }
+    if ((rc = hica_realloc(h, &chain_d, (int64_t)NN_MAX_CLUSTER * n))) { cudaFree(Zraw); cudaFree(size_d); return rc; }
+    auto cleanup = [&]() { cudaFree(Zraw); cudaFree(size_d); cudaFree(chain_d); };
+    const int nwords = (int)((h->s32_ld + 31) / 32);
+    const size_t base_smem = nn2::base_smem(nwords), chain_smem = sizeof(int32_t) * (size_t)n;
+    const bool chain_in_smem = base_smem + chain_smem <= 200 * 1024;
+    hica_timer t(h, HICA_T_LINKAGE);
+    k_fill_i32<<<(unsigned)((NN_MAX_CLUSTER * n + 255) / 256), 256, 0, h->stream>>>(size_d, NN_MAX_CLUSTER * n, 1);
+    HICA_LAUNCHED(h);
+    cudaMemsetAsync(h->misc_d + 64, 0, 144 * sizeof(long long), h->stream);
+    int launched = -1;
+    int cs_max = NN_MAX_CLUSTER;
+    if (const char *e = getenv("HICA_NN_CLUSTER")) cs_max = std::max(1, std::min(NN_MAX_CLUSTER, atoi(e)));
+    for (int cs = cs_max; cs >= 1 && launched != HICA_OK; cs >>= 1) {
+        launched = chain_in_smem ? launch_nn_chain2_f32<true>(h, cs, base_smem + chain_smem, h->W32, (int)n, h->s32_ld, size_d, chain_d, Zraw)
+                                 : launch_nn_chain2_f32<false>(h, cs, base_smem, h->W32, (int)n, h->s32_ld, size_d, chain_d, Zraw);
+        if (launched > 0) { cleanup(); return launched; }
+    }
+    if (launched != HICA_OK) { cleanup(); return hica_set_error(h, HICA_ERR_CUDA, "no cluster configuration could be launched"); }
+    t.stop();
+    std::vector<double> raw(4 * (n - 1));
+    cudaError_t e = cudaMemcpyAsync(raw.data(), Zraw, sizeof(double) * raw.size(), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    {
+        long long st[8] = {0};
+        cudaMemcpy(st, h->misc_d + 64, sizeof(st), cudaMemcpyDeviceToHost);
+        for (int i = 0; i < 8; i++) h->nn_stats[i] = st[i];
+    }
+    cleanup();
+    if (e != cudaSuccess) return hica_set_error(h, HICA_ERR_CUDA, "s32 linkage: %s", cudaGetErrorString(e));
+    hica_timer t2(h, HICA_T_LEAFORDER);
+    std::vector<double> Z;
+    std::vector<int32_t> leaves;
+    label_and_order(raw, n, Z, leaves);
+    if (Z_host) std::copy(Z.begin(), Z.end(), Z_host);
+    if (leaves_host) std::copy(leaves.begin(), leaves.end(), leaves_host);
+    t2.stop();
+    return HICA_OK;
+}

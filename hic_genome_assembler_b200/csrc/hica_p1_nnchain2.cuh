@@ -63,9 +63,22 @@ __device__ __forceinline__ unsigned long long ld_volatile_shared_u64(const unsig
     return v;
 }
 
-template <bool CHAIN_SMEM>
+// Storage type of the working matrix: fp64 (bit-exact with scipy) or fp32 (the 10 kb configuration: 160,000 bins
+// do not fit one GPU in fp64).  Values are compared and updated in fp64 either way; an fp32 matrix rounds the
+// update once, on store - and the value handed on (patch slot, height) is the stored one.
+__device__ __forceinline__ double2 ld_cg_x2(const double *p) { return ld_cg_f64x2(p); }
+__device__ __forceinline__ double2 ld_cg_x2(const float *p)
+{
+    float2 v;
+    asm volatile("ld.global.cg.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+    return make_double2((double)v.x, (double)v.y);
+}
+__device__ __forceinline__ double as_stored(double v, const double *) { return v; }
+__device__ __forceinline__ double as_stored(double v, const float *) { return (double)__double2float_rn(v); }
+
+template <bool CHAIN_SMEM, typename WT = double>
 __global__ void __launch_bounds__(MAX_THREADS, 1)
-k_nn_chain2(double *__restrict__ W, const int n, const int64_t ld, int32_t *__restrict__ size_g,
+k_nn_chain2(WT *__restrict__ W, const int n, const int64_t ld, int32_t *__restrict__ size_g,
             int32_t *__restrict__ chain_g, double *__restrict__ Zraw, long long *__restrict__ stats)
 {
     cg::cluster_group cluster = cg::this_cluster();
@@ -129,7 +142,7 @@ k_nn_chain2(double *__restrict__ W, const int n, const int64_t ld, int32_t *__re
             seq++;
             const int par = seq & 1;
             const long long ts0 = clock64();
-            const double *row = W + (int64_t)x * ld;
+            const WT *row = W + (int64_t)x * ld;
             Best b;
             b.hi = NONE; b.lo = NONE; b.ic = NONE;
             for (int c0 = lo + 2 * tid; c0 < hi; c0 += 8 * T) {
@@ -137,7 +150,7 @@ k_nn_chain2(double *__restrict__ W, const int n, const int64_t ld, int32_t *__re
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
                     const int c = c0 + 2 * T * u;
-                    if (c < hi) v[u] = ld_cg_f64x2(row + c);
+                    if (c < hi) v[u] = ld_cg_x2(row + c);
                 }
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
@@ -242,33 +255,33 @@ k_nn_chain2(double *__restrict__ W, const int n, const int64_t ld, int32_t *__re
             nxt = fa;
         }
         {   // pull this CTA's slice of that row towards L2 while the update runs
-            const double *nrow = W + (int64_t)nxt * ld;
-            for (int c = lo + 16 * tid; c < hi; c += 16 * T)
+            const WT *nrow = W + (int64_t)nxt * ld;
+            for (int c = lo + (int)(128 / sizeof(WT)) * tid; c < hi; c += (int)(128 / sizeof(WT)) * T)
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(nrow + c));
         }
         const unsigned tag = (unsigned)k + 1u;
         const int nx = size[x], ny = size[y];
         const double dnx = (double)nx, dny = (double)ny, dsum = (double)(nx + ny);
-        const double *rowx = W + (int64_t)x * ld;
-        double *rowy = W + (int64_t)y * ld;
+        const WT *rowx = W + (int64_t)x * ld;
+        WT *rowy = W + (int64_t)y * ld;
         for (int c = lo + 2 * tid; c < hi; c += 2 * T) {
             const uint32_t bits = alive[c >> 5] >> (c & 31);
             const bool u0 = (bits & 1u) && c != x && c != y;
             const bool u1 = (bits & 2u) && c + 1 != x && c + 1 != y;
             if (!(u0 || u1)) continue;
-            const double2 vx = ld_cg_f64x2(rowx + c), vy = ld_cg_f64x2(rowy + c);
+            const double2 vx = ld_cg_x2(rowx + c), vy = ld_cg_x2(rowy + c);
             double vnext = 0.;
             bool have_next = false;
             if (u0) {
-                const double v = __ddiv_rn(__dadd_rn(__dmul_rn(dnx, vx.x), __dmul_rn(dny, vy.x)), dsum);
-                rowy[c] = v;
-                W[(int64_t)c * ld + y] = v;
+                const double v = as_stored(__ddiv_rn(__dadd_rn(__dmul_rn(dnx, vx.x), __dmul_rn(dny, vy.x)), dsum), rowy);
+                rowy[c] = (WT)v;
+                W[(int64_t)c * ld + y] = (WT)v;
                 if (c == nxt) { vnext = v; have_next = true; }
             }
             if (u1) {
-                const double v = __ddiv_rn(__dadd_rn(__dmul_rn(dnx, vx.y), __dmul_rn(dny, vy.y)), dsum);
-                rowy[c + 1] = v;
-                W[(int64_t)(c + 1) * ld + y] = v;
+                const double v = as_stored(__ddiv_rn(__dadd_rn(__dmul_rn(dnx, vx.y), __dmul_rn(dny, vy.y)), dsum), rowy);
+                rowy[c + 1] = (WT)v;
+                W[(int64_t)(c + 1) * ld + y] = (WT)v;
                 if (c + 1 == nxt) { vnext = v; have_next = true; }
             }
             if (have_next) {  // (a): W[nxt][y] for the CTA that scans column y in the next search

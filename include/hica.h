@@ -275,6 +275,33 @@ int hica_p2_order_groups(hica_handle h, int32_t ngroups, const int32_t *grp_ptr,
 int hica_p2_score_orders(hica_handle h, const int32_t *orders, int64_t B, int32_t L, double total,
                          double carried, double *best, int64_t *best_idx, double *scores_or_null);
 
+/* ---- 10 kb configuration (BASELINE.json configs[4]): fp32 storage, row-block sharding over the GPUs ----------
+ * 160,000 bins: the ICE matrix is 102 GB in fp32 and is cut into contiguous row blocks, one per GPU (one process and
+ * one handle per GPU); the sequential linkage runs on ONE GPU, which additionally holds the mirrored working matrix
+ * (102 GB).  Replaces convertMatrix(distance=True) :138-147 + squareform :194 + hierarchy.average :197 for a matrix
+ * the reference itself cannot hold.  Arithmetic is fp64 on fp32 storage (one rounding per stored value); parity is
+ * against this library's own fp64 path at <= 32,000 bins (stated tolerance, tests/test_gpu_shard32.py).
+ *   hica_s32_alloc      rows [r0, r1) of the n x n matrix on this GPU (+ the working matrix when
+ *                       with_linkage_matrix != 0)
+ *   hica_s32_buffer     device pointer / bytes of which = 0: the row block (fp32, (r1-r0) x n, filled by the caller
+ *                       - e.g. as a zero-copy torch tensor), 1: the working matrix (fp32, n x ld, ld = n rounded up
+ *                       to 16), 2: the n row sums (fp64; the caller all-gathers the blocks the other GPUs computed)
+ *   hica_s32_row_sums   s_i of the own rows (fp64 accumulation)
+ *   hica_s32_build_w    rows [r0, r1) of the mirrored working matrix, W[i][j] = (1 - A_ij / s_min(i,j)) + 1, written
+ *                       to W_dst (row-major, leading dimension ld): NULL = this GPU's own working matrix, otherwise
+ *                       e.g. the linkage GPU's, mapped with hica_s32_ipc_open - the transform and the gather over
+ *                       NVLink are then ONE kernel
+ *   hica_s32_ipc_*      CUDA IPC export / open / close of a buffer (64-byte handle), for one process per GPU
+ *   hica_s32_linkage    hierarchy.average + dendrogram leaf order on the fp32 working matrix (Z may be NULL) */
+int hica_s32_alloc(hica_handle h, int64_t n, int64_t r0, int64_t r1, int with_linkage_matrix);
+int hica_s32_buffer(hica_handle h, int which, void **ptr, int64_t *bytes);
+int hica_s32_row_sums(hica_handle h);
+int hica_s32_build_w(hica_handle h, void *W_dst, int64_t ld);
+int hica_s32_ipc_export(hica_handle h, int which, void *handle64);
+int hica_s32_ipc_open(hica_handle h, const void *handle64, void **ptr);
+int hica_s32_ipc_close(hica_handle h, void *ptr);
+int hica_s32_linkage(hica_handle h, double *Z_host, int32_t *leaves_host);
+
 /* ---- loaders either side of the hot path ------------------ */
 
 /* buildAdjacencyMatrix (scaffoldToChromosomes.py:70-98): the sparse HiC-Pro

@@ -2,6 +2,7 @@
 import os
 import socket
 
+import numpy as np
 import pytest
 import torch
 import torch.distributed as dist
@@ -87,3 +88,40 @@ def test_two_rank_gloo_merge_and_argmax(tmp_path):
     world = 2
     mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
     assert all(os.path.exists(os.path.join(str(tmp_path), "ok%d" % r)) for r in range(world))
+
+
+def _gen_worker(rank, world, port, out_dir):
+    import torch
+    import torch.distributed as dist
+    from hic_genome_assembler_b200 import dist10kb
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        n = 203
+        layout = dist10kb.ShardLayout(n, 4, seed=3, scaffolds_per_chrom=5)
+        blocks = dist10kb.row_blocks(n, world)
+        r0, r1 = blocks[rank]
+        M = torch.empty((r1 - r0, n), dtype=torch.float32)
+        dist10kb.generate_shard(M, layout, r0, r1, blocks, ice_sweeps=7, dist_mod=dist)
+        np.save(os.path.join(out_dir, "shard_%d.npy" % rank), M.numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_generator_does_not_depend_on_the_number_of_ranks(tmp_path):
+    """dist10kb.generate_shard (the 10 kb workload, generated in place by row block): 2 gloo ranks give the very
+    rows one rank gives - row sums are the only exchange - and the matrix is exactly symmetric."""
+    import torch
+    import torch.multiprocessing as mp
+    from hic_genome_assembler_b200 import dist10kb
+    mp.spawn(_gen_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    n = 203
+    layout = dist10kb.ShardLayout(n, 4, seed=3, scaffolds_per_chrom=5)
+    M = torch.empty((n, n), dtype=torch.float32)
+    dist10kb.generate_shard(M, layout, 0, n, [(0, n)], ice_sweeps=7)
+    full = M.numpy()
+    got = np.concatenate([np.load(os.path.join(str(tmp_path), "shard_%d.npy" % r)) for r in range(2)])
+    assert np.array_equal(got, full)
+    assert np.array_equal(full, full.T)
+    assert np.allclose(full.sum(1), 1000.0, rtol=1e-3)

@@ -65,6 +65,7 @@ def test_tie_report_matches_oracle(hica, monkeypatch, name, make, overlap):
 def test_no_tie_information_for_a_rank_matrix_from_the_host(hica):
     A = _sparse_map(120, 3, 2, 0.5)
     ref = _oracle(A)
+    hica.p1_upload(A)          # (a rank matrix must have the size of the resident matrix)
     hica.p1_set_rank(ref["R"].astype(np.int64))
     init, amb = hica.p1_breakpoints(5, 0.0)
     assert init == ref["init"]
