@@ -98,7 +98,7 @@ def load_library():
     L.hica_s32_alloc.argtypes = [vp, i64, i64, i64, C.c_int]
     L.hica_s32_buffer.argtypes = [vp, C.c_int, vp, vp]
     L.hica_s32_row_sums.argtypes = [vp]
-    L.hica_s32_build_w.argtypes = [vp, vp, i64]
+    L.hica_s32_build_w.argtypes = [vp, vp, i64, i64]
     L.hica_s32_ipc_export.argtypes = [vp, C.c_int, vp]
     L.hica_s32_ipc_open.argtypes = [vp, vp, vp]
     L.hica_s32_ipc_close.argtypes = [vp, vp]
@@ -365,8 +365,8 @@ class Handle:
     def s32_row_sums(self):
         self._check(self._L.hica_s32_row_sums(self._h))
 
-    def s32_build_w(self, dst_ptr: int = 0, ld: int = 0):
-        self._check(self._L.hica_s32_build_w(self._h, C.c_void_p(dst_ptr) if dst_ptr else None, int(ld)))
+    def s32_build_w(self, dst_ptr: int = 0, ld: int = 0, dst_row0: int = 0):
+        self._check(self._L.hica_s32_build_w(self._h, C.c_void_p(dst_ptr) if dst_ptr else None, int(ld), int(dst_row0)))
 
     def s32_ipc_export(self, which: int) -> bytes:
         buf = C.create_string_buffer(64)

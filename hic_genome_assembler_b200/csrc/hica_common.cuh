@@ -83,6 +83,8 @@ struct hica_ctx {
     double *s32_sum = nullptr;   // n row sums (own rows computed here, the others gathered by the caller)
     float *W32 = nullptr;        // n x ld mirrored working matrix, on the linkage GPU only
     std::vector<void *> ipc_open;  // peer mappings opened with hica_s32_ipc_open
+    void *s32_scratch = nullptr;   // raw merges | cluster sizes | chains of hica_s32_linkage (grow-only)
+    int64_t s32_scratch_cap = 0;
 
     // ---- Part 2 state ---------------------------------------------------
     double *G = nullptr;   // genome matrix (owned unless g_is_A)

@@ -572,13 +572,19 @@ extern "C" int hica_s32_linkage(hica_handle h, double *Z_host, int32_t *leaves_h
     HICA_CHECK_HANDLE(h);
     if (!h->W32) return hica_set_error(h, HICA_ERR_STATE, "this GPU holds no working matrix (hica_s32_alloc with_linkage_matrix)");
     const int64_t n = h->s32_n;
-    double *Zraw = nullptr;
-    int32_t *size_d = nullptr, *chain_d = nullptr;
-    int rc;
-    if ((rc = hica_realloc(h, &Zraw, 4 * (n - 1)))) return rc;
-    if ((rc = hica_realloc(h, &size_d, (int64_t)NN_MAX_CLUSTER * n))) { cudaFree(Zraw); return rc; }
-    if ((rc = hica_realloc(h, &chain_d, (int64_t)NN_MAX_CLUSTER * n))) { cudaFree(Zraw); cudaFree(size_d); return rc; }
-    auto cleanup = [&]() { cudaFree(Zraw); cudaFree(size_d); cudaFree(chain_d); };
+    // scratch kept in the handle (grow-only): cudaMalloc / cudaFree next to a 100 GB allocation cost ~0.1 s each
+    const int64_t zb = (8 * 4 * (n - 1) + 255) / 256 * 256, ib = ((int64_t)NN_MAX_CLUSTER * n * 4 + 255) / 256 * 256;
+    if (h->s32_scratch_cap < zb + 2 * ib) {
+        if (h->s32_scratch) cudaFree(h->s32_scratch);
+        h->s32_scratch = nullptr;
+        h->s32_scratch_cap = 0;
+        HICA_CUDA(cudaMalloc(&h->s32_scratch, (size_t)(zb + 2 * ib)));
+        h->s32_scratch_cap = zb + 2 * ib;
+    }
+    double *Zraw = reinterpret_cast<double *>(h->s32_scratch);
+    int32_t *size_d = reinterpret_cast<int32_t *>((char *)h->s32_scratch + zb);
+    int32_t *chain_d = reinterpret_cast<int32_t *>((char *)h->s32_scratch + zb + ib);
+    auto cleanup = [&]() {};
     const int nwords = (int)((h->s32_ld + 31) / 32);
     const size_t base_smem = nn2::base_smem(nwords), chain_smem = sizeof(int32_t) * (size_t)n;
     const bool chain_in_smem = base_smem + chain_smem <= 200 * 1024;

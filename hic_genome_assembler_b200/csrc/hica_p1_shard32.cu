@@ -85,6 +85,9 @@ void hica_s32_release(hica_ctx *h)   // hica_destroy
 {
     for (void *p : h->ipc_open) cudaIpcCloseMemHandle(p);
     h->ipc_open.clear();
+    cudaFree(h->s32_scratch);
+    h->s32_scratch = nullptr;
+    h->s32_scratch_cap = 0;
     free_s32(h);
 }
 
@@ -133,14 +136,16 @@ extern "C" int hica_s32_row_sums(hica_handle h)
     return HICA_OK;
 }
 
-extern "C" int hica_s32_build_w(hica_handle h, void *W_dst, int64_t ld)
+extern "C" int hica_s32_build_w(hica_handle h, void *W_dst, int64_t ld, int64_t dst_row0)
 {
     HICA_CHECK_HANDLE(h);
     if (!h->A32) return hica_set_error(h, HICA_ERR_STATE, "call hica_s32_alloc first");
     float *dst = W_dst ? reinterpret_cast<float *>(W_dst) : h->W32;
     if (!dst) return hica_set_error(h, HICA_ERR_STATE, "no destination: this GPU holds no working matrix and none was given");
-    if (!W_dst) ld = h->s32_ld;
+    if (!W_dst) { ld = h->s32_ld; dst_row0 = 0; }
     if (ld < h->s32_n || (ld & 3)) return hica_set_error(h, HICA_ERR_ARG, "bad leading dimension");
+    if (dst_row0 < 0 || dst_row0 > h->s32_r0) return hica_set_error(h, HICA_ERR_ARG, "dst_row0 must lie in [0, r0]");
+    dst -= dst_row0 * ld;   // row i of the matrix lands in row i - dst_row0 of the destination
     hica_timer t(h, HICA_T_DISTANCE);
     const int64_t rows = h->s32_r1 - h->s32_r0, n = h->s32_n;
     for (int64_t y0 = 0; y0 < rows; y0 += 65535) {

@@ -73,7 +73,7 @@ class ShardLayout:
 
 
 def generate_shard(M, layout: ShardLayout, r0: int, r1: int, blocks, *, noise_sigma: float = 0.15, ice_sweeps: int = 50,
-                   row_sum_target: float = 1000.0, dist_mod=None):
+                   row_sum_target: float = 1000.0, dist_mod=None, distance_scale: Optional[float] = None):
     """Fill ``M`` (a torch tensor, (r1-r0) x n, fp32 or fp64, any device) with rows [r0, r1) of the portable
     synthetic ICE matrix.  Every operation is row-local except the row sums, which are all-gathered once per
     ICE sweep; the result is bit-identical for every number of ranks."""
@@ -82,13 +82,20 @@ def generate_shard(M, layout: ShardLayout, r0: int, r1: int, blocks, *, noise_si
     n = layout.n
     dev = M.device
     fdtype = M.dtype
+    if distance_scale is None:
+        # contacts decay with GENOMIC distance: one bin of a finer map is a shorter stretch of DNA.  SURVEY 8d's
+        # recipe counts in bins and was tuned at 100 kb (16,000 bins); finer maps scale the bin distance back to
+        # 100 kb units, otherwise the two halves of a 8,000-bin chromosome touch each other less than the 0.3
+        # inter-chromosome background and no clustering can keep the chromosome together.
+        distance_scale = min(1.0, 16000.0 / n)
     conv = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.int64), device=dev)  # noqa: E731
     t_all, c_of, p_of = conv(layout.perm), conv(layout.chrom_of), conv(layout.pos_in_chrom)
     rows = r1 - r0
     blk = max(1, min(max(rows, 1), (1 << 24) // n))
     for b0 in range(0, rows, blk):
         b1 = min(rows, b0 + blk)
-        M[b0:b1] = portable_tile(t_all[r0 + b0:r0 + b1], t_all, c_of, p_of, layout.seed, noise_sigma, fdtype, torch)
+        M[b0:b1] = portable_tile(t_all[r0 + b0:r0 + b1], t_all, c_of, p_of, layout.seed, noise_sigma, fdtype, torch,
+                                 dscale=distance_scale)
     s = torch.zeros(n, dtype=torch.float64, device=dev)
 
     def sums():
@@ -177,7 +184,7 @@ class Shard32:
         elif self.peer_W:
             self.h.s32_build_w(self.peer_W, self.ld)
         else:
-            self.h.s32_build_w(self._stage.data_ptr(), self.ld)
+            self.h.s32_build_w(self._stage.data_ptr(), self.ld, self.r0)
         k1_ms = self.h.timers()["distance"]
         if self.world > 1 and not self.peer_W and self.transport.startswith("NCCL"):
             if self.is_linkage:

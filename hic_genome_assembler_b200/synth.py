@@ -175,7 +175,7 @@ def _as_f(x, like):
     return x.to(like)
 
 
-def portable_tile(ti, tj, chrom_of, pos_in_chrom, seed, noise_sigma, fdtype, xp):
+def portable_tile(ti, tj, chrom_of, pos_in_chrom, seed, noise_sigma, fdtype, xp, dscale=1.0):
     """Un-normalised contacts between ground-truth bins ``ti`` (rows) and ``tj`` (columns): int64 vectors of the
     array type ``xp`` works on (numpy or torch)."""
     ci, cj = chrom_of[ti], chrom_of[tj]
@@ -195,6 +195,8 @@ def portable_tile(ti, tj, chrom_of, pos_in_chrom, seed, noise_sigma, fdtype, xp)
     for c in (1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.5, 1.0, 1.0):
         e = e * t + c
     d = _as_f(xp.abs(pi[:, None] - pj[None, :]), fdtype)
+    if dscale != 1.0:
+        d = d * dscale          # bin distance in units of the resolution the recipe was tuned at (see dist10kb)
     # (torch evaluates `scalar / tensor` as reciprocal * scalar: keep both operands arrays)
     base = xp.where(ci[:, None] == cj[None, :], (d * 0.0 + 100.0) / (d + 1.0), d * 0.0 + 0.3)
     return base * e

@@ -288,15 +288,16 @@ int hica_p2_score_orders(hica_handle h, const int32_t *orders, int64_t B, int32_
  *                       to 16), 2: the n row sums (fp64; the caller all-gathers the blocks the other GPUs computed)
  *   hica_s32_row_sums   s_i of the own rows (fp64 accumulation)
  *   hica_s32_build_w    rows [r0, r1) of the mirrored working matrix, W[i][j] = (1 - A_ij / s_min(i,j)) + 1, written
- *                       to W_dst (row-major, leading dimension ld): NULL = this GPU's own working matrix, otherwise
- *                       e.g. the linkage GPU's, mapped with hica_s32_ipc_open - the transform and the gather over
- *                       NVLink are then ONE kernel
+ *                       to W_dst (row-major, leading dimension ld; matrix row i goes to row i - dst_row0): NULL = this
+ *                       GPU's own working matrix, otherwise e.g. the linkage GPU's (dst_row0 = 0), mapped with
+ *                       hica_s32_ipc_open - the transform and the gather over NVLink are then ONE kernel -
+ *                       or a staging buffer of r1 - r0 rows (dst_row0 = r0) for a transport without peer mappings
  *   hica_s32_ipc_*      CUDA IPC export / open / close of a buffer (64-byte handle), for one process per GPU
  *   hica_s32_linkage    hierarchy.average + dendrogram leaf order on the fp32 working matrix (Z may be NULL) */
 int hica_s32_alloc(hica_handle h, int64_t n, int64_t r0, int64_t r1, int with_linkage_matrix);
 int hica_s32_buffer(hica_handle h, int which, void **ptr, int64_t *bytes);
 int hica_s32_row_sums(hica_handle h);
-int hica_s32_build_w(hica_handle h, void *W_dst, int64_t ld);
+int hica_s32_build_w(hica_handle h, void *W_dst, int64_t ld, int64_t dst_row0);
 int hica_s32_ipc_export(hica_handle h, int which, void *handle64);
 int hica_s32_ipc_open(hica_handle h, const void *handle64, void **ptr);
 int hica_s32_ipc_close(hica_handle h, void *ptr);

@@ -51,7 +51,8 @@ def test_fp32_sharded_front_end_matches_fp64_path(hica, n, nc):
     hica.p1_distance()
     Z64, leaves64 = hica.p1_linkage(want_Z=True)
     assert np.allclose(Z32[:, 2], Z64[:, 2], rtol=HEIGHT_RTOL, atol=0)
-    assert np.array_equal(Z32[:, 3][-nc:], Z64[:, 3][-nc:])            # the top merges join the same cluster sizes
+    # (merges whose heights agree to within the tolerance may swap places in the sorted list - the inter-chromosome
+    #  merges all sit within 1e-4 of 2.0 - so the merge LIST is not compared entry by entry; the clusters are)
     assert np.array_equal(_clusters(Z32, nc), _clusters(Z64, nc))      # chromosome-level clusters identical
     assert dist10kb.chromosome_breaks(leaves32, layout.true_chrom_of_bin) == nc - 1
     assert sorted(leaves32.tolist()) == list(range(n))
