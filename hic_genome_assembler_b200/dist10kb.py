@@ -273,9 +273,10 @@ def bench(args, rank, world, local_rank):
     secs = max(time.perf_counter() - w0, e0.elapsed_time(e1) / 1e3)
     t = torch.tensor([secs], dtype=torch.float64, device=dev)
     k1 = torch.tensor([res[-1][0]["k1_kernel_ms"]], dtype=torch.float64, device=dev)
+    k1_all = [k1.clone() for _ in range(world)]
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(k1, op=dist.ReduceOp.MAX)
+        dist.all_gather(k1_all, k1)
     clocks = sampler.stop([(w0, time.perf_counter())])
     launches = h.launches - l0
     sh.close()
@@ -288,7 +289,8 @@ def bench(args, rank, world, local_rank):
     pairs = n * (n - 1) // 2
     peak, peak_src = B.hbm_peak()
     rows = sh.r1 - sh.r0
-    k1_ms = float(k1.item())
+    k1_per_rank = [float(v.item()) for v in k1_all]
+    k1_ms = k1_per_rank[0]             # the linkage rank's own row block: local loads, local stores -> HBM-bound
     k1_bytes = 8.0 * rows * n          # 4 B read + 4 B written per entry of the row block
     inbound = 4.0 * (n - rows) * sh.ld  # bytes the linkage GPU receives over NVLink
     link_ms = st["linkage_kernel_ms"]
@@ -313,9 +315,10 @@ def bench(args, rank, world, local_rank):
         "roofline": {"bound": "hbm", "kernel": "k_build_w32 (K1 fp32: distance transform of a row block, stores into the linkage GPU's W)",
                      "achieved": k1_bytes / (k1_ms / 1e3) / 1e9 if k1_ms else None, "peak": peak, "unit": "GB/s",
                      "frac": (k1_bytes / (k1_ms / 1e3) / 1e9 / peak) if k1_ms else None, "peak_source": peak_src,
-                     "alg_bytes_per_launch": k1_bytes, "kernel_ms_max_over_ranks": k1_ms,
-                     "note": "for ranks other than the linkage rank the stores cross NVLink: the bound is then the link, see nvlink",
-                     "nvlink": {"inbound_bytes_linkage_gpu": inbound,
+                     "alg_bytes_per_launch": k1_bytes, "kernel_ms": k1_ms, "kernel_ms_per_rank": k1_per_rank,
+                     "note": "achieved/frac: the linkage rank's launch (local loads and stores, HBM-bound). On the other ranks the "
+                             "same kernel stores across NVLink and is bound by the linkage GPU's inbound link: see nvlink",
+                     "nvlink": {"inbound_bytes_linkage_gpu": inbound, "peak_GBps_per_direction": 900.0,
                                 "GBps": inbound / (st["distance_and_gather_ms"] / 1e3) / 1e9 if world > 1 else None},
                      "linkage": {"kernel_ms": link_ms, "merges_per_s": (n - 1) / (link_ms / 1e3) if link_ms else None,
                                  "alg_bytes": 12.0 * n * n, "GBps": 12.0 * n * n / (link_ms / 1e3) / 1e9 if link_ms else None,
