@@ -244,6 +244,104 @@ __device__ double pairwise_f(const F &f, int off, int n)
     return pairwise_generic(f, off, n);
 }
 
+// numpy's pairwise sum of f(off .. off+n) by ONE WARP (all 32 lanes call; the result is valid in lane 0).  The
+// recursion of DOUBLE_pairwise_sum is a fixed binary tree over leaf blocks of at most 128 terms; lane 0 lists the
+// leaves (left to right), the warp sums four leaves at a time - lane j of an aligned 8-lane group owns numpy's
+// accumulator r[j] of one leaf, a 3-step xor-shuffle reproduces ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)), the group's
+// first lane adds the tail one by one - and lane 0 combines the leaf sums by walking the same tree.  One thread per
+// sum (pairwise_f) is a chain of n dependent gathers + additions; here the chain is ~n/8 long per leaf and four leaves
+// run side by side.  `sh` = 4 * PW_WARP_LEAVES bytes * 4 of shared memory private to the warp (see pw_warp_smem).
+constexpr int PW_WARP_LEAVES = 64;   // leaves hold 57..128 terms: sums of up to ~3,600 terms; longer ones fall back to lane 0
+struct PwWarpSmem {
+    int off[PW_WARP_LEAVES], len[PW_WARP_LEAVES];
+    double sum[PW_WARP_LEAVES];
+};
+template <class F>
+__device__ double pairwise_warp(const F &f, int off, int n, PwWarpSmem *sh)
+{
+    const int lane = threadIdx.x & 31, j = lane & 7, grp = lane >> 3;
+    constexpr int DEPTH = 28;
+    // ---- lane 0: the leaves, left to right
+    int nl = 0;
+    if (lane == 0) {
+        int s_off[DEPTH], s_n[DEPTH], sp = 0;
+        s_off[0] = off; s_n[0] = n;
+        while (sp >= 0) {
+            const int o = s_off[sp], m = s_n[sp];
+            sp--;
+            if (m <= 128) {
+                if (nl < PW_WARP_LEAVES) { sh->off[nl] = o; sh->len[nl] = m; }
+                nl++;
+            } else {
+                int m2 = m / 2;
+                m2 -= m2 % 8;
+                sp++; s_off[sp] = o + m2; s_n[sp] = m - m2;   // right half: popped after the left one
+                sp++; s_off[sp] = o;      s_n[sp] = m2;
+            }
+        }
+    }
+    nl = __shfl_sync(0xffffffffu, nl, 0);
+    if (nl > PW_WARP_LEAVES) {   // too long for the leaf table: one thread, the plain way
+        double r = 0.;
+        if (lane == 0) r = pairwise_f(f, off, n);
+        return r;
+    }
+    __syncwarp();
+    // ---- leaf sums, four leaves per round
+    for (int base = 0; base < nl; base += 4) {
+        const int li = base + grp;
+        const int lo = li < nl ? sh->off[li] : 0, ln = li < nl ? sh->len[li] : 0;
+        const int n8 = ln - (ln & 7);
+        double acc = 0., res = 0.;
+        if (ln >= 8) {
+            acc = f(lo + j);
+            int i = 8;
+            for (; i + 32 <= n8; i += 32) {   // four gathers in flight per lane, added in numpy's order
+                const double v0 = f(lo + i + j), v1 = f(lo + i + 8 + j), v2 = f(lo + i + 16 + j), v3 = f(lo + i + 24 + j);
+                acc = __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(acc, v0), v1), v2), v3);
+            }
+            for (; i < n8; i += 8) acc = __dadd_rn(acc, f(lo + i + j));
+        }
+        acc = __dadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, 1));
+        acc = __dadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, 2));
+        acc = __dadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, 4));
+        if (j == 0 && li < nl) {
+            if (ln >= 8) {
+                res = acc;
+                for (int i = n8; i < ln; i++) res = __dadd_rn(res, f(lo + i));
+            } else {
+                for (int i = 0; i < ln; i++) res = __dadd_rn(res, f(lo + i));
+            }
+            sh->sum[li] = res;
+        }
+    }
+    __syncwarp();
+    // ---- lane 0: the tree above the leaves, the same walk as pairwise_generic with the leaf sums in visiting order
+    double ret = 0.;
+    if (lane == 0) {
+        int s_n[DEPTH];
+        double s_left[DEPTH];
+        unsigned char s_state[DEPTH];
+        int sp = 0, next = 0;
+        s_n[0] = n; s_state[0] = 0;
+        for (;;) {
+            const int m = s_n[sp];
+            if (m <= 128) {
+                ret = sh->sum[next++];
+            } else {
+                int m2 = m / 2;
+                m2 -= m2 % 8;
+                if (s_state[sp] == 0) { s_state[sp] = 1; sp++; s_n[sp] = m2; s_state[sp] = 0; continue; }
+                if (s_state[sp] == 1) { s_left[sp] = ret; s_state[sp] = 2; sp++; s_n[sp] = m - m2; s_state[sp] = 0; continue; }
+                ret = __dadd_rn(s_left[sp], ret);
+            }
+            if (sp == 0) break;
+            sp--;
+        }
+    }
+    return ret;
+}
+
 // order-preserving map double -> uint64 (for atomicMax on scores)
 __device__ __forceinline__ unsigned long long f64_order_key(double v)
 {

@@ -184,22 +184,31 @@ size_t smem_bytes(int n, int nslots) { return sizeof(double) * n + sizeof(int32_
 
 // ---------------------------------------------------------------------------
 // total = sum_k numpy.trace(M, k) of the phase's layout (:343/:448/:506), then the weights of the closed form
-__global__ void __launch_bounds__(128) k_g_total(const GroupDev *gs, Phase ph, int want_weights)
+// One WARP per diagonal (TOT_WARPS diagonals per CTA): numpy.trace's pairwise tree over the n - k gathered
+// contacts of diagonal k, leaf blocks on 8-lane groups (pairwise_warp).  One thread per diagonal - a chain of up to
+// n dependent gathers - took 110 us per call at 800 bins and 807 us at 1,600, ~70 calls per step.
+constexpr int TOT_WARPS = 8;
+__global__ void __launch_bounds__(TOT_WARPS * 32) k_g_total(const GroupDev *gs, Phase ph, int want_weights)
 {
     extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ PwWarpSmem pw[TOT_WARPS];
     const GroupDev &g = gs[blockIdx.y];
     const PhaseParams pp = phase_params(g, ph);
     if (!pp.active) return;
     const int n = pp.n;
     SmemPlan sp = carve(smem, n, n, pp.nslots);
     build_order_cta(SrcLayout{g.layout}, pp.nslots, g.seg_ptr, g.seg_bins, sp.o, sp.spos, sp.sent, n);
-    const int k = blockIdx.x * blockDim.x + threadIdx.x + 1;
-    if (k < n) {
-        const int32_t *o = sp.o;
-        const double *S = g.S;
-        const int L = g.L;
-        auto f = [&](int r) { return S[(int64_t)o[r] * L + o[r + k]]; };
-        g.tr[k] = pairwise_f(f, 0, n - k);
+    {
+        // long diagonals first inside the CTA's share would not matter: every warp of the grid has one diagonal
+        const int k = blockIdx.x * TOT_WARPS + (threadIdx.x >> 5) + 1;
+        if (k < n) {
+            const int32_t *o = sp.o;
+            const double *S = g.S;
+            const int L = g.L;
+            auto f = [&](int r) { return S[(int64_t)o[r] * L + o[r + k]]; };
+            const double t = pairwise_warp(f, 0, n - k, &pw[threadIdx.x >> 5]);
+            if ((threadIdx.x & 31) == 0) g.tr[k] = t;
+        }
     }
     __threadfence();
     __shared__ int last;
@@ -208,7 +217,7 @@ __global__ void __launch_bounds__(128) k_g_total(const GroupDev *gs, Phase ph, i
     __syncthreads();
     if (!last) return;
     __shared__ double t_s;
-    __shared__ double chunk_s[128];
+    __shared__ double chunk_s[TOT_WARPS * 32];
     __threadfence();
     for (int kk = 1 + threadIdx.x; kk < n; kk += blockDim.x) sp.tr[kk] = ld_cg_f64(g.tr + kk);  // staged: one round trip
     __syncthreads();
@@ -1075,7 +1084,7 @@ extern "C" int hica_p2_order_groups(hica_handle h, int32_t ngroups, const int32_
     const size_t tab_smem = sizeof(double) * Lmax + sizeof(int32_t) * (Lmax + 2 * (nseg_max + 1) + 2);
     ENG_CUDA(cudaFuncSetAttribute(k_g_tables, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tab_smem));
     const unsigned G = (unsigned)ngroups;
-    const unsigned tot_blocks = (unsigned)std::max(1, (Lmax - 1 + 127) / 128);
+    const unsigned tot_blocks = (unsigned)std::max(1, (Lmax - 1 + TOT_WARPS - 1) / TOT_WARPS);
 
     // HICA_P2_PROFILE=1: CUDA events between the launches, summed per kernel and printed to stderr (diagnostic)
     const bool prof = getenv("HICA_P2_PROFILE") != nullptr;
@@ -1116,7 +1125,7 @@ extern "C" int hica_p2_order_groups(hica_handle h, int32_t ngroups, const int32_
     // ---- brute force over the k largest scaffolds (:573-576)
     {
         Phase ph = {PH_BRUTE, 0, 0};
-        k_g_total<<<dim3(tot_blocks, G), 128, ex_smem, s>>>(gdev, ph, 1);
+        k_g_total<<<dim3(tot_blocks, G), TOT_WARPS * 32, ex_smem, s>>>(gdev, ph, 1);
         mark(1);
         k_g_anchor<<<dim3(1, G), EX_THREADS, ex_smem, s>>>(gdev, ph);
         mark(2);
@@ -1134,7 +1143,7 @@ extern "C" int hica_p2_order_groups(hica_handle h, int32_t ngroups, const int32_
             ENG_CUDA(cudaEventRecord(h->ev_fork, s));
             ENG_CUDA(cudaStreamWaitEvent(s2, h->ev_fork, 0));
         }
-        k_g_total<<<dim3(tot_blocks, G), 128, ex_smem, s>>>(gdev, ph, 0);
+        k_g_total<<<dim3(tot_blocks, G), TOT_WARPS * 32, ex_smem, s>>>(gdev, ph, 0);
         mark(1);
         k_g_ins_rows<<<dim3((unsigned)((Lmax + INS_ROWS - 1) / INS_ROWS), G), 256, tot_smem, s2>>>(gdev, ph);
         mark(8);
@@ -1158,7 +1167,7 @@ extern "C" int hica_p2_order_groups(hica_handle h, int32_t ngroups, const int32_
         Phase ph0 = {PH_SCAN, 0, scan};
         k_g_reset_for_scan<<<G, 32, 0, s>>>(gdev);
         mark(13);
-        k_g_total<<<dim3(tot_blocks, G), 128, ex_smem, s>>>(gdev, ph0, 1);
+        k_g_total<<<dim3(tot_blocks, G), TOT_WARPS * 32, ex_smem, s>>>(gdev, ph0, 1);
         mark(1);
         k_g_anchor<<<dim3(1, G), EX_THREADS, ex_smem, s>>>(gdev, ph0);
         mark(2);
