@@ -212,3 +212,72 @@ def test_reference_pipeline_on_gpu(hica, tmp_path, per_call):
     run_launcher(hica, ref, write_config(tmp_path), extra={"per_call_part2": per_call}.items())
     assert hica.launches > l0
     compare_outputs(tmp_path)
+
+
+def _load_pipeline_maker():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden_pipeline", os.path.join(ROOT, "tests", "golden", "make_golden_pipeline.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+@pytest.mark.gpu
+def test_reference_pipeline_500kb_on_gpu(hica, tmp_path):
+    """BASELINE.json configs[0] - the reference's own CPU-runnable case: 1.6 Gb genome at 500 kb (3,200 bins),
+    `run_hicAssembler.py -part1 -part2` through the launcher on the GPU, six output files byte-identical to what the
+    unmodified reference wrote in the build container (274 s there; tests/golden/pipeline_3200).  The HiC-Pro input
+    files (120 MB of text, %.6f values - so exact ties exist) are regenerated here and checked by digest."""
+    import json
+    import time
+    ref = reference_dir()
+    meta_path = os.path.join(ROOT, "tests", "golden", "pipeline_3200", "meta.json")
+    if ref is None or not os.path.exists(meta_path):
+        pytest.skip("reference tree or pipeline_3200 golden not available")
+    meta = json.load(open(meta_path))
+    mk = _load_pipeline_maker()
+    inp, out = os.path.join(str(tmp_path), "in"), os.path.join(str(tmp_path), "out")
+    g = mk.write_inputs(meta["bins"], meta["chroms"], meta["seed"], inp)
+    for f, want in meta["inputs_sha"].items():
+        assert mk.file_sha(os.path.join(inp, f)) == want, "regenerated input differs: " + f
+    os.makedirs(out)
+    cfg = os.path.join(str(tmp_path), "config.txt")
+    open(cfg, "w").write(mk.CONFIG.format(res=g.resolution, out=out, inp=inp))
+    t0 = time.time()
+    run_launcher(hica, ref, cfg)
+    secs = time.time() - t0
+    for name, want in meta["outputs_sha"].items():
+        assert mk.file_sha(os.path.join(out, name)) == want, name
+    rep = hica.tie_report()
+    print("launcher -part1 -part2 at 500 kb: %.1f s (reference in the build container: %.0f s); tie report %s"
+          % (secs, meta["reference_seconds_build_container"], rep))
+    rec = os.environ.get("HICA_LAUNCHER_RECORD")
+    if rec:
+        json.dump({"bins": meta["bins"], "launcher_seconds": secs, "reference_seconds_build_container":
+                   meta["reference_seconds_build_container"], "files_identical": True, "tie_report": rep}, open(rec, "w"))
+
+
+@pytest.mark.reference
+def test_reference_pipeline_500kb_over_oracle_backed_handle(tmp_path):
+    """The same at the reference's own CPU-runnable size (BASELINE configs[0], 3,200 bins, %.6f inputs with exact
+    ties) with the oracle answering the C-ABI calls: pins the host side of the fast lane against the six files the
+    unmodified reference wrote (320 s in the build container; about 1 min here)."""
+    import json
+    ref = reference_dir()
+    meta_path = os.path.join(ROOT, "tests", "golden", "pipeline_3200", "meta.json")
+    if ref is None or not os.path.exists(meta_path):
+        pytest.skip("reference tree or pipeline_3200 golden not available")
+    meta = json.load(open(meta_path))
+    mk = _load_pipeline_maker()
+    inp, out = os.path.join(str(tmp_path), "in"), os.path.join(str(tmp_path), "out")
+    g = mk.write_inputs(meta["bins"], meta["chroms"], meta["seed"], inp)
+    for f, want in meta["inputs_sha"].items():
+        assert mk.file_sha(os.path.join(inp, f)) == want, "regenerated input differs: " + f
+    os.makedirs(out)
+    cfg = os.path.join(str(tmp_path), "config.txt")
+    open(cfg, "w").write(mk.CONFIG.format(res=g.resolution, out=out, inp=inp))
+    h = OracleHandle()
+    run_launcher(h, ref, cfg)
+    for name, want in meta["outputs_sha"].items():
+        assert mk.file_sha(os.path.join(out, name)) == want, name
+    assert h.calls == ["p1_upload", "p2_upload", "p2_order_groups"], h.calls
