@@ -194,6 +194,18 @@ __device__ __forceinline__ void bar_arrive(int id, int count)
     asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
 
+// split-phase hardware cluster barrier: arrive.release makes the thread's earlier global stores visible to every
+// thread of the cluster that has passed the matching wait.acquire
+__device__ __forceinline__ void cluster_arrive_release()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ void cluster_wait_acquire()
+{
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 // ---- reduction inside the CTA, all-to-all exchange over DSMEM -----------------------------------------------
 // Every warp reduces its candidates and leaves them in shared memory; ONE warp combines the 16 partial results,
 // posts them into every peer's slot, spins until the peers' posts have arrived and broadcasts the outcome; all
@@ -204,9 +216,13 @@ __device__ __forceinline__ void bar_arrive(int id, int count)
 // latency overlaps the combine step.  The barrier every thread passes at the end also tells it that all threads
 // of the CTA are done with the merge.
 // Named barriers: 1 = result ready, 2 = partial results in shared memory, 3 = merge stores fenced.
+// SPLIT (fused only): nobody waits for the merge stores here.  Every thread releases them with a split-phase
+// cluster barrier ARRIVE once its part of the exchange is done (the 14 sleeping warps right away, the two posting
+// warps after the result is out) and the caller executes the matching WAIT before the next read of W
+// (k_nn_chain3: `pending`) - the completion of the column scatter, ~1 k cycles, leaves the critical path.
 template <bool FUSED, bool STATS>
 __device__ __forceinline__ Exchanged exchange(const XCtx &cx, unsigned &seq, BestT b, BestT b2, const int qpar,
-                                              long long &t_sync, long long &t_post)
+                                              long long &t_sync, long long &t_post, const bool split = false)
 {
     const int lane = cx.lane, warp = cx.warp, nwarps = cx.nwarps, nranks = cx.nranks;
     const int T = nwarps * 32;
@@ -225,8 +241,12 @@ __device__ __forceinline__ Exchanged exchange(const XCtx &cx, unsigned &seq, Bes
     if (!poster) {
         bar_arrive(2, T);
         if (FUSED) {
-            asm volatile("fence.acq_rel.cluster;" ::: "memory");
-            bar_arrive(3, T);
+            if (split) {
+                cluster_arrive_release();
+            } else {
+                asm volatile("fence.acq_rel.cluster;" ::: "memory");
+                bar_arrive(3, T);
+            }
         }
     } else {
         const int half = warp;  // 0: search result (+ queue count), 1: merged row
@@ -241,9 +261,11 @@ __device__ __forceinline__ Exchanged exchange(const XCtx &cx, unsigned &seq, Bes
         c = warp_best_t(c);
         unsigned q = 0;
         if (FUSED) {
-            asm volatile("fence.acq_rel.cluster;" ::: "memory");
-            bar_sync(3, T);  // every thread of the CTA has fenced its merge stores
-            if (half == 0) q = (unsigned)cx.cnt[qpar];
+            if (!split) {
+                asm volatile("fence.acq_rel.cluster;" ::: "memory");
+                bar_sync(3, T);  // every thread of the CTA has fenced its merge stores
+            }
+            if (half == 0) q = (unsigned)cx.cnt[qpar];  // complete: every thread has passed barrier 2
         }
         if (lane < nranks) {
             const unsigned remote = mapa_u32(smem_u32(cx.slots + par * MAX_CLUSTER + cx.rank), (unsigned)lane) + 32 * half;
@@ -279,6 +301,7 @@ __device__ __forceinline__ Exchanged exchange(const XCtx &cx, unsigned &seq, Bes
         __threadfence_block();
     }
     bar_sync(1, T);
+    if (FUSED && split && poster) cluster_arrive_release();
     Exchanged r;
     r.g.hi = res[0]; r.g.lo = res[1]; r.g.ic = res[2] & IC_NONE; r.g.tie = res[2] >> 31;
     r.queued = 0; r.queued_max = 0;
@@ -363,6 +386,8 @@ k_nn_chain3(double *__restrict__ W, const int n, const int64_t ld, int32_t *__re
     int len = 1, top = 0, second = -1, first_alive = 0;
     chain_set(0, 0);
     bool have = false;  // the fused search has already produced the result for the current chain top
+    const bool split = !(flags & 2u);
+    bool pending = false;  // a cluster-barrier arrive of the last merge has not been waited for yet
     int have_y = -1;
     double have_gv = 0.;
 
@@ -402,6 +427,7 @@ k_nn_chain3(double *__restrict__ W, const int n, const int64_t ld, int32_t *__re
                     // ---- ordinary full search of row x ------------------------------------------------------
                     long long ts0 = 0, ts1 = 0, ts2 = 0, ts3 = 0, ts4 = 0;
                     if (STATS) ts0 = clock64();
+                    if (pending) { cluster_wait_acquire(); pending = false; }  // the last merge's stores
                     const double *row = W + (int64_t)x * ld;
                     BestT b, bnone;
                     best_init(b);
@@ -442,6 +468,7 @@ k_nn_chain3(double *__restrict__ W, const int n, const int64_t ld, int32_t *__re
         // ---- merge (x, y -> y), fused with the search of the row that becomes the chain top ---------------
         long long t_mid = 0, tm1 = 0, tm2 = 0, tm3 = 0, tm4 = 0, tm5 = 0;
         if (STATS) { t_mid = clock64(); cy_search += t_mid - t_begin; }
+        if (pending) { cluster_wait_acquire(); pending = false; }
         int x = top;
         len -= 2;
         if (x > y) { int t = x; x = y; y = t; }
@@ -544,7 +571,8 @@ k_nn_chain3(double *__restrict__ W, const int n, const int64_t ld, int32_t *__re
         if (last) break;
         if (!scan_next) b = b2;
         if (STATS) tm2 = clock64();
-        const Exchanged r = exchange<true, STATS>(cx, seq, b, b2, k & 1, tm3, tm4);
+        const Exchanged r = exchange<true, STATS>(cx, seq, b, b2, k & 1, tm3, tm4, split);
+        pending = split;
         if (STATS) tm5 = clock64();
         st_fused++;
         // every thread is past the barrier inside exchange(): nobody reads the old sizes any more
@@ -555,6 +583,7 @@ k_nn_chain3(double *__restrict__ W, const int n, const int64_t ld, int32_t *__re
             // slow path: some row's minimum moved to (or now ties with) the merged cluster.  All CTAs are here
             // and none has used the cache since the merge.
             st_slow++;
+            if (pending) { cluster_wait_acquire(); pending = false; }  // cluster.sync() below uses the same barrier
             if (r.queued_max > (unsigned)LIST_CAP) {
                 for (int i = tid; i < (int)ld; i += T) ent[i] = ENT_INVALID;
             } else {
@@ -592,6 +621,7 @@ k_nn_chain3(double *__restrict__ W, const int n, const int64_t ld, int32_t *__re
             cy_fused_poll += tm5 - tm4;
         }
     }
+    if (pending) cluster_wait_acquire();
     cluster.sync();  // no CTA may exit while a peer can still write into its shared memory
     if (tid == 0 && stats) {
         if (rank == 0) {
