@@ -64,6 +64,7 @@ struct hica_ctx {
     int32_t *size_d = nullptr;   // cluster sizes
     int32_t *chain_d = nullptr;  // per-CTA chain copies
     long long nn_stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // searches, cycles in searches, cycles in merges (last linkage)
+    int nn_kernel_used = 0;  // generation of the chain kernel the last linkage ran (diagnostics)
     // cuts scratch
     int32_t *x_d = nullptr;      // window counts
     uint8_t *sig_d = nullptr;

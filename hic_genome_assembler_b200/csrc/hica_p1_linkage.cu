@@ -232,6 +232,7 @@ k_nn_chain(double *__restrict__ W, const int n, const int64_t ld, int32_t *__res
 
 #include "hica_p1_nnchain2.cuh"
 #include "hica_p1_nnchain3.cuh"
+#include "hica_p1_nnchain4.cuh"
 
 namespace {
 
@@ -403,6 +404,44 @@ int launch_nn_chain3(hica_ctx *h, int cluster_size, const double *nn0_val, const
     return HICA_OK;
 }
 
+// k_nn_chain4: k_nn_chain3 without the column scatter (stale elements are read from the mirror row on demand).
+// One pass over the slice per step and the chain in shared memory: returns -1 when that does not hold.
+template <int FU, bool STATS>
+int launch_nn_chain4(hica_ctx *h, int cluster_size, int threads, const double *nn0_val, const uint32_t *nn0_ent,
+                     unsigned flags)
+{
+    auto kern = nn4::k_nn_chain4<FU, STATS>;
+    const int n32 = (int)h->n;
+    const int per = nn4::slice_len(n32, cluster_size);
+    if (per > 2 * FU * threads) return -1;
+    const size_t smem_bytes = nn4::make_layout(n32, h->ld, per).total;
+    if (smem_bytes > 227 * 1024) return -1;
+    HICA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+    if (cluster_size > 8) HICA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(cluster_size);
+    cfg.blockDim = dim3(threads);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = h->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cluster_size;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int max_clusters = 0;
+    cudaError_t e = cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg);
+    if (e != cudaSuccess || max_clusters < 1) {
+        cudaGetLastError();
+        return -1;  // caller retries with a smaller cluster
+    }
+    HICA_CUDA(cudaLaunchKernelEx(&cfg, kern, h->W, n32, h->ld, h->Zraw, reinterpret_cast<long long *>(h->misc_d + 64),
+                                 nn0_val, nn0_ent, flags));
+    HICA_LAUNCHED(h);
+    return HICA_OK;
+}
+
 }  // namespace
 
 int hica_presort_start(hica_ctx *h);  // hica_p1_rank.cu
@@ -444,8 +483,9 @@ extern "C" int hica_p1_linkage(hica_handle h, double *Z_host, int32_t *leaves_ho
     if (!h->Zraw && (rc = hica_realloc(h, &h->Zraw, 4 * (n - 1)))) return rc;
     if (!h->size_d && (rc = hica_realloc(h, &h->size_d, (int64_t)NN_MAX_CLUSTER * n))) return rc;
     const char *ver_env = getenv("HICA_NN_KERNEL");
-    int version = 3;  // 3: NN cache (default), 2: every search in full, 1: first-generation kernel
-    if (ver_env && ver_env[0] >= '1' && ver_env[0] <= '3') version = ver_env[0] - '0';
+    // 4: NN cache, no column scatter (default), 3: NN cache, 2: every search in full, 1: first-generation kernel
+    int version = 4;
+    if (ver_env && ver_env[0] >= '1' && ver_env[0] <= '4') version = ver_env[0] - '0';
     if (n > nn3::MAX_N || n < 2) version = std::min(version, 2);
 
     const int nwords = (int)((h->ld + 31) / 32);
@@ -462,8 +502,9 @@ extern "C" int hica_p1_linkage(hica_handle h, double *Z_host, int32_t *leaves_ho
     HICA_CUDA(cudaEventRecord(h->ev_fork, h->stream));  // the rank pre-sort may start from here on (stream2)
     int launched = -1;
     int cs_max = NN_MAX_CLUSTER;
+    h->nn_kernel_used = 0;
     if (const char *e = getenv("HICA_NN_CLUSTER")) cs_max = std::max(1, std::min(NN_MAX_CLUSTER, atoi(e)));
-    if (version == 3) {
+    if (version >= 3) {
         // nearest neighbour of every row, all SMs; q_d is free until the cut search
         double *nn0_val = reinterpret_cast<double *>(h->q_d);
         uint32_t *nn0_ent = reinterpret_cast<uint32_t *>(nn0_val + n);
@@ -473,6 +514,17 @@ extern "C" int hica_p1_linkage(hica_handle h, double *Z_host, int32_t *leaves_ho
         unsigned flags = 0;
         if (const char *e = getenv("HICA_NN_FLAGS")) flags = (unsigned)atoi(e);
         const bool chain_global = getenv("HICA_NN_CHAIN_GLOBAL") != nullptr;  // tests: force the large-N variant
+        int threads4 = nn4::MAX_THREADS;
+        if (const char *e = getenv("HICA_NN_THREADS")) threads4 = std::max(64, std::min(nn4::MAX_THREADS, atoi(e) / 32 * 32));
+        for (int cs = cs_max; version == 4 && !chain_global && cs >= 1 && launched != HICA_OK; cs >>= 1) {
+            launched = dbg ? launch_nn_chain4<1, true>(h, cs, threads4, nn0_val, nn0_ent, flags)
+                           : launch_nn_chain4<1, false>(h, cs, threads4, nn0_val, nn0_ent, flags);
+            if (launched < 0)
+                launched = dbg ? launch_nn_chain4<2, true>(h, cs, threads4, nn0_val, nn0_ent, flags)
+                               : launch_nn_chain4<2, false>(h, cs, threads4, nn0_val, nn0_ent, flags);
+            if (launched > 0) return launched;  // a real error
+            if (launched == HICA_OK) h->nn_kernel_used = 4;
+        }
         for (int cs = cs_max; cs >= 1 && launched != HICA_OK; cs >>= 1) {
             launched = chain_global ? -1
                        : dbg        ? launch_nn_chain3<true, true>(h, cs, nn0_val, nn0_ent, flags)
@@ -510,8 +562,8 @@ extern "C" int hica_p1_linkage(hica_handle h, double *Z_host, int32_t *leaves_ho
         for (int i = 0; i < 8; i++) h->nn_stats[i] = st[i];
         if (getenv("HICA_NN_DEBUG")) {
             const long long nf = std::max(1ll, st[8]);
-            fprintf(stderr, "[hica nn] fused %lld full %lld cached %lld slow %lld; cycles search %lld merge+fused %lld\n",
-                    st[8], st[9], st[6], st[7], st[1], st[2]);
+            fprintf(stderr, "[hica nn] kernel %d fused %lld full %lld cached %lld slow %lld gathers %lld; cycles search %lld merge+fused %lld\n",
+                    h->nn_kernel_used, st[8], st[9], st[6], st[7], st[10], st[1], st[2]);
             for (int r = 0; r < 16; r++) {
                 const long long *rs = st + 16 + 8 * r;
                 if (!rs[6]) continue;

@@ -249,6 +249,9 @@ def test_symmetric_upload_reads_only_the_upper_triangle(hica, n):
 @pytest.mark.parametrize("env", [{"HICA_NN_CHAIN_GLOBAL": "1"}, {"HICA_NN_KERNEL": "2"}, {"HICA_NN_KERNEL": "1"},
                                  {"HICA_NN_CLUSTER": "8"}, {"HICA_NN_CLUSTER": "2"}, {"HICA_NN_CLUSTER": "1"},
                                  {"HICA_NN_THREADS": "128"}, {"HICA_NN_DEBUG": "1"},
+                                 {"HICA_NN_KERNEL": "3"}, {"HICA_NN_KERNEL": "3", "HICA_NN_FLAGS": "2"},  # scatter; + fence
+                                 {"HICA_NN_KERNEL": "3", "HICA_NN_DEBUG": "1"}, {"HICA_NN_KERNEL": "3", "HICA_NN_CLUSTER": "2"},
+                                 {"HICA_NN_FLAGS": "1"}, {"HICA_NN_CLUSTER": "4", "HICA_NN_THREADS": "64"},
                                  {"HICA_NN_CLUSTER": "1", "HICA_NN_THREADS": "128"}])  # several passes over the slice
 @pytest.mark.parametrize("n,tie", [(3, False), (70, True), (333, True), (1200, False)])
 def test_linkage_kernel_variants_bitwise(hica, n, tie, env, monkeypatch):
