@@ -55,7 +55,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     with ThreadPoolExecutor(max_workers=6) as ex:
         list(ex.map(run, jobs))
     if force or jobs or _stale(LIB, objs):
-        run([nvcc, "-shared", "-o", LIB] + objs + ["-lcudart"])
+        run([nvcc, "-shared", "-o", LIB] + objs + ["-lcudart", "-lpthread"])
     return LIB
 
 

@@ -3,6 +3,9 @@
 #include <stdio.h>
 
 #include <algorithm>
+#include <atomic>
+#include <cstring>
+#include <thread>
 
 #include "hica_common.cuh"
 
@@ -77,6 +80,7 @@ extern "C" int hica_create(int device, hica_handle *out)
         cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreate(&h->ev_pre0) != cudaSuccess || cudaEventCreate(&h->ev_pre1) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_sseq, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess) {
         delete h;
         return hica_set_error(nullptr, HICA_ERR_CUDA, "stream/event creation failed");
@@ -106,6 +110,7 @@ static void free_p1(hica_ctx *h)
     cudaFree(h->q_d); h->q_d = nullptr;
     cudaFree(h->plan_d); h->plan_d = nullptr; h->plan_n = 0;
     h->have_s_pair = h->have_s_seq = h->have_W = h->have_order = false;
+    h->s_seq_state = 0;
     h->rank_bytes = h->rank_rows_bytes = 0;
     h->n = h->ld = 0;
     h->A_kind = 0;
@@ -144,6 +149,9 @@ extern "C" int hica_destroy(hica_handle h)
     cudaEventDestroy(h->ev_join);
     cudaEventDestroy(h->ev_pre0);
     cudaEventDestroy(h->ev_pre1);
+    cudaEventDestroy(h->ev_sseq);
+    if (h->stage_h) cudaFreeHost(h->stage_h);
+    for (int i = 0; i < 3; i++) if (h->stage_ev[i]) cudaEventDestroy(h->stage_ev[i]);
     cudaStreamDestroy(h->stream2);
     cudaEventDestroy(h->ev0);
     cudaEventDestroy(h->ev1);
@@ -172,10 +180,104 @@ static int p1_alloc(hica_ctx *h, int64_t n)
         if ((rc = hica_realloc(h, &h->q_d, 4 * (n + 16)))) return rc;
     }
     h->have_s_pair = h->have_s_seq = h->have_W = h->have_order = false;
+    h->s_seq_state = 0;
     h->rank_bytes = h->rank_rows_bytes = 0;
     h->A_kind = 0;
     return HICA_OK;
 }
+
+// ---- uploads from PAGEABLE host memory ---------------------------------------------------------------------------
+// cudaMemcpy from ordinary (numpy) memory is staged by the driver through one thread: 11 GB/s measured on the B200
+// boxes, 97 ms for the 1.06 GB upper triangle at 16,000 bins.  Here the host copy into pinned staging slots is done
+// by several threads and overlaps the DMA of the previous slot (three slots): the link (55 GB/s) becomes the bound.
+namespace {
+
+struct Region2D {  // rows x width doubles: src (pitch sp) -> device dst (pitch dp)
+    const double *src;
+    double *dst;
+    int64_t sp, dp, width, rows;
+};
+
+bool is_pageable(const void *p)
+{
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return true;
+    }
+    return at.type == cudaMemoryTypeUnregistered;
+}
+
+constexpr int STAGE_SLOTS = 3;
+constexpr int64_t STAGE_SLOT_BYTES = 24ll << 20;
+
+int staged_upload(hica_ctx *h, const std::vector<Region2D> &regions)
+{
+    if (!h->stage_h) {
+        HICA_CUDA(cudaHostAlloc(&h->stage_h, (size_t)(STAGE_SLOTS * STAGE_SLOT_BYTES), cudaHostAllocDefault));
+        h->stage_cap = STAGE_SLOTS * STAGE_SLOT_BYTES;
+        for (int i = 0; i < STAGE_SLOTS; i++) HICA_CUDA(cudaEventCreateWithFlags(&h->stage_ev[i], cudaEventDisableTiming));
+    }
+    // chunks: whole rows of one region, at most one slot each
+    std::vector<Region2D> chunks;
+    for (const Region2D &r : regions) {
+        if (r.rows <= 0 || r.width <= 0) continue;
+        const int64_t per = std::max<int64_t>(1, STAGE_SLOT_BYTES / (8 * r.width));
+        for (int64_t r0 = 0; r0 < r.rows; r0 += per) {
+            Region2D c = r;
+            c.src = r.src + r0 * r.sp;
+            c.dst = r.dst + r0 * r.dp;
+            c.rows = std::min(per, r.rows - r0);
+            chunks.push_back(c);
+        }
+    }
+    const int nc = (int)chunks.size();
+    if (!nc) return HICA_OK;
+    int nt = (int)std::thread::hardware_concurrency();
+    if (const char *e = getenv("HICA_UPLOAD_THREADS")) nt = atoi(e);
+    nt = std::max(1, std::min(16, nt > 2 ? nt - 1 : nt));
+    std::vector<std::atomic<int>> slot_free(nc), done(nc);
+    for (int c = 0; c < nc; c++) { slot_free[c].store(c < STAGE_SLOTS ? 1 : 0); done[c].store(0); }
+    char *base = static_cast<char *>(h->stage_h);
+    auto worker = [&](int t) {
+        for (int c = 0; c < nc; c++) {
+            while (!slot_free[c].load(std::memory_order_acquire)) std::this_thread::yield();
+            const Region2D &ch = chunks[c];
+            double *slot = reinterpret_cast<double *>(base + (int64_t)(c % STAGE_SLOTS) * STAGE_SLOT_BYTES);
+            const int64_t lo = ch.rows * t / nt, hi = ch.rows * (t + 1) / nt;
+            for (int64_t r = lo; r < hi; r++) memcpy(slot + r * ch.width, ch.src + r * ch.sp, sizeof(double) * ch.width);
+            done[c].fetch_add(1, std::memory_order_release);
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < nt; t++) pool.emplace_back(worker, t);
+    cudaError_t err = cudaSuccess;
+    // the calling thread copies its share of chunk c as well, then issues the DMA
+    for (int c = 0; c < nc; c++) {
+        const Region2D &ch = chunks[c];
+        double *slot = reinterpret_cast<double *>(base + (int64_t)(c % STAGE_SLOTS) * STAGE_SLOT_BYTES);
+        {
+            const int64_t lo = 0, hi = ch.rows * 1 / nt;
+            for (int64_t r = lo; r < hi; r++) memcpy(slot + r * ch.width, ch.src + r * ch.sp, sizeof(double) * ch.width);
+            done[c].fetch_add(1, std::memory_order_release);
+        }
+        while (done[c].load(std::memory_order_acquire) < nt) std::this_thread::yield();
+        if (err == cudaSuccess)
+            err = cudaMemcpy2DAsync(ch.dst, sizeof(double) * ch.dp, slot, sizeof(double) * ch.width, sizeof(double) * ch.width,
+                                    (size_t)ch.rows, cudaMemcpyHostToDevice, h->stream);
+        if (err == cudaSuccess) err = cudaEventRecord(h->stage_ev[c % STAGE_SLOTS], h->stream);
+        // the slot of chunk c - 1 is reused by chunk c - 1 + SLOTS: free it once its DMA is through
+        if (c >= 1 && c - 1 + STAGE_SLOTS < nc) {
+            if (err == cudaSuccess) err = cudaEventSynchronize(h->stage_ev[(c - 1) % STAGE_SLOTS]);
+            slot_free[c - 1 + STAGE_SLOTS].store(1, std::memory_order_release);
+        }
+    }
+    for (std::thread &th : pool) th.join();
+    if (err != cudaSuccess) return hica_set_error(h, HICA_ERR_CUDA, "staged upload: %s", cudaGetErrorString(err));
+    return HICA_OK;
+}
+
+}  // namespace
 
 extern "C" int hica_p1_upload(hica_handle h, const double *A_host, int64_t n)
 {
@@ -184,7 +286,11 @@ extern "C" int hica_p1_upload(hica_handle h, const double *A_host, int64_t n)
     int rc = p1_alloc(h, n);
     if (rc) return rc;
     hica_timer t(h, HICA_T_UPLOAD);
-    HICA_CUDA(cudaMemcpyAsync(h->A, A_host, sizeof(double) * n * n, cudaMemcpyHostToDevice, h->stream));
+    if (n >= 2048 && is_pageable(A_host)) {
+        if ((rc = staged_upload(h, {Region2D{A_host, h->A, n, n, n, n}}))) return rc;
+    } else {
+        HICA_CUDA(cudaMemcpyAsync(h->A, A_host, sizeof(double) * n * n, cudaMemcpyHostToDevice, h->stream));
+    }
     t.stop();
     HICA_CUDA(cudaStreamSynchronize(h->stream));
     return HICA_OK;
@@ -219,10 +325,17 @@ extern "C" int hica_p1_upload_symmetric(hica_handle h, const double *A_host, int
     hica_timer t(h, HICA_T_UPLOAD);
     // row blocks of BS rows: the columns from the block's first row onwards (a 2-D copy each)
     const int64_t BS = 512;
-    for (int64_t r0 = 0; r0 < n; r0 += BS) {
-        const int64_t rows = std::min(BS, n - r0);
-        HICA_CUDA(cudaMemcpy2DAsync(h->A + r0 * n + r0, sizeof(double) * n, A_host + r0 * n + r0, sizeof(double) * n,
-                                    sizeof(double) * (n - r0), rows, cudaMemcpyHostToDevice, h->stream));
+    if (n >= 2048 && is_pageable(A_host)) {
+        std::vector<Region2D> regions;
+        for (int64_t r0 = 0; r0 < n; r0 += BS)
+            regions.push_back(Region2D{A_host + r0 * n + r0, h->A + r0 * n + r0, n, n, n - r0, std::min(BS, n - r0)});
+        if ((rc = staged_upload(h, regions))) return rc;
+    } else {
+        for (int64_t r0 = 0; r0 < n; r0 += BS) {
+            const int64_t rows = std::min(BS, n - r0);
+            HICA_CUDA(cudaMemcpy2DAsync(h->A + r0 * n + r0, sizeof(double) * n, A_host + r0 * n + r0, sizeof(double) * n,
+                                        sizeof(double) * (n - r0), rows, cudaMemcpyHostToDevice, h->stream));
+        }
     }
     const unsigned nb = (unsigned)((n + 31) / 32);
     k_mirror_lower<<<dim3(nb, nb), 256, 0, h->stream>>>(h->A, n);
@@ -251,7 +364,16 @@ extern "C" int hica_p1_upload_rows(hica_handle h, const double *rows_host, int64
     if (r0 < 0 || r1 > n || r0 > r1) return hica_set_error(h, HICA_ERR_ARG, "bad row block [%lld, %lld)", (long long)r0, (long long)r1);
     if (r1 > r0 && !rows_host) return hica_set_error(h, HICA_ERR_ARG, "rows_host is NULL");
     hica_timer t(h, HICA_T_UPLOAD);
-    if (!symmetric) {
+    if (n >= 2048 && r1 > r0 && is_pageable(rows_host)) {
+        std::vector<Region2D> regions;
+        const int64_t BS = 512;
+        if (!symmetric) regions.push_back(Region2D{rows_host, h->A + r0 * n, n, n, n, r1 - r0});
+        else
+            for (int64_t b0 = r0; b0 < r1; b0 += BS)
+                regions.push_back(Region2D{rows_host + (b0 - r0) * n + b0, h->A + b0 * n + b0, n, n, n - b0, std::min(BS, r1 - b0)});
+        int rc = staged_upload(h, regions);
+        if (rc) return rc;
+    } else if (!symmetric) {
         if (r1 > r0)
             HICA_CUDA(cudaMemcpyAsync(h->A + r0 * n, rows_host, sizeof(double) * (r1 - r0) * n, cudaMemcpyHostToDevice, h->stream));
     } else {
@@ -326,6 +448,10 @@ extern "C" int hica_p1_get_row_sums(hica_handle h, double *s_host)
 {
     HICA_CHECK_HANDLE(h);
     if (!h->have_s_seq) return hica_set_error(h, HICA_ERR_STATE, "row sums not set; call hica_p1_set_row_sums first");
+    {
+        int rc = hica_need_s_seq(h, h->stream);
+        if (rc) return rc;
+    }
     HICA_CUDA(cudaMemcpyAsync(s_host, h->s_seq, sizeof(double) * h->n, cudaMemcpyDeviceToHost, h->stream));
     HICA_CUDA(cudaStreamSynchronize(h->stream));
     return HICA_OK;

@@ -36,6 +36,10 @@ struct hica_ctx {
     double *s_pair = nullptr;  // numpy-pairwise row sums (distance transform)
     double *s_seq = nullptr;   // left-to-right row sums (binList[i].rowSum)
     bool have_s_pair = false, have_s_seq = false;
+    // left-to-right row sums computed by the library: 0 = in s_seq (or not asked for), 1 = asked for, not launched yet
+    // (hica_p1_linkage launches them on stream2 next to the chain), 2 = launched on stream2 (ev_sseq)
+    int s_seq_state = 0;
+    cudaEvent_t ev_sseq = nullptr;
     double *W = nullptr;       // mirrored working matrix for linkage, n x ld
     bool have_W = false;
     int A_kind = 0;  // 0: ICE contacts; 1: distance matrix D (hica_p1_upload_distance); 2: similarity S (hica_p1_upload_similarity)
@@ -46,6 +50,9 @@ struct hica_ctx {
     int rank_bytes = 0;          // 2 or 4, 0 = none
     int rank_rows_bytes = 0;     // element size of R once allocated (rows may still be missing: hica_p1_rank_rows)
     // rank pre-sort (hica_p1_rank_presort): rows sorted in matrix order while the linkage runs
+    void *stage_h = nullptr;     // pinned staging slots for uploads from pageable host memory (hica_api.cu)
+    int64_t stage_cap = 0;
+    cudaEvent_t stage_ev[3] = {nullptr, nullptr, nullptr};
     void *pre_buf = nullptr;     // Rpre (n*n uint16) | tie masks (n * tie_words uint32) | anytie (n) | redo (n) | iota (n)
     int64_t pre_cap = 0;
     bool presort_pending = false, presort_valid = false;
@@ -158,9 +165,14 @@ static inline int hica_realloc(hica_ctx *h, T **p, int64_t count)
 // The pre-sort reads A, s_pair and s_seq on stream2: anything that changes them waits for it and drops its result.
 static inline void hica_presort_cancel(hica_ctx *h)
 {
-    if (h->presort_pending) cudaStreamSynchronize(h->stream2);
+    if (h->presort_pending || h->s_seq_state == 2) cudaStreamSynchronize(h->stream2);
+    if (h->s_seq_state == 2) h->s_seq_state = 0;
     h->presort_pending = h->presort_valid = false;
 }
+
+// hica_p1_distance.cu: make s_seq usable by work enqueued on `stream` from now on (launches the deferred row sums
+// there, or makes the stream wait for the ones in flight on stream2)
+int hica_need_s_seq(hica_ctx *h, cudaStream_t stream);
 
 // ---- device helpers ----------------------------------------------------------
 #ifdef __CUDACC__

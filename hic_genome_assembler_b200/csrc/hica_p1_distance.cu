@@ -244,21 +244,65 @@ __global__ void __launch_bounds__(64) k_rowsum_sequential(const double *__restri
 
 }  // namespace
 
+static int launch_rowsum_sequential(hica_ctx *h, cudaStream_t stream)
+{
+    int64_t blocks = (h->n + 63) / 64;
+    k_rowsum_sequential<<<(unsigned)blocks, 64, 0, stream>>>(h->A, h->n, h->s_seq);
+    HICA_LAUNCHED(h);
+    HICA_CUDA(cudaGetLastError());
+    return HICA_OK;
+}
+
+// The left-to-right sums are a pass of their own over A (a dependent chain per row, it cannot share the pairwise
+// pass) and nothing needs them before the similarity ranking.  With HICA_ROWSUM_DEFER=1 hica_p1_set_row_sums(NULL)
+// only notes the request, hica_p1_linkage launches the kernel on stream2 next to the chain (which leaves 132 SMs
+// idle), and whoever reads s_seq first on another stream calls hica_need_s_seq.  Measured at 16,000 bins: the 0.56 ms
+// leave the critical path but the latency-bound chain next to it slows down by 1.6 ms (55.3 -> 56.9 ms) - any
+// memory traffic beside the chain costs more than it hides - so the default computes them at once.
+int hica_need_s_seq(hica_ctx *h, cudaStream_t stream)
+{
+    if (h->s_seq_state == 1) {
+        h->s_seq_state = 0;
+        return launch_rowsum_sequential(h, stream);
+    }
+    if (h->s_seq_state == 2 && stream != h->stream2) {
+        HICA_CUDA(cudaStreamWaitEvent(stream, h->ev_sseq, 0));
+        if (stream == h->stream) h->s_seq_state = 0;  // everything enqueued on the main stream from here on is ordered
+    }
+    return HICA_OK;
+}
+
+// called by hica_p1_linkage once the chain kernel is in the main stream (ev_fork recorded in front of it)
+int hica_s_seq_side_launch(hica_ctx *h)
+{
+    if (h->s_seq_state != 1) return HICA_OK;
+    HICA_CUDA(cudaStreamWaitEvent(h->stream2, h->ev_fork, 0));
+    int rc = launch_rowsum_sequential(h, h->stream2);
+    if (rc) return rc;
+    HICA_CUDA(cudaEventRecord(h->ev_sseq, h->stream2));
+    h->s_seq_state = 2;
+    return HICA_OK;
+}
+
 extern "C" int hica_p1_set_row_sums(hica_handle h, const double *rs)
 {
     HICA_CHECK_HANDLE(h);
     if (!h->A) return hica_set_error(h, HICA_ERR_STATE, "no matrix uploaded");
     hica_presort_cancel(h);
+    h->s_seq_state = 0;
     if (rs) {
         HICA_CUDA(cudaMemcpyAsync(h->s_seq, rs, sizeof(double) * h->n, cudaMemcpyHostToDevice, h->stream));
+        HICA_CUDA(cudaStreamSynchronize(h->stream));
     } else {
         if (h->A_kind != 0) return hica_set_error(h, HICA_ERR_STATE, "row sums of a distance/similarity matrix must be supplied");
-        int64_t blocks = (h->n + 63) / 64;
-        k_rowsum_sequential<<<(unsigned)blocks, 64, 0, h->stream>>>(h->A, h->n, h->s_seq);
-        HICA_LAUNCHED(h);
-        HICA_CUDA(cudaGetLastError());
+        h->s_seq_state = 1;
+        const char *e = getenv("HICA_ROWSUM_DEFER");
+        if (!e || atoi(e) == 0) {
+            int rc = hica_need_s_seq(h, h->stream);
+            if (rc) return rc;
+            HICA_CUDA(cudaStreamSynchronize(h->stream));
+        }
     }
-    HICA_CUDA(cudaStreamSynchronize(h->stream));
     h->have_s_seq = true;
     return HICA_OK;
 }

@@ -445,6 +445,7 @@ int launch_nn_chain4(hica_ctx *h, int cluster_size, int threads, const double *n
 }  // namespace
 
 int hica_presort_start(hica_ctx *h);  // hica_p1_rank.cu
+int hica_s_seq_side_launch(hica_ctx *h);  // hica_p1_distance.cu
 
 int hica_set_order_internal(hica_ctx *h, const int32_t *order_host)
 {
@@ -549,6 +550,7 @@ extern "C" int hica_p1_linkage(hica_handle h, double *Z_host, int32_t *leaves_ho
     HICA_CUDA(cudaGetLastError());
     // The chain keeps one cluster (16 SMs) busy for its whole duration: sort the rows of the similarity matrix on
     // the other SMs meanwhile, in matrix order (low-priority stream; hica_p1_rank then only relabels the columns)
+    if ((rc = hica_s_seq_side_launch(h))) return rc;  // the deferred left-to-right row sums, if any
     if ((rc = hica_presort_start(h))) return rc;
     t.stop();
     h->have_W = false;  // W has been consumed

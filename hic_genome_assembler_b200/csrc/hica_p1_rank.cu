@@ -204,6 +204,8 @@ static bool presort_uses_chunks(hica_ctx *h)
     return h->n > rankremap::MAX_N || (algo && algo[0] == 'b');
 }
 
+int hica_s_seq_side_launch(hica_ctx *h);  // hica_p1_distance.cu
+
 bool hica_presort_possible(hica_ctx *h)
 {
     if (const char *e = getenv("HICA_RANK_OVERLAP")) if (atoi(e) == 0) return false;
@@ -238,6 +240,10 @@ int hica_presort_start(hica_ctx *h)
     }
     const PreBuf b = pre_layout(h);
     HICA_CUDA(cudaStreamWaitEvent(h->stream2, h->ev_fork, 0));
+    {
+        int rc0 = hica_s_seq_side_launch(h);  // row sums still owed: in front of the sort, same stream
+        if (rc0) return rc0;
+    }
     HICA_CUDA(cudaEventRecord(h->ev_pre0, h->stream2));
     k_iota<<<(unsigned)((n + 255) / 256), 256, 0, h->stream2>>>(b.iota, n);
     HICA_LAUNCHED(h);
@@ -399,6 +405,10 @@ __global__ void __launch_bounds__(256) k_tie_mask(const double *__restrict__ A, 
 int hica_tie_ensure(hica_ctx *h)
 {
     if (h->tie_epoch == h->rank_epoch) return HICA_OK;
+    if (h->have_s_seq) {
+        int rc0 = hica_need_s_seq(h, h->stream);
+        if (rc0) return rc0;
+    }
     h->tie_epoch = h->rank_epoch;
     h->tie_src = 0;
     h->tie_rows = -1;
@@ -444,7 +454,9 @@ void hica_tie_info(hica_ctx *h, const uint32_t **bits, const int32_t **map, int 
 extern "C" int hica_p1_rank(hica_handle h)
 {
     HICA_CHECK_HANDLE(h);
-    int rc = rank_range(h, 0, h->n);
+    int rc = h->have_s_seq ? hica_need_s_seq(h, h->stream) : HICA_OK;
+    if (rc) return rc;
+    rc = rank_range(h, 0, h->n);
     if (rc) return rc;
     h->rank_bytes = h->rank_rows_bytes;
     return HICA_OK;
@@ -456,6 +468,8 @@ extern "C" int hica_p1_rank(hica_handle h)
 extern "C" int hica_p1_rank_rows(hica_handle h, int64_t r0, int64_t r1)
 {
     HICA_CHECK_HANDLE(h);
+    int rc = h->have_s_seq ? hica_need_s_seq(h, h->stream) : HICA_OK;
+    if (rc) return rc;
     return rank_range(h, r0, r1);
 }
 
@@ -544,6 +558,10 @@ extern "C" int hica_p1_get_reordered(hica_handle h, int what, double *out_host)
     if (h->A_kind == 0 && !h->have_s_pair) return hica_set_error(h, HICA_ERR_STATE, "call hica_p1_distance first");
     if (what == 1 && h->A_kind != 2 && !h->have_s_seq) return hica_set_error(h, HICA_ERR_STATE, "row sums not set");
     if (what != 0 && what != 1) return hica_set_error(h, HICA_ERR_ARG, "what must be 0 or 1");
+    if (h->have_s_seq) {
+        int rc0 = hica_need_s_seq(h, h->stream);
+        if (rc0) return rc0;
+    }
     const int64_t n = h->n;
     double *out = nullptr;
     int rc = hica_realloc(h, &out, n * n);

@@ -246,6 +246,49 @@ def test_symmetric_upload_reads_only_the_upper_triangle(hica, n):
     assert np.array_equal(hica.p1_get_row_sums(), rs_full)
 
 
+def test_deferred_row_sums_give_the_same_rank_and_cuts(hica, monkeypatch):
+    """HICA_ROWSUM_DEFER=1: the left-to-right row sums are launched next to the linkage chain instead of at once;
+    every consumer (rank pre-sort, one-step rank, get_row_sums) still sees them."""
+    n = 700
+    A = _rand_sym(n, 5)
+    ref = O.part1_cut_indices(A, min_size=5, min_frac=0.0, psig=.05)
+    for overlap in ("1", "0"):
+        monkeypatch.setenv("HICA_ROWSUM_DEFER", "1")
+        monkeypatch.setenv("HICA_RANK_OVERLAP", overlap)
+        hica.p1_upload(A)
+        hica.p1_set_row_sums(None)
+        hica.p1_distance()
+        Z, leaves = hica.p1_linkage()
+        assert np.array_equal(Z, ref["Z"]) and list(leaves) == list(ref["leaves"])
+        hica.p1_rank()
+        assert np.array_equal(hica.p1_get_row_sums(), O.sequential_row_sums(A))
+        cuts, _ = hica.p1_breakpoints(5, 0.0)
+        assert list(cuts) == ref["initial_cuts"]
+
+
+@pytest.mark.parametrize("threads", ["1", "3", ""])
+def test_uploads_from_pageable_memory_are_staged_by_several_threads(hica, threads, monkeypatch):
+    """n >= 2048 from ordinary numpy memory goes through the pinned staging slots (hica_api.cu staged_upload):
+    several chunks per region, more chunks than slots, full and upper-triangle uploads - same matrix on the device
+    as seen through the distance transform and both kinds of row sums."""
+    if threads:
+        monkeypatch.setenv("HICA_UPLOAD_THREADS", threads)
+    n = 2304
+    A = _rand_sym(n, 77)
+    D_ref = O.convert_distance(A)
+    for sym in (False, True):
+        B = A.copy()
+        if sym:
+            B[np.tril_indices(n, -1)] = -1.0
+            hica.p1_upload_symmetric(B)
+        else:
+            hica.p1_upload(B)
+        hica.p1_set_row_sums(None)
+        hica.p1_distance()
+        assert np.array_equal(hica.p1_get_distance(), D_ref)
+        assert np.array_equal(hica.p1_get_row_sums(), O.sequential_row_sums(A))
+
+
 @pytest.mark.parametrize("env", [{"HICA_NN_CHAIN_GLOBAL": "1"}, {"HICA_NN_KERNEL": "2"}, {"HICA_NN_KERNEL": "1"},
                                  {"HICA_NN_CLUSTER": "8"}, {"HICA_NN_CLUSTER": "2"}, {"HICA_NN_CLUSTER": "1"},
                                  {"HICA_NN_THREADS": "128"}, {"HICA_NN_DEBUG": "1"},
