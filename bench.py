@@ -39,8 +39,9 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 
-# DRAM bytes of one linkage-kernel launch measured with `ncu --set full` (bins -> bytes); see profiles/
-NCU_DRAM_BYTES = {16000: 4.95e9}
+# DRAM bytes of one linkage-kernel launch measured with `ncu --set full` (bins -> bytes):
+# profiles/r02_ncu_full_summary.txt, nn4::k_nn_chain4 (1.588 GB read + 0.659 GB written; k_nn_chain3 of round 1: 4.95 GB)
+NCU_DRAM_BYTES = {16000: 2.247e9}
 
 
 def parse_args():
@@ -595,7 +596,8 @@ def main():
                          "note": "same step from ordinary (pageable) numpy memory through hica_p1_upload_symmetric's staged copies"},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "nn3::k_nn_chain3 (linkage: one thread-block cluster, latency-bound chain)",
+        "roofline": {"bound": "hbm", "kernel": "nn4::k_nn_chain4 (linkage: one thread-block cluster, latency-bound chain)" if n <= 21000 else
+                               "nn3::k_nn_chain3 (linkage: one thread-block cluster, latency-bound chain)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": NCU_DRAM_BYTES.get(n), "traffic_source": "profiles/ (ncu --set full, "
                      "dram__bytes_read.sum + dram__bytes_write.sum per launch)" if n in NCU_DRAM_BYTES else None,

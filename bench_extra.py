@@ -19,8 +19,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 
-# DRAM / L2 bytes of one k_score launch of this configuration (ncu --set full; profiles/r02_k_score_*.txt)
-NCU_K_SCORE = {}
+# DRAM / L2 bytes of one k_score launch of this configuration on ONE GPU (ncu --set full; profiles/r02_ncu_full_summary.txt):
+# 3.08 MB from DRAM, 8.453 G sectors = 270.5 GB through L2 (69.8 % of the L2 throughput peak)
+NCU_K_SCORE = {"dram_bytes": 3.08e6, "lts_bytes": 270.5e9}
 
 
 def _chromosome(seed, device):
@@ -166,7 +167,9 @@ def candidates_config(args, rank, world, local_rank):
                      "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
                      "alg_bytes_per_launch": alg, "kernel_ms": k_ms,
                      "traffic": NCU_K_SCORE.get("dram_bytes"), "lts_bytes": NCU_K_SCORE.get("lts_bytes"),
-                     "note": "frac > 1 is an L2 rate: every candidate re-reads the same 5.1 MB matrix"},
+                     "note": "frac > 1 is an L2 rate: every candidate re-reads the same 5.1 MB matrix (ncu, 1 GPU: 3 MB from "
+                             "DRAM, 270.5 GB through L2 = 69.8 % of the L2 throughput peak); traffic / lts_bytes are the "
+                             "single-GPU launch's"},
         "cpu_baseline": {"value": len(rows) * pairs / t_cpu, "unit": "bin-pairs/s", "cores": 1, "kind": "port",
                          "sample": "numpy.ix_ gather + numba costFunction (orderGenome.py:463) on the first %d candidates, %.1f s; "
                                    "C restatement of the score alone: %d candidates in %.2f s" % (len(rows), t_cpu, NP, t_c)},
