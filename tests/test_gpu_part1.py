@@ -289,7 +289,8 @@ def test_uploads_from_pageable_memory_are_staged_by_several_threads(hica, thread
         assert np.array_equal(hica.p1_get_row_sums(), O.sequential_row_sums(A))
 
 
-@pytest.mark.parametrize("env", [{"HICA_NN_CHAIN_GLOBAL": "1"}, {"HICA_NN_KERNEL": "2"}, {"HICA_NN_KERNEL": "1"},
+@pytest.mark.parametrize("env", [{"HICA_NN_CHAIN_GLOBAL": "1"}, {"HICA_NN_CHAIN_GLOBAL": "1", "HICA_NN_KERNEL": "3"},
+                                 {"HICA_NN_CHAIN_GLOBAL": "1", "HICA_NN_CLUSTER": "2", "HICA_NN_DEBUG": "1"}, {"HICA_NN_KERNEL": "2"}, {"HICA_NN_KERNEL": "1"},
                                  {"HICA_NN_CLUSTER": "8"}, {"HICA_NN_CLUSTER": "2"}, {"HICA_NN_CLUSTER": "1"},
                                  {"HICA_NN_THREADS": "128"}, {"HICA_NN_DEBUG": "1"},
                                  {"HICA_NN_KERNEL": "3"}, {"HICA_NN_KERNEL": "3", "HICA_NN_FLAGS": "2"},  # scatter; + fence
