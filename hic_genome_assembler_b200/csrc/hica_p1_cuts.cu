@@ -707,9 +707,9 @@ int find_breakpoints(hica_ctx *h, int64_t start, int64_t min_size, int64_t world
 // Run-ahead form of the break-search loop of pre_process_all_matrix_breakpoints (:513-551).  Every search starts
 // where the previous one found its first cut, so the searches are strictly sequential - but the common case (the
 // significances are evaluated once, the sliding window of width min_size finds a hit) needs no host decision at
-// all.  The start index lives in device memory, a one-thread kernel applies the reference's rules after each
-// search, and the host enqueues several searches back to back with ONE read-back per batch instead of one per
-// search.  Anything else (>= 90 % significant rows -> M shrinks, no hit -> narrower windows, tiny remainders) sets
+// all.  The start index lives in device memory, a one-CTA kernel (k_ra_decide) compares the counts with the critical
+// counts, runs the sliding pass and applies the reference's rules after each search, and the host enqueues several
+// searches (two launches each) back to back with ONE read-back per batch instead of one per search.  Anything else (>= 90 % significant rows -> M shrinks, no hit -> narrower windows, tiny remainders) sets
 // need_host and the host-driven find_breakpoints() repeats that search from the same index.
 constexpr int RA_MAX_CUTS = 4096;
 constexpr int RA_BATCH = 8;
@@ -717,12 +717,6 @@ struct RaState {
     int32_t ind, done, need_host, count, amb, searches, tie, pad1;  // tie: decisions that depend on the order of exact ties
     int32_t cuts[RA_MAX_CUTS];
 };
-
-__global__ void k_ra_reset(int32_t *__restrict__ misc, int iters)
-{
-    const int i = threadIdx.x;
-    if (i < iters * 8) misc[i] = ((i & 7) == 1) ? INT_MAX : 0;
-}
 
 template <typename RankT>
 __global__ void __launch_bounds__(128) k_ra_counts(const RankT *__restrict__ R, int64_t n, const RaState *__restrict__ st,
@@ -755,25 +749,6 @@ __global__ void __launch_bounds__(128) k_ra_counts(const RankT *__restrict__ R, 
     }
 }
 
-__global__ void k_ra_sig(const int32_t *__restrict__ x, const int32_t *__restrict__ crit, int64_t n,
-                         const RaState *__restrict__ st, double psig, uint8_t *__restrict__ sig, int32_t *__restrict__ misc,
-                         const int2 *__restrict__ xt)
-{
-    if (st->done | st->need_host) return;
-    const int64_t Lw = n - st->ind;
-    if (Lw <= 1) return;
-    sig_cmp0_one((int64_t)blockIdx.x * blockDim.x + threadIdx.x, x, crit, Lw, Lw, psig, sig, misc, xt);
-}
-
-__global__ void k_ra_hits(const uint8_t *__restrict__ sig, int64_t n, const RaState *__restrict__ st, int w,
-                          int32_t *__restrict__ misc)
-{
-    if (st->done | st->need_host) return;
-    const int64_t Lw = n - st->ind;
-    if (Lw <= 1 || w >= Lw) return;  // no sliding pass (:487: ws < Lw)
-    break_hit_one((int64_t)blockIdx.x * blockDim.x + threadIdx.x, sig, Lw, w, misc);
-}
-
 // One CTA.  Common case (thread 0): < 90 % significant rows and a hit at width min_size -> commit the cut.
 // Otherwise, when the remaining world is small (the end game inside the last chromosome, where M shrinks and the
 // windows narrow), the whole of find_matrix_pvalue_breakpoints' control flow (:437-511) runs here: up to five
@@ -782,7 +757,7 @@ __global__ void k_ra_hits(const uint8_t *__restrict__ sig, int64_t n, const RaSt
 // count ambiguous decisions, never produce a cut).  Larger worlds that need this go back to the host.
 constexpr int RA_DECIDE_THREADS = 512;
 constexpr int RA_SLOW_MAX = 4096;
-__global__ void __launch_bounds__(RA_DECIDE_THREADS) k_ra_decide(RaState *st, const int32_t *__restrict__ misc, int64_t n,
+__global__ void __launch_bounds__(RA_DECIDE_THREADS) k_ra_decide(RaState *st, int64_t n,
                                                                  int min_size, int64_t stop_ind, const int32_t *__restrict__ x,
                                                                  int32_t *__restrict__ crit, uint8_t *__restrict__ sig, double psig,
                                                                  const int2 *__restrict__ xt)
@@ -792,7 +767,15 @@ __global__ void __launch_bounds__(RA_DECIDE_THREADS) k_ra_decide(RaState *st, co
     if (st->done | st->need_host) return;
     const int64_t start = st->ind, Lw = n - start;
     if (Lw <= 1 || min_size >= Lw) { if (t == 0) st->need_host = 1; return; }
-    int sum = misc[0], first = misc[1], hits = misc[2], amb1 = misc[3], tie1 = misc[6];
+    // first evaluation: world size M = Lw, critical counts from the counting launch (k_ra_counts); the compare and
+    // the sliding pass over <= n entries are done by this one CTA (two tiny launches less per search)
+    if (t < 8) sm[t] = (t == 1) ? INT_MAX : 0;
+    __syncthreads();
+    for (int64_t c = t; c < Lw; c += RA_DECIDE_THREADS) sig_cmp0_one(c, x, crit, Lw, Lw, psig, sig, sm, xt);
+    __syncthreads();
+    for (int64_t tt = t; tt < Lw; tt += RA_DECIDE_THREADS) break_hit_one(tt, sig, Lw, min_size, sm);  // min_size < Lw here
+    __syncthreads();
+    int sum = sm[0], first = sm[1], hits = sm[2], amb1 = sm[3], tie1 = sm[6];
     auto commit = [&](int amb_total, int tie_total) {  // thread 0: leftmost hit + min_size (:488, :540), then the stop rules (:541-549)
         if (st->count >= RA_MAX_CUTS) { st->need_host = 2; return; }
         st->amb += amb_total;
@@ -810,7 +793,7 @@ __global__ void __launch_bounds__(RA_DECIDE_THREADS) k_ra_decide(RaState *st, co
     if (Lw > RA_SLOW_MAX) { if (t == 0) st->need_host = 1; return; }
     long long M = Lw;
     int ws = min_size, break_sig = 0, loop_count = 0, amb = 0, tie = 0;
-    bool have_eval = true;  // the first evaluation came from k_ra_sig / k_ra_hits
+    bool have_eval = true;  // the first evaluation was done above
     for (;;) {
         const bool slide = (ws == min_size && ws < Lw);
         for (;;) {
@@ -923,23 +906,17 @@ extern "C" int hica_p1_breakpoints(hica_handle h, int64_t min_size, double min_f
             HICA_CUDA(cudaMallocHost((void **)&h->ra_h, sizeof(RaState)));
         }
         RaState *st_d = reinterpret_cast<RaState *>(h->ra_d), *st_h = reinterpret_cast<RaState *>(h->ra_h);
-        int32_t *misc_ra = h->ra_d + RA_INTS;
         memset(st_h, 0, 8 * sizeof(int32_t));
         HICA_CUDA(cudaMemcpyAsync(st_d, st_h, 8 * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
         int32_t *crit = reinterpret_cast<int32_t *>(h->q_d + (n + 16));
         const unsigned ncrit = (unsigned)((n + 127) / 128);
         bool finished = false;
         while (!finished) {
-            k_ra_reset<<<1, 8 * RA_BATCH, 0, h->stream>>>(misc_ra, RA_BATCH);
-            HICA_LAUNCHED(h);
             int rc = with_rank(h, [&](auto *R) {
                 for (int it = 0; it < RA_BATCH; it++) {
-                    int32_t *mi = misc_ra + 8 * it;
                     k_ra_counts<<<(unsigned)(n - 1) + ncrit, 128, 0, h->stream>>>(R, n, st_d, h->x_d, (int)ncrit, .05, crit, ti, h->xt_d);
-                    k_ra_sig<<<ncrit, 128, 0, h->stream>>>(h->x_d, crit, n, st_d, .05, h->sig_d, mi, h->xt_d);
-                    k_ra_hits<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->sig_d, n, st_d, (int)min_size, mi);
-                    k_ra_decide<<<1, RA_DECIDE_THREADS, 0, h->stream>>>(st_d, mi, n, (int)min_size, stop_ind, h->x_d, crit, h->sig_d, .05, h->xt_d);
-                    h->launches += 4;
+                    k_ra_decide<<<1, RA_DECIDE_THREADS, 0, h->stream>>>(st_d, n, (int)min_size, stop_ind, h->x_d, crit, h->sig_d, .05, h->xt_d);
+                    h->launches += 2;
                 }
                 HICA_CUDA(cudaGetLastError());
                 return (int)HICA_OK;
