@@ -600,9 +600,13 @@ __device__ __forceinline__ InsertCand insert_cand(int c, int ne)
 
 // D[a] for every placed position (INS_ROWS per CTA, one warp per row at a time) -> ins_d[a].
 constexpr int INS_ROWS = 16;
-__global__ void __launch_bounds__(256) k_g_ins_rows(const GroupDev *gs, Phase ph)
+// Blocks [0, row_blocks) compute D[a]; block row_blocks + c computes X(c), the contacts of the new scaffold with the
+// placed bins for candidate c (slot, orientation) -> rel[c].  The two do not depend on each other, so they share
+// one launch; k_g_ins_select adds F(p) = sum_{a < p} D[a] afterwards.
+__global__ void __launch_bounds__(256) k_g_ins_rows(const GroupDev *gs, Phase ph, const int row_blocks)
 {
     extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ double red[8];
     const GroupDev &g = gs[blockIdx.y];
     const PhaseParams pp = phase_params(g, ph);
     if (!pp.active || g.st->inexact) return;  // negative / asymmetric contacts: every candidate is scored exactly
@@ -613,6 +617,44 @@ __global__ void __launch_bounds__(256) k_g_ins_rows(const GroupDev *gs, Phase ph
     const double *Hp = g.Hp;
     const int seg = ne >> 1;
     const int Ls = g.seg_ptr[seg + 1] - g.seg_ptr[seg], P = n - Ls;
+    if ((int)blockIdx.x >= row_blocks) {
+        const int c = (int)blockIdx.x - row_blocks;
+        if (c >= 2 * (m + 1)) return;
+        const int b0 = g.seg_ptr[seg];
+        SmemPlan sp = carve(smem, 0, n, m + 1);
+        if (m >= 1) build_order_cta(SrcLayout{g.layout}, m, g.seg_ptr, g.seg_bins, sp.o, sp.spos, sp.sent, P);
+        const InsertCand cd = insert_cand(c, ne);
+        const int p = (m >= 1) ? sp.spos[cd.i] : 0;
+        const int32_t *o = sp.o;
+        const double hn = Hp[n - 1];  // total * w(d) = Hp[n - 1] - Hp[d - 1]
+        const int L = g.L;
+        double acc = 0.;
+        for (int a = threadIdx.x; a < P; a += blockDim.x) {
+            const int oa = o[a];
+            if (a < p) {
+                const double *Srow = g.S + (int64_t)oa * L;
+                for (int t = 0; t < Ls; t++) {
+                    const int nb = g.seg_bins[b0 + (cd.ori ? (Ls - 1 - t) : t)];
+                    acc += Srow[nb] * (hn - Hp[p + t - a - 1]);
+                }
+            } else {
+                const double *Trow = g.St + (int64_t)oa * L;  // St[oa][nb] = S[nb][oa]
+                for (int t = 0; t < Ls; t++) {
+                    const int nb = g.seg_bins[b0 + (cd.ori ? (Ls - 1 - t) : t)];
+                    acc += Trow[nb] * (hn - Hp[a + Ls - p - t - 1]);
+                }
+            }
+        }
+        for (int d = 16; d >= 1; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+        if (lane == 0) red[warp] = acc;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double xsum = 0.;
+            for (int w = 0; w < (int)blockDim.x / 32; w++) xsum += red[w];
+            g.rel[c] = xsum;
+        }
+        return;
+    }
     if (m < 1 || (int)(blockIdx.x * INS_ROWS) >= P) return;
     SmemPlan sp = carve(smem, 0, n, m + 1);
     build_order_cta(SrcLayout{g.layout}, m, g.seg_ptr, g.seg_bins, sp.o, sp.spos, sp.sent, P);
@@ -637,73 +679,93 @@ __global__ void __launch_bounds__(256) k_g_ins_rows(const GroupDev *gs, Phase ph
     }
 }
 
-// closed-form score of every candidate (relative to the constant terms)
-__global__ void __launch_bounds__(128) k_g_ins_rel(const GroupDev *gs, Phase ph)
-{
-    extern __shared__ __align__(16) unsigned char smem[];
-    __shared__ double red[4];
-    const GroupDev &g = gs[blockIdx.y];
-    const PhaseParams pp = phase_params(g, ph);
-    if (!pp.active || g.st->inexact) return;
-    const int m = pp.m, n = pp.n, c = blockIdx.x;
-    if (n < 2 || c >= 2 * (m + 1)) return;
-    const int ne = g.layout[m], seg = ne >> 1;
-    const int b0 = g.seg_ptr[seg], Ls = g.seg_ptr[seg + 1] - b0, P = n - Ls;
-    SmemPlan sp = carve(smem, 0, n, m + 1);
-    if (m >= 1) build_order_cta(SrcLayout{g.layout}, m, g.seg_ptr, g.seg_bins, sp.o, sp.spos, sp.sent, P);
-    const InsertCand cd = insert_cand(c, ne);
-    const int p = (m >= 1) ? sp.spos[cd.i] : 0;
-    const int32_t *o = sp.o;
-    const double *Hp = g.Hp;
-    const double hn = Hp[n - 1];  // total * w(d) = Hp[n - 1] - Hp[d - 1]
-    const int L = g.L;
-    double acc = 0.;
-    for (int a = threadIdx.x; a < p; a += blockDim.x) acc += g.ins_d[a];
-    for (int a = threadIdx.x; a < P; a += blockDim.x) {
-        const int oa = o[a];
-        if (a < p) {
-            const double *Srow = g.S + (int64_t)oa * L;
-            for (int t = 0; t < Ls; t++) {
-                const int nb = g.seg_bins[b0 + (cd.ori ? (Ls - 1 - t) : t)];
-                acc += Srow[nb] * (hn - Hp[p + t - a - 1]);
-            }
-        } else {
-            const double *Trow = g.St + (int64_t)oa * L;  // St[oa][nb] = S[nb][oa]
-            for (int t = 0; t < Ls; t++) {
-                const int nb = g.seg_bins[b0 + (cd.ori ? (Ls - 1 - t) : t)];
-                acc += Trow[nb] * (hn - Hp[a + Ls - p - t - 1]);
-            }
-        }
-    }
-    for (int d = 16; d >= 1; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double rel = 0.;
-        for (int w = 0; w < (int)blockDim.x / 32; w++) rel += red[w];
-        g.rel[c] = rel;
-        atomicMax(&g.st->w0.amax_key, f64_order_key(rel));
-        if (c == 0) g.st->w0.rel0 = rel;
-    }
-}
-
-// candidates that can still be the exact winner
+// closed-form score of every candidate (relative to the constant terms) = F(p) + X(c), F(p) = sum_{a < p} D[a] with p
+// the first position of the candidate's slot, and the candidates that can still be the exact winner.  One CTA per
+// group: an inclusive scan of D in shared memory, the maximum by a block reduction.
 __global__ void __launch_bounds__(128) k_g_ins_select(const GroupDev *gs, Phase ph)
 {
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ double wsum[4];
+    __shared__ unsigned long long wmax[4];
     const GroupDev &g = gs[blockIdx.y];
     const PhaseParams pp = phase_params(g, ph);
     if (!pp.active) return;
     GroupState *st = g.st;
-    const int B = 2 * (pp.m + 1);
-    const bool all = st->inexact || pp.n < 2 || st->total == 0.0;
+    const int m = pp.m, n = pp.n, B = 2 * (m + 1);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool all = st->inexact || n < 2 || st->total == 0.0;
+    if (all) {
+        for (int c = tid; c < B; c += blockDim.x) g.near_id[atomicAdd(&st->w0.near_count, 1)] = c;
+        return;
+    }
+    const int ne = g.layout[m], seg = ne >> 1;
+    const int Ls = g.seg_ptr[seg + 1] - g.seg_ptr[seg], P = n - Ls;
+    double *D = reinterpret_cast<double *>(smem);             // P entries: inclusive prefix sums of ins_d
+    int32_t *spos = reinterpret_cast<int32_t *>(D + g.L);     // m + 1 entries: first position of every slot
+    // slot starts (as build_order_cta: lengths by all threads, shuffle scan by warp 0)
+    for (int sl = tid; sl < m; sl += blockDim.x) {
+        const int sg = g.layout[sl] >> 1;
+        spos[sl + 1] = g.seg_ptr[sg + 1] - g.seg_ptr[sg];
+    }
+    const int chunk = (P + (int)blockDim.x - 1) / (int)blockDim.x;
+    const int a0 = min(P, tid * chunk), a1 = min(P, a0 + chunk);
+    double run = 0.;
+    if (m >= 1)
+        for (int a = a0; a < a1; a++) { run += g.ins_d[a]; D[a] = run; }
+    __syncthreads();
+    if (warp == 0) {
+        int carry = 0;
+        for (int base = 0; base < m; base += 32) {
+            const int sl = base + lane;
+            int v = (sl < m) ? spos[sl + 1] : 0;
+            for (int d = 1; d < 32; d <<= 1) {
+                const int u = __shfl_up_sync(0xffffffffu, v, d);
+                if (lane >= d) v += u;
+            }
+            if (sl < m) spos[sl + 1] = carry + v;
+            carry += __shfl_sync(0xffffffffu, v, 31);
+        }
+        if (lane == 0) spos[0] = 0;
+    }
+    // exclusive offsets of the threads' chunks: scan of the chunk sums
+    double inc = run;
+    for (int d = 1; d < 32; d <<= 1) {
+        const double u = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += u;
+    }
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    double off = inc - run;
+    for (int w = 0; w < warp; w++) off += wsum[w];
+    if (m >= 1)
+        for (int a = a0; a < a1; a++) D[a] += off;
+    __syncthreads();
+    // scores, their maximum, the near list
+    unsigned long long kmax = 0ull;
+    for (int c = tid; c < B; c += blockDim.x) {
+        const InsertCand cd = insert_cand(c, ne);
+        const int p = (m >= 1) ? spos[cd.i] : 0;
+        const double rel = g.rel[c] + (p > 0 ? D[p - 1] : 0.);
+        g.rel[c] = rel;
+        const unsigned long long key = f64_order_key(rel);
+        kmax = key > kmax ? key : kmax;
+    }
+    for (int d = 16; d >= 1; d >>= 1) {
+        const unsigned long long u = __shfl_xor_sync(0xffffffffu, kmax, d);
+        kmax = u > kmax ? u : kmax;
+    }
+    if (lane == 0) wmax[warp] = kmax;
+    __syncthreads();
+    for (int w = 0; w < (int)blockDim.x / 32; w++) kmax = wmax[w] > kmax ? wmax[w] : kmax;
+    if (tid == 0) st->w0.amax_key = kmax;
     // The closed form differs from the exact score by a few n ulp of the score itself, and no score exceeds
     // H_{n-1} = sum_{k<n} 1/k (the traces add up to total, and w(k) <= w(1) = H_{n-1} / total): the tolerance
     // is taken relative to that bound, which needs no absolute anchor.  Whether the best score beats the
     // initial bestCost of 0. (:338) is decided on the exact scores in k_g_pick_insert.
-    const double hn = g.Hp[pp.n - 1] * fabs(st->total);  // the closed-form scores of this step are total x cost
-    const double thr = f64_from_order_key(st->w0.amax_key) - near_tol(pp.n) * hn;
-    for (int c = threadIdx.x; c < B; c += blockDim.x) {
-        const bool near = all || !(g.rel[c] < thr);
+    const double hn = g.Hp[n - 1] * fabs(st->total);  // the closed-form scores of this step are total x cost
+    const double thr = f64_from_order_key(kmax) - near_tol(n) * hn;
+    for (int c = tid; c < B; c += blockDim.x) {
+        const bool near = !(g.rel[c] < thr);
         if (near) g.near_id[atomicAdd(&st->w0.near_count, 1)] = c;
     }
 }
@@ -1074,12 +1136,13 @@ extern "C" int hica_p2_order_groups(hica_handle h, int32_t ngroups, const int32_
 
     const size_t ex_smem = smem_bytes(Lmax, nseg_max + 1);
     const size_t tot_smem = sizeof(int32_t) * (Lmax + 2 * (nseg_max + 1) + 2);
+    const size_t sel_smem = sizeof(double) * Lmax + sizeof(int32_t) * (nseg_max + 2);
     if (ex_smem > 200 * 1024) return hica_set_error(h, HICA_ERR_ARG, "chromosome too large for shared memory");
     ENG_CUDA(cudaFuncSetAttribute(k_g_exact_near, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex_smem));
     ENG_CUDA(cudaFuncSetAttribute(k_g_anchor, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex_smem));
     ENG_CUDA(cudaFuncSetAttribute(k_g_insert_scores, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex_smem));
     ENG_CUDA(cudaFuncSetAttribute(k_g_ins_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tot_smem));
-    ENG_CUDA(cudaFuncSetAttribute(k_g_ins_rel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tot_smem));
+    ENG_CUDA(cudaFuncSetAttribute(k_g_ins_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sel_smem));
     ENG_CUDA(cudaFuncSetAttribute(k_g_total, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex_smem));
     const size_t tab_smem = sizeof(double) * Lmax + sizeof(int32_t) * (Lmax + 2 * (nseg_max + 1) + 2);
     ENG_CUDA(cudaFuncSetAttribute(k_g_tables, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tab_smem));
@@ -1145,21 +1208,20 @@ extern "C" int hica_p2_order_groups(hica_handle h, int32_t ngroups, const int32_
         }
         k_g_total<<<dim3(tot_blocks, G), TOT_WARPS * 32, ex_smem, s>>>(gdev, ph, 0);
         mark(1);
-        k_g_ins_rows<<<dim3((unsigned)((Lmax + INS_ROWS - 1) / INS_ROWS), G), 256, tot_smem, s2>>>(gdev, ph);
+        const unsigned row_blocks = (unsigned)((Lmax + INS_ROWS - 1) / INS_ROWS);
+        k_g_ins_rows<<<dim3(row_blocks + nb_c, G), 256, tot_smem, s2>>>(gdev, ph, (int)row_blocks);
         mark(8);
-        k_g_ins_rel<<<dim3(nb_c, G), 128, tot_smem, s2>>>(gdev, ph);
-        mark(9);
         if (!prof) {
             ENG_CUDA(cudaEventRecord(h->ev_join, s2));
             ENG_CUDA(cudaStreamWaitEvent(s, h->ev_join, 0));
         }
-        k_g_ins_select<<<dim3(1, G), 128, 0, s>>>(gdev, ph);
+        k_g_ins_select<<<dim3(1, G), 128, sel_smem, s>>>(gdev, ph);
         mark(10);
         k_g_insert_scores<<<dim3(std::min(nb_c, 8u) * EX_SPLIT, G), EX_THREADS, ex_smem, s>>>(gdev, ph);
         mark(11);
         k_g_pick_insert<<<dim3(1, G), 32, 0, s>>>(gdev, ph);
         mark(12);
-        h->launches += 6;
+        h->launches += 5;
     }
     // ---- sliding-window scan (:579-580)
     std::vector<GroupState> hst(ngroups);
