@@ -1137,6 +1137,12 @@ extern "C" int hica_p2_order_groups(hica_handle h, int32_t ngroups, const int32_
     const size_t ex_smem = smem_bytes(Lmax, nseg_max + 1);
     const size_t tot_smem = sizeof(int32_t) * (Lmax + 2 * (nseg_max + 1) + 2);
     const size_t sel_smem = sizeof(double) * Lmax + sizeof(int32_t) * (nseg_max + 2);
+    // threads per CTA of the cluster-split exact scores: one thread per pair of diagonals (n / 2 pairs over EX_SPLIT
+    // CTAs).  The kernels need ~124 registers per thread, so a 512-thread CTA owns an SM; with only as many threads as
+    // there are pairs, several clusters share an SM and the near lists of all groups fit in one wave.
+    int ex_cl_threads = (int)(((Lmax / 2 + EX_SPLIT - 1) / EX_SPLIT + 31) / 32 * 32);
+    ex_cl_threads = std::max(128, std::min(EX_THREADS, ex_cl_threads));
+    if (const char *e = getenv("HICA_P2_EX_THREADS")) ex_cl_threads = std::max(32, std::min(EX_THREADS, atoi(e) / 32 * 32));
     if (ex_smem > 200 * 1024) return hica_set_error(h, HICA_ERR_ARG, "chromosome too large for shared memory");
     ENG_CUDA(cudaFuncSetAttribute(k_g_exact_near, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex_smem));
     ENG_CUDA(cudaFuncSetAttribute(k_g_anchor, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex_smem));
@@ -1177,7 +1183,7 @@ extern "C" int hica_p2_order_groups(hica_handle h, int32_t ngroups, const int32_
         mark(4);
         k_g_select<<<dim3(nb_c, G), 256, 0, s>>>(gdev, ph, tb);
         mark(5);
-        k_g_exact_near<<<dim3((unsigned)std::min<long long>(B, 32) * EX_SPLIT, G), EX_THREADS, ex_smem, s>>>(gdev, ph, tb);
+        k_g_exact_near<<<dim3((unsigned)std::min<long long>(B, 32) * EX_SPLIT, G), ex_cl_threads, ex_smem, s>>>(gdev, ph, tb);
         mark(6);
         k_g_pick_window<<<dim3(1, G), 256, 0, s>>>(gdev, ph, tb);
         mark(7);
@@ -1217,7 +1223,7 @@ extern "C" int hica_p2_order_groups(hica_handle h, int32_t ngroups, const int32_
         }
         k_g_ins_select<<<dim3(1, G), 128, sel_smem, s>>>(gdev, ph);
         mark(10);
-        k_g_insert_scores<<<dim3(std::min(nb_c, 8u) * EX_SPLIT, G), EX_THREADS, ex_smem, s>>>(gdev, ph);
+        k_g_insert_scores<<<dim3(std::min(nb_c, 8u) * EX_SPLIT, G), ex_cl_threads, ex_smem, s>>>(gdev, ph);
         mark(11);
         k_g_pick_insert<<<dim3(1, G), 32, 0, s>>>(gdev, ph);
         mark(12);
@@ -1248,7 +1254,7 @@ extern "C" int hica_p2_order_groups(hica_handle h, int32_t ngroups, const int32_
                 mark(4);
                 k_g_select<<<dim3(nb_c, G, (unsigned)zb), 256, 0, s>>>(gdev, phb, tb);
                 mark(5);
-                k_g_exact_near<<<dim3((unsigned)std::min<long long>(Bscan, 8) * EX_SPLIT, G, (unsigned)zb), EX_THREADS, ex_smem, s>>>(gdev, phb, tb);
+                k_g_exact_near<<<dim3((unsigned)std::min<long long>(Bscan, 8) * EX_SPLIT, G, (unsigned)zb), ex_cl_threads, ex_smem, s>>>(gdev, phb, tb);
                 mark(6);
                 k_gb_pick<<<dim3(1, G), 256, 0, s>>>(gdev, phb, tb);
                 mark(7);
