@@ -233,6 +233,7 @@ k_nn_chain(double *__restrict__ W, const int n, const int64_t ld, int32_t *__res
 #include "hica_p1_nnchain2.cuh"
 #include "hica_p1_nnchain3.cuh"
 #include "hica_p1_nnchain4.cuh"
+#include "hica_p1_nnchain3g.cuh"
 
 namespace {
 
@@ -619,6 +620,41 @@ int launch_nn_chain2_f32(hica_ctx *h, int cluster_size, size_t smem_bytes, float
     return HICA_OK;
 }
 
+// k_nn_chain3g<float>: nearest-neighbour cache + fused merge/search with the per-row tables in global memory
+template <bool STATS>
+int launch_nn_chain3g_f32(hica_ctx *h, int cluster_size, float *W, int n, int64_t ld, int32_t *chain_d, double *Zraw,
+                          const double *nn0_val, const unsigned long long *nn0_ent, unsigned long long *ent_g,
+                          uint32_t *size_g)
+{
+    auto kern = nn3g::k_nn_chain3g<float, STATS>;
+    const size_t smem_bytes = nn3g::make_layout(ld, nn3g::slice_len(n, cluster_size)).total;
+    if (smem_bytes > 227 * 1024) return -1;
+    HICA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+    if (cluster_size > 8) HICA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(cluster_size);
+    cfg.blockDim = dim3(512);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = h->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cluster_size;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int max_clusters = 0;
+    cudaError_t e = cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg);
+    if (e != cudaSuccess || max_clusters < 1) {
+        cudaGetLastError();
+        return -1;
+    }
+    HICA_CUDA(cudaLaunchKernelEx(&cfg, kern, W, n, ld, chain_d, Zraw, reinterpret_cast<long long *>(h->misc_d + 64), nn0_val,
+                                 nn0_ent, 0u, ent_g, size_g));
+    HICA_LAUNCHED(h);
+    return HICA_OK;
+}
+
 }  // namespace
 
 extern "C" int hica_s32_linkage(hica_handle h, double *Z_host, int32_t *leaves_host)
@@ -627,17 +663,26 @@ extern "C" int hica_s32_linkage(hica_handle h, double *Z_host, int32_t *leaves_h
     if (!h->W32) return hica_set_error(h, HICA_ERR_STATE, "this GPU holds no working matrix (hica_s32_alloc with_linkage_matrix)");
     const int64_t n = h->s32_n;
     // scratch kept in the handle (grow-only): cudaMalloc / cudaFree next to a 100 GB allocation cost ~0.1 s each
+    const int64_t ldw = h->s32_ld;
     const int64_t zb = (8 * 4 * (n - 1) + 255) / 256 * 256, ib = ((int64_t)NN_MAX_CLUSTER * n * 4 + 255) / 256 * 256;
-    if (h->s32_scratch_cap < zb + 2 * ib) {
+    // k_nn_chain3g: per-CTA tables (64-bit cache entries, 32-bit sizes) + the initial nearest neighbours
+    const int64_t eb = ((int64_t)NN_MAX_CLUSTER * ldw * 8 + 255) / 256 * 256, sb = ((int64_t)NN_MAX_CLUSTER * ldw * 4 + 255) / 256 * 256;
+    const int64_t nb0 = (n * 8 + 255) / 256 * 256;
+    const int64_t scratch_need = zb + 2 * ib + eb + sb + 2 * nb0;
+    if (h->s32_scratch_cap < scratch_need) {
         if (h->s32_scratch) cudaFree(h->s32_scratch);
         h->s32_scratch = nullptr;
         h->s32_scratch_cap = 0;
-        HICA_CUDA(cudaMalloc(&h->s32_scratch, (size_t)(zb + 2 * ib)));
-        h->s32_scratch_cap = zb + 2 * ib;
+        HICA_CUDA(cudaMalloc(&h->s32_scratch, (size_t)scratch_need));
+        h->s32_scratch_cap = scratch_need;
     }
     double *Zraw = reinterpret_cast<double *>(h->s32_scratch);
     int32_t *size_d = reinterpret_cast<int32_t *>((char *)h->s32_scratch + zb);
     int32_t *chain_d = reinterpret_cast<int32_t *>((char *)h->s32_scratch + zb + ib);
+    unsigned long long *ent_g = reinterpret_cast<unsigned long long *>((char *)h->s32_scratch + zb + 2 * ib);
+    uint32_t *size_g = reinterpret_cast<uint32_t *>((char *)h->s32_scratch + zb + 2 * ib + eb);
+    double *nn0_val = reinterpret_cast<double *>((char *)h->s32_scratch + zb + 2 * ib + eb + sb);
+    unsigned long long *nn0_ent = reinterpret_cast<unsigned long long *>((char *)h->s32_scratch + zb + 2 * ib + eb + sb + nb0);
     auto cleanup = [&]() {};
     const int nwords = (int)((h->s32_ld + 31) / 32);
     const size_t base_smem = nn2::base_smem(nwords), chain_smem = sizeof(int32_t) * (size_t)n;
@@ -649,6 +694,20 @@ extern "C" int hica_s32_linkage(hica_handle h, double *Z_host, int32_t *leaves_h
     int launched = -1;
     int cs_max = NN_MAX_CLUSTER;
     if (const char *e = getenv("HICA_NN_CLUSTER")) cs_max = std::max(1, std::min(NN_MAX_CLUSTER, atoi(e)));
+    // default: the cached kernel (k_nn_chain3g); HICA_S32_NN=2: every search in full (k_nn_chain2<float>)
+    const char *s32nn = getenv("HICA_S32_NN");
+    h->nn_kernel_used = 2;
+    if (!(s32nn && s32nn[0] == '2') && n >= 2 && n <= nn3g::MAX_N) {
+        nn3g::k_nn_init<float><<<(unsigned)n, 256, 0, h->stream>>>(h->W32, (int)n, ldw, nn0_val, nn0_ent);
+        HICA_LAUNCHED(h);
+        const bool dbg = getenv("HICA_NN_DEBUG") != nullptr;
+        for (int cs = cs_max; cs >= 1 && launched != HICA_OK; cs >>= 1) {
+            launched = dbg ? launch_nn_chain3g_f32<true>(h, cs, h->W32, (int)n, ldw, chain_d, Zraw, nn0_val, nn0_ent, ent_g, size_g)
+                           : launch_nn_chain3g_f32<false>(h, cs, h->W32, (int)n, ldw, chain_d, Zraw, nn0_val, nn0_ent, ent_g, size_g);
+            if (launched > 0) { cleanup(); return launched; }
+        }
+        if (launched == HICA_OK) h->nn_kernel_used = 3;
+    }
     for (int cs = cs_max; cs >= 1 && launched != HICA_OK; cs >>= 1) {
         launched = chain_in_smem ? launch_nn_chain2_f32<true>(h, cs, base_smem + chain_smem, h->W32, (int)n, h->s32_ld, size_d, chain_d, Zraw)
                                  : launch_nn_chain2_f32<false>(h, cs, base_smem, h->W32, (int)n, h->s32_ld, size_d, chain_d, Zraw);

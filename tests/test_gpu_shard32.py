@@ -59,6 +59,30 @@ def test_fp32_sharded_front_end_matches_fp64_path(hica, n, nc):
     sh.close()
 
 
+@pytest.mark.parametrize("n,nc,cluster", [(36, 1, ""), (72, 2, ""), (1200, 6, ""), (3000, 20, ""), (1500, 6, "2"), (900, 4, "1")])
+def test_fp32_cached_chain_equals_the_full_search_chain_bitwise(hica, n, nc, cluster, monkeypatch):
+    """k_nn_chain3g<float> (nearest-neighbour cache, tables in global memory; the default of hica_s32_linkage) against
+    nn2::k_nn_chain2<float> (every search in full): same fp32 working matrix, same merge order, same heights - bit for
+    bit, ties included (the fp32 rounding creates plenty)."""
+    if cluster:
+        monkeypatch.setenv("HICA_NN_CLUSTER", cluster)
+    dev = torch.device("cuda", 0)
+    out = {}
+    for which in ("2", "3"):
+        monkeypatch.setenv("HICA_S32_NN", which)
+        layout = dist10kb.ShardLayout(n, nc, seed=9, scaffolds_per_chrom=3 if n < 100 else 8)
+        sh = dist10kb.Shard32(hica, n, dev)
+        dist10kb.generate_shard(sh.A, layout, 0, n, sh.blocks, ice_sweeps=20)
+        sh.distance_and_gather()
+        out[which] = sh.linkage(want_Z=True)
+        st = hica.linkage_stats()
+        if which == "3" and n >= 72:
+            assert st["cached_searches"] > 0
+        sh.close()
+    assert np.array_equal(out["2"][0], out["3"][0])
+    assert np.array_equal(out["2"][1], out["3"][1])
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
