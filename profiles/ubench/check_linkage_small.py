@@ -1,5 +1,6 @@
 import os, sys, numpy as np
-sys.path.insert(0, os.getcwd()); sys.path.insert(0, os.path.join(os.getcwd(), "oracle"))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import hica_oracle as O
 from hic_genome_assembler_b200._lib import Handle
 def sym(n, seed):
