@@ -214,7 +214,16 @@ constexpr int64_t STAGE_SLOT_BYTES = 24ll << 20;
 int staged_upload(hica_ctx *h, const std::vector<Region2D> &regions)
 {
     if (!h->stage_h) {
-        HICA_CUDA(cudaHostAlloc(&h->stage_h, (size_t)(STAGE_SLOTS * STAGE_SLOT_BYTES), cudaHostAllocDefault));
+        if (cudaHostAlloc(&h->stage_h, (size_t)(STAGE_SLOTS * STAGE_SLOT_BYTES), cudaHostAllocDefault) != cudaSuccess) {
+            // no pinned memory to be had: let the driver stage the copies (slower, same result)
+            cudaGetLastError();
+            h->stage_h = nullptr;
+            for (const Region2D &r : regions)
+                if (r.rows > 0 && r.width > 0)
+                    HICA_CUDA(cudaMemcpy2DAsync(r.dst, sizeof(double) * r.dp, r.src, sizeof(double) * r.sp,
+                                                sizeof(double) * r.width, (size_t)r.rows, cudaMemcpyHostToDevice, h->stream));
+            return HICA_OK;
+        }
         h->stage_cap = STAGE_SLOTS * STAGE_SLOT_BYTES;
         for (int i = 0; i < STAGE_SLOTS; i++) HICA_CUDA(cudaEventCreateWithFlags(&h->stage_ev[i], cudaEventDisableTiming));
     }
