@@ -288,6 +288,15 @@ int staged_upload(hica_ctx *h, const std::vector<Region2D> &regions)
 
 }  // namespace
 
+int hica_upload_2d(hica_ctx *h, const double *src, double *dst, int64_t sp, int64_t dp, int64_t width, int64_t rows)
+{
+    if (rows <= 0 || width <= 0) return HICA_OK;
+    if (rows * width >= 2048 * 2048 && is_pageable(src)) return staged_upload(h, {Region2D{src, dst, sp, dp, width, rows}});
+    HICA_CUDA(cudaMemcpy2DAsync(dst, sizeof(double) * dp, src, sizeof(double) * sp, sizeof(double) * width, (size_t)rows,
+                                cudaMemcpyHostToDevice, h->stream));
+    return HICA_OK;
+}
+
 extern "C" int hica_p1_upload(hica_handle h, const double *A_host, int64_t n)
 {
     HICA_CHECK_HANDLE(h);

@@ -170,6 +170,10 @@ static inline void hica_presort_cancel(hica_ctx *h)
     h->presort_pending = h->presort_valid = false;
 }
 
+// hica_api.cu: copy of rows x width doubles (pitches sp / dp in elements) from host to device on h->stream; host memory
+// that is not pinned is staged through pinned slots by several host threads (the driver's own staging is one thread)
+int hica_upload_2d(hica_ctx *h, const double *src, double *dst, int64_t sp, int64_t dp, int64_t width, int64_t rows);
+
 // hica_p1_distance.cu: make s_seq usable by work enqueued on `stream` from now on (launches the deferred row sums
 // there, or makes the stream wait for the ones in flight on stream2)
 int hica_need_s_seq(hica_ctx *h, cudaStream_t stream);

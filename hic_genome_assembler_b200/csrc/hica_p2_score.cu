@@ -221,7 +221,10 @@ extern "C" int hica_p2_upload(hica_handle h, const double *G_host, int64_t n)
         if (rc) { h->gn = 0; return rc; }
         h->gn = n;
     }
-    HICA_CUDA(cudaMemcpyAsync(h->G, G_host, sizeof(double) * n * n, cudaMemcpyHostToDevice, h->stream));
+    {
+        int rc = hica_upload_2d(h, G_host, h->G, n, n, n, n);  // pageable numpy memory is staged by several threads
+        if (rc) return rc;
+    }
     HICA_CUDA(cudaStreamSynchronize(h->stream));
     h->L = 0;
     return HICA_OK;
