@@ -267,7 +267,7 @@ __global__ void __launch_bounds__(EX_THREADS, 1) k_g_anchor(const GroupDev *gs, 
 //   tab_out[((s*2+o) << m) | before]                : scaffold s (orientation o) against all bins outside the
 //                                                      window, `before` = window scaffolds placed before s
 //   tab_win[((((s*m+s2)*2+o)*2+o2) << m) | between] : s placed before s2 with the scaffolds `between` in between
-constexpr int TAB_MPC = 4;  // table entries (sets before s) per CTA of the outside part
+constexpr int TAB_MPC = 8;  // sets before s per CTA of the outside part (x 2 orientations = 16 table entries per CTA)
 __global__ void __launch_bounds__(128) k_g_tables(const GroupDev *gs, Phase ph, Tables tb)
 {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -278,12 +278,12 @@ __global__ void __launch_bounds__(128) k_g_tables(const GroupDev *gs, Phase ph, 
     const int m = pp.m, ws = pp.ws, nslots = pp.nslots, n = pp.n;
     const int nmask = 1 << (m - 1);                                  // sets of the other m-1 window scaffolds
     const int nchunk = (nmask + TAB_MPC - 1) / TAB_MPC;
-    const int nvo = 2 * m * nchunk;
+    const int nvo = m * nchunk;
     const int bx = blockIdx.x;
     const WinView wv = win_view(g, ph, m, (long long)tb.n_ord[m] * tb.n_ori[m], z);
     if (bx >= nvo + m * m) return;
     __shared__ int wlen[8], woff[8];
-    __shared__ double red[4][TAB_MPC];
+    __shared__ double red[4][2 * TAB_MPC];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid < m) {  // (a serial walk over the slots in front of the window cost every CTA a chain of global loads)
         const int sg = g.layout[ws + tid] >> 1;
@@ -294,11 +294,12 @@ __global__ void __launch_bounds__(128) k_g_tables(const GroupDev *gs, Phase ph, 
     const int full = (1 << m) - 1;
     const int L = g.L;
     if (bx < nvo) {
-        // ---- scaffold s in orientation o against all bins outside the window, for TAB_MPC of the 2^(m-1) sets of
-        //      window scaffolds placed before it.  The sets only shift s by q bins, so every contact that is read
-        //      is weighted TAB_MPC ways: one entry per CTA was bound by L2 traffic (430 MB per launch at 100 kb).
-        const int so = bx / nchunk, chunk = bx - so * nchunk;
-        const int s = so >> 1, o = so & 1;
+        // ---- scaffold s in BOTH orientations against all bins outside the window, for TAB_MPC of the 2^(m-1) sets
+        //      of window scaffolds placed before it.  The sets only shift s by q bins and the orientation only
+        //      mirrors the offset inside s, so every contact that is read is weighted 2 x TAB_MPC ways: the kernel is
+        //      bound by L2 traffic (one entry per CTA: 430 MB per launch at 100 kb; 4 sets x 1 orientation per CTA:
+        //      557 us per scan round), and every entry is still summed in the same order.
+        const int s = bx / nchunk, chunk = bx - s * nchunk;
         double *wt_s = reinterpret_cast<double *>(smem);             // n weights
         int32_t *ord = reinterpret_cast<int32_t *>(wt_s + n);        // position -> bin of the current layout
         int32_t *spos = ord + n, *sent = spos + nslots + 1;
@@ -319,9 +320,9 @@ __global__ void __launch_bounds__(128) k_g_tables(const GroupDev *gs, Phase ph, 
             q[i] = qq;
             maskv[i] = mask;
         }
-        double acc[TAB_MPC];
+        double acc[2][TAB_MPC];
 #pragma unroll
-        for (int i = 0; i < TAB_MPC; i++) acc[i] = 0.;
+        for (int i = 0; i < TAB_MPC; i++) acc[0][i] = acc[1][i] = 0.;
         for (int a0 = tid; a0 < n_outside; a0 += blockDim.x) {
             const bool before = a0 < p0;
             const int apos = before ? a0 : a0 + wtot;
@@ -337,22 +338,30 @@ __global__ void __launch_bounds__(128) k_g_tables(const GroupDev *gs, Phase ph, 
 #pragma unroll
                 for (int k = 0; k < 8; k++) {
                     const int t = min(t0 + k, len - 1);
-                    const int off = o ? (len - 1 - t) : t;
-                    const int d0 = before ? (p0 + off - apos) : (apos - p0 - off);  // distance to position p0 + off
 #pragma unroll
-                    for (int i = 0; i < TAB_MPC; i++) acc[i] += v[k] * wt_s[before ? d0 + q[i] : d0 - q[i]];
+                    for (int o = 0; o < 2; o++) {
+                        const int off = o ? (len - 1 - t) : t;
+                        const int d0 = before ? (p0 + off - apos) : (apos - p0 - off);  // distance to position p0 + off
+#pragma unroll
+                        for (int i = 0; i < TAB_MPC; i++) acc[o][i] += v[k] * wt_s[before ? d0 + q[i] : d0 - q[i]];
+                    }
                 }
             }
         }
 #pragma unroll
-        for (int i = 0; i < TAB_MPC; i++) {
-            double r = acc[i];
-            for (int d = 16; d >= 1; d >>= 1) r += __shfl_xor_sync(0xffffffffu, r, d);
-            if (lane == 0) red[warp][i] = r;
-        }
+        for (int o = 0; o < 2; o++)
+#pragma unroll
+            for (int i = 0; i < TAB_MPC; i++) {
+                double r = acc[o][i];
+                for (int d = 16; d >= 1; d >>= 1) r += __shfl_xor_sync(0xffffffffu, r, d);
+                if (lane == 0) red[warp][o * TAB_MPC + i] = r;
+            }
         __syncthreads();
-        if (tid < TAB_MPC && chunk * TAB_MPC + tid < nmask)
-            wv.tab_out[(((s << 1) | o) << m) | maskv[tid]] = (red[0][tid] + red[1][tid]) + (red[2][tid] + red[3][tid]);
+        if (tid < 2 * TAB_MPC) {
+            const int o = tid / TAB_MPC, i = tid - o * TAB_MPC;
+            if (chunk * TAB_MPC + i < nmask)
+                wv.tab_out[(((s << 1) | o) << m) | maskv[i]] = (red[0][tid] + red[1][tid]) + (red[2][tid] + red[3][tid]);
+        }
     } else {
         // ---- scaffold pair (s, s2) in orientations (o, o2), one warp each, for EVERY set of window scaffolds
         //      between them (2^(m-2) entries, 8 at a time): the sets only change the gap
@@ -1175,7 +1184,7 @@ extern "C" int hica_p2_order_groups(hica_handle h, int32_t ngroups, const int32_
     };
     mark(0);
     auto window_search = [&](Phase ph, int m, long long B) {
-        const unsigned nb_tab = (unsigned)(2 * m * (((1 << (m - 1)) + TAB_MPC - 1) / TAB_MPC) + m * m);
+        const unsigned nb_tab = (unsigned)(m * (((1 << (m - 1)) + TAB_MPC - 1) / TAB_MPC) + m * m);
         const unsigned nb_c = (unsigned)((B + 255) / 256);
         k_g_tables<<<dim3(nb_tab, G), 128, tab_smem, s>>>(gdev, ph, tb);
         mark(3);
@@ -1243,7 +1252,7 @@ extern "C" int hica_p2_order_groups(hica_handle h, int32_t ngroups, const int32_
         ENG_CUDA(cudaGetLastError());
         // batches of zb windows (see k_gb_pick); a few batches between two looks at the converged flags
         const Phase phb = {PH_SCAN, 0, scan, zb};
-        const unsigned nb_tab = (unsigned)(2 * scan * (((1 << (scan - 1)) + TAB_MPC - 1) / TAB_MPC) + scan * scan);
+        const unsigned nb_tab = (unsigned)(scan * (((1 << (scan - 1)) + TAB_MPC - 1) / TAB_MPC) + scan * scan);
         const unsigned nb_c = (unsigned)((Bscan + 255) / 256);
         int reps = 3;
         for (int pass = 0; pass < 100000; pass++) {
