@@ -267,7 +267,6 @@ __global__ void __launch_bounds__(EX_THREADS, 1) k_g_anchor(const GroupDev *gs, 
 //   tab_out[((s*2+o) << m) | before]                : scaffold s (orientation o) against all bins outside the
 //                                                      window, `before` = window scaffolds placed before s
 //   tab_win[((((s*m+s2)*2+o)*2+o2) << m) | between] : s placed before s2 with the scaffolds `between` in between
-constexpr int TAB_MPC = 8;  // sets before s per CTA of the outside part (x 2 orientations = 16 table entries per CTA)
 __global__ void __launch_bounds__(128) k_g_tables(const GroupDev *gs, Phase ph, Tables tb)
 {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -277,13 +276,11 @@ __global__ void __launch_bounds__(128) k_g_tables(const GroupDev *gs, Phase ph, 
     if (!pp.active || g.st->skip) return;
     const int m = pp.m, ws = pp.ws, nslots = pp.nslots, n = pp.n;
     const int nmask = 1 << (m - 1);                                  // sets of the other m-1 window scaffolds
-    const int nchunk = (nmask + TAB_MPC - 1) / TAB_MPC;
-    const int nvo = m * nchunk;
+    const int nvo = m;  // outside part: one CTA per window scaffold
     const int bx = blockIdx.x;
     const WinView wv = win_view(g, ph, m, (long long)tb.n_ord[m] * tb.n_ori[m], z);
     if (bx >= nvo + m * m) return;
     __shared__ int wlen[8], woff[8];
-    __shared__ double red[4][2 * TAB_MPC];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid < m) {  // (a serial walk over the slots in front of the window cost every CTA a chain of global loads)
         const int sg = g.layout[ws + tid] >> 1;
@@ -294,73 +291,73 @@ __global__ void __launch_bounds__(128) k_g_tables(const GroupDev *gs, Phase ph, 
     const int full = (1 << m) - 1;
     const int L = g.L;
     if (bx < nvo) {
-        // ---- scaffold s in BOTH orientations against all bins outside the window, for TAB_MPC of the 2^(m-1) sets
-        //      of window scaffolds placed before it.  The sets only shift s by q bins and the orientation only
-        //      mirrors the offset inside s, so every contact that is read is weighted 2 x TAB_MPC ways: the kernel is
-        //      bound by L2 traffic (one entry per CTA: 430 MB per launch at 100 kb; 4 sets x 1 orientation per CTA:
-        //      557 us per scan round), and every entry is still summed in the same order.
-        const int s = bx / nchunk, chunk = bx - s * nchunk;
+        // ---- scaffold s in both orientations against all bins outside the window, for EVERY set of window scaffolds
+        //      placed before it (2^(m-1) sets x 2 orientations table entries per CTA).
+        // The sets only shift s by q bins: a contact between an outside bin and a bin of s is weighted by
+        // w(e + q) (outside bin in front of the window) or w(e - q) (behind it), e = their distance when s stands
+        // first in the window.  So the contacts are first summed by e - one pass over them per orientation, thread e
+        // adds its <= len terms in a fixed order - and every table entry is then a dot product of ~n terms with
+        // the shifted weights: n * len * 2 loads and adds + 2^m * n multiply-adds per CTA instead of
+        // n * len * 2^m multiply-adds with a shared-memory weight look-up each (which bound the kernel: 468 us per
+        // scan round at 100 kb).  The order of summation differs from the per-contact form; these scores only feed
+        // the near-list filter, whose tolerance holds for any order (near_tol).
+        const int s = bx;
         double *wt_s = reinterpret_cast<double *>(smem);             // n weights
-        int32_t *ord = reinterpret_cast<int32_t *>(wt_s + n);        // position -> bin of the current layout
+        double *hb = wt_s + n;                                       // [n]: contacts in front of the window, by e
+        double *ha = hb + n;                                         // [n]: contacts behind the window, by e
+        int32_t *ord = reinterpret_cast<int32_t *>(ha + n);          // position -> bin of the current layout
         int32_t *spos = ord + n, *sent = spos + nslots + 1;
         for (int d = tid; d < n; d += blockDim.x) wt_s[d] = g.Wt[d];
         build_order_cta(SrcLayout{g.layout}, nslots, g.seg_ptr, g.seg_bins, ord, spos, sent, n);
         int wtot = 0;
         for (int j = 0; j < m; j++) wtot += wlen[j];
         const int len = wlen[s], p0 = spos[ws];  // first position of the window
-        const int n_outside = n - wtot;
+        const int pend = p0 + wtot;              // first position behind the window
         const int32_t *sbins = g.seg_bins + woff[s];
-        int q[TAB_MPC], maskv[TAB_MPC];
+        for (int o = 0; o < 2; o++) {
+            // hb[e], e = p0 + off - apos in [1, p0 + len - 1];  ha[e], e = apos - p0 - off in [wtot - len + 1, n - 1 - p0]
+            for (int e = tid; e < n; e += blockDim.x) {
+                double sb = 0., sa = 0.;
+                if (e >= 1) {
+                    for (int t0 = 0; t0 < len; t0 += 8) {  // 8 contacts in flight per thread
+                        double vb[8], va[8];
 #pragma unroll
-        for (int i = 0; i < TAB_MPC; i++) {
-            const int u = min(chunk * TAB_MPC + i, nmask - 1);
-            const int mask = (u & ((1 << s) - 1)) | ((u >> s) << (s + 1));  // bit s stays clear
-            int qq = 0;
-            for (int j = 0; j < m; j++) if ((mask >> j) & 1) qq += wlen[j];
-            q[i] = qq;
-            maskv[i] = mask;
-        }
-        double acc[2][TAB_MPC];
+                        for (int k = 0; k < 8; k++) {
+                            const int t = t0 + k;
+                            vb[k] = va[k] = 0.;
+                            if (t < len) {
+                                const int off = o ? (len - 1 - t) : t;
+                                const int ab = p0 + off - e, aa = e + p0 + off;
+                                // the reference reads M[row of the earlier position][column of the later one]; St / S so
+                                // that neighbouring threads (neighbouring e) touch neighbouring addresses
+                                if (ab >= 0 && ab < p0) vb[k] = g.St[(int64_t)sbins[t] * L + ord[ab]];
+                                if (aa >= pend && aa < n) va[k] = g.S[(int64_t)sbins[t] * L + ord[aa]];
+                            }
+                        }
 #pragma unroll
-        for (int i = 0; i < TAB_MPC; i++) acc[0][i] = acc[1][i] = 0.;
-        for (int a0 = tid; a0 < n_outside; a0 += blockDim.x) {
-            const bool before = a0 < p0;
-            const int apos = before ? a0 : a0 + wtot;
-            const int abin = ord[apos];
-            // the reference reads M[row of the earlier position][column of the later one]; both branches walk a
-            // row of S / S^T so that neighbouring threads (neighbouring outside bins) touch neighbouring addresses
-            const double *base = (before ? g.St : g.S) + abin;
-            // 8 contacts in flight per thread: the loop is a chain of L2 round trips otherwise
-            for (int t0 = 0; t0 < len; t0 += 8) {
-                double v[8];
-#pragma unroll
-                for (int k = 0; k < 8; k++) v[k] = (t0 + k < len) ? base[(int64_t)sbins[t0 + k] * L] : 0.;
-#pragma unroll
-                for (int k = 0; k < 8; k++) {
-                    const int t = min(t0 + k, len - 1);
-#pragma unroll
-                    for (int o = 0; o < 2; o++) {
-                        const int off = o ? (len - 1 - t) : t;
-                        const int d0 = before ? (p0 + off - apos) : (apos - p0 - off);  // distance to position p0 + off
-#pragma unroll
-                        for (int i = 0; i < TAB_MPC; i++) acc[o][i] += v[k] * wt_s[before ? d0 + q[i] : d0 - q[i]];
+                        for (int k = 0; k < 8; k++) { sb += vb[k]; sa += va[k]; }
                     }
                 }
+                hb[e] = sb;
+                ha[e] = sa;
             }
-        }
-#pragma unroll
-        for (int o = 0; o < 2; o++)
-#pragma unroll
-            for (int i = 0; i < TAB_MPC; i++) {
-                double r = acc[o][i];
-                for (int d = 16; d >= 1; d >>= 1) r += __shfl_xor_sync(0xffffffffu, r, d);
-                if (lane == 0) red[warp][o * TAB_MPC + i] = r;
+            __syncthreads();
+            // table entries of this orientation: one warp per set at a time
+            for (int u = warp; u < nmask; u += (int)blockDim.x / 32) {
+                const int mask = (u & ((1 << s) - 1)) | ((u >> s) << (s + 1));  // bit s stays clear
+                int q = 0;
+                for (int j = 0; j < m; j++) if ((mask >> j) & 1) q += wlen[j];
+                double acc = 0.;
+                for (int e = 1 + lane; e < n; e += 32) {
+                    double w1 = 0., w2 = 0.;
+                    if (e + q < n) w1 = wt_s[e + q];
+                    if (e - q >= 1) w2 = wt_s[e - q];
+                    acc += hb[e] * w1 + ha[e] * w2;
+                }
+                for (int d = 16; d >= 1; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+                if (lane == 0) wv.tab_out[(((s << 1) | o) << m) | mask] = acc;
             }
-        __syncthreads();
-        if (tid < 2 * TAB_MPC) {
-            const int o = tid / TAB_MPC, i = tid - o * TAB_MPC;
-            if (chunk * TAB_MPC + i < nmask)
-                wv.tab_out[(((s << 1) | o) << m) | maskv[i]] = (red[0][tid] + red[1][tid]) + (red[2][tid] + red[3][tid]);
+            __syncthreads();  // hb / ha are reused by the other orientation
         }
     } else {
         // ---- scaffold pair (s, s2) in orientations (o, o2), one warp each, for EVERY set of window scaffolds
@@ -1159,7 +1156,8 @@ extern "C" int hica_p2_order_groups(hica_handle h, int32_t ngroups, const int32_
     ENG_CUDA(cudaFuncSetAttribute(k_g_ins_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tot_smem));
     ENG_CUDA(cudaFuncSetAttribute(k_g_ins_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sel_smem));
     ENG_CUDA(cudaFuncSetAttribute(k_g_total, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex_smem));
-    const size_t tab_smem = sizeof(double) * Lmax + sizeof(int32_t) * (Lmax + 2 * (nseg_max + 1) + 2);
+    const size_t tab_smem = sizeof(double) * 3 * Lmax + sizeof(int32_t) * (Lmax + 2 * (nseg_max + 1) + 2);
+    if (tab_smem > 227 * 1024) return hica_set_error(h, HICA_ERR_ARG, "chromosome too large for shared memory");
     ENG_CUDA(cudaFuncSetAttribute(k_g_tables, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tab_smem));
     const unsigned G = (unsigned)ngroups;
     const unsigned tot_blocks = (unsigned)std::max(1, (Lmax - 1 + TOT_WARPS - 1) / TOT_WARPS);
@@ -1184,7 +1182,7 @@ extern "C" int hica_p2_order_groups(hica_handle h, int32_t ngroups, const int32_
     };
     mark(0);
     auto window_search = [&](Phase ph, int m, long long B) {
-        const unsigned nb_tab = (unsigned)(m * (((1 << (m - 1)) + TAB_MPC - 1) / TAB_MPC) + m * m);
+        const unsigned nb_tab = (unsigned)(m + m * m);
         const unsigned nb_c = (unsigned)((B + 255) / 256);
         k_g_tables<<<dim3(nb_tab, G), 128, tab_smem, s>>>(gdev, ph, tb);
         mark(3);
@@ -1252,7 +1250,7 @@ extern "C" int hica_p2_order_groups(hica_handle h, int32_t ngroups, const int32_
         ENG_CUDA(cudaGetLastError());
         // batches of zb windows (see k_gb_pick); a few batches between two looks at the converged flags
         const Phase phb = {PH_SCAN, 0, scan, zb};
-        const unsigned nb_tab = (unsigned)(scan * (((1 << (scan - 1)) + TAB_MPC - 1) / TAB_MPC) + scan * scan);
+        const unsigned nb_tab = (unsigned)(scan + scan * scan);
         const unsigned nb_c = (unsigned)((Bscan + 255) / 256);
         int reps = 3;
         for (int pass = 0; pass < 100000; pass++) {
