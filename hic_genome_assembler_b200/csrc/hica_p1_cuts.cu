@@ -1015,13 +1015,14 @@ extern "C" int hica_p1_filter(hica_handle h, const int64_t *cuts_in, int64_t n_i
                 char *base = (char *)h->cut_buf;
                 int32_t *fx = (int32_t *)base;
                 int32_t *fflags = (int32_t *)(base + (int64_t)ne * rows * 4);
-                int32_t *fcrit = fflags + (int64_t)ne * nb;
+                int32_t *fmisc = fflags + (int64_t)ne * nb;  // the chunk's counters, right behind its flags: one read-back
+                int32_t *fcrit = fmisc + 16;
                 int32_t *fcrit2 = fcrit + 2 * ne;
                 uint8_t *fsig = (uint8_t *)(fcrit2 + 2 * (int64_t)ne * nb);
                 int2 *fxt = (int2 *)(((uintptr_t)(fsig + (int64_t)ne * rows) + 15) & ~(uintptr_t)15);
                 const int64_t *eval = h->q_d + i0;
                 int rc;
-                if ((rc = reset_misc(h))) return rc;
+                HICA_CUDA(cudaMemsetAsync(fmisc, 0, 16 * sizeof(int32_t), h->stream));
                 rc = with_rank(h, [&](auto *R) {
                     k_fb_counts<<<dim3((unsigned)rows + 1 + (unsigned)((nb + 127) / 128), (unsigned)ne), 128, 0, h->stream>>>(
                         R, n, start, eval, rows, fx, M, psig, fcrit, h->q_d, nb, fcrit2, ti, fxt);
@@ -1030,16 +1031,28 @@ extern "C" int hica_p1_filter(hica_handle h, const int64_t *cuts_in, int64_t n_i
                 });
                 if (rc) return rc;
                 k_fb_sig<<<(unsigned)((rows * ne + 255) / 256), 256, 0, h->stream>>>(fx, rows, eval, ne, start, M, psig,
-                                                                                  fcrit, fsig, h->misc_d, fxt);
+                                                                                  fcrit, fsig, fmisc, fxt);
                 k_fb_intervals<<<dim3((unsigned)nb, (unsigned)ne), 32, 0, h->stream>>>(fsig, rows, start, h->q_d, nb, eval,
-                                                                                    M, psig, fflags, h->misc_d, fcrit2);
+                                                                                    M, psig, fflags, fmisc, fcrit2);
                 h->launches += 2;
                 HICA_CUDA(cudaGetLastError());
-                HICA_CUDA(cudaMemcpyAsync(all_flags.data(), fflags, sizeof(int32_t) * ne * nb, cudaMemcpyDeviceToHost,
-                                          h->stream));
-                if ((rc = fetch_misc(h, 12))) return rc;
-                amb += h->misc_h[3];
-                for (int q = 0; q < CHUNK; q++) tie_chunk[q] = h->misc_h[8 + q];
+                // flags + counters come back in ONE copy into the pinned mirror (a copy into the pageable vector is
+                // staged by the driver); only a list too long for the mirror takes two
+                const int64_t nfl = (int64_t)ne * nb;
+                const int32_t *mh;
+                if (nfl + 16 <= 4096) {
+                    HICA_CUDA(cudaMemcpyAsync(h->misc_h, fflags, sizeof(int32_t) * (nfl + 16), cudaMemcpyDeviceToHost, h->stream));
+                    HICA_CUDA(cudaStreamSynchronize(h->stream));
+                    std::copy(h->misc_h, h->misc_h + nfl, all_flags.begin());
+                    mh = h->misc_h + nfl;
+                } else {
+                    HICA_CUDA(cudaMemcpyAsync(all_flags.data(), fflags, sizeof(int32_t) * nfl, cudaMemcpyDeviceToHost, h->stream));
+                    HICA_CUDA(cudaMemcpyAsync(h->misc_h, fmisc, sizeof(int32_t) * 16, cudaMemcpyDeviceToHost, h->stream));
+                    HICA_CUDA(cudaStreamSynchronize(h->stream));
+                    mh = h->misc_h;
+                }
+                amb += mh[3];
+                for (int q = 0; q < CHUNK; q++) tie_chunk[q] = mh[8 + q];
                 chunk_lo = i0;
                 chunk_hi = i0 + ne;
                 return HICA_OK;
