@@ -232,6 +232,7 @@ def gpu_step(h, wl, args, source, rank, world, dist):
                                                      wl["scaffold_names"], wl["scaffold_sizes"])
             index_of = wl["row_of_bin_id"]
         h.p2_use_p1_matrix()
+        part2.flush_stats()
         part2.STATS.update(candidates=0, bin_pairs=0, calls=0, exact=0, exact_pairs=0)
         nbins = [len(g) if args.p2_host_loop else sum(len(ids) for _, ids in g) for g in groups]
         mine = hdist.shard_groups(nbins, world, rank)
@@ -242,14 +243,16 @@ def gpu_step(h, wl, args, source, rank, world, dist):
             got, cost, rounds, stats = part2.order_groups_device(h, index_of, [groups[ci] for ci in mine], 6, 5)
             for k, ci in enumerate(mine):
                 orderings[ci] = (got[k], float(cost[k]), int(rounds[k]))
-            out["p2_exact"] = part2.STATS.get("exact", 0)
-            out["p2_exact_pairs"] = part2.STATS.get("exact_pairs", 0)
             out["p2_host_ms"] = h.debug_stats()
         if world > 1:  # every rank ends the step with all orderings (one small all_gather_object)
             orderings = dict(enumerate(hdist.merge_orderings(orderings, len(groups))))
-        p2_pairs, p2_cands, p2_calls = part2.STATS["bin_pairs"], part2.STATS["candidates"], part2.STATS["calls"]
         out["n_groups"] = len(groups)
     t2 = time.perf_counter()
+    if not args.part1_only:  # work accounting of the step (reference-equivalent pairs): outside the timed region
+        st = part2.flush_stats()
+        out["p2_exact"] = st.get("exact", 0)
+        out["p2_exact_pairs"] = st.get("exact_pairs", 0)
+        p2_pairs, p2_cands, p2_calls = st["bin_pairs"], st["candidates"], st["calls"]
     out.update(orderings=orderings, t_part2=t2 - t1, t_total=t2 - t0, p2_pairs=p2_pairs, p2_cands=p2_cands,
                p2_calls=p2_calls)
     return out

@@ -139,6 +139,8 @@ extern "C" int hica_destroy(hica_handle h)
     cudaFreeHost(h->misc_h);
     cudaFree(h->ra_d);
     cudaFreeHost(h->ra_h);
+    if (h->zraw_h) cudaFreeHost(h->zraw_h);
+    if (h->p2_pin) cudaFreeHost(h->p2_pin);
     cudaFree(h->red_d);
     cudaFreeHost(h->red_h);
     hica_s32_release(h);

@@ -79,6 +79,10 @@ struct hica_ctx {
     int32_t *misc_h = nullptr;   // pinned mirror
     int64_t *q_d = nullptr;      // query buffer for hypergeom batches
     int32_t *ra_d = nullptr, *ra_h = nullptr;  // run-ahead state of the break-search loop (device / pinned)
+    void *p2_pin = nullptr;      // pinned landing area of the Part2 engine's group states and layouts
+    size_t p2_pin_cap = 0;
+    double *zraw_h = nullptr;    // pinned landing buffer of the raw merge list + kernel statistics (hica_p1_linkage)
+    int64_t zraw_h_cap = 0;
     int64_t scratch_n = 0;
     // pairwise-sum plan (leaf table + combine tree) for rows of length plan_n
     int32_t *plan_d = nullptr;

@@ -556,12 +556,23 @@ extern "C" int hica_p1_linkage(hica_handle h, double *Z_host, int32_t *leaves_ho
     t.stop();
     h->have_W = false;  // W has been consumed
 
-    std::vector<double> raw(4 * (n - 1));
-    HICA_CUDA(cudaMemcpyAsync(raw.data(), h->Zraw, sizeof(double) * raw.size(), cudaMemcpyDeviceToHost, h->stream));
+    // merge list and kernel statistics land in pinned memory with one synchronisation (a copy into a pageable vector
+    // is staged by the driver, a second blocking copy is a second round trip)
+    const int64_t nraw = 4 * (n - 1), nst = 144;
+    if (h->zraw_h_cap < nraw + nst) {
+        if (h->zraw_h) cudaFreeHost(h->zraw_h);
+        h->zraw_h = nullptr;
+        h->zraw_h_cap = 0;
+        HICA_CUDA(cudaMallocHost((void **)&h->zraw_h, sizeof(double) * (size_t)(nraw + nst)));
+        h->zraw_h_cap = nraw + nst;
+    }
+    HICA_CUDA(cudaMemcpyAsync(h->zraw_h, h->Zraw, sizeof(double) * nraw, cudaMemcpyDeviceToHost, h->stream));
+    HICA_CUDA(cudaMemcpyAsync(h->zraw_h + nraw, h->misc_d + 64, sizeof(long long) * nst, cudaMemcpyDeviceToHost, h->stream));
     HICA_CUDA(cudaStreamSynchronize(h->stream));
+    std::vector<double> raw(h->zraw_h, h->zraw_h + nraw);
     {
-        long long st[144] = {0};
-        cudaMemcpy(st, h->misc_d + 64, sizeof(st), cudaMemcpyDeviceToHost);
+        long long st[144];
+        memcpy(st, h->zraw_h + nraw, sizeof(st));
         for (int i = 0; i < 8; i++) h->nn_stats[i] = st[i];
         if (getenv("HICA_NN_DEBUG")) {
             const long long nf = std::max(1ll, st[8]);

@@ -1044,8 +1044,11 @@ extern "C" int hica_p2_order_groups(hica_handle h, int32_t ngroups, const int32_
         tab_bytes += padded<uint8_t>((size_t)(ord_brute_off[k + 1] - ord_brute_off[k])) +
                      padded<uint8_t>((size_t)(ori_brute_off[k + 1] - ori_brute_off[k]));
     Arena ar;
+    int total_segs = 0;
+    for (int gi = 0; gi < ngroups; gi++) total_segs += gs[gi].nseg;
     const size_t cap = arena_bytes + tab_bytes + padded<GroupDev>(ngroups) + padded<int32_t>(total_bins) +
-                       padded<int32_t>(ngroups) + (2u << 20);  // + the lists of existing table entries
+                       padded<int32_t>(ngroups) + padded<GroupState>(ngroups) + padded<int32_t>(total_segs + ngroups) +
+                       (2u << 20);  // + the lists of existing table entries
     h->dbg[0] = since(t_h0);  // host-side validation and sizing
     auto t_h1 = clk::now();
     // The arena is kept in the handle and only ever grows: cudaMalloc / cudaFree of a few hundred MB cost
@@ -1095,12 +1098,17 @@ extern "C" int hica_p2_order_groups(hica_handle h, int32_t ngroups, const int32_
     std::vector<GroupDev> hdev(ngroups);
     std::vector<GroupState *> st_ptr(ngroups);
     std::vector<int32_t *> lay_ptr(ngroups);
+    // the groups' states and layouts are contiguous: the host reads them back with ONE copy each (into pinned memory)
+    // instead of one small copy per group per scan round
+    GroupState *st_all = ar.take<GroupState>(ngroups);
+    int32_t *lay_all = ar.take<int32_t>((size_t)total_segs + ngroups);
+    ENG_CUDA(cudaMemsetAsync(st_all, 0, sizeof(GroupState) * ngroups, s));
     for (int gi = 0; gi < ngroups; gi++) {
         HostGroup &g = gs[gi];
         GroupDev &d = hdev[gi];
         d.S = ar.take<double>((size_t)g.L * g.L);
         d.St = ar.take<double>((size_t)g.L * g.L);
-        int32_t *sp = ar.take<int32_t>(g.nseg + 1), *cum = ar.take<int32_t>(g.nseg + 1), *lay = ar.take<int32_t>(g.nseg + 1);
+        int32_t *sp = ar.take<int32_t>(g.nseg + 1), *cum = ar.take<int32_t>(g.nseg + 1), *lay = lay_all + (g.seg0 + gi);
         int32_t *sb = ar.take<int32_t>(g.L);
         d.seg_ptr = sp; d.seg_bins = sb; d.cum = cum; d.layout = lay;
         d.L = g.L; d.nseg = g.nseg; d.k = g.k; d.scanning = g.nseg > n_scaffolds ? 1 : 0;
@@ -1115,7 +1123,7 @@ extern "C" int hica_p2_order_groups(hica_handle h, int32_t ngroups, const int32_
         d.rel = ar.take<double>(nb_cand);
         d.near_score = ar.take<double>(nb_cand);
         d.near_id = ar.take<int32_t>(nb_cand);
-        d.st = ar.take<GroupState>(1);
+        d.st = st_all + gi;
         d.win = ar.take<WinState>(std::max(1, zb));
         st_ptr[gi] = d.st;
         lay_ptr[gi] = lay;
@@ -1125,7 +1133,6 @@ extern "C" int hica_p2_order_groups(hica_handle h, int32_t ngroups, const int32_
         for (int sg = 0; sg <= g.nseg; sg++) hp[sg] = seg_ptr[g.seg0 + sg] - bin0;
         for (int b = 0; b < g.L; b++) hb[b] = b;
         for (int sg = 0; sg < g.nseg; sg++) hl[sg] = sg << 1;
-        ENG_CUDA(cudaMemsetAsync(d.st, 0, sizeof(GroupState), s));
         ENG_CUDA(cudaMemsetAsync(d.win, 0, sizeof(WinState) * std::max(1, zb), s));
         ENG_CUDA(cudaMemcpyAsync(sp, hp.data(), sizeof(int32_t) * (g.nseg + 1), cudaMemcpyHostToDevice, s));
         ENG_CUDA(cudaMemcpyAsync(cum, hp.data(), sizeof(int32_t) * (g.nseg + 1), cudaMemcpyHostToDevice, s));
@@ -1237,7 +1244,17 @@ extern "C" int hica_p2_order_groups(hica_handle h, int32_t ngroups, const int32_
         h->launches += 5;
     }
     // ---- sliding-window scan (:579-580)
-    std::vector<GroupState> hst(ngroups);
+    // pinned landing area: states + layouts
+    const size_t pin_need = sizeof(GroupState) * ngroups + sizeof(int32_t) * ((size_t)total_segs + ngroups) + 64;
+    if (h->p2_pin_cap < pin_need) {
+        if (h->p2_pin) cudaFreeHost(h->p2_pin);
+        h->p2_pin = nullptr;
+        h->p2_pin_cap = 0;
+        ENG_CUDA(cudaMallocHost(&h->p2_pin, pin_need));
+        h->p2_pin_cap = pin_need;
+    }
+    GroupState *hst = reinterpret_cast<GroupState *>(h->p2_pin);
+    int32_t *hlay = reinterpret_cast<int32_t *>(reinterpret_cast<char *>(h->p2_pin) + sizeof(GroupState) * ngroups);
     if (any_scan) {
         Phase ph0 = {PH_SCAN, 0, scan};
         k_g_reset_for_scan<<<G, 32, 0, s>>>(gdev);
@@ -1269,8 +1286,7 @@ extern "C" int hica_p2_order_groups(hica_handle h, int32_t ngroups, const int32_
             }
             reps = 1;
             bool all_done = true;
-            for (int gi = 0; gi < ngroups; gi++)
-                ENG_CUDA(cudaMemcpyAsync(&hst[gi], st_ptr[gi], sizeof(GroupState), cudaMemcpyDeviceToHost, s));
+            ENG_CUDA(cudaMemcpyAsync(hst, st_all, sizeof(GroupState) * ngroups, cudaMemcpyDeviceToHost, s));
             ENG_CUDA(cudaStreamSynchronize(s));
             for (int gi = 0; gi < ngroups; gi++)
                 if (gs[gi].nseg > n_scaffolds && !hst[gi].converged) all_done = false;
@@ -1281,12 +1297,11 @@ extern "C" int hica_p2_order_groups(hica_handle h, int32_t ngroups, const int32_
     h->dbg[3] = since(t_h2);  // enqueue + scan-round synchronisations
     auto t_h3 = clk::now();
     ENG_CUDA(cudaGetLastError());
-    for (int gi = 0; gi < ngroups; gi++) {
-        ENG_CUDA(cudaMemcpyAsync(&hst[gi], st_ptr[gi], sizeof(GroupState), cudaMemcpyDeviceToHost, s));
-        ENG_CUDA(cudaMemcpyAsync(out_layout + gs[gi].seg0, lay_ptr[gi], sizeof(int32_t) * gs[gi].nseg,
-                                 cudaMemcpyDeviceToHost, s));
-    }
+    ENG_CUDA(cudaMemcpyAsync(hst, st_all, sizeof(GroupState) * ngroups, cudaMemcpyDeviceToHost, s));
+    ENG_CUDA(cudaMemcpyAsync(hlay, lay_all, sizeof(int32_t) * ((size_t)total_segs + ngroups), cudaMemcpyDeviceToHost, s));
     ENG_CUDA(cudaStreamSynchronize(s));
+    for (int gi = 0; gi < ngroups; gi++)
+        std::copy(hlay + gs[gi].seg0 + gi, hlay + gs[gi].seg0 + gi + gs[gi].nseg, out_layout + gs[gi].seg0);
     int err_group = -1;
     for (int gi = 0; gi < ngroups; gi++) {
         if (out_cost) out_cost[gi] = hst[gi].best_cost;
