@@ -1047,7 +1047,8 @@ extern "C" int hica_p2_order_groups(hica_handle h, int32_t ngroups, const int32_
     int total_segs = 0;
     for (int gi = 0; gi < ngroups; gi++) total_segs += gs[gi].nseg;
     const size_t cap = arena_bytes + tab_bytes + padded<GroupDev>(ngroups) + padded<int32_t>(total_bins) +
-                       padded<int32_t>(ngroups) + padded<GroupState>(ngroups) + padded<int32_t>(total_segs + ngroups) +
+                       padded<int32_t>(ngroups) + padded<GroupState>(ngroups) + 3 * padded<int32_t>(total_segs + ngroups) +
+                       padded<int32_t>(total_bins) + padded<WinState>((size_t)ngroups * std::max(1, zb)) +
                        (2u << 20);  // + the lists of existing table entries
     h->dbg[0] = since(t_h0);  // host-side validation and sizing
     auto t_h1 = clk::now();
@@ -1103,13 +1104,19 @@ extern "C" int hica_p2_order_groups(hica_handle h, int32_t ngroups, const int32_
     GroupState *st_all = ar.take<GroupState>(ngroups);
     int32_t *lay_all = ar.take<int32_t>((size_t)total_segs + ngroups);
     ENG_CUDA(cudaMemsetAsync(st_all, 0, sizeof(GroupState) * ngroups, s));
+    // ... and so are the segment tables and window states: four copies and one memset set all groups up
+    const int zb1 = std::max(1, zb);
+    int32_t *sp_all = ar.take<int32_t>((size_t)total_segs + ngroups), *cumd_all = ar.take<int32_t>((size_t)total_segs + ngroups);
+    int32_t *sb_all = ar.take<int32_t>(total_bins);
+    WinState *win_all = ar.take<WinState>((size_t)ngroups * zb1);
+    std::vector<int32_t> h_sp((size_t)total_segs + ngroups), h_sb(total_bins), h_lay((size_t)total_segs + ngroups, 0);
     for (int gi = 0; gi < ngroups; gi++) {
         HostGroup &g = gs[gi];
         GroupDev &d = hdev[gi];
         d.S = ar.take<double>((size_t)g.L * g.L);
         d.St = ar.take<double>((size_t)g.L * g.L);
-        int32_t *sp = ar.take<int32_t>(g.nseg + 1), *cum = ar.take<int32_t>(g.nseg + 1), *lay = lay_all + (g.seg0 + gi);
-        int32_t *sb = ar.take<int32_t>(g.L);
+        int32_t *sp = sp_all + (g.seg0 + gi), *cum = cumd_all + (g.seg0 + gi), *lay = lay_all + (g.seg0 + gi);
+        int32_t *sb = sb_all + seg_ptr[g.seg0];
         d.seg_ptr = sp; d.seg_bins = sb; d.cum = cum; d.layout = lay;
         d.L = g.L; d.nseg = g.nseg; d.k = g.k; d.scanning = g.nseg > n_scaffolds ? 1 : 0;
         d.Wt = ar.take<double>(g.L + 1);
@@ -1124,21 +1131,21 @@ extern "C" int hica_p2_order_groups(hica_handle h, int32_t ngroups, const int32_
         d.near_score = ar.take<double>(nb_cand);
         d.near_id = ar.take<int32_t>(nb_cand);
         d.st = st_all + gi;
-        d.win = ar.take<WinState>(std::max(1, zb));
+        d.win = win_all + (size_t)gi * zb1;
         st_ptr[gi] = d.st;
         lay_ptr[gi] = lay;
-        std::vector<int32_t> hp(g.nseg + 1), hb(g.L), hl(g.nseg + 1, 0);
         const int bin0 = seg_ptr[g.seg0];
         row_off[gi] = bin0;
+        int32_t *hp = h_sp.data() + (g.seg0 + gi), *hb = h_sb.data() + bin0, *hl = h_lay.data() + (g.seg0 + gi);
         for (int sg = 0; sg <= g.nseg; sg++) hp[sg] = seg_ptr[g.seg0 + sg] - bin0;
         for (int b = 0; b < g.L; b++) hb[b] = b;
         for (int sg = 0; sg < g.nseg; sg++) hl[sg] = sg << 1;
-        ENG_CUDA(cudaMemsetAsync(d.win, 0, sizeof(WinState) * std::max(1, zb), s));
-        ENG_CUDA(cudaMemcpyAsync(sp, hp.data(), sizeof(int32_t) * (g.nseg + 1), cudaMemcpyHostToDevice, s));
-        ENG_CUDA(cudaMemcpyAsync(cum, hp.data(), sizeof(int32_t) * (g.nseg + 1), cudaMemcpyHostToDevice, s));
-        ENG_CUDA(cudaMemcpyAsync(sb, hb.data(), sizeof(int32_t) * g.L, cudaMemcpyHostToDevice, s));
-        ENG_CUDA(cudaMemcpyAsync(lay, hl.data(), sizeof(int32_t) * (g.nseg + 1), cudaMemcpyHostToDevice, s));
     }
+    ENG_CUDA(cudaMemsetAsync(win_all, 0, sizeof(WinState) * (size_t)ngroups * zb1, s));
+    ENG_CUDA(cudaMemcpyAsync(sp_all, h_sp.data(), sizeof(int32_t) * h_sp.size(), cudaMemcpyHostToDevice, s));
+    ENG_CUDA(cudaMemcpyAsync(cumd_all, h_sp.data(), sizeof(int32_t) * h_sp.size(), cudaMemcpyHostToDevice, s));
+    ENG_CUDA(cudaMemcpyAsync(sb_all, h_sb.data(), sizeof(int32_t) * h_sb.size(), cudaMemcpyHostToDevice, s));
+    ENG_CUDA(cudaMemcpyAsync(lay_all, h_lay.data(), sizeof(int32_t) * h_lay.size(), cudaMemcpyHostToDevice, s));
     GroupDev *gdev = ar.take<GroupDev>(ngroups);
     int32_t *rows_d = ar.take<int32_t>(total_bins), *row_off_d = ar.take<int32_t>(ngroups);
     ENG_CUDA(cudaMemcpyAsync(gdev, hdev.data(), sizeof(GroupDev) * ngroups, cudaMemcpyHostToDevice, s));
