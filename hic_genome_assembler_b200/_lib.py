@@ -29,7 +29,8 @@ ABI_SYMBOLS = (
     "hica_p2_score_candidates", "hica_p2_score_window", "hica_p2_score_orders", "hica_p2_order_groups",
     "hica_s32_alloc", "hica_s32_buffer", "hica_s32_row_sums", "hica_s32_build_w", "hica_s32_ipc_export", "hica_s32_ipc_open",
     "hica_s32_ipc_close", "hica_s32_linkage",
-    "hica_io_read_matrix", "hica_io_last_error", "hica_io_log_transform",
+    "hica_io_read_matrix", "hica_io_last_error", "hica_io_log_transform", "hica_io_read_loci", "hica_io_loci_fetch",
+    "hica_p1_order_stats", "hica_order_stats_host",
 )
 
 _lib = None
@@ -105,6 +106,10 @@ def load_library():
     L.hica_s32_linkage.argtypes = [vp, vp, vp]
     L.hica_io_read_matrix.argtypes = [C.c_char_p, vp, i64, i64, vp, C.c_int, vp, vp]
     L.hica_io_log_transform.argtypes = [vp, vp, i64, dbl, dbl, C.c_int, C.c_int]
+    L.hica_io_read_loci.argtypes = [C.c_char_p, C.c_char_p, vp, i64, vp, vp]
+    L.hica_io_loci_fetch.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.hica_p1_order_stats.argtypes = [vp, C.c_int, C.c_int32, vp, vp, vp]
+    L.hica_order_stats_host.argtypes = [vp, vp, i64, C.c_int32, vp, vp, vp]
     L.hica_io_last_error.argtypes = []
     L.hica_io_last_error.restype = C.c_char_p
     _lib = L
@@ -296,6 +301,24 @@ class Handle:
         self._check(self._L.hica_p1_get_reordered(self._h, int(what), _ptr(out)))
         return out
 
+    def p1_order_stats(self, what: int, ranks):
+        """hica_p1_order_stats: the elements at the given zero-based ascending ranks of D (what = 0), S (1) or
+        the resident matrix as stored (2), and the number of NaN elements."""
+        k = np.ascontiguousarray(ranks, dtype=np.int64)
+        out = np.empty(k.size)
+        nan = C.c_int64(0)
+        self._check(self._L.hica_p1_order_stats(self._h, int(what), int(k.size), _ptr(k), _ptr(out), C.byref(nan)))
+        return out, nan.value
+
+    def order_stats_host(self, x: np.ndarray, ranks):
+        """hica_order_stats_host: the same for a float64 array in host memory (flattened)."""
+        a = np.ascontiguousarray(x, dtype=np.float64)
+        k = np.ascontiguousarray(ranks, dtype=np.int64)
+        out = np.empty(k.size)
+        nan = C.c_int64(0)
+        self._check(self._L.hica_order_stats_host(self._h, _ptr(a), int(a.size), int(k.size), _ptr(k), _ptr(out), C.byref(nan)))
+        return out, nan.value
+
     def p1_rank(self):
         self._check(self._L.hica_p1_rank(self._h))
 
@@ -472,6 +495,39 @@ class Handle:
         self._check(self._L.hica_p2_score_orders(self._h, _ptr(orders), B, n, total, carried, C.byref(best),
                                                  C.byref(bi), _ptr(sc)))
         return best.value, bi.value, sc
+
+
+def io_read_loci(bed_file: str, bias_file: str, keep_ids=None):
+    """hica_io_read_loci + hica_io_loci_fetch: (ids, starts, stops, biases, chromosome names) of the bins
+    initiateLoci keeps (host side, no GPU needed).  Raises ValueError where the reference raises."""
+    L = load_library()
+    n, cb = C.c_int64(0), C.c_int64(0)
+    if keep_ids is None:
+        keep, nk = None, -1
+    else:
+        keep = np.unique(np.asarray(list(keep_ids), dtype=np.int64))
+        nk = int(keep.size)
+    rc = L.hica_io_read_loci(os.fsencode(bed_file), os.fsencode(bias_file), _ptr(keep), nk, C.byref(n), C.byref(cb))
+    if rc:
+        msg = L.hica_io_last_error().decode()
+        raise (FileNotFoundError if msg.startswith("cannot open") else ValueError)(msg)
+    ids, starts, stops = (np.empty(n.value, dtype=np.int64) for _ in range(3))
+    bias = np.empty(n.value)
+    off = np.empty(n.value + 1, dtype=np.int64)
+    buf = np.empty(max(1, cb.value), dtype=np.uint8)
+    rc = L.hica_io_loci_fetch(_ptr(ids), _ptr(starts), _ptr(stops), _ptr(bias), _ptr(off), _ptr(buf))
+    if rc:
+        raise ValueError(L.hica_io_last_error().decode())
+    raw = buf.tobytes()
+    names, cache = [], {}
+    o = off.tolist()
+    for i in range(n.value):
+        b = raw[o[i]:o[i + 1]]
+        s = cache.get(b)
+        if s is None:
+            s = cache[b] = b.decode()
+        names.append(s)
+    return ids, starts, stops, bias, names
 
 
 def io_log_transform(M: np.ndarray, base: float = 10.0, reverse: bool = False, threads: int = 0,

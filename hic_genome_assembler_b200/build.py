@@ -12,7 +12,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "_obj")
 LIB = os.path.join(HERE, "libhica.so")
 SOURCES = ["hica_api.cu", "hica_p1_distance.cu", "hica_p1_linkage.cu", "hica_p1_rank.cu", "hica_p1_shard32.cu", "hica_p1_cuts.cu", "hica_p2_engine.cu",
-           "hica_p2_score.cu", "hica_io.cu"]
+           "hica_p2_score.cu", "hica_io.cu", "hica_plot.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-fmad=false",  # numpy/scipy/numba on x86-64 do not contract a*b+c; neither may we
               "-Xcompiler", "-fPIC", "-Xcompiler", "-O2"]

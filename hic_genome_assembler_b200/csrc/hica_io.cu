@@ -254,3 +254,126 @@ extern "C" int hica_io_log_transform(const double *in, double *out, int64_t coun
     if (bad.load() >= 0) return io_fail("%s: math domain error at entry %lld%s", "logTransformMatrix", (long long)bad.load(), "");
     return HICA_OK;
 }
+
+// initiateLoci (scaffoldToChromosomes.py:35-68, orderGenome.py:30-63): the HiC-Pro bed file ("chrom<TAB>start<TAB>
+// stop<TAB>binID") read in step with the bias file (one value per line) -> the list of genomic bins.  The reference
+// builds one Python object per line; here both files are read whole, walked once and returned as columns (ids,
+// starts, stops, biases, chromosome names as one byte string + offsets).  Semantics kept from the reference:
+//   * text mode with universal newlines: "\n", "\r\n" and a lone "\r" all end a line; the last line may be open;
+//   * a bias line is consumed for every bed line, also for bins the filter skips (:45-46), and a bias file that ends
+//     early yields '' -> float('') fails -> bias 0.0 (:58-61);
+//   * bed columns go through int() (:50) - a line with fewer than four columns or a non-integer field makes the
+//     reference raise (IndexError / ValueError) before the filter is looked at: the call fails with the line number;
+//   * binID_dict (:53-55): only ids in the set are kept;
+//   * a bias that is exactly the string "nan" drops the bin (:57); anything else float() cannot parse becomes 0.0,
+//     and spellings float() does parse to a NaN ("NaN", " nan", "+nan") keep the bin with a NaN bias.
+namespace {
+
+struct LociResult {
+    std::vector<int64_t> id, start, stop, chrom_off;
+    std::vector<double> bias;
+    std::string chrom;
+};
+thread_local LociResult g_loci;
+
+bool read_whole(const char *path, std::string *out)
+{
+    FILE *f = fopen(path, "rb");
+    if (!f) return false;
+    char buf[1 << 16];
+    size_t got;
+    while ((got = fread(buf, 1, sizeof(buf), f)) > 0) out->append(buf, got);
+    const bool ok = !ferror(f);
+    fclose(f);
+    return ok;
+}
+
+// next line of [*p, e) under universal newlines; false at end of data
+bool next_line(const char **p, const char *e, const char **lb, const char **le)
+{
+    if (*p >= e) return false;
+    const char *q = *p;
+    *lb = q;
+    while (q < e && *q != '\n' && *q != '\r') q++;
+    *le = q;
+    if (q < e) q += (*q == '\r' && q + 1 < e && q[1] == '\n') ? 2 : 1;
+    *p = q;
+    return true;
+}
+
+inline bool is_space(char c) { return c == ' ' || (c >= '\t' && c <= '\r'); }
+
+}  // namespace
+
+extern "C" int hica_io_read_loci(const char *bed_path, const char *bias_path, const int64_t *keep_ids_sorted,
+                                 int64_t n_keep, int64_t *n_bins, int64_t *chrom_bytes)
+{
+    if (!bed_path || !bias_path || !n_bins || !chrom_bytes || (n_keep > 0 && !keep_ids_sorted))
+        return io_fail("%s: bad argument%.0lld%s", "hica_io_read_loci", 0, "");
+    LociResult &R = g_loci;
+    R = LociResult();
+    std::string bed, bias;
+    if (!read_whole(bed_path, &bed)) return io_fail("cannot open %s%.0lld%s", bed_path, 0, "");
+    if (!read_whole(bias_path, &bias)) return io_fail("cannot open %s%.0lld%s", bias_path, 0, "");
+    const char *bp = bed.data(), *be = bp + bed.size(), *ip = bias.data(), *ie = ip + bias.size();
+    const char *lb, *le, *vb, *ve;
+    int64_t line = 0;
+    R.chrom_off.push_back(0);
+    while (next_line(&bp, be, &lb, &le)) {
+        line++;
+        const bool have_bias = next_line(&ip, ie, &vb, &ve);
+        const char *col[5];
+        int nc = 0;
+        col[nc++] = lb;
+        for (const char *q = lb; q < le && nc < 5; q++)
+            if (*q == '\t') col[nc++] = q + 1;
+        if (nc < 4) return io_fail("%s: line %lld: %s", bed_path, (long long)line, "fewer than four tab-separated columns");
+        const char *end3 = nc == 5 ? col[4] - 1 : le;
+        int64_t start, stop, id;
+        auto field = [&](const char *b, const char *e, int64_t *out) {
+            while (b < e && is_space(*b)) b++;
+            while (e > b && is_space(e[-1])) e--;
+            return parse_int(b, e, out);
+        };
+        if (!field(col[1], col[2] - 1, &start) || !field(col[2], col[3] - 1, &stop) || !field(col[3], end3, &id))
+            return io_fail("%s: line %lld: %s", bed_path, (long long)line, "start / stop / bin id is not an integer");
+        if (n_keep >= 0 && !std::binary_search(keep_ids_sorted, keep_ids_sorted + n_keep, id)) continue;
+        double bv = 0.0;
+        if (have_bias) {
+            if (ve - vb == 3 && memcmp(vb, "nan", 3) == 0) continue;
+            const char *b = vb, *e = ve;
+            while (b < e && is_space(*b)) b++;
+            while (e > b && is_space(e[-1])) e--;
+            if (b == e || memchr(b, '(', (size_t)(e - b)) || !parse_float(b, e, &bv)) bv = 0.0;
+        }
+        R.id.push_back(id);
+        R.start.push_back(start);
+        R.stop.push_back(stop);
+        R.bias.push_back(bv);
+        R.chrom.append(col[0], (size_t)(col[1] - 1 - col[0]));
+        R.chrom_off.push_back((int64_t)R.chrom.size());
+    }
+    *n_bins = (int64_t)R.id.size();
+    *chrom_bytes = (int64_t)R.chrom.size();
+    return HICA_OK;
+}
+
+extern "C" int hica_io_loci_fetch(int64_t *ids, int64_t *starts, int64_t *stops, double *bias, int64_t *chrom_off,
+                                  char *chrom_buf)
+{
+    LociResult &R = g_loci;
+    if (R.chrom_off.empty()) return io_fail("%s: no result to fetch (call hica_io_read_loci first)%.0lld%s", "hica_io_loci_fetch", 0, "");
+    const size_t n = R.id.size();
+    if (n && (!ids || !starts || !stops || !bias)) return io_fail("%s: bad argument%.0lld%s", "hica_io_loci_fetch", 0, "");
+    if (!chrom_off || (!chrom_buf && !R.chrom.empty())) return io_fail("%s: bad argument%.0lld%s", "hica_io_loci_fetch", 0, "");
+    if (n) {
+        memcpy(ids, R.id.data(), sizeof(int64_t) * n);
+        memcpy(starts, R.start.data(), sizeof(int64_t) * n);
+        memcpy(stops, R.stop.data(), sizeof(int64_t) * n);
+        memcpy(bias, R.bias.data(), sizeof(double) * n);
+    }
+    memcpy(chrom_off, R.chrom_off.data(), sizeof(int64_t) * (n + 1));
+    if (!R.chrom.empty()) memcpy(chrom_buf, R.chrom.data(), R.chrom.size());
+    R = LociResult();
+    return HICA_OK;
+}

@@ -50,6 +50,17 @@ def read_loci(bed_file: str, bias_file: str, keep_ids=None) -> List[Bin]:
     return bins
 
 
+def read_loci_native(bed_file: str, bias_file: str, keep_ids=None, bin_class=None) -> List[Bin]:
+    """initiateLoci (:35-68) through libhica's reader (hica_io_read_loci): the same bins in the same order with the
+    same field values as :func:`read_loci` / the reference; ``bin_class`` = the class to instantiate (the launcher
+    passes the reference module's own ``Bin``)."""
+    from ._lib import io_read_loci
+    ids, starts, stops, bias, chroms = io_read_loci(bed_file, bias_file, keep_ids)
+    cls = bin_class or Bin
+    return [cls(i, c, a, b, v, 0.0) for i, c, a, b, v in zip(ids.tolist(), chroms, starts.tolist(), stops.tolist(),
+                                                           bias.tolist())]
+
+
 def read_matrix(matrix_file: str, bins: Sequence[Bin]) -> np.ndarray:
     """buildAdjacencyMatrix (:70-98): dense symmetric fill from the sparse HiC-Pro triplets."""
     n = len(bins)
@@ -95,6 +106,20 @@ def remove_zero_rows(A: np.ndarray, bins: List[Bin]) -> Tuple[np.ndarray, List[B
 
 
 # ---- the reference's own names and signatures, for the launcher (function replacement in the loaded modules) ----
+
+def make_initiateLoci(bin_class=None):
+    """Seam for initiateLoci (scaffoldToChromosomes.py:35-68, orderGenome.py:30-63) bound to one module's ``Bin``
+    class: same arguments (``binID_dict``: False or a container of bin ids), same print-out, same list."""
+    def initiateLoci(bedFile, biasFile, binID_dict=False):
+        keep = None if binID_dict is False else [k for k in binID_dict if isinstance(k, (int, np.integer))]
+        binList = read_loci_native(bedFile, biasFile, keep, bin_class)
+        print("Genomic loci found" + '\t' + str(len(binList)))
+        return binList
+    return initiateLoci
+
+
+initiateLoci = make_initiateLoci()
+
 
 def buildAdjacencyMatrix(matrixFile, binList, binID_dict=False):
     """Seam for buildAdjacencyMatrix (scaffoldToChromosomes.py:70-98, orderGenome.py:65-93): same arguments

@@ -106,6 +106,37 @@ class _NumpyShim(types.ModuleType):
         return self.__dict__["_real"].asarray(a, dtype, *args, **kwargs)
 
 
+class _PlotNumpyShim(types.ModuleType):
+    """Stands in for the name ``numpy`` inside plotContactMaps only: forwards everything to numpy except
+    ``percentile(adjMat, q)`` on the matrix that is drawn (plotContactMaps.py:30-31), whose order statistics come
+    from the device."""
+
+    def __init__(self, real, seams: Part1Seams):
+        super().__init__("numpy")
+        self.__dict__["_real"] = real
+        self.__dict__["_seams"] = seams
+
+    def __getattr__(self, name):
+        return getattr(self.__dict__["_real"], name)
+
+    def percentile(self, a, q, *args, **kwargs):
+        if not args and not kwargs and getattr(a, "ndim", 0) == 2 and a.shape[0] * a.shape[1] >= 1 << 16:
+            seen = self.__dict__.get("_seen")
+            if seen is not None and seen[0]() is a:
+                a = seen[1]          # the host copy of a device-resident matrix: read the resident one
+            return self.__dict__["_seams"].percentile(a, q)
+        return self.__dict__["_real"].percentile(a, q, *args, **kwargs)
+
+    def asarray(self, a, dtype=None, *args, **kwargs):
+        # plotContactMap converts its input first (:16-18); the drawing needs the host copy anyway, the
+        # percentiles do not: remember which device state the copy stands for
+        out = self.__dict__["_real"].asarray(a, dtype, *args, **kwargs)
+        if isinstance(a, LazyMatrix) and out.ndim == 2:
+            import weakref
+            self.__dict__["_seen"] = (weakref.ref(out), a)
+        return out
+
+
 class _DescendingRank:
     """Result of the shimmed argsort: the reference immediately takes ``[:, ::-1]`` of it, which gives back the
     device-resident descending rank (a LazyRank); any other use sees the ascending int64 host array."""
@@ -151,6 +182,8 @@ def install(reference_dir: str, device: int = 0, no_plots: bool = False, native_
     part1.pre_process_all_matrix_breakpoints = s1.pre_process_all_matrix_breakpoints
     part1.filter_noisy_breakpoints = s1.filter_noisy_breakpoints
     part1.numpy = _NumpyShim(part1.numpy, s1)
+    if not getattr(plot.plotContactMap, "_hica_noop", False):
+        plot.numpy = _PlotNumpyShim(plot.numpy, s1)
 
     if native_loaders:
         # the HiC-Pro text -> dense matrix step through libhica's mmap parser (same names, same
@@ -161,6 +194,8 @@ def install(reference_dir: str, device: int = 0, no_plots: bool = False, native_
                 mod.buildAdjacencyMatrix = hio.buildAdjacencyMatrix
             if hasattr(mod, "removeRows"):
                 mod.removeRows = hio.removeRows
+            if hasattr(mod, "initiateLoci") and hasattr(mod, "Bin"):
+                mod.initiateLoci = hio.make_initiateLoci(mod.Bin)
             if hasattr(mod, "logTransformMatrix"):   # 8f-3: feeds the plots only, but sits on the critical path
                 mod.logTransformMatrix = hio.logTransformMatrix if mod is part1 else hio.logTransformMatrix_part2
 

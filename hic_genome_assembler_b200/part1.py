@@ -285,6 +285,17 @@ class Seams:
         out = self._lazy(h.n, lambda: h.p1_get_reordered(0), self._fresh("Dperm"), "Dperm")
         return out, [binList[i] for i in order]
 
+    # numpy.percentile(adjMat, lP) / numpy.percentile(adjMat, hP), plotContactMaps.py:30-31 (bound through the plot
+    # module's `numpy` name): the colour-scale clip of the two Part1 plots (:1124, :1156)
+    def percentile(self, adjMat, q):
+        from . import plot as hplot
+        if isinstance(adjMat, LazyMatrix) and adjMat._hica_tag is not None:
+            kind, epoch = adjMat._hica_tag
+            if epoch == self._epoch and kind in ("D", "Dperm", "S"):
+                # the resident matrix in some row order: a percentile does not depend on the order
+                return hplot.percentile_device(self.h, adjMat, q, what=1 if kind == "S" else 0)
+        return hplot.percentile_device(self.h, host_array(adjMat), q)
+
     # numpy.argsort(adjMat, axis=1)[:, ::-1] :1132 (bound through the module's `numpy` name)
     def argsort_desc(self, S) -> LazyRank:
         h = self.h

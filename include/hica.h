@@ -322,6 +322,24 @@ int hica_io_read_matrix(const char *path, const int32_t *index_of_id, int64_t ma
                         double *A_host, int threads, int64_t *n_lines, int64_t *n_edges);
 const char *hica_io_last_error(void);
 
+/* initiateLoci (scaffoldToChromosomes.py:35-68, orderGenome.py:30-63): the
+ * HiC-Pro bed file (chrom, start, stop, bin id) read in step with the bias file
+ * -> the bins that survive (bias != "nan", id in the optional set), as columns.
+ * Host side, no GPU involved.  Two steps: hica_io_read_loci parses and keeps the
+ * result in the calling thread; hica_io_loci_fetch copies it into caller
+ * buffers of n_bins (chrom_off: n_bins + 1, chrom_buf: chrom_bytes) entries and
+ * releases it.  chrom_off[i]..chrom_off[i+1] delimit the chromosome name of bin
+ * i inside chrom_buf.
+ *   keep_ids_sorted / n_keep  binID_dict (:53-55) as an ascending id list;
+ *                             n_keep < 0: no filter
+ * Universal newlines, int() / float() parsing and the error cases of the
+ * reference (a malformed bed line raises there: the call fails here, message
+ * with the line number in hica_io_last_error()) are described in hica_io.cu. */
+int hica_io_read_loci(const char *bed_path, const char *bias_path, const int64_t *keep_ids_sorted,
+                      int64_t n_keep, int64_t *n_bins, int64_t *chrom_bytes);
+int hica_io_loci_fetch(int64_t *ids, int64_t *starts, int64_t *stops, double *bias, int64_t *chrom_off,
+                       char *chrom_buf);
+
 /* logTransformMatrix (scaffoldToChromosomes.py:165-183 with offset = 1,
  * orderGenome.py:160-178 with offset = 0): out[i] = 0 where in[i] == 0, else
  * log(in[i] + offset) / log(base) (reverse = 0) or pow(base, in[i]) - offset
@@ -330,6 +348,29 @@ const char *hica_io_last_error(void);
  * reference's math.log would raise. */
 int hica_io_log_transform(const double *in, double *out, int64_t count, double base, double offset,
                           int reverse, int threads);
+
+/* The colour-scale clip of plotContactMap: numpy.percentile(adjMat, lP) and
+ * numpy.percentile(adjMat, hP) (plotContactMaps.py:30-31) over all n*n values.
+ * A percentile does not depend on the order of the elements, so the resident
+ * matrix answers it without a read-back: exact order statistics by a radix
+ * select over the order-preserving 64-bit keys (6 passes over the matrix, any
+ * number of ranks, four per sweep).
+ *   what  0: D = convertMatrix(distance=True) of the resident matrix (:147)
+ *         1: S = convertMatrix(similarity=True) (:149), row sums as set
+ *         2: the resident matrix as stored
+ *   k     nk zero-based ranks in ascending order of value, among the elements
+ *         that are not NaN; out[i] = that element, bit for bit (-0.0 counts
+ *         as +0.0); a rank outside [0, n*n - nan_count) gives NaN
+ *   nan_count  elements that are NaN (numpy.percentile then returns nan)
+ * The caller interpolates as numpy does (two neighbouring ranks per
+ * percentile; hic_genome_assembler_b200/plot.py restates numpy's arithmetic). */
+int hica_p1_order_stats(hica_handle h, int what, int32_t nk, const int64_t *k, double *out,
+                        int64_t *nan_count);
+/* The same for `count` doubles in host memory (e.g. the closing
+ * convertMatrix(logTransformMatrix(.., reverse=True)) of runPipeline :1155-1156,
+ * which exists on the host only): uploaded once into scratch, then selected. */
+int hica_order_stats_host(hica_handle h, const double *x_host, int64_t count, int32_t nk, const int64_t *k,
+                          double *out, int64_t *nan_count);
 
 #ifdef __cplusplus
 }

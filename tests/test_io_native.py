@@ -203,3 +203,82 @@ def test_native_loader_on_the_golden_hicpro_files():
         A2, b2 = hio.removeRows(got.copy(), [hio.Bin(b.ID, b.chrom, b.start, b.stop, b.bias) for b in bins])
     assert np.array_equal(A1, A2) and [b.ID for b in b1] == [b.ID for b in b2]
     assert [float(b.rowSum) for b in b1] == [float(b.rowSum) for b in b2]
+
+
+# ---- initiateLoci (scaffoldToChromosomes.py:35-68) through hica_io_read_loci ---------------------------------
+
+def _loci_case(tmp_path, n=400, eol="\n", final_newline=True, short_bias=False, seed=0):
+    rs = np.random.RandomState(seed)
+    bed, bias = [], []
+    for i in range(n):
+        chrom = "scaffold_%d" % (i // 17) if i % 29 else "chr Ünï%d" % i
+        bed.append("%s\t%d\t%d\t%d" % (chrom, i * 100000, (i + 1) * 100000, 3 * i + 1) + ("\textra" if i % 31 == 5 else ""))
+        r = i % 13
+        bias.append({0: "nan", 1: "NaN", 2: " nan", 3: "", 4: "abc", 5: "1e-3", 6: "+0.75", 7: " 2.5 ", 8: "inf",
+                     9: "nan(1)", 10: "0x10"}.get(r, repr(float(rs.rand() + 0.5))))
+    if short_bias:
+        bias = bias[: n - 7]
+    bp, ip = str(tmp_path / "g.bed"), str(tmp_path / "g.bias")
+    with open(bp, "w", newline="") as f:
+        f.write(eol.join(bed) + (eol if final_newline and n else ""))
+    with open(ip, "w", newline="") as f:
+        f.write(eol.join(bias) + (eol if final_newline and n else ""))
+    return bp, ip
+
+
+def _same_bins(got, want):
+    assert len(got) == len(want)
+    for a, b in zip(got, want):
+        assert (a.ID, a.chrom, a.start, a.stop) == (b.ID, b.chrom, b.start, b.stop)
+        assert type(a.ID) is type(b.ID) is int and type(a.bias) is type(b.bias) is float
+        assert a.bias == b.bias or (a.bias != a.bias and b.bias != b.bias)
+        assert a.rowSum == b.rowSum == 0.0
+
+
+@pytest.mark.parametrize("kw", [{}, dict(eol="\r\n"), dict(eol="\r", final_newline=False), dict(short_bias=True),
+                                dict(n=1, final_newline=False), dict(n=0)])
+def test_native_loci_reader_equals_the_python_restatement(tmp_path, kw):
+    bp, ip = _loci_case(tmp_path, **kw)
+    _same_bins(hio.read_loci_native(bp, ip), hio.read_loci(bp, ip))
+    keep = {3 * i + 1: True for i in range(0, 400, 3)}
+    _same_bins(hio.read_loci_native(bp, ip, keep), hio.read_loci(bp, ip, keep))
+    _same_bins(hio.read_loci_native(bp, ip, {}), [])
+
+
+def test_native_loci_reader_errors(tmp_path):
+    bp, ip = _loci_case(tmp_path, n=5)
+    with pytest.raises(FileNotFoundError):
+        hio.read_loci_native(str(tmp_path / "nope.bed"), ip)
+    bad = str(tmp_path / "bad.bed")
+    with open(bad, "w") as f:
+        f.write("s\t0\t10\t1\ns\t10\t20\n")
+    with pytest.raises(ValueError, match="line 2"):       # the reference raises IndexError there
+        hio.read_loci_native(bad, ip)
+    with open(bad, "w") as f:
+        f.write("s\t0\t10\t1\n\ns\t10\t20\t2\n")
+    with pytest.raises(ValueError, match="line 2"):       # an empty line: IndexError in the reference
+        hio.read_loci_native(bad, ip)
+    with open(bad, "w") as f:
+        f.write("s\t0\tx\t1\n")
+    with pytest.raises(ValueError, match="line 1"):       # int('x'): ValueError in the reference
+        hio.read_loci_native(bad, ip)
+
+
+@pytest.mark.reference
+@pytest.mark.parametrize("kw", [{}, dict(eol="\r\n"), dict(short_bias=True)])
+def test_initiateLoci_seam_equals_the_reference(tmp_path, kw):
+    if not ref_harness.reference_available():
+        pytest.skip("reference tree not mounted")
+    p1, p2 = ref_harness.load_reference()
+    bp, ip = _loci_case(tmp_path, **kw)
+    for mod in (p1, p2):
+        seam = hio.make_initiateLoci(mod.Bin)
+        for keep in (False, {3 * i + 1: 0 for i in range(0, 400, 5)}):
+            out_ref, out_new = _io.StringIO(), _io.StringIO()
+            with contextlib.redirect_stdout(out_ref):
+                want = mod.initiateLoci(bp, ip, binID_dict=keep)
+            with contextlib.redirect_stdout(out_new):
+                got = seam(bp, ip, binID_dict=keep)
+            assert out_new.getvalue() == out_ref.getvalue()
+            assert all(type(b) is mod.Bin for b in got)
+            _same_bins(got, want)
