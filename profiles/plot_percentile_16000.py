@@ -2,7 +2,7 @@
 16,000-bin distance matrix (plotContactMaps.py:30-31) - device radix select on the resident matrix against numpy on
 a host copy, results compared bit for bit.  Writes gpurun_out/r2_plot_percentile.json.
 
-    python profiles/plot_percentile_16000.py [bins]
+    python profiles/plot_percentile_16000.py [bins] [--device-only]
 """
 import json
 import os
@@ -20,7 +20,9 @@ def main():
     from hic_genome_assembler_b200 import plot as hplot
     from hic_genome_assembler_b200._lib import Handle
     from hic_genome_assembler_b200.synth import make_genome_portable
-    n = int(sys.argv[1]) if len(sys.argv) > 1 else 16000
+    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    device_only = "--device-only" in sys.argv          # for runs under ncu: no numpy comparison, nothing written
+    n = int(args[0]) if args else 16000
     g = make_genome_portable(n, n_chrom=20, seed=7, device="cuda:0")
     out = {"bins": n, "peak_hbm_gbs": None}
     try:
@@ -43,6 +45,9 @@ def main():
             # 6 counting passes over 8 n^2 bytes
             ms[name]["algorithmic_gb"] = 6 * 8.0 * n * n / 1e9
             ms[name]["gb_per_s"] = ms[name]["algorithmic_gb"] / (ms[name]["device_ms_per_call_two_percentiles"] / 1e3)
+        if device_only:
+            print(json.dumps(ms))
+            return
         D = h.p1_get_distance()
         t0 = time.perf_counter()
         want = [np.percentile(D, 1), np.percentile(D, 98)]          # the reference's two calls
