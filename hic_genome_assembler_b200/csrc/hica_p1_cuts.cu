@@ -998,10 +998,18 @@ extern "C" int hica_p1_filter(hica_handle h, const int64_t *cuts_in, int64_t n_i
             // chunk): the loop usually stops at an early cut, so evaluating the whole list at once would waste
             // far more work (later cuts have long windows) than the round trips it saves.
             const int64_t Lw = n - start, rows = std::min<int64_t>(Lw, n / 5 + 1);
-            constexpr int CHUNK = 4;
+            constexpr int CHUNK_MAX = 8;     // the chunk's per-cut counters live in misc[8 .. 16)
+            // cuts per round trip (HICA_FB_CHUNK = 1 .. 8).  Measured at 16,000 bins, 81 cuts in: 2 -> 4.68 ms,
+            // 3 -> 4.95, 4 -> 5.35, 6 -> 6.17, 8 -> 6.99: the speculative evaluations cost more than the round
+            // trips they save (profiles/r02_filter_chunk_sweep.txt)
+            static const int CHUNK = [] {
+                const char *e = getenv("HICA_FB_CHUNK");
+                const int v = e ? atoi(e) : 2;
+                return v < 1 ? 1 : (v > CHUNK_MAX ? CHUNK_MAX : v);
+            }();
             std::vector<int32_t> all_flags((size_t)CHUNK * nb);
             int chunk_lo = 0, chunk_hi = 0;  // cuts [chunk_lo, chunk_hi) of the list have flags in all_flags
-            int64_t tie_chunk[CHUNK] = {0, 0, 0, 0};  // tie-sensitive row decisions per evaluated cut
+            int64_t tie_chunk[CHUNK_MAX] = {0, 0, 0, 0, 0, 0, 0, 0};  // tie-sensitive row decisions per evaluated cut
             auto eval_chunk = [&](int i0) -> int {
                 const int ne = std::min(CHUNK, nb - i0);
                 const int64_t need = (int64_t)ne * rows * 13 + (int64_t)ne * nb * 12 + (int64_t)ne * 8 + 1024 + 64;
